@@ -1,0 +1,90 @@
+"""ctypes binding of libecamp_b200.so (the C ABI declared in include/ecamp_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libecamp_b200.so")
+
+GEMM_GELU, GEMM_DGELU, GEMM_DROPOUT = 1, 2, 4
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [
+        ("bias", ctypes.c_void_p),
+        ("aux_in", ctypes.c_void_p),
+        ("aux_out", ctypes.c_void_p),
+        ("ld_aux", ctypes.c_int32),
+        ("residual", ctypes.c_void_p),
+        ("ld_res", ctypes.c_int32),
+        ("out_f32", ctypes.c_void_p),
+        ("ld_f32", ctypes.c_int32),
+        ("out_bf16", ctypes.c_void_p),
+        ("ld_bf16", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
+        ("drop_p", ctypes.c_float),
+        ("seed", ctypes.c_uint64),
+        ("site", ctypes.c_uint64),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"ecamp_b200: {LIB_PATH} is missing - build it with ecamp_b200/csrc/build.sh "
+                "(or __graft_entry__.build()); there is no CPU or PyTorch fallback")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.ecamp_last_error.restype = ctypes.c_char_p
+        _lib.ecamp_abi_version.restype = ctypes.c_int
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().ecamp_last_error()
+        raise RuntimeError(f"ecamp_b200: {what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def cur_stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, bias=None, aux_in=None, aux_out=None,
+         residual=None, out_f32=None, out_bf16=None, flags=0, drop_p=0.0, seed=0, site=0, tile_n=0):
+    """D = epilogue(A . B^T) on the tcgen05 kernel.  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(-1) == 1 and b.stride(-1) == 1
+    if M is None:
+        M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    if N is None:
+        N = b.shape[1] if b_mn else b.shape[0]
+    ep = Epilogue()
+    ep.bias = bias.data_ptr() if bias is not None else None
+    ep.aux_in = aux_in.data_ptr() if aux_in is not None else None
+    ep.aux_out = aux_out.data_ptr() if aux_out is not None else None
+    aux = aux_in if aux_in is not None else aux_out
+    ep.ld_aux = aux.stride(0) if aux is not None else 0
+    ep.residual = residual.data_ptr() if residual is not None else None
+    ep.ld_res = residual.stride(0) if residual is not None else 0
+    ep.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+    ep.ld_f32 = out_f32.stride(0) if out_f32 is not None else 0
+    ep.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+    ep.ld_bf16 = out_bf16.stride(0) if out_bf16 is not None else 0
+    ep.flags, ep.drop_p, ep.seed, ep.site = flags, drop_p, seed, site
+    rc = lib().ecamp_gemm_bf16(ptr(a), ctypes.c_int32(a.stride(0)), ctypes.c_int32(int(a_mn)), ptr(b),
+                               ctypes.c_int32(b.stride(0)), ctypes.c_int32(int(b_mn)), ctypes.c_int32(M),
+                               ctypes.c_int32(N), ctypes.c_int32(K), ctypes.byref(ep), ctypes.c_int32(tile_n),
+                               cur_stream())
+    check(rc, "ecamp_gemm_bf16")

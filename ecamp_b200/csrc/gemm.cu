@@ -1,0 +1,471 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, STAGES-deep mbarrier ring)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM)
+//   warp 2      TMEM allocator (512 columns = two accumulator stages, so the epilogue of tile i
+//                               overlaps the main loop of tile i+1)
+//   warps 4-11  epilogue       (tcgen05.ld -> bias / GELU / dGELU / dropout / residual -> global)
+//
+// Operands may be K-major (the contraction index is contiguous in memory) or MN-major (the
+// output index is contiguous); the latter is what dgrad (weights) and wgrad (both operands)
+// need, so no transposed copies of activations or weights are ever made.
+//
+// Replaces the cuBLAS calls behind every nn.Linear of the reference hot path
+// (ECAMP/Pre-training/module/model_ecamp.py:60-90, timm Block, HF BertLayer).
+#include "gemm.cuh"
+
+#include <cuda.h>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <unordered_map>
+
+namespace ecamp {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kNumEpiWarps = 8;
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 192) ? 5 : 6);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+};
+
+struct EpiArgs {
+  GemmEpilogue ep;
+  int vec_ok;
+};
+
+// ---------------------------------------------------------------------------------------------
+// epilogue for one thread: one output row, 32 consecutive columns
+// ---------------------------------------------------------------------------------------------
+ECAMP_DEVINL void epilogue_row32(const EpiArgs& ea, float (&v)[32], int row, int col0, int N) {
+  const GemmEpilogue& ep = ea.ep;
+  const bool full = ea.vec_ok && (col0 + 32 <= N);
+  const int nvalid = min(32, N - col0);
+
+  if (ep.bias) {
+    if (full) {
+      const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(bp + i);
+        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) v[i] += __ldg(ep.bias + col0 + i);
+    }
+  }
+  if (ep.flags & GEMM_GELU) {
+    // the reference applies GELU to the half-precision Linear output; keep forward and backward
+    // consistent by activating the rounded value that is saved for backward
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = bf2f(f2bf(v[i]));
+    if (ep.aux_out) {
+      bf16* ap = ep.aux_out + (size_t)row * ep.ld_aux + col0;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+          u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+          reinterpret_cast<uint4*>(ap)[i] = u;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < nvalid) ap[i] = f2bf(v[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (ep.flags & GEMM_DGELU) {
+    const bf16* ap = ep.aux_in + (size_t)row * ep.ld_aux + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(ap) + i);
+        float2 f;
+        f = unpack_bf16x2(u.x); v[8 * i + 0] *= gelu_erf_grad(f.x); v[8 * i + 1] *= gelu_erf_grad(f.y);
+        f = unpack_bf16x2(u.y); v[8 * i + 2] *= gelu_erf_grad(f.x); v[8 * i + 3] *= gelu_erf_grad(f.y);
+        f = unpack_bf16x2(u.z); v[8 * i + 4] *= gelu_erf_grad(f.x); v[8 * i + 5] *= gelu_erf_grad(f.y);
+        f = unpack_bf16x2(u.w); v[8 * i + 6] *= gelu_erf_grad(f.x); v[8 * i + 7] *= gelu_erf_grad(f.y);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) v[i] *= gelu_erf_grad(bf2f(ap[i]));
+    }
+  }
+  if (ep.flags & GEMM_DROPOUT) {
+    const Philox ph(ep.seed);
+    const uint32_t thr = dropout_threshold(ep.drop_p);
+    const float scale = 1.0f / (1.0f - ep.drop_p);
+    const uint64_t base = (uint64_t)row * (uint64_t)N + (uint64_t)col0;  // N % 4 == 0 checked on the host
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 r = ph((base >> 2) + i, ep.stream);
+      v[4 * i + 0] = (r.x >= thr) ? v[4 * i + 0] * scale : 0.f;
+      v[4 * i + 1] = (r.y >= thr) ? v[4 * i + 1] * scale : 0.f;
+      v[4 * i + 2] = (r.z >= thr) ? v[4 * i + 2] * scale : 0.f;
+      v[4 * i + 3] = (r.w >= thr) ? v[4 * i + 3] * scale : 0.f;
+    }
+  }
+  if (ep.residual) {
+    const float* rp = ep.residual + (size_t)row * ep.ld_res + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 r = reinterpret_cast<const float4*>(rp)[i];
+        v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) v[i] += rp[i];
+    }
+  }
+  if (ep.out_f32) {
+    float* op = ep.out_f32 + (size_t)row * ep.ld_f32 + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<float4*>(op)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) op[i] = v[i];
+    }
+  }
+  if (ep.out_bf16) {
+    bf16* op = ep.out_bf16 + (size_t)row * ep.ld_bf16 + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        reinterpret_cast<uint4*>(op)[i] = u;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) op[i] = f2bf(v[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
+                    int N, int K, EpiArgs ea) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * C::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * C::A_BYTES;
+          uint8_t* b_dst = sB + stage * C::B_BYTES;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(a_dst + j * (BK * 128), &tma_a, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(b_dst + j * (BK * 128), &tma_b, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (lane == 0) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * C::A_BYTES);
+          const uint32_t b_base = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major:  rows of 128 B, 8-row groups 1024 B apart; 16 k-elements = 32 B inside the swizzle span.
+            // MN-major: 64 mn-elements per 128 B row, one row per k, 8-k groups 1024 B apart (SBO),
+            //           64-wide mn groups BK*128 B apart (LBO); 16 k-elements = 16 rows = 2048 B.
+            const uint64_t adesc = A_MN ? umma_smem_desc_sw128(a_base + k * 2048, BK * 128, 1024)
+                                        : umma_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_base + k * 2048, BK * 128, 1024)
+                                        : umma_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns
+    constexpr int HALF_N = BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < HALF_N / 32; ++c) {
+        const int tcol = acc * BN + half * HALF_N + c * 32;
+        const int col0 = n_blk * BN + half * HALF_N + c * 32;
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tcol, raw);
+        tmem_ld_wait();
+        if (c == HALF_N / 32 - 1) {
+          // all of this warp's TMEM reads for the tile are done: hand the accumulator stage back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (row < M && col0 < N) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          epilogue_row32(ea, v, row, col0, N);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 matrix stored row-major [outer, inner] with a row pitch; box = [box_outer, box_inner = 64].
+int make_tmap(CUtensorMap* map, const bf16* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+              uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  ECAMP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  ECAMP_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand base must be 16-byte aligned");
+  ECAMP_REQUIRE((pitch_elems * 2) % 16 == 0, "GEMM operand pitch must be a multiple of 16 bytes (got %llu elements)",
+                (unsigned long long)pitch_elems);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ECAMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (inner %llu outer %llu pitch %llu box %u)",
+                (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems,
+                box_outer);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int pick_bn(int M, int N) {
+  const int sms = num_sms();
+  const int m_tiles = (M + BM - 1) / BM;
+  const int cand[3] = {256, 192, 128};
+  const float eff[3] = {1.00f, 0.97f, 0.88f};  // smaller tiles put more shared-memory traffic behind each MMA
+  int best = 256;
+  float best_cost = 1e30f;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    const int tiles = m_tiles * ((N + bn - 1) / bn);
+    const int waves = (tiles + sms - 1) / sms;
+    const float cost = (float)waves * (float)bn / eff[i];
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
+  auto kfn = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kfn<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, M, N, K, ea);
+  ECAMP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+                 const EpiArgs& ea, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, M, N, K, ea, st);
+  if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, M, N, K, ea, st);
+  if (a_mn && b_mn) return launch<BN, true, true>(ta, tb, M, N, K, ea, st);
+  return launch<BN, true, false>(ta, tb, M, N, K, ea, st);
+}
+
+}  // namespace
+
+int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
+              const GemmEpilogue& ep, int force_bn, cudaStream_t stream) {
+  ECAMP_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem %d x %d x %d", M, N, K);
+  ECAMP_REQUIRE(ep.out_f32 || ep.out_bf16, "gemm: no output given");
+  if (ep.flags & GEMM_DROPOUT)
+    ECAMP_REQUIRE(N % 4 == 0 && ep.drop_p >= 0.f && ep.drop_p < 1.f, "gemm: dropout needs N %% 4 == 0, 0 <= p < 1");
+  if (ep.flags & GEMM_DGELU) ECAMP_REQUIRE(ep.aux_in != nullptr, "gemm: dGELU needs aux_in");
+  const int bn = force_bn ? force_bn : pick_bn(M, N);
+  ECAMP_REQUIRE(bn == 128 || bn == 192 || bn == 256, "gemm: unsupported tile N %d", bn);
+
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major operand: inner = contraction, outer = rows, box [rows_tile, 64]
+  // MN-major operand: inner = output index, outer = contraction, box [64 (k), 64]
+  rc = a_mn ? make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK)
+            : make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM);
+  if (rc) return rc;
+  rc = b_mn ? make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK)
+            : make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)bn);
+  if (rc) return rc;
+
+  EpiArgs ea;
+  ea.ep = ep;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  ea.vec_ok = 1;
+  if (ep.bias && !al16(ep.bias)) ea.vec_ok = 0;
+  if ((ep.aux_in || ep.aux_out) && (ep.ld_aux % 8 != 0 || !al16(ep.aux_in) || !al16(ep.aux_out))) ea.vec_ok = 0;
+  if (ep.residual && (ep.ld_res % 4 != 0 || !al16(ep.residual))) ea.vec_ok = 0;
+  if (ep.out_f32 && (ep.ld_f32 % 4 != 0 || !al16(ep.out_f32))) ea.vec_ok = 0;
+  if (ep.out_bf16 && (ep.ld_bf16 % 8 != 0 || !al16(ep.out_bf16))) ea.vec_ok = 0;
+
+  if (bn == 256) return launch_major<256>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
+  if (bn == 192) return launch_major<192>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
+  return launch_major<128>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error_cstr() { return g_err; }
+
+}  // namespace ecamp

@@ -1,0 +1,38 @@
+// Internal (C++) interface of the tcgen05 GEMM used by every Linear on the ECAMP hot path.
+#pragma once
+#include "common.cuh"
+
+namespace ecamp {
+
+enum GemmFlags : int {
+  GEMM_GELU = 1,     // v = gelu(bf16(v)); the rounded pre-activation is stored to aux_out (bf16) if given
+  GEMM_DGELU = 2,    // v *= gelu'(aux_in[m, n])   (aux_in = bf16 pre-activation saved by the forward)
+  GEMM_DROPOUT = 4,  // v = keep(m, n) ? v / (1 - p) : 0   (Philox keyed by seed / stream / m * N + n)
+};
+
+struct GemmEpilogue {
+  const float* bias = nullptr;      // [N], added first
+  const bf16* aux_in = nullptr;     // [M, ld_aux]
+  bf16* aux_out = nullptr;          // [M, ld_aux]
+  int ld_aux = 0;
+  const float* residual = nullptr;  // [M, ld_res] fp32, added last (may alias out_f32: accumulate)
+  int ld_res = 0;
+  float* out_f32 = nullptr;
+  int ld_f32 = 0;
+  bf16* out_bf16 = nullptr;
+  int ld_bf16 = 0;
+  int flags = 0;
+  float drop_p = 0.f;
+  unsigned long long seed = 0, stream = 0;
+};
+
+// D[M, N] = A . B^T over the contraction dimension K, bf16 inputs, fp32 accumulation in TMEM.
+//   a_mn == 0: A is stored [M, K] row-major with pitch lda (K-major);  a_mn == 1: stored [K, M] with pitch lda.
+//   b_mn == 0: B is stored [N, K] row-major with pitch ldb (K-major);  b_mn == 1: stored [K, N] with pitch ldb.
+// Forward  y = x W^T      : A = x [M,K] (a_mn 0), B = W [N,K] (b_mn 0)
+// dgrad    dx = dy W      : A = dy [M,N'] (a_mn 0), B = W [N',K'] stored [contraction, out] (b_mn 1)
+// wgrad    dW = dy^T x    : A = dy stored [rows, N'] (a_mn 1), B = x stored [rows, K'] (b_mn 1)
+int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
+              const GemmEpilogue& ep, int force_bn, cudaStream_t stream);
+
+}  // namespace ecamp
