@@ -32,6 +32,42 @@ class Epilogue(ctypes.Structure):
     ]
 
 
+class Shape(ctypes.Structure):
+    _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("len_keep", ctypes.c_int32), ("has_big", ctypes.c_int32),
+                ("ce_rows", ctypes.c_int32)]
+
+
+class Batch(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("image", "ids", "labels", "attention_mask", "type_ids", "weights",
+                                               "column", "row", "noise")]
+
+
+class Attn(ctypes.Structure):
+    _fields_ = [("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("v", ctypes.c_void_p),
+                ("ldq", ctypes.c_int32), ("ldk", ctypes.c_int32), ("ldv", ctypes.c_int32),
+                ("o", ctypes.c_void_p), ("ldo", ctypes.c_int32), ("lse", ctypes.c_void_p),
+                ("key_mask", ctypes.c_void_p),
+                ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("Sq", ctypes.c_int32), ("Sk", ctypes.c_int32),
+                ("D", ctypes.c_int32), ("scale", ctypes.c_float), ("drop_p", ctypes.c_float),
+                ("seed", ctypes.c_uint64), ("site", ctypes.c_uint64),
+                ("d_o", ctypes.c_void_p), ("ld_do", ctypes.c_int32), ("delta", ctypes.c_void_p),
+                ("dq", ctypes.c_void_p), ("dk", ctypes.c_void_p), ("dv", ctypes.c_void_p),
+                ("lddq", ctypes.c_int32), ("lddk", ctypes.c_int32), ("lddv", ctypes.c_int32)]
+
+
+# every symbol include/ecamp_b200.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "ecamp_abi_version", "ecamp_last_error", "ecamp_gemm_bf16", "ecamp_random_masking", "ecamp_resize_patchify",
+    "ecamp_layernorm_fwd", "ecamp_layernorm_bwd", "ecamp_layernorm_ws_floats", "ecamp_attention_fwd",
+    "ecamp_attention_bwd", "ecamp_mim_loss", "ecamp_sr_loss_fwd", "ecamp_sr_loss_bwd", "ecamp_sr_ws_floats",
+    "ecamp_pred_grad", "ecamp_ce_rows", "ecamp_param_count", "ecamp_param_name", "ecamp_param_numel",
+    "ecamp_param_decay", "ecamp_param_grad_offset", "ecamp_grad_floats", "ecamp_shadow_bytes",
+    "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_ctx_create", "ecamp_ctx_destroy", "ecamp_ctx_bind",
+    "ecamp_workspace_bytes", "ecamp_ctx_set_workspace", "ecamp_refresh_shadows", "ecamp_forward",
+    "ecamp_backward_stage_count", "ecamp_backward_stage_range", "ecamp_backward", "ecamp_adamw_step",
+    "ecamp_debug_buffer",
+]
+
 _lib = None
 
 
@@ -45,6 +81,15 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.ecamp_last_error.restype = ctypes.c_char_p
         _lib.ecamp_abi_version.restype = ctypes.c_int
+        _lib.ecamp_param_name.restype = ctypes.c_char_p
+        for f in ("ecamp_param_numel", "ecamp_param_grad_offset", "ecamp_grad_floats", "ecamp_shadow_bytes",
+                  "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_workspace_bytes"):
+            getattr(_lib, f).restype = ctypes.c_int64
+        for f in ("ecamp_layernorm_ws_floats", "ecamp_sr_ws_floats"):
+            getattr(_lib, f).restype = ctypes.c_size_t
+        _lib.ecamp_debug_buffer.restype = ctypes.c_void_p
+        _lib.ecamp_ctx_destroy.restype = None
+        _lib.ecamp_ctx_destroy.argtypes = [ctypes.c_void_p]
     return _lib
 
 

@@ -3,12 +3,38 @@
 
 #include "common.cuh"
 #include "gemm.cuh"
+#include "kernels.cuh"
+#include "model.cuh"
 
 namespace ecamp {
 const char* last_error_cstr();
 }
-
 using namespace ecamp;
+
+struct ecamp_ctx {
+  Ctx* impl;
+};
+
+namespace {
+cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+AttnArgs to_args(const ecamp_attn* a) {
+  AttnArgs r;
+  r.q = static_cast<const bf16*>(a->q); r.k = static_cast<const bf16*>(a->k); r.v = static_cast<const bf16*>(a->v);
+  r.ldq = a->ldq; r.ldk = a->ldk; r.ldv = a->ldv;
+  r.o = static_cast<bf16*>(a->o); r.ldo = a->ldo; r.lse = a->lse; r.key_mask = a->key_mask;
+  r.B = a->B; r.H = a->H; r.Sq = a->Sq; r.Sk = a->Sk; r.D = a->D; r.scale = a->scale;
+  r.drop.p = a->drop_p; r.drop.seed = a->seed; r.drop.site = a->site;
+  r.d_o = static_cast<const bf16*>(a->d_o); r.ld_do = a->ld_do; r.delta = a->delta;
+  r.dq = static_cast<bf16*>(a->dq); r.dk = static_cast<bf16*>(a->dk); r.dv = static_cast<bf16*>(a->dv);
+  r.lddq = a->lddq; r.lddk = a->lddk; r.lddv = a->lddv;
+  return r;
+}
+Shape to_shape(const ecamp_shape* s) {
+  Shape r;
+  r.B = s->B; r.T = s->T; r.keep = s->len_keep; r.has_big = s->has_big; r.ce_rows = s->ce_rows > 0 ? s->ce_rows : 2048;
+  return r;
+}
+}  // namespace
 
 extern "C" {
 
@@ -34,7 +60,134 @@ int ecamp_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int
   e.seed = ep->seed;
   e.stream = ep->site;
   return gemm_bf16(static_cast<const bf16*>(A), lda, a_mn, static_cast<const bf16*>(B), ldb, b_mn, M, N, K, e, tile_n,
-                   static_cast<cudaStream_t>(stream));
+                   S(stream));
+}
+
+int ecamp_random_masking(const float* noise, int32_t B, int32_t L, int32_t len_keep, int64_t* ids_restore,
+                         int64_t* ids_keep, float* mask, void* scratch_i32, void* stream) {
+  ECAMP_REQUIRE(noise && ids_restore && ids_keep && mask && scratch_i32, "ecamp_random_masking: null argument");
+  int32_t* r32 = static_cast<int32_t*>(scratch_i32);
+  return random_masking(noise, B, L, len_keep, r32, r32 + (size_t)B * L, mask, ids_restore, ids_keep, S(stream));
+}
+
+int ecamp_resize_patchify(const float* big, int32_t B, int32_t side_in, float* tgt, void* stream) {
+  ECAMP_REQUIRE(big && tgt, "ecamp_resize_patchify: null argument");
+  if (side_in == 224) return patchify224(big, B, tgt, S(stream));
+  return resize_bicubic_patchify(big, B, side_in, tgt, S(stream));
+}
+
+int ecamp_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t M, int32_t D,
+                        void* out_bf16, float* out_f32, float* mean, float* rstd, void* stream) {
+  return layernorm_fwd(x, gamma, beta, eps, M, D, static_cast<bf16*>(out_bf16), out_f32, mean, rstd, S(stream));
+}
+int ecamp_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                        int32_t M, int32_t D, const float* addend, float* dx_f32, void* dx_bf16, float* dgamma,
+                        float* dbeta, int32_t accumulate, float* ws, void* stream) {
+  return layernorm_bwd(dy, x, mean, rstd, gamma, M, D, addend, dx_f32, static_cast<bf16*>(dx_bf16), DropoutCfg(),
+                       dgamma, dbeta, accumulate, ws, S(stream));
+}
+size_t ecamp_layernorm_ws_floats(void) { return layernorm_bwd_ws_floats(768); }
+
+int ecamp_attention_fwd(const ecamp_attn* a, void* stream) {
+  ECAMP_REQUIRE(a && a->q && a->k && a->v && a->o, "ecamp_attention_fwd: null argument");
+  return attention_fwd(to_args(a), S(stream));
+}
+int ecamp_attention_bwd(const ecamp_attn* a, void* stream) {
+  ECAMP_REQUIRE(a && a->q && a->k && a->v && a->o, "ecamp_attention_bwd: null argument");
+  return attention_bwd(to_args(a), S(stream));
+}
+
+int ecamp_mim_loss(const float* pred, const float* tgt, const float* mask, int32_t B, float* loss, float* ws,
+                   void* stream) {
+  return mim_loss_fwd(pred, 197, tgt, mask, B, 196, 768, loss, ws, S(stream));
+}
+int ecamp_sr_loss_fwd(const float* pred, const float* big, const int64_t* column, const int64_t* row, const float* w1,
+                      const float* b1, const float* w2, const float* b2, int32_t B, float* loss, float* ws,
+                      void* stream) {
+  return sr_loss_fwd(pred, big, column, row, w1, b1, w2, b2, B, loss, ws, S(stream));
+}
+int ecamp_sr_loss_bwd(const float* pred, const float* big, const int64_t* column, const int64_t* row, const float* w1,
+                      const float* b1, const float* w2, const float* b2, int32_t B, const float* g_res, float* d_u,
+                      float* d_conv, int32_t accumulate, float* ws, void* stream) {
+  return sr_loss_bwd(pred, big, column, row, w1, b1, w2, b2, B, g_res, d_u, d_conv, accumulate, ws, S(stream));
+}
+size_t ecamp_sr_ws_floats(int32_t B) { return sr_ws_floats(B); }
+int ecamp_pred_grad(const float* pred, const float* tgt, const float* mask, const float* d_u, const float* g_mim,
+                    int32_t B, void* d_pred_bf16, void* stream) {
+  return pred_grad(pred, tgt, mask, d_u, g_mim, B, static_cast<bf16*>(d_pred_bf16), S(stream));
+}
+int ecamp_ce_rows(void* logits_bf16, int32_t ld, int32_t rows, int32_t V, const int64_t* labels, const float* weights,
+                  float* row_loss, const float* g, float inv_total_rows, int32_t write_grad, void* stream) {
+  return ce_chunk(static_cast<bf16*>(logits_bf16), ld, rows, V, labels, weights, row_loss, g, inv_total_rows,
+                  write_grad, S(stream));
+}
+
+// ---- runtime -----------------------------------------------------------------------------------
+int32_t ecamp_param_count(void) { return (int32_t)param_specs().size(); }
+const char* ecamp_param_name(int32_t i) {
+  return (i >= 0 && i < ecamp_param_count()) ? param_specs()[i].name.c_str() : nullptr;
+}
+int64_t ecamp_param_numel(int32_t i) { return (i >= 0 && i < ecamp_param_count()) ? param_specs()[i].numel : -1; }
+int32_t ecamp_param_decay(int32_t i) { return (i >= 0 && i < ecamp_param_count()) ? param_specs()[i].decay : -1; }
+int64_t ecamp_param_grad_offset(int32_t i) { return (i >= 0 && i < ecamp_param_count()) ? param_specs()[i].g_off : -1; }
+int64_t ecamp_grad_floats(void) { return grad_total_floats(); }
+int64_t ecamp_shadow_bytes(void) { return ((shadow_bf16_elems() + 7) & ~7LL) * 2 + shadow_f32_elems() * 4 + 64; }
+int64_t ecamp_adam_table_bytes(void) { return (int64_t)ctx_adam_table_bytes(); }
+int64_t ecamp_adam_chunk_bytes(void) { return (int64_t)ctx_adam_chunk_bytes(); }
+
+int ecamp_ctx_create(ecamp_ctx** out) {
+  ECAMP_REQUIRE(out != nullptr, "ecamp_ctx_create: null output");
+  *out = new ecamp_ctx{ctx_new()};
+  return 0;
+}
+void ecamp_ctx_destroy(ecamp_ctx* ctx) {
+  if (!ctx) return;
+  ctx_free(ctx->impl);
+  delete ctx;
+}
+int ecamp_ctx_bind(ecamp_ctx* ctx, float* const* params_host, int32_t n, float* grads, float* adam_m, float* adam_v,
+                   void* shadows, const float* pos_embed, const float* decoder_pos_embed, void* adam_table,
+                   void* adam_chunks) {
+  ECAMP_REQUIRE(ctx && params_host, "ecamp_ctx_bind: null argument");
+  return ctx_bind(ctx->impl, params_host, n, grads, adam_m, adam_v, shadows, pos_embed, decoder_pos_embed, adam_table,
+                  adam_chunks);
+}
+int64_t ecamp_workspace_bytes(const ecamp_shape* s) { return s ? (int64_t)workspace_bytes(to_shape(s)) : -1; }
+int ecamp_ctx_set_workspace(ecamp_ctx* ctx, void* ws, int64_t bytes, const ecamp_shape* s) {
+  ECAMP_REQUIRE(ctx && ws && s, "ecamp_ctx_set_workspace: null argument");
+  return ctx_set_workspace(ctx->impl, ws, (size_t)bytes, to_shape(s));
+}
+int ecamp_refresh_shadows(ecamp_ctx* ctx, void* stream) {
+  ECAMP_REQUIRE(ctx, "ecamp_refresh_shadows: null context");
+  return ctx_refresh_shadows(ctx->impl, S(stream));
+}
+int ecamp_forward(ecamp_ctx* ctx, const ecamp_batch* b, int32_t flags, float drop_p, uint64_t seed, float* losses,
+                  float* mask, int64_t* ids_restore, int64_t* ids_keep, void* stream) {
+  ECAMP_REQUIRE(ctx && b, "ecamp_forward: null argument");
+  Batch bb;
+  bb.image = b->image; bb.ids = b->ids; bb.labels = b->labels; bb.attention_mask = b->attention_mask;
+  bb.type_ids = b->type_ids; bb.weights = b->weights; bb.column = b->column; bb.row = b->row; bb.noise = b->noise;
+  return ctx_forward(ctx->impl, bb, flags, drop_p, seed, losses, mask, ids_restore, ids_keep, S(stream));
+}
+int32_t ecamp_backward_stage_count(void) { return backward_stage_count(); }
+int ecamp_backward_stage_range(int32_t stage, int64_t* begin, int64_t* end) {
+  long long b = 0, e = 0;
+  const int rc = backward_stage_range(stage, &b, &e);
+  if (rc) return rc;
+  *begin = b; *end = e;
+  return 0;
+}
+int ecamp_backward(ecamp_ctx* ctx, const float* g3, int32_t accumulate, int32_t stage, void* stream) {
+  ECAMP_REQUIRE(ctx, "ecamp_backward: null context");
+  return ctx_backward(ctx->impl, g3, accumulate, stage, S(stream));
+}
+int ecamp_adamw_step(ecamp_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                     float grad_scale, void* stream) {
+  ECAMP_REQUIRE(ctx, "ecamp_adamw_step: null context");
+  return ctx_adamw(ctx->impl, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
+}
+const void* ecamp_debug_buffer(ecamp_ctx* ctx, const char* name) {
+  return (ctx && name) ? ctx_debug_ptr(ctx->impl, name) : nullptr;
 }
 
 }  // extern "C"

@@ -1,0 +1,488 @@
+// Fused attention forward / backward for the four shapes of the ECAMP step:
+//   ViT encoder 12 heads x 64, S = 50;  ViT decoder 16 heads x 32, S = 197            (timm Attention)
+//   BERT self-attention 6 heads x 128, S = T, additive key-padding mask, prob-dropout  (HF BertSelfAttention)
+//   cross-attention text -> 49 image tokens, 6 heads x 128                             (context_fusion.py:45-53)
+// Scores are never written to memory: one CTA owns 64 rows of one (batch, head), keeps the whole
+// K/V (or Q/dO) of that head in shared memory and runs an online softmax over 64-column blocks.
+// Tensor-core path: mma.sync m16n8k16 bf16 (legacy HMMA issue path; attention is 2.4 % of the step's
+// FLOPs — moving it onto tcgen05 is a later-round item).
+//
+// Backward is two passes of ONE kernel template: pass "dQ" walks key blocks for a query tile, pass
+// "dK/dV" walks query blocks for a key tile (the transposed problem); no atomics, deterministic.
+#include "kernels.cuh"
+
+namespace ecamp {
+namespace {
+
+ECAMP_DEVINL void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+ECAMP_DEVINL void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+ECAMP_DEVINL void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+
+// A fragment (16 rows x 16 k) of a row-major [rows][LDS] bf16 tile: row0 = first row, k0 = first column.
+template <int LDS>
+ECAMP_DEVINL void load_a_frag(uint32_t (&a)[4], const bf16* tile, int row0, int k0, int lane) {
+  const bf16* p = tile + (size_t)(row0 + (lane & 15)) * LDS + k0 + ((lane >> 4) << 3);
+  ldsm_x4(a, smem_u32(p));
+}
+// B fragments for two adjacent n-tiles from a tile stored [n][k] (k contiguous): r[0..1] -> n-tile 0, r[2..3] -> n-tile 1.
+template <int LDS>
+ECAMP_DEVINL void load_b_frag_nk(uint32_t (&r)[4], const bf16* tile, int n0, int k0, int lane) {
+  const bf16* p = tile + (size_t)(n0 + (lane & 7) + ((lane >> 4) << 3)) * LDS + k0 + (((lane >> 3) & 1) << 3);
+  ldsm_x4(r, smem_u32(p));
+}
+// B fragments for two adjacent n-tiles from a tile stored [k][n] (n contiguous): transposing load.
+template <int LDS>
+ECAMP_DEVINL void load_b_frag_kn(uint32_t (&r)[4], const bf16* tile, int k0, int n0, int lane) {
+  const bf16* p = tile + (size_t)(k0 + (lane & 15)) * LDS + n0 + ((lane >> 4) << 3);
+  ldsm_x4_t(r, smem_u32(p));
+}
+
+// cooperative copy of `rows` rows (zero-filled from `valid` on) of width D from global (row pitch ld) to smem
+template <int D, int LDS>
+ECAMP_DEVINL void load_tile(bf16* dst, const bf16* src, int ld, int rows, int valid, int tid, int nthreads) {
+  constexpr int CPR = D / 8;
+  for (int idx = tid; idx < rows * CPR; idx += nthreads) {
+    const int r = idx / CPR, c = idx % CPR;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < valid) v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld + c * 8);
+    *reinterpret_cast<uint4*>(dst + (size_t)r * LDS + c * 8) = v;
+  }
+}
+
+ECAMP_DEVINL float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+ECAMP_DEVINL float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// keep-decision of attention-probability dropout for (query i, key j) of head-instance bh
+ECAMP_DEVINL bool attn_keep(const Philox& ph, uint32_t thr, uint64_t site, uint64_t bh, int Sq, int Sk, int i, int j) {
+  const uint64_t idx = (bh * (uint64_t)Sq + (uint64_t)i) * (uint64_t)Sk + (uint64_t)j;
+  return philox_word(ph, idx, site) >= thr;
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+template <int D>
+__global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
+  constexpr int LDS = D + 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int Skp = (a.Sk + 15) & ~15;
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sK = sQ + 64 * LDS;
+  bf16* sV = sK + (size_t)Skp * LDS;
+  float* sBias = reinterpret_cast<float*>(sV + (size_t)Skp * LDS);  // additive key mask: 0 or -inf
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  load_tile<D, LDS>(sQ, a.q + ((size_t)b * a.Sq + q0) * a.ldq + h * D, a.ldq, 64, min(64, a.Sq - q0), tid, 128);
+  load_tile<D, LDS>(sK, a.k + (size_t)b * a.Sk * a.ldk + h * D, a.ldk, Skp, a.Sk, tid, 128);
+  load_tile<D, LDS>(sV, a.v + (size_t)b * a.Sk * a.ldv + h * D, a.ldv, Skp, a.Sk, tid, 128);
+  for (int j = tid; j < Skp; j += 128) {
+    bool ok = j < a.Sk;
+    if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + j] != 0;
+    sBias[j] = ok ? 0.f : -INFINITY;
+  }
+  __syncthreads();
+
+  uint32_t qf[D / 16][4];
+#pragma unroll
+  for (int kt = 0; kt < D / 16; ++kt) load_a_frag<LDS>(qf[kt], sQ, warp * 16, kt * 16, lane);
+
+  float o[D / 8][4];
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+  const Philox ph(a.drop.seed);
+  const uint32_t thr = dropout_threshold(a.drop.p);
+  const float keep_scale = a.drop.p > 0.f ? 1.0f / (1.0f - a.drop.p) : 1.0f;
+  const uint64_t bh = (uint64_t)b * a.H + h;
+  const int row_g = q0 + warp * 16 + g;  // this thread's rows: row_g and row_g + 8
+
+  for (int kb = 0; kb < Skp; kb += 64) {
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < D / 16; ++kt) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        if (kb + jp * 16 < Skp) {
+          uint32_t bf[4];
+          load_b_frag_nk<LDS>(bf, sK, kb + jp * 16, kt * 16, lane);
+          mma_bf16_16816(s[2 * jp], qf[kt], bf[0], bf[1]);
+          mma_bf16_16816(s[2 * jp + 1], qf[kt], bf[2], bf[3]);
+        }
+      }
+    }
+    // scale + mask, block row-max
+    float bm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = kb + j * 8 + t4 * 2 + (e & 1);
+        const float bias = col < Skp ? sBias[col] : -INFINITY;
+        s[j][e] = s[j][e] * a.scale + bias;
+        bm[e >> 1] = fmaxf(bm[e >> 1], s[j][e]);
+      }
+    }
+    float corr[2], m_use[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float m_new = fmaxf(m_run[r], quad_max(bm[r]));
+      m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
+      corr[r] = __expf(m_run[r] - m_use[r]);  // m_run = -inf -> 0
+      m_run[r] = m_new;
+      l_run[r] *= corr[r];
+    }
+#pragma unroll
+    for (int j = 0; j < D / 8; ++j) {
+      o[j][0] *= corr[0]; o[j][1] *= corr[0];
+      o[j][2] *= corr[1]; o[j][3] *= corr[1];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float p = __expf(s[j][e] - m_use[e >> 1]);
+        l_run[e >> 1] += p;
+        if (a.drop.p > 0.f) {
+          const int col = kb + j * 8 + t4 * 2 + (e & 1);
+          const int row = row_g + (e >> 1) * 8;
+          p = attn_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, row, col) ? p * keep_scale : 0.f;
+        }
+        s[j][e] = p;
+      }
+    }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (kb + kk * 16 < Skp) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < D / 16; ++dp) {
+          uint32_t vf[4];
+          load_b_frag_kn<LDS>(vf, sV, kb + kk * 16, dp * 16, lane);
+          mma_bf16_16816(o[2 * dp], pa, vf[0], vf[1]);
+          mma_bf16_16816(o[2 * dp + 1], pa, vf[2], vf[3]);
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float l = quad_sum(l_run[r]);
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    const int row = row_g + r * 8;
+    if (row < a.Sq) {
+      bf16* orow = a.o + ((size_t)b * a.Sq + row) * a.ldo + h * D;
+#pragma unroll
+      for (int j = 0; j < D / 8; ++j)
+        *reinterpret_cast<uint32_t*>(orow + j * 8 + t4 * 2) = pack_bf16x2(o[j][2 * r] * inv, o[j][2 * r + 1] * inv);
+      if (t4 == 0 && a.lse) a.lse[(bh * a.Sq) + row] = (l > 0.f) ? m_run[r] + __logf(l) : -INFINITY;
+    }
+  }
+}
+
+// delta[b, h, i] = sum_d dO[i, d] * O[i, d]; one warp per (b, h, i)
+__global__ void attn_delta_kernel(AttnArgs a) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int total = a.B * a.H * a.Sq;
+  if (gw >= total) return;
+  const int i = gw % a.Sq, h = (gw / a.Sq) % a.H, b = gw / (a.Sq * a.H);
+  const bf16* orow = a.o + ((size_t)b * a.Sq + i) * a.ldo + h * a.D;
+  const bf16* grow = a.d_o + ((size_t)b * a.Sq + i) * a.ld_do + h * a.D;
+  float s = 0.f;
+  for (int d = lane * 2; d < a.D; d += 64) {
+    const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(orow + d));
+    const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(grow + d));
+    s += x.x * y.x + x.y * y.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) a.delta[gw] = s;
+}
+
+// =============================================================================================
+// backward.  TR = false: rows = queries (R1 = Q, R2 = dO), columns = keys (C1 = K, C2 = V); out = dQ = dS K.
+//            TR = true : rows = keys    (R1 = K, R2 = V),  columns = queries (C1 = Q, C2 = dO);
+//                        out1 = dK = dS^T Q, out2 = dV = Pdrop^T dO.
+// =============================================================================================
+template <int D, bool TR>
+__global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
+  constexpr int LDS = D + 8;
+  constexpr int CB = TR ? 32 : 64;  // column block
+  constexpr int NT = CB / 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int Sr = TR ? a.Sk : a.Sq;  // row-side length
+  const int Sc = TR ? a.Sq : a.Sk;  // column-side length
+  const int Scp = (Sc + 15) & ~15;
+  bf16* sR1 = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sR2 = sR1 + 64 * LDS;
+  bf16* sC1 = sR2 + 64 * LDS;
+  bf16* sC2 = sC1 + (size_t)Scp * LDS;
+  float* sColA = reinterpret_cast<float*>(sC2 + (size_t)Scp * LDS);  // !TR: key bias (0/-inf); TR: lse per query
+  float* sColB = sColA + Scp;                                        // TR: delta per query
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int g = lane >> 2, t4 = lane & 3;
+  const uint64_t bh = (uint64_t)b * a.H + h;
+
+  const bf16* gQ = a.q + (size_t)b * a.Sq * a.ldq + h * D;
+  const bf16* gK = a.k + (size_t)b * a.Sk * a.ldk + h * D;
+  const bf16* gV = a.v + (size_t)b * a.Sk * a.ldv + h * D;
+  const bf16* gdO = a.d_o + (size_t)b * a.Sq * a.ld_do + h * D;
+  const int rvalid = min(64, Sr - r0);
+  if (!TR) {
+    load_tile<D, LDS>(sR1, gQ + (size_t)r0 * a.ldq, a.ldq, 64, rvalid, tid, 128);
+    load_tile<D, LDS>(sR2, gdO + (size_t)r0 * a.ld_do, a.ld_do, 64, rvalid, tid, 128);
+    load_tile<D, LDS>(sC1, gK, a.ldk, Scp, Sc, tid, 128);
+    load_tile<D, LDS>(sC2, gV, a.ldv, Scp, Sc, tid, 128);
+    for (int j = tid; j < Scp; j += 128) {
+      bool ok = j < Sc;
+      if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + j] != 0;
+      sColA[j] = ok ? 0.f : -INFINITY;
+    }
+  } else {
+    load_tile<D, LDS>(sR1, gK + (size_t)r0 * a.ldk, a.ldk, 64, rvalid, tid, 128);
+    load_tile<D, LDS>(sR2, gV + (size_t)r0 * a.ldv, a.ldv, 64, rvalid, tid, 128);
+    load_tile<D, LDS>(sC1, gQ, a.ldq, Scp, Sc, tid, 128);
+    load_tile<D, LDS>(sC2, gdO, a.ld_do, Scp, Sc, tid, 128);
+    for (int i = tid; i < Scp; i += 128) {
+      sColA[i] = i < Sc ? a.lse[bh * a.Sq + i] : INFINITY;  // +inf -> p = 0 for padded queries
+      sColB[i] = i < Sc ? a.delta[bh * a.Sq + i] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // per-row statistics / validity for this thread's two rows
+  const int row_g = r0 + warp * 16 + g;
+  float row_a[2], row_b[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row_g + r * 8;
+    if (!TR) {
+      row_a[r] = row < Sr ? a.lse[bh * a.Sq + row] : INFINITY;
+      row_b[r] = row < Sr ? a.delta[bh * a.Sq + row] : 0.f;
+    } else {
+      bool ok = row < Sr;
+      if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + row] != 0;
+      row_a[r] = ok ? 0.f : -INFINITY;  // key bias
+      row_b[r] = 0.f;
+    }
+  }
+
+  float acc1[D / 8][4];
+  float acc2[TR ? D / 8 : 1][4];
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) acc1[j][0] = acc1[j][1] = acc1[j][2] = acc1[j][3] = 0.f;
+#pragma unroll
+  for (int j = 0; j < (TR ? D / 8 : 1); ++j) acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f;
+
+  const Philox ph(a.drop.seed);
+  const uint32_t thr = dropout_threshold(a.drop.p);
+  const float keep_scale = a.drop.p > 0.f ? 1.0f / (1.0f - a.drop.p) : 1.0f;
+
+  for (int cb = 0; cb < Scp; cb += CB) {
+    float s[NT][4], dp[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+    }
+#pragma unroll
+    for (int kt = 0; kt < D / 16; ++kt) {
+      uint32_t a1[4], a2[4];
+      load_a_frag<LDS>(a1, sR1, warp * 16, kt * 16, lane);
+      load_a_frag<LDS>(a2, sR2, warp * 16, kt * 16, lane);
+#pragma unroll
+      for (int jp = 0; jp < NT / 2; ++jp) {
+        if (cb + jp * 16 < Scp) {
+          uint32_t bf[4];
+          load_b_frag_nk<LDS>(bf, sC1, cb + jp * 16, kt * 16, lane);
+          mma_bf16_16816(s[2 * jp], a1, bf[0], bf[1]);
+          mma_bf16_16816(s[2 * jp + 1], a1, bf[2], bf[3]);
+          load_b_frag_nk<LDS>(bf, sC2, cb + jp * 16, kt * 16, lane);
+          mma_bf16_16816(dp[2 * jp], a2, bf[0], bf[1]);
+          mma_bf16_16816(dp[2 * jp + 1], a2, bf[2], bf[3]);
+        }
+      }
+    }
+    // p = exp(scale * s + key_bias - lse); ds = p * (dp_eff - delta) * scale
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = cb + j * 8 + t4 * 2 + (e & 1);
+        const int r = e >> 1;
+        const bool cin = col < Scp;
+        float lse, delta, bias;
+        if (!TR) {
+          lse = row_a[r]; delta = row_b[r]; bias = cin ? sColA[col] : -INFINITY;
+        } else {
+          lse = cin ? sColA[col] : INFINITY; delta = cin ? sColB[col] : 0.f; bias = row_a[r];
+        }
+        float p = __expf(s[j][e] * a.scale + bias - lse);  // masked / padded -> exp(-inf) = 0
+        float dpe = dp[j][e];
+        float pd = p;
+        if (a.drop.p > 0.f) {
+          const int row = row_g + r * 8;
+          const int qi = TR ? col : row, kj = TR ? row : col;
+          const bool keep = attn_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, qi, kj);
+          dpe = keep ? dpe * keep_scale : 0.f;
+          pd = keep ? p * keep_scale : 0.f;
+        }
+        s[j][e] = p * (dpe - delta) * a.scale;  // dS
+        dp[j][e] = pd;                          // dropped probabilities (only used when TR)
+      }
+    }
+    // out1 += dS . C1 ; (TR) out2 += Pdrop . C2
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      if (cb + kk * 16 < Scp) {
+        uint32_t da[4], pa[4];
+        da[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        da[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        da[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        da[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        if (TR) {
+          pa[0] = pack_bf16x2(dp[2 * kk][0], dp[2 * kk][1]);
+          pa[1] = pack_bf16x2(dp[2 * kk][2], dp[2 * kk][3]);
+          pa[2] = pack_bf16x2(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+          pa[3] = pack_bf16x2(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+        }
+#pragma unroll
+        for (int dd = 0; dd < D / 16; ++dd) {
+          uint32_t cf[4];
+          load_b_frag_kn<LDS>(cf, sC1, cb + kk * 16, dd * 16, lane);
+          mma_bf16_16816(acc1[2 * dd], da, cf[0], cf[1]);
+          mma_bf16_16816(acc1[2 * dd + 1], da, cf[2], cf[3]);
+          if (TR) {
+            load_b_frag_kn<LDS>(cf, sC2, cb + kk * 16, dd * 16, lane);
+            mma_bf16_16816(acc2[2 * dd], pa, cf[0], cf[1]);
+            mma_bf16_16816(acc2[2 * dd + 1], pa, cf[2], cf[3]);
+          }
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row_g + r * 8;
+    if (row < Sr) {
+      if (!TR) {
+        bf16* orow = a.dq + ((size_t)b * a.Sq + row) * a.lddq + h * D;
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j)
+          *reinterpret_cast<uint32_t*>(orow + j * 8 + t4 * 2) = pack_bf16x2(acc1[j][2 * r], acc1[j][2 * r + 1]);
+      } else {
+        bf16* krow = a.dk + ((size_t)b * a.Sk + row) * a.lddk + h * D;
+        bf16* vrow = a.dv + ((size_t)b * a.Sk + row) * a.lddv + h * D;
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j) {
+          *reinterpret_cast<uint32_t*>(krow + j * 8 + t4 * 2) = pack_bf16x2(acc1[j][2 * r], acc1[j][2 * r + 1]);
+          *reinterpret_cast<uint32_t*>(vrow + j * 8 + t4 * 2) =
+              pack_bf16x2(acc2[TR ? j : 0][2 * r], acc2[TR ? j : 0][2 * r + 1]);
+        }
+      }
+    }
+  }
+}
+
+size_t fwd_smem(int D, int Sk) {
+  const int LDS = D + 8, Skp = (Sk + 15) & ~15;
+  return (size_t)(64 + 2 * Skp) * LDS * 2 + (size_t)Skp * 4;
+}
+size_t bwd_smem(int D, int Sc) {
+  const int LDS = D + 8, Scp = (Sc + 15) & ~15;
+  return (size_t)(128 + 2 * Scp) * LDS * 2 + (size_t)Scp * 8;
+}
+
+int check_args(const AttnArgs& a, bool bwd) {
+  ECAMP_REQUIRE(a.D == 32 || a.D == 64 || a.D == 128, "attention: head_dim must be 32, 64 or 128 (got %d)", a.D);
+  ECAMP_REQUIRE(a.B > 0 && a.H > 0 && a.Sq > 0 && a.Sk > 0, "attention: empty problem");
+  ECAMP_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0,
+                "attention: row pitches must be multiples of 8 elements");
+  ECAMP_REQUIRE(a.drop.p >= 0.f && a.drop.p < 1.f, "attention: dropout p out of range");
+  const size_t sm = bwd ? (bwd_smem(a.D, a.Sk) > bwd_smem(a.D, a.Sq) ? bwd_smem(a.D, a.Sk) : bwd_smem(a.D, a.Sq))
+                        : fwd_smem(a.D, a.Sk);
+  ECAMP_REQUIRE(sm <= 227 * 1024, "attention: sequence too long for the single-pass kernel (smem %zu B)", sm);
+  if (bwd) {
+    ECAMP_REQUIRE(a.d_o && a.delta && a.lse && a.dq && a.dk && a.dv, "attention_bwd: missing pointers");
+    ECAMP_REQUIRE(a.ld_do % 8 == 0 && a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0,
+                  "attention_bwd: row pitches must be multiples of 8 elements");
+  }
+  return 0;
+}
+
+template <int D>
+int launch_fwd(const AttnArgs& a, cudaStream_t st) {
+  const size_t sm = fwd_smem(D, a.Sk);
+  ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  dim3 grid((a.Sq + 63) / 64, a.H, a.B);
+  attn_fwd_kernel<D><<<grid, 128, sm, st>>>(a);
+  ECAMP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template <int D>
+int launch_bwd(const AttnArgs& a, cudaStream_t st) {
+  const int total = a.B * a.H * a.Sq;
+  attn_delta_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(a);
+  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_CUDA_OK(
+      cudaFuncSetAttribute(attn_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  ECAMP_CUDA_OK(
+      cudaFuncSetAttribute(attn_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  dim3 gq((a.Sq + 63) / 64, a.H, a.B);
+  attn_bwd_kernel<D, false><<<gq, 128, bwd_smem(D, a.Sk), st>>>(a);
+  ECAMP_CUDA_OK(cudaGetLastError());
+  dim3 gk((a.Sk + 63) / 64, a.H, a.B);
+  attn_bwd_kernel<D, true><<<gk, 128, bwd_smem(D, a.Sq), st>>>(a);
+  ECAMP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int attention_fwd(const AttnArgs& a, cudaStream_t st) {
+  if (int rc = check_args(a, false)) return rc;
+  if (a.D == 32) return launch_fwd<32>(a, st);
+  if (a.D == 64) return launch_fwd<64>(a, st);
+  return launch_fwd<128>(a, st);
+}
+int attention_bwd(const AttnArgs& a, cudaStream_t st) {
+  if (int rc = check_args(a, true)) return rc;
+  if (a.D == 32) return launch_bwd<32>(a, st);
+  if (a.D == 64) return launch_bwd<64>(a, st);
+  return launch_bwd<128>(a, st);
+}
+
+}  // namespace ecamp

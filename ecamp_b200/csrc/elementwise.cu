@@ -1,0 +1,608 @@
+// HBM-bound glue kernels of the ECAMP hot path: random masking (stable rank sort), bicubic resize into
+// patch layout, kept-patch gather, encoder / decoder sequence assembly and their backward, BERT
+// embeddings forward / backward, bias-gradient column sums.  Every kernel cites the reference lines
+// it replaces.
+#include "kernels.cuh"
+
+namespace ecamp {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// model_ecamp.py:168-193.  rank_i = #{j : n_j < n_i or (n_j == n_i and j < i)} is the position of i in the
+// stable ascending argsort, i.e. ids_restore[i]; ids_shuffle[rank_i] = i.  Bit-exact by construction.
+// ---------------------------------------------------------------------------------------------
+__global__ void random_masking_kernel(const float* __restrict__ noise, int L, int len_keep,
+                                      int32_t* __restrict__ ids_restore, int32_t* __restrict__ ids_keep,
+                                      float* __restrict__ mask, int64_t* __restrict__ ids_restore64,
+                                      int64_t* __restrict__ ids_keep64) {
+  extern __shared__ float s_noise[];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) s_noise[i] = noise[(size_t)b * L + i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float ni = s_noise[i];
+    int rank = 0;
+    for (int j = 0; j < L; ++j) {
+      const float nj = s_noise[j];
+      rank += (nj < ni || (nj == ni && j < i)) ? 1 : 0;
+    }
+    ids_restore[(size_t)b * L + i] = rank;
+    if (ids_restore64) ids_restore64[(size_t)b * L + i] = rank;
+    mask[(size_t)b * L + i] = rank >= len_keep ? 1.f : 0.f;
+    if (rank < len_keep) {
+      ids_keep[(size_t)b * len_keep + rank] = i;
+      if (ids_keep64) ids_keep64[(size_t)b * len_keep + rank] = i;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// model_ecamp.py:318 — torchvision Resize([224,224], BICUBIC) on a tensor = upsample_bicubic2d,
+// align_corners=False, antialias off.  Scale 2 => source centre 2*d + 0.5 => taps 2d-1..2d+2 with the
+// fixed weights cubic(A=-0.75, t=0.5) = [-3/32, 19/32, 19/32, -3/32], indices clamped at the border.
+// Output goes straight to patch layout tgt[b, hy*14+wx, (p*16+q)*3+c] (the layout of decoder_pred).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(224) resize_patchify_kernel(const float* __restrict__ big, int Hin,
+                                                              float* __restrict__ tgt) {
+  const int y = blockIdx.x % 224, b = blockIdx.x / 224;
+  const int x = threadIdx.x;
+  const float w[4] = {-0.09375f, 0.59375f, 0.59375f, -0.09375f};
+  int ys[4], xs[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ys[i] = min(max(2 * y - 1 + i, 0), Hin - 1);
+    xs[i] = min(max(2 * x - 1 + i, 0), Hin - 1);
+  }
+  const int hy = y >> 4, p = y & 15, wx = x >> 4, q = x & 15;
+  float* dst = tgt + ((size_t)b * 196 + hy * 14 + wx) * 768 + (p * 16 + q) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* src = big + ((size_t)b * 3 + c) * Hin * Hin;
+    float rows[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* r = src + (size_t)ys[i] * Hin;
+      rows[i] = r[xs[0]] * w[0] + r[xs[1]] * w[1] + r[xs[2]] * w[2] + r[xs[3]] * w[3];
+    }
+    dst[c] = rows[0] * w[0] + rows[1] * w[1] + rows[2] * w[2] + rows[3] * w[3];
+  }
+}
+
+__global__ void __launch_bounds__(224) patchify224_kernel(const float* __restrict__ imgs, float* __restrict__ tgt) {
+  const int y = blockIdx.x % 224, b = blockIdx.x / 224;
+  const int x = threadIdx.x;
+  const int hy = y >> 4, p = y & 15, wx = x >> 4, q = x & 15;
+  float* dst = tgt + ((size_t)b * 196 + hy * 14 + wx) * 768 + (p * 16 + q) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) dst[c] = imgs[(((size_t)b * 3 + c) * 224 + y) * 224 + x];
+}
+
+// one block per output row, D/4 threads
+__global__ void gather_patches_kernel(const float* __restrict__ tgt, const int32_t* __restrict__ ids_keep, int L,
+                                      int keep, int PD, bf16* __restrict__ out) {
+  const int r = blockIdx.x, b = r / keep;
+  const int src_l = ids_keep[r];
+  const float4 v = reinterpret_cast<const float4*>(tgt + ((size_t)b * L + src_l) * PD)[threadIdx.x];
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  reinterpret_cast<uint2*>(out + (size_t)r * PD)[threadIdx.x] = u;
+}
+
+__global__ void assemble_enc_kernel(const float* __restrict__ pe, const float* __restrict__ cls,
+                                    const float* __restrict__ pos, const int32_t* __restrict__ ids_keep, int keep,
+                                    int D, float* __restrict__ x0) {
+  const int r = blockIdx.x, b = r / (keep + 1), s = r % (keep + 1);
+  const int c4 = threadIdx.x;
+  float4 a, p;
+  if (s == 0) {
+    a = reinterpret_cast<const float4*>(cls)[c4];
+    p = reinterpret_cast<const float4*>(pos)[c4];
+  } else {
+    a = reinterpret_cast<const float4*>(pe + ((size_t)b * keep + s - 1) * D)[c4];
+    p = reinterpret_cast<const float4*>(pos + (size_t)(1 + ids_keep[(size_t)b * keep + s - 1]) * D)[c4];
+  }
+  reinterpret_cast<float4*>(x0 + (size_t)r * D)[c4] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+}
+
+__global__ void assemble_enc_bwd_kernel(const float* __restrict__ dx0, int keep, int D, bf16* __restrict__ d_pe) {
+  const int r = blockIdx.x, b = r / keep, j = r % keep;
+  const float4 v = reinterpret_cast<const float4*>(dx0 + ((size_t)b * (keep + 1) + 1 + j) * D)[threadIdx.x];
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  reinterpret_cast<uint2*>(d_pe + (size_t)r * D)[threadIdx.x] = u;
+}
+
+// out[d] (+)= sum_b x[b * stride + d]
+__global__ void strided_rowsum_kernel(const float* __restrict__ x, int B, size_t stride, int D,
+                                      float* __restrict__ out, int accumulate) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += x[(size_t)b * stride + d];
+  out[d] = accumulate ? out[d] + s : s;
+}
+
+__global__ void assemble_dec_kernel(const bf16* __restrict__ e, const float* __restrict__ mask_token,
+                                    const float* __restrict__ dpos, const int32_t* __restrict__ ids_restore, int L,
+                                    int keep, int D, float* __restrict__ xd) {
+  const int r = blockIdx.x, b = r / (L + 1), t = r % (L + 1);
+  const int c4 = threadIdx.x;
+  float4 a;
+  int src = -1;
+  if (t == 0) {
+    src = 0;
+  } else {
+    const int rr = ids_restore[(size_t)b * L + t - 1];
+    if (rr < keep) src = 1 + rr;
+  }
+  if (src >= 0) {
+    const uint2 u = reinterpret_cast<const uint2*>(e + ((size_t)b * (keep + 1) + src) * D)[c4];
+    const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+    a = make_float4(lo.x, lo.y, hi.x, hi.y);
+  } else {
+    // torch.cat of the half-precision decoder_embed output with the fp32 mask token promotes to fp32
+    // (model_ecamp.py:245-246): the mask token is NOT rounded
+    a = reinterpret_cast<const float4*>(mask_token)[c4];
+  }
+  const float4 p = reinterpret_cast<const float4*>(dpos + (size_t)t * D)[c4];
+  reinterpret_cast<float4*>(xd + (size_t)r * D)[c4] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+}
+
+__global__ void assemble_dec_bwd_kernel(const float* __restrict__ dxd, const int32_t* __restrict__ ids_restore, int L,
+                                        int keep, int D, bf16* __restrict__ d_e) {
+  const int r = blockIdx.x, b = r / (L + 1), t = r % (L + 1);
+  int dst = -1;
+  if (t == 0) {
+    dst = 0;
+  } else {
+    const int rr = ids_restore[(size_t)b * L + t - 1];
+    if (rr < keep) dst = 1 + rr;
+  }
+  if (dst < 0) return;
+  const float4 v = reinterpret_cast<const float4*>(dxd + (size_t)r * D)[threadIdx.x];
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  reinterpret_cast<uint2*>(d_e + ((size_t)b * (keep + 1) + dst) * D)[threadIdx.x] = u;
+}
+
+// ws[b, d] = sum over masked positions l of dxd[b, 1 + l, d]
+__global__ void mask_token_grad_kernel(const float* __restrict__ dxd, const int32_t* __restrict__ ids_restore, int L,
+                                       int keep, int D, float* __restrict__ ws) {
+  const int b = blockIdx.x;
+  const int c4 = threadIdx.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < L; ++l) {
+    if (ids_restore[(size_t)b * L + l] >= keep) {
+      const float4 v = reinterpret_cast<const float4*>(dxd + ((size_t)b * (L + 1) + 1 + l) * D)[c4];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  reinterpret_cast<float4*>(ws + (size_t)b * D)[c4] = acc;
+}
+
+__global__ void split_latent_gap_kernel(const bf16* __restrict__ lat2, int keep, int D, bf16* __restrict__ img_tok,
+                                        bf16* __restrict__ gap) {
+  const int b = blockIdx.x, c4 = threadIdx.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < keep; ++j) {
+    const uint2 u = reinterpret_cast<const uint2*>(lat2 + ((size_t)b * (keep + 1) + 1 + j) * D)[c4];
+    reinterpret_cast<uint2*>(img_tok + ((size_t)b * keep + j) * D)[c4] = u;
+    const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+    acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
+  }
+  const float inv = 1.0f / keep;
+  uint2 o;
+  o.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+  o.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+  reinterpret_cast<uint2*>(gap + (size_t)b * D)[c4] = o;
+}
+
+__global__ void split_latent_gap_bwd_kernel(const bf16* __restrict__ d_img_tok, const bf16* __restrict__ d_gap,
+                                            int keep, int D, bf16* __restrict__ d_lat2) {
+  const int r = blockIdx.x, b = r / (keep + 1), s = r % (keep + 1);
+  const int c4 = threadIdx.x;
+  uint2 o = make_uint2(0u, 0u);
+  if (s > 0) {
+    const uint2 u = reinterpret_cast<const uint2*>(d_img_tok + ((size_t)b * keep + s - 1) * D)[c4];
+    const uint2 g = reinterpret_cast<const uint2*>(d_gap + (size_t)b * D)[c4];
+    const float inv = 1.0f / keep;
+    const float2 ul = unpack_bf16x2(u.x), uh = unpack_bf16x2(u.y), gl = unpack_bf16x2(g.x), gh = unpack_bf16x2(g.y);
+    o.x = pack_bf16x2(ul.x + gl.x * inv, ul.y + gl.y * inv);
+    o.y = pack_bf16x2(uh.x + gh.x * inv, uh.y + gh.y * inv);
+  }
+  reinterpret_cast<uint2*>(d_lat2 + (size_t)r * D)[c4] = o;
+}
+
+__global__ void add_batch_rowvec_kernel(bf16* __restrict__ y, const bf16* __restrict__ vec, int T, int D) {
+  const int r = blockIdx.x, b = r / T, c4 = threadIdx.x;
+  uint2 u = reinterpret_cast<uint2*>(y + (size_t)r * D)[c4];
+  const uint2 g = reinterpret_cast<const uint2*>(vec + (size_t)b * D)[c4];
+  const float2 ul = unpack_bf16x2(u.x), uh = unpack_bf16x2(u.y), gl = unpack_bf16x2(g.x), gh = unpack_bf16x2(g.y);
+  u.x = pack_bf16x2(ul.x + gl.x, ul.y + gl.y);
+  u.y = pack_bf16x2(uh.x + gh.x, uh.y + gh.y);
+  reinterpret_cast<uint2*>(y + (size_t)r * D)[c4] = u;
+}
+
+__global__ void add_batch_rowvec_oop_kernel(const bf16* __restrict__ x, const bf16* __restrict__ vec, int T, int D,
+                                            bf16* __restrict__ y) {
+  const int r = blockIdx.x, b = r / T, c4 = threadIdx.x;
+  uint2 u = reinterpret_cast<const uint2*>(x + (size_t)r * D)[c4];
+  const uint2 g = reinterpret_cast<const uint2*>(vec + (size_t)b * D)[c4];
+  const float2 ul = unpack_bf16x2(u.x), uh = unpack_bf16x2(u.y), gl = unpack_bf16x2(g.x), gh = unpack_bf16x2(g.y);
+  u.x = pack_bf16x2(ul.x + gl.x, ul.y + gl.y);
+  u.y = pack_bf16x2(uh.x + gh.x, uh.y + gh.y);
+  reinterpret_cast<uint2*>(y + (size_t)r * D)[c4] = u;
+}
+
+__global__ void gelu_bwd_bf16_kernel(const float* __restrict__ d, const bf16* __restrict__ pre, bf16* __restrict__ out,
+                                     size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = f2bf(d[i] * gelu_erf_grad(bf2f(pre[i])));
+}
+
+__global__ void batch_colsum_kernel(const bf16* __restrict__ x, int T, int D, bf16* __restrict__ out) {
+  const int b = blockIdx.x, c4 = threadIdx.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < T; ++t) {
+    const uint2 u = reinterpret_cast<const uint2*>(x + ((size_t)b * T + t) * D)[c4];
+    const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+    acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
+  }
+  uint2 o;
+  o.x = pack_bf16x2(acc.x, acc.y);
+  o.y = pack_bf16x2(acc.z, acc.w);
+  reinterpret_cast<uint2*>(out + (size_t)b * D)[c4] = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// HF BertEmbeddings.forward (called at bert_modeling.py:113-119): (word[id] + type[tt]) + pos[t] -> LN -> dropout
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bert_emb_fwd_kernel(
+    const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids, const float* __restrict__ word,
+    const float* __restrict__ type, const float* __restrict__ pos, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, int M, int T, DropoutCfg drop, float* __restrict__ pre,
+    float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ out_bf16,
+    float* __restrict__ out_f32) {
+  constexpr int NV = 6, D = 768;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= M) return;
+  const int t = row % T;
+  const long long id = ids[row], tt = type_ids[row];
+  const float4* wr = reinterpret_cast<const float4*>(word + (size_t)id * D);
+  const float4* tr = reinterpret_cast<const float4*>(type + (size_t)tt * D);
+  const float4* pr = reinterpret_cast<const float4*>(pos + (size_t)t * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = i * 32 + lane;
+    const float4 a = __ldg(wr + c4), b = __ldg(tr + c4), c = __ldg(pr + c4);
+    v[i] = make_float4((a.x + b.x) + c.x, (a.y + b.y) + c.y, (a.z + b.z) + c.z, (a.w + b.w) + c.w);
+    reinterpret_cast<float4*>(pre + (size_t)row * D)[c4] = v[i];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  const Philox ph(drop.seed);
+  const uint32_t thr = dropout_threshold(drop.p);
+  const float ks = drop.p > 0.f ? 1.0f / (1.0f - drop.p) : 1.0f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = i * 32 + lane;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (drop.p > 0.f) {
+      const uint4 rnd = ph(((uint64_t)row * D + (uint64_t)c4 * 4) >> 2, drop.site);
+      y.x = rnd.x >= thr ? y.x * ks : 0.f;
+      y.y = rnd.y >= thr ? y.y * ks : 0.f;
+      y.z = rnd.z >= thr ? y.z * ks : 0.f;
+      y.w = rnd.w >= thr ? y.w * ks : 0.f;
+    }
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)row * D)[c4] = y;
+    uint2 u;
+    u.x = pack_bf16x2(y.x, y.y);
+    u.y = pack_bf16x2(y.z, y.w);
+    reinterpret_cast<uint2*>(out_bf16 + (size_t)row * D)[c4] = u;
+  }
+}
+
+// in-place dropout backward on an fp32 gradient (embedding-output dropout site)
+__global__ void dropout_bwd_f32_kernel(float* __restrict__ g, size_t n4, DropoutCfg drop) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const Philox ph(drop.seed);
+  const uint32_t thr = dropout_threshold(drop.p);
+  const float ks = 1.0f / (1.0f - drop.p);
+  const uint4 rnd = ph(i, drop.site);
+  float4 v = reinterpret_cast<float4*>(g)[i];
+  v.x = rnd.x >= thr ? v.x * ks : 0.f;
+  v.y = rnd.y >= thr ? v.y * ks : 0.f;
+  v.z = rnd.z >= thr ? v.z * ks : 0.f;
+  v.w = rnd.w >= thr ? v.w * ks : 0.f;
+  reinterpret_cast<float4*>(g)[i] = v;
+}
+
+// word-embedding gradient: scatter-add rows (padding_idx = 0 receives nothing)
+__global__ void emb_word_bwd_kernel(const float* __restrict__ d_pre, const int64_t* __restrict__ ids, int D,
+                                    float* __restrict__ d_word) {
+  const int row = blockIdx.x;
+  const long long id = ids[row];
+  if (id == 0) return;
+  const float4 v = reinterpret_cast<const float4*>(d_pre + (size_t)row * D)[threadIdx.x];
+  float* dst = d_word + (size_t)id * D + threadIdx.x * 4;
+  atomicAdd(dst + 0, v.x);
+  atomicAdd(dst + 1, v.y);
+  atomicAdd(dst + 2, v.z);
+  atomicAdd(dst + 3, v.w);
+}
+
+// one block per position t: position gradient (sum over batch) and per-type partial sums
+__global__ void emb_pos_type_bwd_kernel(const float* __restrict__ d_pre, const int64_t* __restrict__ type_ids, int B,
+                                        int T, int D, float* __restrict__ d_pos, int accumulate,
+                                        float* __restrict__ type_ws) {
+  const int t = blockIdx.x, c4 = threadIdx.x;
+  float4 ap = make_float4(0.f, 0.f, 0.f, 0.f), a1 = ap;
+  for (int b = 0; b < B; ++b) {
+    const size_t row = (size_t)b * T + t;
+    const float4 v = reinterpret_cast<const float4*>(d_pre + row * D)[c4];
+    ap.x += v.x; ap.y += v.y; ap.z += v.z; ap.w += v.w;
+    if (type_ids[row] != 0) { a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w; }
+  }
+  float4* dp = reinterpret_cast<float4*>(d_pos + (size_t)t * D) + c4;
+  if (accumulate) {
+    const float4 o = *dp;
+    *dp = make_float4(o.x + ap.x, o.y + ap.y, o.z + ap.z, o.w + ap.w);
+  } else {
+    *dp = ap;
+  }
+  // type 0 = total - type 1
+  reinterpret_cast<float4*>(type_ws + ((size_t)t * 2 + 0) * D)[c4] =
+      make_float4(ap.x - a1.x, ap.y - a1.y, ap.z - a1.z, ap.w - a1.w);
+  reinterpret_cast<float4*>(type_ws + ((size_t)t * 2 + 1) * D)[c4] = a1;
+}
+
+__global__ void emb_type_finalize_kernel(const float* __restrict__ type_ws, int T, int D, float* __restrict__ d_type,
+                                         int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 2*D
+  if (i >= 2 * D) return;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += type_ws[(size_t)t * 2 * D + i];
+  d_type[i] = accumulate ? d_type[i] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bias gradients
+// ---------------------------------------------------------------------------------------------
+constexpr int kColsumChunks = 32;
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int ld, int M, int N,
+                                                     float* __restrict__ ws) {
+  __shared__ float2 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 64 + lane * 2;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float2 acc = make_float2(0.f, 0.f);
+  if (col < N) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(x + (size_t)r * ld + col);
+      const float2 f = unpack_bf16x2(u);
+      acc.x += f.x;
+      acc.y += f.y;
+    }
+  }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && col < N) {
+    float2 s = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      s.x += red[w][lane].x;
+      s.y += red[w][lane].y;
+    }
+    ws[(size_t)blockIdx.y * N + col] = s.x;
+    if (col + 1 < N) ws[(size_t)blockIdx.y * N + col + 1] = s.y;
+  }
+}
+__global__ void colsum_finalize_kernel(const float* __restrict__ ws, int chunks, int N, float* __restrict__ out,
+                                       int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += ws[(size_t)c * N + n];
+  out[n] = accumulate ? out[n] + s : s;
+}
+
+__global__ void scale_f32_kernel(float* __restrict__ x, const float* __restrict__ scale, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= *scale;
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = f2bf(x[i]);
+}
+__global__ void permute_pe_grad_kernel(const float* __restrict__ dw_pqc, float* __restrict__ grad_cpq, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // canonical index n*768 + c*256 + pq
+  if (i >= 768 * 768) return;
+  const int n = i / 768, k = i % 768, c = k / 256, pq = k % 256;
+  const float v = dw_pqc[(size_t)n * 768 + pq * 3 + c];
+  grad_cpq[i] = accumulate ? grad_cpq[i] + v : v;
+}
+
+}  // namespace
+
+#define LAUNCH_OK() ECAMP_CUDA_OK(cudaGetLastError())
+
+int random_masking(const float* noise, int B, int L, int len_keep, int32_t* ids_restore, int32_t* ids_keep,
+                   float* mask, int64_t* ids_restore64, int64_t* ids_keep64, cudaStream_t st) {
+  ECAMP_REQUIRE(L > 0 && L <= 4096 && len_keep >= 0 && len_keep <= L, "random_masking: bad L %d / len_keep %d", L,
+                len_keep);
+  if (B <= 0) return 0;
+  random_masking_kernel<<<B, 256, L * sizeof(float), st>>>(noise, L, len_keep, ids_restore, ids_keep, mask,
+                                                           ids_restore64, ids_keep64);
+  LAUNCH_OK();
+  return 0;
+}
+
+int resize_bicubic_patchify(const float* big, int B, int Hin, float* tgt, cudaStream_t st) {
+  ECAMP_REQUIRE(Hin == 448, "resize: only 448 -> 224 is on the reference path (got %d)", Hin);
+  if (B <= 0) return 0;
+  resize_patchify_kernel<<<B * 224, 224, 0, st>>>(big, Hin, tgt);
+  LAUNCH_OK();
+  return 0;
+}
+int patchify224(const float* imgs, int B, float* tgt, cudaStream_t st) {
+  if (B <= 0) return 0;
+  patchify224_kernel<<<B * 224, 224, 0, st>>>(imgs, tgt);
+  LAUNCH_OK();
+  return 0;
+}
+int gather_patches(const float* tgt, const int32_t* ids_keep, int B, int L, int keep, int PD, bf16* out,
+                   cudaStream_t st) {
+  if (B * keep <= 0) return 0;
+  gather_patches_kernel<<<B * keep, PD / 4, 0, st>>>(tgt, ids_keep, L, keep, PD, out);
+  LAUNCH_OK();
+  return 0;
+}
+int assemble_encoder_input(const float* pe, const float* cls, const float* pos, const int32_t* ids_keep, int B,
+                           int keep, int D, float* x0, cudaStream_t st) {
+  assemble_enc_kernel<<<B * (keep + 1), D / 4, 0, st>>>(pe, cls, pos, ids_keep, keep, D, x0);
+  LAUNCH_OK();
+  return 0;
+}
+int assemble_encoder_input_bwd(const float* dx0, int B, int keep, int D, bf16* d_pe, float* d_cls, int accumulate,
+                               cudaStream_t st) {
+  if (keep > 0) {
+    assemble_enc_bwd_kernel<<<B * keep, D / 4, 0, st>>>(dx0, keep, D, d_pe);
+    LAUNCH_OK();
+  }
+  strided_rowsum_kernel<<<(D + 127) / 128, 128, 0, st>>>(dx0, B, (size_t)(keep + 1) * D, D, d_cls, accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+int assemble_decoder_input(const bf16* e, const float* mask_token, const float* dpos, const int32_t* ids_restore,
+                           int B, int L, int keep, int D, float* xd, cudaStream_t st) {
+  assemble_dec_kernel<<<B * (L + 1), D / 4, 0, st>>>(e, mask_token, dpos, ids_restore, L, keep, D, xd);
+  LAUNCH_OK();
+  return 0;
+}
+int assemble_decoder_input_bwd(const float* dxd, const int32_t* ids_restore, int B, int L, int keep, int D, bf16* d_e,
+                               float* d_mask_token, int accumulate, float* ws, cudaStream_t st) {
+  assemble_dec_bwd_kernel<<<B * (L + 1), D / 4, 0, st>>>(dxd, ids_restore, L, keep, D, d_e);
+  LAUNCH_OK();
+  mask_token_grad_kernel<<<B, D / 4, 0, st>>>(dxd, ids_restore, L, keep, D, ws);
+  LAUNCH_OK();
+  strided_rowsum_kernel<<<(D + 127) / 128, 128, 0, st>>>(ws, B, (size_t)D, D, d_mask_token, accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+int split_latent_gap(const bf16* lat2, int B, int keep, int D, bf16* img_tok, bf16* gap, cudaStream_t st) {
+  split_latent_gap_kernel<<<B, D / 4, 0, st>>>(lat2, keep, D, img_tok, gap);
+  LAUNCH_OK();
+  return 0;
+}
+int split_latent_gap_bwd(const bf16* d_img_tok, const bf16* d_gap, int B, int keep, int D, bf16* d_lat2,
+                         cudaStream_t st) {
+  split_latent_gap_bwd_kernel<<<B * (keep + 1), D / 4, 0, st>>>(d_img_tok, d_gap, keep, D, d_lat2);
+  LAUNCH_OK();
+  return 0;
+}
+int add_batch_rowvec(bf16* y, const bf16* vec, int B, int T, int D, cudaStream_t st) {
+  add_batch_rowvec_kernel<<<B * T, D / 4, 0, st>>>(y, vec, T, D);
+  LAUNCH_OK();
+  return 0;
+}
+int add_batch_rowvec_oop(const bf16* x, const bf16* vec, int B, int T, int D, bf16* y, cudaStream_t st) {
+  add_batch_rowvec_oop_kernel<<<B * T, D / 4, 0, st>>>(x, vec, T, D, y);
+  LAUNCH_OK();
+  return 0;
+}
+int gelu_bwd_bf16(const float* d, const bf16* pre, bf16* out, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  gelu_bwd_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, pre, out, n);
+  LAUNCH_OK();
+  return 0;
+}
+int batch_colsum(const bf16* x, int B, int T, int D, bf16* out, cudaStream_t st) {
+  batch_colsum_kernel<<<B, D / 4, 0, st>>>(x, T, D, out);
+  LAUNCH_OK();
+  return 0;
+}
+int bert_embeddings_fwd(const int64_t* ids, const int64_t* type_ids, const float* word, const float* type,
+                        const float* pos, const float* gamma, const float* beta, float eps, int B, int T, int D,
+                        DropoutCfg drop, float* pre, float* mean, float* rstd, bf16* out_bf16, float* out_f32,
+                        cudaStream_t st) {
+  ECAMP_REQUIRE(D == 768, "bert embeddings: hidden size must be 768");
+  const int M = B * T;
+  bert_emb_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, type_ids, word, type, pos, gamma, beta, eps, M, T, drop, pre,
+                                                   mean, rstd, out_bf16, out_f32);
+  LAUNCH_OK();
+  return 0;
+}
+int dropout_bwd_f32(float* g, size_t n, DropoutCfg drop, cudaStream_t st) {
+  if (drop.p <= 0.f || n == 0) return 0;
+  const size_t n4 = n / 4;
+  dropout_bwd_f32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(g, n4, drop);
+  LAUNCH_OK();
+  return 0;
+}
+int bert_embeddings_bwd(const float* d_pre, const int64_t* ids, const int64_t* type_ids, int B, int T, int D,
+                        float* d_word, float* d_type, float* d_pos, int accumulate, float* ws, cudaStream_t st) {
+  const int M = B * T;
+  if (!accumulate) ECAMP_CUDA_OK(cudaMemsetAsync(d_word, 0, (size_t)30000 * D * sizeof(float), st));
+  emb_word_bwd_kernel<<<M, D / 4, 0, st>>>(d_pre, ids, D, d_word);
+  LAUNCH_OK();
+  emb_pos_type_bwd_kernel<<<T, D / 4, 0, st>>>(d_pre, type_ids, B, T, D, d_pos, accumulate, ws);
+  LAUNCH_OK();
+  emb_type_finalize_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(ws, T, D, d_type, accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+size_t colsum_ws_floats(int N) { return (size_t)kColsumChunks * N; }
+int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate, float* ws, cudaStream_t st) {
+  ECAMP_REQUIRE(ld % 2 == 0, "colsum: ld must be even");
+  const int chunks = M < kColsumChunks * 8 ? 1 : kColsumChunks;
+  dim3 grid((N + 63) / 64, chunks);
+  colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, ws);
+  LAUNCH_OK();
+  colsum_finalize_kernel<<<(N + 255) / 256, 256, 0, st>>>(ws, chunks, N, out, accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+int scale_f32(float* x, const float* scale_dev, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  scale_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, scale_dev, n);
+  LAUNCH_OK();
+  return 0;
+}
+int cast_f32_to_bf16(const float* x, bf16* y, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n);
+  LAUNCH_OK();
+  return 0;
+}
+int permute_pe_weight_grad(const float* dw_pqc, float* grad_cpq, int accumulate, cudaStream_t st) {
+  permute_pe_grad_kernel<<<(768 * 768 + 255) / 256, 256, 0, st>>>(dw_pqc, grad_cpq, accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace ecamp

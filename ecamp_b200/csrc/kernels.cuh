@@ -1,0 +1,139 @@
+// Internal C++ launch interface of the non-GEMM kernels of the ECAMP hot path (all sm_100a, all
+// asynchronous on the given stream, all returning 0 or a negative error code).
+#pragma once
+#include "common.cuh"
+
+namespace ecamp {
+
+struct DropoutCfg {
+  float p = 0.f;
+  unsigned long long seed = 0, site = 0;
+};
+
+// ---- layernorm.cu -----------------------------------------------------------------------------
+// y = LN(x) * gamma + beta, fp32 statistics; D in {512, 768}.  Any of out_bf16 / out_f32 may be null.
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int D, bf16* out_bf16,
+                  float* out_f32, float* mean, float* rstd, cudaStream_t st);
+// dx = addend + LNbwd(dy); dx_bf16 = dropout_bwd(dx) (optional, mask of the forward's dense-output dropout);
+// dgamma/dbeta partials are reduced and ADDED to dgamma/dbeta when accumulate != 0, else stored.
+int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
+                  int D, const float* addend, float* dx_f32, bf16* dx_bf16, DropoutCfg drop, float* dgamma,
+                  float* dbeta, int accumulate, float* partial_ws, cudaStream_t st);
+size_t layernorm_bwd_ws_floats(int D);
+
+// ---- elementwise.cu ---------------------------------------------------------------------------
+// model_ecamp.py:168-193 on given noise: stable ascending rank == ids_restore; ids_keep; mask (1 = removed).
+int random_masking(const float* noise, int B, int L, int len_keep, int32_t* ids_restore, int32_t* ids_keep,
+                   float* mask, int64_t* ids_restore64, int64_t* ids_keep64, cudaStream_t st);
+// bicubic 448 -> 224 (antialias off, A = -0.75, align_corners = False) written in patch layout
+// tgt[b, l, (p*16+q)*3 + c]  (model_ecamp.py:318 + the layout of patchify with p = 16).
+int resize_bicubic_patchify(const float* big, int B, int Hin, float* tgt, cudaStream_t st);
+int patchify224(const float* imgs, int B, float* tgt, cudaStream_t st);
+// A_pe[b*keep + j, :] = bf16(tgt[b, ids_keep[b, j], :])
+int gather_patches(const float* tgt, const int32_t* ids_keep, int B, int L, int keep, int PD, bf16* out,
+                   cudaStream_t st);
+// x0[b, 0] = cls + pos[0]; x0[b, 1 + j] = pe[b*keep + j] + pos[1 + ids_keep[b, j]]      (model_ecamp.py:222-230)
+int assemble_encoder_input(const float* pe, const float* cls, const float* pos, const int32_t* ids_keep, int B,
+                           int keep, int D, float* x0, cudaStream_t st);
+// backward of the above: d_pe (bf16, GEMM operand) and d_cls (sum over batch of row 0)
+int assemble_encoder_input_bwd(const float* dx0, int B, int keep, int D, bf16* d_pe, float* d_cls, int accumulate,
+                               cudaStream_t st);
+// xd[b, 0] = e[b, 0] + dpos[0]; xd[b, 1 + l] = (r = ids_restore[b, l]) < keep ? e[b, 1 + r] : mask_token, + dpos[1 + l]
+int assemble_decoder_input(const bf16* e, const float* mask_token, const float* dpos, const int32_t* ids_restore,
+                           int B, int L, int keep, int D, float* xd, cudaStream_t st);
+int assemble_decoder_input_bwd(const float* dxd, const int32_t* ids_restore, int B, int L, int keep, int D, bf16* d_e,
+                               float* d_mask_token, int accumulate, float* ws, cudaStream_t st);
+// img_tok[b*keep + j] = lat2[b, 1 + j]; gap[b] = mean_j lat2[b, 1 + j]                  (model_ecamp.py:269-271)
+int split_latent_gap(const bf16* lat2, int B, int keep, int D, bf16* img_tok, bf16* gap, cudaStream_t st);
+// d_lat2[b, 0] = 0; d_lat2[b, 1 + j] = d_img_tok[b*keep + j] + d_gap[b] / keep
+int split_latent_gap_bwd(const bf16* d_img_tok, const bf16* d_gap, int B, int keep, int D, bf16* d_lat2,
+                         cudaStream_t st);
+// y[b*T + t, :] += vec[b, :]   (context_fusion.py:54-55)
+int add_batch_rowvec(bf16* y, const bf16* vec, int B, int T, int D, cudaStream_t st);
+// out[b, :] = sum_t x[b*T + t, :]  (bf16 in, bf16 out, fp32 accumulate)
+int batch_colsum(const bf16* x, int B, int T, int D, bf16* out, cudaStream_t st);
+// BertEmbeddings: e = word[id] + type[tt] + pos[t] -> pre (fp32, saved); LN(1e-12) -> dropout -> bf16 + fp32
+int bert_embeddings_fwd(const int64_t* ids, const int64_t* type_ids, const float* word, const float* type,
+                        const float* pos, const float* gamma, const float* beta, float eps, int B, int T, int D,
+                        DropoutCfg drop, float* pre, float* mean, float* rstd, bf16* out_bf16, float* out_f32,
+                        cudaStream_t st);
+// in-place inverted-dropout backward on an fp32 gradient (n % 4 == 0)
+int dropout_bwd_f32(float* g, size_t n, DropoutCfg drop, cudaStream_t st);
+// scatter-add of d_pre into the three tables (word row padding_idx = 0 receives nothing)
+int bert_embeddings_bwd(const float* d_pre, const int64_t* ids, const int64_t* type_ids, int B, int T, int D,
+                        float* d_word, float* d_type, float* d_pos, int accumulate, float* ws, cudaStream_t st);
+// bias gradient: out[n] (+)= sum_m x[m, n]
+int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate, float* ws, cudaStream_t st);
+size_t colsum_ws_floats(int N);
+// y = dropout(x) elementwise on bf16 (used for the dropout behind LayerNorm-less sites), in place allowed
+int scale_f32(float* x, const float* scale_dev, size_t n, cudaStream_t st);
+int cast_f32_to_bf16(const float* x, bf16* y, size_t n, cudaStream_t st);
+// patch-embed weight: canonical [768, (c, p, q)] <-> GEMM K-order [768, (p, q, c)]
+int permute_pe_weight_grad(const float* dw_pqc, float* grad_cpq, int accumulate, cudaStream_t st);
+// out = bf16(d * gelu'(pre))   (LM-head transform: dense -> GELU -> LayerNorm, bert_modeling.py:208)
+int gelu_bwd_bf16(const float* d, const bf16* pre, bf16* out, size_t n, cudaStream_t st);
+// y = x + vec[b] broadcast over the T rows of each batch element (out of place)
+int add_batch_rowvec_oop(const bf16* x, const bf16* vec, int B, int T, int D, bf16* y, cudaStream_t st);
+
+// ---- attention.cu -----------------------------------------------------------------------------
+struct AttnArgs {
+  const bf16 *q = nullptr, *k = nullptr, *v = nullptr;  // head h lives at columns [h*D, (h+1)*D) of each row
+  int ldq = 0, ldk = 0, ldv = 0;
+  bf16* o = nullptr;
+  int ldo = 0;
+  float* lse = nullptr;              // [B, H, Sq]
+  const int64_t* key_mask = nullptr;  // [B, Sk], nonzero = attend (HF attention_mask); null = all valid
+  int B = 0, H = 0, Sq = 0, Sk = 0, D = 0;
+  float scale = 1.f;
+  DropoutCfg drop;
+  // backward only
+  const bf16* d_o = nullptr;
+  int ld_do = 0;
+  float* delta = nullptr;  // [B, H, Sq] scratch
+  bf16 *dq = nullptr, *dk = nullptr, *dv = nullptr;
+  int lddq = 0, lddk = 0, lddv = 0;
+};
+int attention_fwd(const AttnArgs& a, cudaStream_t st);
+int attention_bwd(const AttnArgs& a, cudaStream_t st);
+
+// ---- losses.cu --------------------------------------------------------------------------------
+// mim = sum_{masked patches} (pred - tgt)^2 / (B*3*224*224)       (model_ecamp.py:288-297)
+int mim_loss_fwd(const float* pred, int ld_pred_rows, const float* tgt, const float* mask, int B, int L, int PD,
+                 float* loss_out, float* ws, cudaStream_t st);
+// SR branch forward loss (model_ecamp.py:37-46,196-215,286,291-299) and backward (d_u + conv grads)
+int sr_loss_fwd(const float* pred, const float* big, const int64_t* column, const int64_t* row, const float* w1,
+                const float* b1, const float* w2, const float* b2, int B, float* loss_out, float* ws,
+                cudaStream_t st);
+int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, const int64_t* row, const float* w1,
+                const float* b1, const float* w2, const float* b2, int B, const float* g_res, float* d_u,
+                float* d_conv /*168: w1,b1,w2,b2*/, int accumulate, float* ws, cudaStream_t st);
+size_t sr_ws_floats(int B);
+// d_pred[b, 0] = 0; d_pred[b, 1 + l, e] = g_mim * 2 * mask * (pred - tgt) / Nmim + bilinear^T(d_u) (if d_u)
+int pred_grad(const float* pred, const float* tgt, const float* mask, const float* d_u, const float* g_mim, int B,
+              bf16* d_pred, cudaStream_t st);
+// weighted cross-entropy over a chunk of rows, logits bf16 [rows, V] (ld = ldl); optionally overwrites the
+// logits with d_logits = (softmax - onehot) * w * g / total_rows           (bert_modeling.py:211-217)
+int ce_chunk(bf16* logits, int ldl, int rows, int V, const int64_t* labels, const float* weights, float* row_loss,
+             const float* g_mlm, float inv_total, int write_grad, cudaStream_t st);
+int sum_to_scalar(const float* x, size_t n, float scale, float* out, cudaStream_t st);
+
+// ---- adamw.cu ---------------------------------------------------------------------------------
+struct AdamTensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  bf16* shadow;        // bf16 GEMM copy, may be null
+  float* shadow32;     // fp32 copy (fused q|k|v bias vectors), may be null
+  long long numel;
+  int decay;           // 1 = apply weight decay
+  int shadow_kind;     // 0 plain, 1 patch-embed (c,p,q)->(p,q,c)
+};
+int adamw_build_tables(const AdamTensor* host, int n, void* dev_table, void* dev_chunks, long long* n_chunks);
+int adamw_step(const void* dev_table, const void* dev_chunks, long long n_chunks, float lr, float beta1, float beta2,
+               float eps, float wd, int step, float grad_scale, cudaStream_t st);
+int refresh_shadows(const void* dev_table, const void* dev_chunks, long long n_chunks, cudaStream_t st);
+size_t adamw_table_bytes(int n);
+size_t adamw_chunk_bytes(const AdamTensor* host, int n);
+
+}  // namespace ecamp

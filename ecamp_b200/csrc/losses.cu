@@ -1,0 +1,554 @@
+// Loss kernels of the ECAMP step (all HBM / CUDA-core bound):
+//   * masked-pixel MSE computed in patch space, no mask tensors materialised      (model_ecamp.py:196-215,276-300)
+//   * super-resolution branch: bilinear x2 -> conv3x3 -> ReLU -> conv3x3 -> +skip -> ReLU -> windowed MSE,
+//     one fused stencil kernel forward, one backward                                (model_ecamp.py:28-46,286,291-299)
+//   * re-weighted cross-entropy over the 30 000-word vocabulary, per row chunk     (bert_modeling.py:211-217)
+#include "kernels.cuh"
+
+namespace ecamp {
+namespace {
+
+constexpr int IMG = 224, BIG = 448, GRID = 14, PATCH = 16, PD = 768;
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) mim_rows_kernel(const float* __restrict__ pred, int rows_per_batch,
+                                                       const float* __restrict__ tgt, const float* __restrict__ mask,
+                                                       int L, float* __restrict__ ws) {
+  __shared__ float red[32];
+  const int r = blockIdx.x, b = r / L, l = r % L;
+  float s = 0.f;
+  if (mask[r] != 0.f) {
+    const float4 p = reinterpret_cast<const float4*>(pred + ((size_t)b * rows_per_batch + 1 + l) * PD)[threadIdx.x];
+    const float4 t = reinterpret_cast<const float4*>(tgt + (size_t)r * PD)[threadIdx.x];
+    const float a = p.x - t.x, c = p.y - t.y, d = p.z - t.z, e = p.w - t.w;
+    s = a * a + c * c + d * d + e * e;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) ws[r] = s;
+}
+
+__global__ void __launch_bounds__(1024) sum_to_scalar_kernel(const float* __restrict__ x, size_t n, float scale,
+                                                             float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out = s * scale;
+}
+
+// ---------------------------------------------------------------------------------------------
+// super-resolution branch
+// ---------------------------------------------------------------------------------------------
+struct SrWeights {
+  float w1[81], b1[3], w2[81], b2[3];
+};
+
+ECAMP_DEVINL float pred_pixel(const float* __restrict__ pred_b, int c, int y, int x) {
+  // pred_b: [197, 768] of one sample, row 0 = cls; unpatchify 'nhwpqc->nchpwq' (model_ecamp.py:153-165)
+  return pred_b[(size_t)(1 + (y >> 4) * GRID + (x >> 4)) * PD + (((y & 15) << 4) + (x & 15)) * 3 + c];
+}
+// F.interpolate(scale_factor=2, mode='bilinear', align_corners=False): source index and weight of output index Y
+ECAMP_DEVINL void bilinear_src(int Y, int& y0, int& y1, float& lam) {
+  const float src = fmaxf(0.f, (float)Y * 0.5f - 0.25f);
+  y0 = (int)src;
+  y1 = min(y0 + 1, IMG - 1);
+  lam = src - (float)y0;
+}
+
+// Forward of the SR head on an OUT x OUT output region whose top-left output pixel is (Y0, X0):
+//   sU: (OUT+4)^2 x 3 up-sampled input, origin (Y0-2, X0-2), zero outside the image (conv zero padding)
+//   sH: (OUT+2)^2 x 3 relu(conv1), origin (Y0-1, X0-1), zero outside the image
+template <int OUT>
+ECAMP_DEVINL void sr_forward_region(const float* __restrict__ pred_b, const SrWeights& w, int Y0, int X0, float* sU,
+                                    float* sH) {
+  constexpr int UW = OUT + 4, HW = OUT + 2;
+  for (int i = threadIdx.x; i < UW * UW; i += blockDim.x) {
+    const int uy = i / UW, ux = i % UW;
+    const int Y = Y0 - 2 + uy, X = X0 - 2 + ux;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (Y >= 0 && Y < BIG && X >= 0 && X < BIG) {
+      int y0, y1, x0, x1;
+      float ly, lx;
+      bilinear_src(Y, y0, y1, ly);
+      bilinear_src(X, x0, x1, lx);
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      v0 = w00 * pred_pixel(pred_b, 0, y0, x0) + w01 * pred_pixel(pred_b, 0, y0, x1) +
+           w10 * pred_pixel(pred_b, 0, y1, x0) + w11 * pred_pixel(pred_b, 0, y1, x1);
+      v1 = w00 * pred_pixel(pred_b, 1, y0, x0) + w01 * pred_pixel(pred_b, 1, y0, x1) +
+           w10 * pred_pixel(pred_b, 1, y1, x0) + w11 * pred_pixel(pred_b, 1, y1, x1);
+      v2 = w00 * pred_pixel(pred_b, 2, y0, x0) + w01 * pred_pixel(pred_b, 2, y0, x1) +
+           w10 * pred_pixel(pred_b, 2, y1, x0) + w11 * pred_pixel(pred_b, 2, y1, x1);
+    }
+    sU[i] = v0;
+    sU[UW * UW + i] = v1;
+    sU[2 * UW * UW + i] = v2;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HW * HW; i += blockDim.x) {
+    const int hy = i / HW, hx = i % HW;
+    const int Y = Y0 - 1 + hy, X = X0 - 1 + hx;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (Y >= 0 && Y < BIG && X >= 0 && X < BIG) {
+      a0 = w.b1[0]; a1 = w.b1[1]; a2 = w.b1[2];
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float u = sU[ci * UW * UW + (hy + ky) * UW + hx + kx];
+            a0 += w.w1[(0 * 3 + ci) * 9 + ky * 3 + kx] * u;
+            a1 += w.w1[(1 * 3 + ci) * 9 + ky * 3 + kx] * u;
+            a2 += w.w1[(2 * 3 + ci) * 9 + ky * 3 + kx] * u;
+          }
+      a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f);
+    }
+    sH[i] = a0;
+    sH[HW * HW + i] = a1;
+    sH[2 * HW * HW + i] = a2;
+  }
+  __syncthreads();
+}
+
+// pre-activation output of the head at region pixel (oy, ox): conv2(h1) + b2 + u
+template <int OUT>
+ECAMP_DEVINL void sr_out_pixel(const SrWeights& w, const float* sU, const float* sH, int oy, int ox, float (&o)[3]) {
+  constexpr int UW = OUT + 4, HW = OUT + 2;
+  o[0] = w.b2[0] + sU[(oy + 2) * UW + ox + 2];
+  o[1] = w.b2[1] + sU[UW * UW + (oy + 2) * UW + ox + 2];
+  o[2] = w.b2[2] + sU[2 * UW * UW + (oy + 2) * UW + ox + 2];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float hv = sH[ci * HW * HW + (oy + ky) * HW + ox + kx];
+        o[0] += w.w2[(0 * 3 + ci) * 9 + ky * 3 + kx] * hv;
+        o[1] += w.w2[(1 * 3 + ci) * 9 + ky * 3 + kx] * hv;
+        o[2] += w.w2[(2 * 3 + ci) * 9 + ky * 3 + kx] * hv;
+      }
+}
+
+ECAMP_DEVINL void load_sr_weights(SrWeights* sw, const float* w1, const float* b1, const float* w2, const float* b2) {
+  for (int i = threadIdx.x; i < 81; i += blockDim.x) {
+    sw->w1[i] = w1[i];
+    sw->w2[i] = w2[i];
+  }
+  if (threadIdx.x < 3) {
+    sw->b1[threadIdx.x] = b1[threadIdx.x];
+    sw->b2[threadIdx.x] = b2[threadIdx.x];
+  }
+  __syncthreads();
+}
+
+// window of sample b in 32-px tiles: rows [c0, c1), cols [r0, r1) (model_ecamp.py:207-208: slices clip at 14)
+ECAMP_DEVINL void sr_window(const int64_t* column, const int64_t* row, int b, int& c0, int& c1, int& r0, int& r1) {
+  const long long c = column[b], r = row[b];
+  c0 = (int)max(0LL, min((long long)GRID, c));
+  c1 = (int)max(0LL, min((long long)GRID, c + 12));
+  r0 = (int)max(0LL, min((long long)GRID, r));
+  r1 = (int)max(0LL, min((long long)GRID, r + 12));
+}
+
+__global__ void __launch_bounds__(256) sr_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ big,
+                                                     const int64_t* __restrict__ column,
+                                                     const int64_t* __restrict__ row, const float* w1, const float* b1,
+                                                     const float* w2, const float* b2, float* __restrict__ ws) {
+  constexpr int OUT = 32, UW = OUT + 4, HW = OUT + 2;
+  __shared__ SrWeights sw;
+  __shared__ float sU[3 * UW * UW];
+  __shared__ float sH[3 * HW * HW];
+  __shared__ float red[32];
+  const int tile = blockIdx.x % (GRID * GRID), b = blockIdx.x / (GRID * GRID);
+  const int ty = tile / GRID, tx = tile % GRID;
+  int c0, c1, r0, r1;
+  sr_window(column, row, b, c0, c1, r0, r1);
+  if (ty < c0 || ty >= c1 || tx < r0 || tx >= r1) {
+    if (threadIdx.x == 0) ws[blockIdx.x] = 0.f;
+    return;
+  }
+  load_sr_weights(&sw, w1, b1, w2, b2);
+  const float* pred_b = pred + (size_t)b * 197 * PD;
+  const int Y0 = ty * 32, X0 = tx * 32;
+  sr_forward_region<OUT>(pred_b, sw, Y0, X0, sU, sH);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < OUT * OUT; i += blockDim.x) {
+    const int oy = i / OUT, ox = i % OUT;
+    float o[3];
+    sr_out_pixel<OUT>(sw, sU, sH, oy, ox, o);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = fmaxf(o[c], 0.f) - big[(((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox];
+      s += d * d;
+    }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) ws[blockIdx.x] = s;
+}
+
+// backward: one CTA per 32x32 tile of d_u.  Dynamic smem layout: U 40^2x3 | H 38^2x3 | dOut 36^2x3 | dH 34^2x3
+constexpr int SR_BWD_SMEM_FLOATS = 3 * (40 * 40 + 38 * 38 + 36 * 36 + 34 * 34);
+__global__ void __launch_bounds__(256) sr_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ big,
+                                                     const int64_t* __restrict__ column,
+                                                     const int64_t* __restrict__ row, const float* w1, const float* b1,
+                                                     const float* w2, const float* b2, int B,
+                                                     const float* __restrict__ g_res, float* __restrict__ d_u,
+                                                     float* __restrict__ ws) {
+  constexpr int OUT = 36, UW = 40, HW = 38, OW = 36, GW = 34;
+  extern __shared__ float sm[];
+  float* sU = sm;
+  float* sH = sU + 3 * UW * UW;
+  float* sDO = sH + 3 * HW * HW;
+  float* sDH = sDO + 3 * OW * OW;
+  __shared__ SrWeights sw;
+  __shared__ float redw[8][84];
+  const int tile = blockIdx.x % (GRID * GRID), b = blockIdx.x / (GRID * GRID);
+  const int ty = tile / GRID, tx = tile % GRID;
+  const int Y0 = ty * 32, X0 = tx * 32;  // origin of the owned 32x32 region
+  int c0, c1, r0, r1;
+  sr_window(column, row, b, c0, c1, r0, r1);
+  const int wy0 = c0 * 32, wy1 = c1 * 32, wx0 = r0 * 32, wx1 = r1 * 32;  // window in pixels
+  float* ws_t = ws + (size_t)blockIdx.x * 168;
+  // does the 36x36 d_out neighbourhood touch the window at all?
+  const bool touches = (Y0 - 2 < wy1) && (Y0 + 34 > wy0) && (X0 - 2 < wx1) && (X0 + 34 > wx0);
+  if (!touches) {
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+      const int oy = i >> 5, ox = i & 31;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) d_u[(((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox] = 0.f;
+    }
+    for (int i = threadIdx.x; i < 168; i += blockDim.x) ws_t[i] = 0.f;
+    return;
+  }
+  load_sr_weights(&sw, w1, b1, w2, b2);
+  const float* pred_b = pred + (size_t)b * 197 * PD;
+  sr_forward_region<OUT>(pred_b, sw, Y0 - 2, X0 - 2, sU, sH);
+  const float gscale = 2.0f * (*g_res) / ((float)B * 3.f * BIG * BIG);
+
+  // d_out (pre-ReLU) on the 36x36 region with origin (Y0-2, X0-2)
+  for (int i = threadIdx.x; i < OW * OW; i += blockDim.x) {
+    const int oy = i / OW, ox = i % OW;
+    const int Y = Y0 - 2 + oy, X = X0 - 2 + ox;
+    float d[3] = {0.f, 0.f, 0.f};
+    if (Y >= wy0 && Y < wy1 && X >= wx0 && X < wx1) {  // inside the window (hence inside the image)
+      float o[3];
+      sr_out_pixel<OUT>(sw, sU, sH, oy, ox, o);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        d[c] = o[c] > 0.f ? gscale * (o[c] - big[(((size_t)b * 3 + c) * BIG + Y) * BIG + X]) : 0.f;
+    }
+    sDO[i] = d[0];
+    sDO[OW * OW + i] = d[1];
+    sDO[2 * OW * OW + i] = d[2];
+  }
+  __syncthreads();
+  // d_h1 (pre-ReLU) on the 34x34 region with origin (Y0-1, X0-1)
+  for (int i = threadIdx.x; i < GW * GW; i += blockDim.x) {
+    const int gy = i / GW, gx = i % GW;
+    const int Y = Y0 - 1 + gy, X = X0 - 1 + gx;
+    float d[3] = {0.f, 0.f, 0.f};
+    if (Y >= 0 && Y < BIG && X >= 0 && X < BIG) {
+      // H region coords of (Y, X): (gy + 2, gx + 2); dOut region coords of (Y - ky + 1, X - kx + 1): (gy + 2 - ky, gx + 2 - kx)
+#pragma unroll
+      for (int co = 0; co < 3; ++co)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float g = sDO[co * OW * OW + (gy + 2 - ky) * OW + gx + 2 - kx];
+            d[0] += sw.w2[(co * 3 + 0) * 9 + ky * 3 + kx] * g;
+            d[1] += sw.w2[(co * 3 + 1) * 9 + ky * 3 + kx] * g;
+            d[2] += sw.w2[(co * 3 + 2) * 9 + ky * 3 + kx] * g;
+          }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (!(sH[c * HW * HW + (gy + 2) * HW + gx + 2] > 0.f)) d[c] = 0.f;
+    }
+    sDH[i] = d[0];
+    sDH[GW * GW + i] = d[1];
+    sDH[2 * GW * GW + i] = d[2];
+  }
+  __syncthreads();
+  // d_u on the owned 32x32 region: skip path + conv1^T
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+    const int oy = i >> 5, ox = i & 31;
+    float d[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[c] = sDO[c * OW * OW + (oy + 2) * OW + ox + 2];
+#pragma unroll
+    for (int co = 0; co < 3; ++co)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          // dH region coords of (Y - ky + 1, X - kx + 1) with (Y, X) = (Y0 + oy, X0 + ox): (oy + 2 - ky, ox + 2 - kx)
+          const float g = sDH[co * GW * GW + (oy + 2 - ky) * GW + ox + 2 - kx];
+          d[0] += sw.w1[(co * 3 + 0) * 9 + ky * 3 + kx] * g;
+          d[1] += sw.w1[(co * 3 + 1) * 9 + ky * 3 + kx] * g;
+          d[2] += sw.w1[(co * 3 + 2) * 9 + ky * 3 + kx] * g;
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d_u[(((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox] = d[c];
+  }
+  // conv weight gradients over the OWNED 32x32 pixels only (each pixel is owned by exactly one tile)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    float acc[84];
+#pragma unroll
+    for (int k = 0; k < 84; ++k) acc[k] = 0.f;
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+      const int oy = i >> 5, ox = i & 31;
+      if (which == 0) {
+        // conv2: d_w2[co][ci][ky][kx] += dOut(Y, X)[co] * H(Y + ky - 1, X + kx - 1)[ci]
+        float g[3];
+#pragma unroll
+        for (int co = 0; co < 3; ++co) g[co] = sDO[co * OW * OW + (oy + 2) * OW + ox + 2];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float hv = sH[ci * HW * HW + (oy + 2 + ky) * HW + ox + 2 + kx];
+#pragma unroll
+              for (int co = 0; co < 3; ++co) acc[(co * 3 + ci) * 9 + ky * 3 + kx] += g[co] * hv;
+            }
+#pragma unroll
+        for (int co = 0; co < 3; ++co) acc[81 + co] += g[co];
+      } else {
+        // conv1: d_w1[co][ci][ky][kx] += dH(Y, X)[co] * U(Y + ky - 1, X + kx - 1)[ci]
+        float g[3];
+#pragma unroll
+        for (int co = 0; co < 3; ++co) g[co] = sDH[co * GW * GW + (oy + 1) * GW + ox + 1];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float uv = sU[ci * UW * UW + (oy + 3 + ky) * UW + ox + 3 + kx];
+#pragma unroll
+              for (int co = 0; co < 3; ++co) acc[(co * 3 + ci) * 9 + ky * 3 + kx] += g[co] * uv;
+            }
+#pragma unroll
+        for (int co = 0; co < 3; ++co) acc[81 + co] += g[co];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 84; ++k) {
+      const float v = warp_sum(acc[k]);
+      if (lane == 0) redw[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 84) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += redw[w][threadIdx.x];
+      // ws layout per tile: [w1 81 | b1 3 | w2 81 | b2 3]
+      ws_t[(which == 0 ? 84 : 0) + threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) sr_wgrad_finalize_kernel(const float* __restrict__ ws, int ntiles,
+                                                                float* __restrict__ d_conv, int accumulate) {
+  __shared__ float red[32];
+  const int k = blockIdx.x;  // 0..167
+  float s = 0.f;
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) s += ws[(size_t)t * 168 + k];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) d_conv[k] = accumulate ? d_conv[k] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// d_pred (bf16, the dY operand of decoder_pred's dgrad / wgrad)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pred_grad_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                        const float* __restrict__ mask, const float* __restrict__ d_u,
+                                                        const float* __restrict__ g_mim, int B,
+                                                        bf16* __restrict__ d_pred) {
+  const int r = blockIdx.x, b = r / 197, t = r % 197;
+  bf16* out = d_pred + (size_t)r * PD;
+  if (t == 0) {
+    for (int e = threadIdx.x; e < PD; e += blockDim.x) out[e] = f2bf(0.f);
+    return;
+  }
+  const int l = t - 1, hy = l / GRID, wx = l % GRID;
+  const float m = mask[(size_t)b * 196 + l];
+  const float gm = m != 0.f ? 2.0f * (*g_mim) / ((float)B * 3.f * IMG * IMG) : 0.f;
+  for (int e = threadIdx.x; e < PD; e += blockDim.x) {
+    float g = 0.f;
+    if (gm != 0.f) g = gm * (pred[(size_t)r * PD + e] - tgt[((size_t)b * 196 + l) * PD + e]);
+    if (d_u) {
+      const int c = e % 3, pq = e / 3, p = pq >> 4, q = pq & 15;
+      const int y = hy * PATCH + p, x = wx * PATCH + q;
+      const float* du = d_u + ((size_t)b * 3 + c) * BIG * BIG;
+      float acc = 0.f;
+#pragma unroll
+      for (int dy = -1; dy <= 2; ++dy) {
+        const int Y = 2 * y + dy;
+        if (Y < 0 || Y >= BIG) continue;
+        int y0, y1;
+        float ly;
+        bilinear_src(Y, y0, y1, ly);
+        const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
+        if (wy == 0.f) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 2; ++dx) {
+          const int X = 2 * x + dx;
+          if (X < 0 || X >= BIG) continue;
+          int x0, x1;
+          float lx;
+          bilinear_src(X, x0, x1, lx);
+          const float wxx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+          if (wxx != 0.f) acc += wy * wxx * du[(size_t)Y * BIG + X];
+        }
+      }
+      g += acc;
+    }
+    out[e] = f2bf(g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-entropy over one chunk of rows; the row is staged in shared memory so logits are read once
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ce_rows_kernel(bf16* __restrict__ logits, int ldl, int V,
+                                                      const int64_t* __restrict__ labels,
+                                                      const float* __restrict__ weights, float* __restrict__ row_loss,
+                                                      const float* __restrict__ g_mlm, float inv_total,
+                                                      int write_grad) {
+  extern __shared__ __align__(16) uint8_t ce_smem[];
+  bf16* srow = reinterpret_cast<bf16*>(ce_smem);
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  bf16* grow = logits + (size_t)r * ldl;
+  const int nv = V / 8;  // V % 8 == 0 checked on the host
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(grow)[i];
+    reinterpret_cast<uint4*>(srow)[i] = u;
+    float2 f;
+    f = unpack_bf16x2(u.x); mx = fmaxf(mx, fmaxf(f.x, f.y));
+    f = unpack_bf16x2(u.y); mx = fmaxf(mx, fmaxf(f.x, f.y));
+    f = unpack_bf16x2(u.z); mx = fmaxf(mx, fmaxf(f.x, f.y));
+    f = unpack_bf16x2(u.w); mx = fmaxf(mx, fmaxf(f.x, f.y));
+  }
+  // block max
+  mx = warp_max(mx);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(srow)[i];
+    float2 f;
+    f = unpack_bf16x2(u.x); se += __expf(f.x - mx) + __expf(f.y - mx);
+    f = unpack_bf16x2(u.y); se += __expf(f.x - mx) + __expf(f.y - mx);
+    f = unpack_bf16x2(u.z); se += __expf(f.x - mx) + __expf(f.y - mx);
+    f = unpack_bf16x2(u.w); se += __expf(f.x - mx) + __expf(f.y - mx);
+  }
+  se = block_sum(se, red);
+  const float lse = mx + __logf(se);
+  const long long label = labels[r];
+  const bool valid = label >= 0 && label < V;  // CrossEntropyLoss ignore_index (-100) -> no loss, no gradient
+  const float w = weights[r];
+  if (threadIdx.x == 0) row_loss[r] = valid ? (lse - bf2f(srow[label])) * w : 0.f;
+  if (!write_grad) return;
+  const float coef = valid ? w * (*g_mlm) * inv_total : 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(srow)[i];
+    float v[8];
+    float2 f;
+    f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+    f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+    f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+    f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float p = __expf(v[k] - lse);
+      if (i * 8 + k == label) p -= 1.f;
+      v[k] = p * coef;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(grow)[i] = o;
+  }
+}
+
+}  // namespace
+
+#define LAUNCH_OK() ECAMP_CUDA_OK(cudaGetLastError())
+
+int sum_to_scalar(const float* x, size_t n, float scale, float* out, cudaStream_t st) {
+  sum_to_scalar_kernel<<<1, 1024, 0, st>>>(x, n, scale, out);
+  LAUNCH_OK();
+  return 0;
+}
+
+int mim_loss_fwd(const float* pred, int rows_per_batch, const float* tgt, const float* mask, int B, int L, int pd,
+                 float* loss_out, float* ws, cudaStream_t st) {
+  ECAMP_REQUIRE(pd == PD && L == 196, "mim loss: only 196 patches x 768 supported");
+  mim_rows_kernel<<<B * L, 192, 0, st>>>(pred, rows_per_batch, tgt, mask, L, ws);
+  LAUNCH_OK();
+  return sum_to_scalar(ws, (size_t)B * L, 1.0f / ((float)B * 3.f * IMG * IMG), loss_out, st);
+}
+
+size_t sr_ws_floats(int B) { return (size_t)B * GRID * GRID * 168; }
+
+int sr_loss_fwd(const float* pred, const float* big, const int64_t* column, const int64_t* row, const float* w1,
+                const float* b1, const float* w2, const float* b2, int B, float* loss_out, float* ws,
+                cudaStream_t st) {
+  sr_fwd_kernel<<<B * GRID * GRID, 256, 0, st>>>(pred, big, column, row, w1, b1, w2, b2, ws);
+  LAUNCH_OK();
+  return sum_to_scalar(ws, (size_t)B * GRID * GRID, 1.0f / ((float)B * 3.f * BIG * BIG), loss_out, st);
+}
+
+int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, const int64_t* row, const float* w1,
+                const float* b1, const float* w2, const float* b2, int B, const float* g_res, float* d_u,
+                float* d_conv, int accumulate, float* ws, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(sr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SR_BWD_SMEM_FLOATS * (int)sizeof(float)));
+    attr = true;
+  }
+  sr_bwd_kernel<<<B * GRID * GRID, 256, SR_BWD_SMEM_FLOATS * sizeof(float), st>>>(pred, big, column, row, w1, b1, w2,
+                                                                                   b2, B, g_res, d_u, ws);
+  LAUNCH_OK();
+  sr_wgrad_finalize_kernel<<<168, 256, 0, st>>>(ws, B * GRID * GRID, d_conv, accumulate);
+  LAUNCH_OK();
+  return 0;
+}
+
+int pred_grad(const float* pred, const float* tgt, const float* mask, const float* d_u, const float* g_mim, int B,
+              bf16* d_pred, cudaStream_t st) {
+  pred_grad_kernel<<<B * 197, 256, 0, st>>>(pred, tgt, mask, d_u, g_mim, B, d_pred);
+  LAUNCH_OK();
+  return 0;
+}
+
+int ce_chunk(bf16* logits, int ldl, int rows, int V, const int64_t* labels, const float* weights, float* row_loss,
+             const float* g_mlm, float inv_total, int write_grad, cudaStream_t st) {
+  ECAMP_REQUIRE(V % 8 == 0 && ldl % 8 == 0, "cross-entropy: vocabulary / pitch must be multiples of 8");
+  ECAMP_REQUIRE((size_t)V * 2 <= 200 * 1024, "cross-entropy: vocabulary row does not fit in shared memory");
+  if (rows <= 0) return 0;
+  static bool attr = false;
+  if (!attr) {
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(ce_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  ce_rows_kernel<<<rows, 256, (size_t)V * 2, st>>>(logits, ldl, V, labels, weights, row_loss, g_mlm, inv_total,
+                                                   write_grad);
+  LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace ecamp

@@ -1,0 +1,66 @@
+// Runtime of the ECAMP pre-training step: parameter table, workspace plan, forward / backward
+// schedules.  One context per process / device; PyTorch owns every byte (parameters, the flat
+// gradient / Adam-state / shadow buffers and the workspace are torch tensors whose base pointers
+// are bound here).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace ecamp {
+
+struct ParamSpec {
+  std::string name;   // reference state_dict key (model_ecamp.py / HF naming)
+  long long numel;
+  int decay;          // timm add_weight_decay: ndim > 1 and not *.bias
+  int shadow;         // 0 none, 1 bf16 copy, 2 bf16 patch-embed permuted copy, 3 fp32 copy (fused bias)
+  long long g_off;    // offset (floats) in the flat gradient / Adam-state buffers
+  long long sh_off;   // offset (bf16 elements) in the bf16 shadow region, or fp32 elements in the fp32 region
+};
+
+const std::vector<ParamSpec>& param_specs();
+long long grad_total_floats();
+long long shadow_bf16_elems();
+long long shadow_f32_elems();
+int param_index(const std::string& name);
+
+struct Shape {
+  int B = 0, T = 0, keep = 49, has_big = 1;
+  int ce_rows = 2048;  // rows of the vocabulary projection materialised at a time
+};
+
+struct Batch {
+  const float* image = nullptr;  // [B,3,448,448] if has_big else [B,3,224,224]
+  const int64_t* ids = nullptr;
+  const int64_t* labels = nullptr;
+  const int64_t* attention_mask = nullptr;
+  const int64_t* type_ids = nullptr;
+  const float* weights = nullptr;
+  const int64_t* column = nullptr;
+  const int64_t* row = nullptr;
+  const float* noise = nullptr;  // [B,196]
+};
+
+struct Ctx;
+Ctx* ctx_new();
+void ctx_free(Ctx*);
+int ctx_bind(Ctx*, float* const* params, int n, float* G, float* M1, float* M2, void* shadows,
+             const float* pos_embed, const float* dec_pos_embed, void* adam_table, void* adam_chunks);
+size_t ctx_adam_table_bytes();
+size_t ctx_adam_chunk_bytes();
+size_t workspace_bytes(const Shape&);
+int ctx_set_workspace(Ctx*, void* ws, size_t bytes, const Shape&);
+int ctx_refresh_shadows(Ctx*, cudaStream_t);
+// flags: 1 = training (saves activations), 2 = defer the MLM loss to backward (fused head)
+int ctx_forward(Ctx*, const Batch&, int flags, float drop_p, unsigned long long seed, float* losses3, float* mask_out,
+                int64_t* ids_restore_out, int64_t* ids_keep_out, cudaStream_t);
+int backward_stage_count();
+int backward_stage_range(int stage, long long* g_begin, long long* g_end);
+// g3: device pointer to the three upstream gradients (mim, res, mlm).  stage = -1 runs every stage.
+int ctx_backward(Ctx*, const float* g3, int accumulate, int stage, cudaStream_t);
+int ctx_adamw(Ctx*, float lr, float b1, float b2, float eps, float wd, int step, float grad_scale, cudaStream_t);
+const void* ctx_debug_ptr(Ctx*, const char* name);
+
+}  // namespace ecamp

@@ -1,27 +1,28 @@
 /*
  * ecamp_b200 — C ABI of the B200-native ECAMP pre-training hot path.
  *
- * The reference (ToniChopp/ECAMP) has no FFI or operator registry for this path: the boundary
- * is the nn.Module returned by `module.model_ecamp.ecamp(**kwargs)`
+ * The reference (ToniChopp/ECAMP) has no FFI or operator registry for this path: the boundary is
+ * the nn.Module returned by `module.model_ecamp.ecamp(**kwargs)`
  * (ECAMP/Pre-training/module/model_ecamp.py:328-333, called at
  * ECAMP/Pre-training/main_pretrain.py:141,233).  The Python mirror of that module
  * (ecamp_b200/model_ecamp.py) binds the entry points below with ctypes; INTEGRATION.md shows the
  * stub a maintainer of the reference would add.  Each entry point cites the reference code whose
- * library kernels it replaces.
+ * library kernels it replaces (paths relative to ECAMP/Pre-training/).
  *
  * Conventions
- *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
- *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
- *   - every function returns 0 on success, a negative code on failure, never throws and never
+ *   - every pointer is a DEVICE pointer unless documented otherwise; `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success and a negative code on failure, never throws, never
  *     exits; `ecamp_last_error()` returns a thread-local description of the last failure;
- *   - all work is enqueued asynchronously on `stream`; asynchronous CUDA errors surface at the
- *     caller's next synchronisation exactly as they do for torch ops;
- *   - nothing allocated by the library is returned to the caller and no argument is retained
- *     past the call.
+ *   - work is enqueued asynchronously on `stream`; asynchronous CUDA errors surface at the
+ *     caller's next synchronisation exactly as for torch ops;
+ *   - the caller (PyTorch) owns every buffer.  A context only remembers the base pointers it was
+ *     bound to; rebind after `.to()`, `load_state_dict` into new storage, etc.
  */
 #ifndef ECAMP_B200_H_
 #define ECAMP_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -38,18 +39,19 @@ extern "C" {
 ECAMP_API int ecamp_abi_version(void);
 ECAMP_API const char* ecamp_last_error(void);
 
-/* ------------------------------------------------------------------------------------------
- * GEMM (tcgen05 / TMEM / TMA): replaces every nn.Linear on the path — timm Block qkv/proj/fc1/fc2
- * (model_ecamp.py:66-68,80-82), decoder_embed / decoder_pred / bert_mlp (model_ecamp.py:73,85,100),
- * HF BertSelfAttention/BertSelfOutput/BertIntermediate/BertOutput (context_fusion.py:12-19),
- * the LM head (bert_modeling.py:209) — forward, dgrad and wgrad.
- * ------------------------------------------------------------------------------------------ */
+/* ==========================================================================================
+ * 1. Operators (each usable on its own; the parity tests call these)
+ * ========================================================================================== */
+
+/* GEMM (tcgen05 / TMEM / TMA): replaces every nn.Linear on the path — timm Block qkv/proj/fc1/fc2
+ * (module/model_ecamp.py:66-68,80-82), decoder_embed / decoder_pred / bert_mlp (:73,85,100),
+ * HF BertSelfAttention/BertSelfOutput/BertIntermediate/BertOutput (module/context_fusion.py:12-19),
+ * the LM head (module/bert_modeling.py:209) — forward, dgrad and wgrad. */
 enum {
   ECAMP_GEMM_GELU = 1,    /* v = gelu(bf16(v)), rounded pre-activation stored to aux_out          */
   ECAMP_GEMM_DGELU = 2,   /* v *= gelu'(aux_in[m, n])                                              */
   ECAMP_GEMM_DROPOUT = 4  /* inverted dropout with a Philox mask keyed by (seed, site, m * N + n)  */
 };
-
 typedef struct ecamp_epilogue {
   const float* bias;     /* [N] or NULL                                   */
   const void* aux_in;    /* bf16 [M, ld_aux] or NULL                      */
@@ -66,11 +68,128 @@ typedef struct ecamp_epilogue {
   uint64_t seed;
   uint64_t site;
 } ecamp_epilogue;
-
 /* D[M,N] = epilogue(A . B^T).  a_mn / b_mn = 0: operand stored [rows, contraction] (contraction
  * contiguous); = 1: stored [contraction, rows].  tile_n = 0 lets the library choose. */
-ECAMP_API int ecamp_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int32_t ldb, int32_t b_mn, int32_t M,
-                    int32_t N, int32_t K, const ecamp_epilogue* ep, int32_t tile_n, void* stream);
+ECAMP_API int ecamp_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int32_t ldb, int32_t b_mn,
+                              int32_t M, int32_t N, int32_t K, const ecamp_epilogue* ep, int32_t tile_n, void* stream);
+
+/* random_masking on caller-supplied noise (module/model_ecamp.py:168-193): stable ascending argsort.
+ * ids_restore / ids_keep int64 as in the reference, mask fp32 {0,1} (1 = removed). */
+ECAMP_API int ecamp_random_masking(const float* noise, int32_t B, int32_t L, int32_t len_keep, int64_t* ids_restore,
+                                   int64_t* ids_keep, float* mask, void* scratch_i32 /* (B*L + B*len_keep) int32 */,
+                                   void* stream);
+
+/* bicubic 448 -> 224 of torchvision Resize (module/model_ecamp.py:318), result in patch layout
+ * tgt[b, l, (p*16+q)*3+c] == patchify(resized) with p = 16. */
+ECAMP_API int ecamp_resize_patchify(const float* big, int32_t B, int32_t side_in, float* tgt, void* stream);
+
+/* LayerNorm forward / backward (fp32 in, bf16 and/or fp32 out). */
+ECAMP_API int ecamp_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t M,
+                                  int32_t D, void* out_bf16, float* out_f32, float* mean, float* rstd, void* stream);
+ECAMP_API int ecamp_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                                  const float* gamma, int32_t M, int32_t D, const float* addend, float* dx_f32,
+                                  void* dx_bf16, float* dgamma, float* dbeta, int32_t accumulate,
+                                  float* ws /* ecamp_layernorm_ws_floats() */, void* stream);
+ECAMP_API size_t ecamp_layernorm_ws_floats(void);
+
+/* fused attention (timm Attention; HF BertSelfAttention eager path incl. key-padding mask and
+ * probability dropout; cross-attention of module/context_fusion.py:45-53). */
+typedef struct ecamp_attn {
+  const void *q, *k, *v;      /* bf16; head h at columns [h*D, (h+1)*D) */
+  int32_t ldq, ldk, ldv;
+  void* o;                    /* bf16 */
+  int32_t ldo;
+  float* lse;                 /* [B, H, Sq] */
+  const int64_t* key_mask;    /* [B, Sk] nonzero = attend, or NULL */
+  int32_t B, H, Sq, Sk, D;
+  float scale;
+  float drop_p;
+  uint64_t seed, site;
+  const void* d_o;            /* backward: bf16 */
+  int32_t ld_do;
+  float* delta;               /* backward scratch [B, H, Sq] */
+  void *dq, *dk, *dv;         /* backward outputs, bf16 */
+  int32_t lddq, lddk, lddv;
+} ecamp_attn;
+ECAMP_API int ecamp_attention_fwd(const ecamp_attn* a, void* stream);
+ECAMP_API int ecamp_attention_bwd(const ecamp_attn* a, void* stream);
+
+/* losses.  pred is [B, 197, 768] fp32 (row 0 of each sample = cls, ignored), tgt [B, 196, 768]. */
+ECAMP_API int ecamp_mim_loss(const float* pred, const float* tgt, const float* mask, int32_t B, float* loss,
+                             float* ws /* B*196 floats */, void* stream);
+ECAMP_API int ecamp_sr_loss_fwd(const float* pred, const float* big, const int64_t* column, const int64_t* row,
+                                const float* w1, const float* b1, const float* w2, const float* b2, int32_t B,
+                                float* loss, float* ws /* ecamp_sr_ws_floats(B) */, void* stream);
+ECAMP_API int ecamp_sr_loss_bwd(const float* pred, const float* big, const int64_t* column, const int64_t* row,
+                                const float* w1, const float* b1, const float* w2, const float* b2, int32_t B,
+                                const float* g_res, float* d_u /* [B,3,448,448] */, float* d_conv /* 168 */,
+                                int32_t accumulate, float* ws, void* stream);
+ECAMP_API size_t ecamp_sr_ws_floats(int32_t B);
+ECAMP_API int ecamp_pred_grad(const float* pred, const float* tgt, const float* mask, const float* d_u,
+                              const float* g_mim, int32_t B, void* d_pred_bf16 /* [B,197,768] */, void* stream);
+/* weighted cross-entropy on materialised bf16 logits [rows, V] (module/bert_modeling.py:211-217);
+ * with write_grad the logits are overwritten by (softmax - onehot) * w * g / total_rows. */
+ECAMP_API int ecamp_ce_rows(void* logits_bf16, int32_t ld, int32_t rows, int32_t V, const int64_t* labels,
+                            const float* weights, float* row_loss, const float* g, float inv_total_rows,
+                            int32_t write_grad, void* stream);
+
+/* ==========================================================================================
+ * 2. The step runtime (what the nn.Module calls): parameter table, context, forward / backward /
+ *    optimizer.  Replaces ECAMP.forward (module/model_ecamp.py:303-325), autograd backward
+ *    (util/misc.py:258) and torch.optim.AdamW.step (main_pretrain.py:254; util/misc.py:267).
+ * ========================================================================================== */
+ECAMP_API int32_t ecamp_param_count(void);
+ECAMP_API const char* ecamp_param_name(int32_t i);     /* reference state_dict key            */
+ECAMP_API int64_t ecamp_param_numel(int32_t i);
+ECAMP_API int32_t ecamp_param_decay(int32_t i);        /* timm add_weight_decay group         */
+ECAMP_API int64_t ecamp_param_grad_offset(int32_t i);  /* floats into the flat grad buffer    */
+ECAMP_API int64_t ecamp_grad_floats(void);
+ECAMP_API int64_t ecamp_shadow_bytes(void);            /* bf16 GEMM copies + fused fp32 biases */
+ECAMP_API int64_t ecamp_adam_table_bytes(void);
+ECAMP_API int64_t ecamp_adam_chunk_bytes(void);
+
+typedef struct ecamp_ctx ecamp_ctx;
+ECAMP_API int ecamp_ctx_create(ecamp_ctx** out);
+ECAMP_API void ecamp_ctx_destroy(ecamp_ctx* ctx);
+/* params_host: HOST array of ecamp_param_count() device pointers in table order.  grads / adam_m /
+ * adam_v: flat fp32 buffers of ecamp_grad_floats() (adam_* may be NULL for inference). */
+ECAMP_API int ecamp_ctx_bind(ecamp_ctx* ctx, float* const* params_host, int32_t n, float* grads, float* adam_m,
+                             float* adam_v, void* shadows, const float* pos_embed, const float* decoder_pos_embed,
+                             void* adam_table, void* adam_chunks);
+typedef struct ecamp_shape {
+  int32_t B, T, len_keep, has_big, ce_rows;
+} ecamp_shape;
+ECAMP_API int64_t ecamp_workspace_bytes(const ecamp_shape* s);
+ECAMP_API int ecamp_ctx_set_workspace(ecamp_ctx* ctx, void* ws, int64_t bytes, const ecamp_shape* s);
+/* re-derive the bf16 / fused copies from the fp32 parameters (after load_state_dict, an external
+ * optimizer step, ...). */
+ECAMP_API int ecamp_refresh_shadows(ecamp_ctx* ctx, void* stream);
+
+typedef struct ecamp_batch {
+  const float* image;             /* [B,3,448,448] (has_big) or [B,3,224,224]                         */
+  const int64_t* ids;             /* [B,T]  batch["ids"]                                              */
+  const int64_t* labels;          /* [B,T]  batch["labels"]                                           */
+  const int64_t* attention_mask;  /* [B,T]                                                            */
+  const int64_t* type_ids;        /* [B,T]                                                            */
+  const float* weights;           /* [B,T]                                                            */
+  const int64_t* column;          /* [B] (has_big)                                                    */
+  const int64_t* row;             /* [B] (has_big)                                                    */
+  const float* noise;             /* [B,196] uniform noise of random_masking                          */
+} ecamp_batch;
+enum { ECAMP_FWD_TRAIN = 1, ECAMP_FWD_DEFER_MLM = 2 };
+/* losses: 3 floats (mim, res, mlm).  mask [B,196] fp32, ids_restore [B,196] / ids_keep [B,len_keep]
+ * int64 are optional outputs. */
+ECAMP_API int ecamp_forward(ecamp_ctx* ctx, const ecamp_batch* batch, int32_t flags, float drop_p, uint64_t seed,
+                            float* losses, float* mask, int64_t* ids_restore, int64_t* ids_keep, void* stream);
+ECAMP_API int32_t ecamp_backward_stage_count(void);
+/* [begin, end) floats of the flat gradient buffer that are final once `stage` has run */
+ECAMP_API int ecamp_backward_stage_range(int32_t stage, int64_t* begin, int64_t* end);
+/* g3: the three upstream gradients d(total)/d(mim, res, mlm).  stage = -1 runs all stages in order. */
+ECAMP_API int ecamp_backward(ecamp_ctx* ctx, const float* g3, int32_t accumulate, int32_t stage, void* stream);
+ECAMP_API int ecamp_adamw_step(ecamp_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
+                               int32_t step, float grad_scale, void* stream);
+/* named intermediate buffers for the parity tests ("latent", "pred", "tgt", ...), NULL if unknown */
+ECAMP_API const void* ecamp_debug_buffer(ecamp_ctx* ctx, const char* name);
 
 #ifdef __cplusplus
 }
