@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the ECAMP pre-training step (BASELINE.json config 2 / 3): forward + backward + fused AdamW in bf16,
+per-GPU batch 256 synthetic pairs (448-px radiograph -> in-model bicubic 224 px -> ViT-B/16 MAE with 75 % masking
++ SR branch; 128-token report through the 6-layer BERT with context fusion; three losses), data-parallel over N GPUs.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port), reported baseline
+
+Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = the same through the public
+module API with pinned-host inputs copied every step and the losses read back every step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_PAIR_STEP = {128: 88.60, 256: 136.25}   # BASELINE.md §3 (2*M*N*K, backward = 2 x forward)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def to_device(batch, dev, stream=None):
+    if stream is None:
+        return {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
+    with torch.cuda.stream(stream):
+        return {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
+
+
+def gemm_roofline(B, T, peak_tflops):
+    """Time every distinct GEMM shape of the step through the C ABI (CUDA events on the launching stream, L2 flushed
+    between launches) and return achieved TFLOP/s over all tcgen05 GEMM launches of one step."""
+    from ecamp_b200 import _lib as L
+    dev = "cuda"
+    Me, Mi, Md, Mt = B * 50, B * 49, B * 197, B * T
+    lin = []  # (rows, out, in, count)
+    lin += [(Mi, 768, 768, 1)]
+    lin += [(Me, 2304, 768, 12), (Me, 768, 768, 12), (Me, 3072, 768, 12), (Me, 768, 3072, 12)]
+    lin += [(Me, 512, 768, 1), (Md, 1536, 512, 4), (Md, 512, 512, 4), (Md, 2048, 512, 4), (Md, 512, 2048, 4), (Md, 768, 512, 1)]
+    lin += [(Me, 768, 768, 1), (Mt, 2304, 768, 7), (Mt, 768, 768, 7 + 2 + 1), (Mi, 1536, 768, 1), (Mt, 1536, 768, 7), (Mt, 768, 1536, 7)]
+    lin += [(Mt, 30000, 768, 1)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    tot_flops = tot_ms = 0.0
+    launches = 0
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=3):
+        fn()
+        ms = []
+        for _ in range(reps):
+            flush.zero_()
+            s.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            ms.append(s.elapsed_time(e))
+        return statistics.median(ms)
+
+    for rows, n_out, n_in, count in lin:
+        r = min(rows, 8192) if n_out == 30000 else rows          # the vocabulary projection runs in row chunks
+        scale = rows / r
+        x = torch.randn(r, n_in, device=dev).to(torch.bfloat16)
+        w = torch.randn(n_out, n_in, device=dev).to(torch.bfloat16)
+        dy = torch.randn(r, n_out, device=dev).to(torch.bfloat16)
+        y = torch.empty(r, n_out, dtype=torch.bfloat16, device=dev)
+        dx = torch.empty(r, n_in, dtype=torch.bfloat16, device=dev)
+        dw = torch.empty(n_out, n_in, dtype=torch.float32, device=dev)
+        t_f = timed(lambda: L.gemm(x, w, out_bf16=y))
+        t_d = timed(lambda: L.gemm(dy, w, b_mn=True, M=r, N=n_in, K=n_out, out_bf16=dx))
+        t_w = timed(lambda: L.gemm(dy, x, a_mn=True, b_mn=True, M=n_out, N=n_in, K=r, out_f32=dw))
+        fl = 2.0 * r * n_out * n_in
+        tot_flops += 3 * fl * scale * count
+        tot_ms += (t_f + t_d + t_w) * scale * count
+        launches += 3 * count * int(round(scale))
+        del x, w, dy, y, dx, dw
+    achieved = tot_flops / (tot_ms * 1e-3) / 1e12
+    return dict(bound="tensor", achieved=round(achieved, 1), peak=peak_tflops, unit="TFLOP/s", frac=round(achieved / peak_tflops, 4),
+                traffic=None, kernel="gemm_tcgen05_kernel (all Linear fwd/dgrad/wgrad launches of one step)",
+                flops_per_step=tot_flops, gemm_ms_per_step=round(tot_ms, 3), launches_per_step=launches)
+
+
+def cpu_baseline(T):
+    """The reference's CPU path (oracle port) on config 1: batch 8, fp32, forward + three losses."""
+    from oracle.ecamp_oracle import ecamp_oracle, synthetic_batch
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = ecamp_oracle().eval()
+    b = synthetic_batch(8, T=T, seed=1234)
+    with torch.no_grad():
+        m(b)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); m(b); ts.append(time.perf_counter() - t0)
+    return dict(value=round(8 / statistics.median(ts), 3), unit="pairs/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"BASELINE config 1: batch 8, fp32, 448-px input, T={T}, forward + 3 losses, median of 3 (1 warm-up)")
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the step (oracle port: the reference cannot be
+    installed or imported unmodified here), forward + backward + torch.optim.AdamW, on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.ecamp_oracle import ecamp_oracle, synthetic_batch
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    Bc = 2
+    m = ecamp_oracle(dropout=0.1).train()
+    decay = [p for n, p in m.named_parameters() if p.requires_grad and not (p.dim() == 1 or n.endswith(".bias"))]
+    no_decay = [p for n, p in m.named_parameters() if p.requires_grad and (p.dim() == 1 or n.endswith(".bias"))]
+    opt = torch.optim.AdamW([dict(params=no_decay, weight_decay=0.0), dict(params=decay, weight_decay=0.05)], lr=1.5e-4, betas=(0.9, 0.95))
+    b = synthetic_batch(Bc, T=args.seq, seed=1234)
+
+    def step():
+        mim, res, mlm = m(b)
+        (mim + res + mlm).backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = Bc * args.steps / dt
+    sample = f"{Bc} pairs per step (448-px input, T={args.seq}), fp32 forward + backward + AdamW, {torch.get_num_threads()} threads"
+    print(json.dumps(dict(impl="reference", metric="pretrain_pairs_per_sec", value=round(v, 4), unit="pairs/s", n_gpus=args.gpus,
+                          steps=args.steps, warmup=args.warmup, ms_per_step=round(1e3 * dt / args.steps, 2), higher_is_better=True,
+                          scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                          config=dict(workload=workload_name(args), seq_len=args.seq, sample_batch=Bc),
+                          cpu_baseline=dict(value=round(v, 4), unit="pairs/s", cores=torch.get_num_threads(), kind="port", sample=sample),
+                          e2e=dict(value=round(v, 4), unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))), flush=True)
+
+
+def workload_name(args):
+    return (f"BASELINE config {'2' if args.gpus == 1 else '3'}: ECAMP pretrain fwd+bwd+AdamW bf16, batch {args.batch}/GPU, 448-px input -> "
+            f"224-px ViT-B/16 (196 patches, mask 0.75) + SR branch, {args.seq}-token reports, dropout 0.1")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="pairs per GPU (BASELINE config 2: 256)")
+    ap.add_argument("--seq", type=int, default=128)
+    ap.add_argument("--no-extras", action="store_true", help="skip the roofline micro-timing and the CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ecamp_b200 import _lib as L
+    from ecamp_b200.model_ecamp import ecamp
+    from ecamp_b200.optim import FusedAdamW
+    from ecamp_b200.parallel import DataParallelStep
+    from ecamp_b200.synthetic import make_batch
+
+    torch.manual_seed(0)                      # identical random-init replicas on every rank
+    model = ecamp(norm_pix_loss=True).to(dev).train()
+    opt = FusedAdamW(model, lr=1.5e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    dp = DataParallelStep(model, opt, bucket_mb=64)
+    torch.manual_seed(1234 + rank)            # per-rank masking noise / dropout (main_pretrain.py:189)
+    host = [make_batch(args.batch, T=args.seq, big=True, seed=1234 + 17 * rank + i, pin=True) for i in range(2)]
+    for hb in host:
+        hb.pop("noise")                       # the module draws torch.rand(N, L) itself, like the reference
+    resident = [to_device(hb, dev) for hb in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- arm 1: inputs resident in HBM ---------------------------------------------------------------------
+    for i in range(args.warmup):
+        dp.step(resident[i % 2])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.lib().ecamp_launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(args.steps):
+        losses = dp.step(resident[i % 2])
+    e.record()
+    barrier()
+    ms = max_over_ranks(s.elapsed_time(e))
+    launches = L.lib().ecamp_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    last_losses = [float(x) for x in losses.tolist()]
+    value = world * args.batch * args.steps / (ms * 1e-3)
+
+    # ---- arm 2: end to end through the public API, pinned-host inputs copied every step, losses read every step ----
+    del resident
+    copy_stream = torch.cuda.Stream()
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    pinned_out = torch.empty(3, dtype=torch.float32).pin_memory()
+    for i in range(2):
+        dp.step(to_device(host[i % 2], dev))
+    barrier()
+    nxt = to_device(host[0], dev, copy_stream)
+    s.record()
+    for i in range(args.steps):
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        cur_batch = nxt
+        for v in cur_batch.values():
+            v.record_stream(torch.cuda.current_stream())
+        if i + 1 < args.steps:
+            nxt = to_device(host[(i + 1) % 2], dev, copy_stream)      # prefetch the next step's inputs
+        losses = dp.step(cur_batch)
+        pinned_out.copy_(losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                      # the step's result is read on the host
+    e.record()
+    barrier()
+    ms_e2e = max_over_ranks(s.elapsed_time(e))
+    e2e_value = world * args.batch * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        gf = GFLOP_PER_PAIR_STEP.get(args.seq)
+        out = dict(metric="pretrain_pairs_per_sec", value=round(value, 2), unit="pairs/s", n_gpus=world, steps=args.steps,
+                   warmup=args.warmup, ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="weak",
+                   vs_baseline=None, dtype="bf16", data="synthetic",
+                   config=dict(workload=workload_name(args), global_batch=world * args.batch, per_gpu_batch=args.batch,
+                               seq_len=args.seq, image_px="448 -> 224", mask_ratio=0.75, parallelism=f"dp{world}",
+                               optimizer="fused AdamW lr 1.5e-4 betas (0.9,0.95) wd 0.05", weights="random init (reference initialize_weights)",
+                               l2="per-step working set (~16 GB of activations) is far larger than the 126 MB L2; two input batches alternate"),
+                   clocks=clocks, gpu_launches=int(launches),
+                   e2e=dict(value=round(e2e_value, 2), unit="pairs/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=12,
+                            ms_per_step=round(ms_e2e / args.steps, 3)),
+                   losses_last_step=last_losses)
+        if gf:
+            tf = value / world * gf / 1e3
+            out["step_tflops_per_gpu"] = round(tf, 1)
+            out["step_frac_of_bf16_peak"] = dict(burst=round(tf / pk["bf16_tflops"], 4), sustained=round(tf / pk["bf16_tflops_sustained"], 4),
+                                                 peaks=pk_kind, gflop_per_pair=gf)
+        if not args.no_extras:
+            del nxt, cur_batch
+            torch.cuda.empty_cache()
+            try:
+                out["roofline"] = gemm_roofline(args.batch, args.seq, pk["bf16_tflops"])
+                out["roofline"]["peak_kind"] = f"{pk_kind} burst bf16 (kernel timed alone)"
+            except Exception as ex:  # noqa
+                out["roofline"] = dict(error=str(ex)[:200])
+            if world == 1:
+                try:
+                    out["cpu_baseline"] = cpu_baseline(args.seq)
+                except Exception as ex:  # noqa
+                    out["cpu_baseline"] = dict(error=str(ex)[:200])
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -57,7 +57,7 @@ class Attn(ctypes.Structure):
 
 # every symbol include/ecamp_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "ecamp_abi_version", "ecamp_last_error", "ecamp_gemm_bf16", "ecamp_random_masking", "ecamp_resize_patchify",
+    "ecamp_abi_version", "ecamp_last_error", "ecamp_launch_count", "ecamp_gemm_bf16", "ecamp_random_masking", "ecamp_resize_patchify",
     "ecamp_layernorm_fwd", "ecamp_layernorm_bwd", "ecamp_layernorm_ws_floats", "ecamp_attention_fwd",
     "ecamp_attention_bwd", "ecamp_mim_loss", "ecamp_sr_loss_fwd", "ecamp_sr_loss_bwd", "ecamp_sr_ws_floats",
     "ecamp_pred_grad", "ecamp_ce_rows", "ecamp_param_count", "ecamp_param_name", "ecamp_param_numel",
@@ -83,7 +83,7 @@ def lib():
         _lib.ecamp_abi_version.restype = ctypes.c_int
         _lib.ecamp_param_name.restype = ctypes.c_char_p
         for f in ("ecamp_param_numel", "ecamp_param_grad_offset", "ecamp_grad_floats", "ecamp_shadow_bytes",
-                  "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_workspace_bytes"):
+                  "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_workspace_bytes", "ecamp_launch_count"):
             getattr(_lib, f).restype = ctypes.c_int64
         for f in ("ecamp_layernorm_ws_floats", "ecamp_sr_ws_floats"):
             getattr(_lib, f).restype = ctypes.c_size_t

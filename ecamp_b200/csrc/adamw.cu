@@ -134,7 +134,7 @@ int adamw_step(const void* dev_table, const void* dev_chunks, long long n_chunks
   adamw_kernel<true><<<(unsigned)n_chunks, 256, 0, st>>>(static_cast<const AdamTensor*>(dev_table),
                                                          static_cast<const Chunk*>(dev_chunks), lr, beta1, beta2,
                                                          eps, wd, bc1, bc2_sqrt, grad_scale);
-  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_LAUNCHED();
   return 0;
 }
 
@@ -143,7 +143,7 @@ int refresh_shadows(const void* dev_table, const void* dev_chunks, long long n_c
   adamw_kernel<false><<<(unsigned)n_chunks, 256, 0, st>>>(static_cast<const AdamTensor*>(dev_table),
                                                           static_cast<const Chunk*>(dev_chunks), 0.f, 0.f, 0.f, 0.f,
                                                           0.f, 1.f, 1.f, 1.f);
-  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_LAUNCHED();
   return 0;
 }
 

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
     const int row = row_g + r * 8;
     if (!TR) {
       row_a[r] = row < Sr ? a.lse[bh * a.Sq + row] : INFINITY;
-      row_b[r] = row < Sr ? a.delta[bh * a.Sq + row] : 0.f;
+      row_b[r] = 0.f;  // delta: produced by pass 0 below
     } else {
       bool ok = row < Sr;
       if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + row] != 0;
@@ -310,6 +310,13 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
   const uint32_t thr = dropout_threshold(a.drop.p);
   const float keep_scale = a.drop.p > 0.f ? 1.0f / (1.0f - a.drop.p) : 1.0f;
 
+  // The dQ kernel runs two passes over the key blocks: pass 0 accumulates delta_i = sum_j P_ij dP_ij in fp32 from
+  // the SAME P / dP that pass 1 uses for dS = P (dP - delta), so the cancellation inside (dP - delta) is exact
+  // (computing delta from the bf16-rounded O, FlashAttention-style, loses it when attention is near-uniform).
+  // delta is also published for the dK/dV kernel, which runs afterwards on the same stream.
+  float dsum[2] = {0.f, 0.f};
+#pragma unroll 1
+  for (int pass = TR ? 1 : 0; pass < 2; ++pass) {
   for (int cb = 0; cb < Scp; cb += CB) {
     float s[NT][4], dp[NT][4];
 #pragma unroll
@@ -359,10 +366,12 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
           dpe = keep ? dpe * keep_scale : 0.f;
           pd = keep ? p * keep_scale : 0.f;
         }
+        if (pass == 0) dsum[r] += p * dpe;
         s[j][e] = p * (dpe - delta) * a.scale;  // dS
         dp[j][e] = pd;                          // dropped probabilities (only used when TR)
       }
     }
+    if (pass == 0) continue;
     // out1 += dS . C1 ; (TR) out2 += Pdrop . C2
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
@@ -392,7 +401,16 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
         }
       }
     }
-  }
+  }  // column blocks
+    if (pass == 0) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        row_b[r] = quad_sum(dsum[r]);
+        const int row = row_g + r * 8;
+        if (t4 == 0 && row < Sr) a.delta[bh * a.Sq + row] = row_b[r];
+      }
+    }
+  }  // passes
 
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -449,24 +467,21 @@ int launch_fwd(const AttnArgs& a, cudaStream_t st) {
   ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   dim3 grid((a.Sq + 63) / 64, a.H, a.B);
   attn_fwd_kernel<D><<<grid, 128, sm, st>>>(a);
-  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_LAUNCHED();
   return 0;
 }
 template <int D>
 int launch_bwd(const AttnArgs& a, cudaStream_t st) {
-  const int total = a.B * a.H * a.Sq;
-  attn_delta_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(a);
-  ECAMP_CUDA_OK(cudaGetLastError());
   ECAMP_CUDA_OK(
       cudaFuncSetAttribute(attn_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ECAMP_CUDA_OK(
       cudaFuncSetAttribute(attn_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   dim3 gq((a.Sq + 63) / 64, a.H, a.B);
   attn_bwd_kernel<D, false><<<gq, 128, bwd_smem(D, a.Sk), st>>>(a);
-  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_LAUNCHED();
   dim3 gk((a.Sk + 63) / 64, a.H, a.B);
   attn_bwd_kernel<D, true><<<gk, 128, bwd_smem(D, a.Sq), st>>>(a);
-  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_LAUNCHED();
   return 0;
 }
 

@@ -17,6 +17,7 @@ typedef __nv_bfloat16 bf16;
 // error plumbing (host)
 // ---------------------------------------------------------------------------------------------
 void set_last_error(const char* fmt, ...);
+void count_launch();  // every kernel launch of the library is counted (ecamp_launch_count)
 #define ECAMP_CUDA_OK(expr)                                                                      \
   do {                                                                                           \
     cudaError_t _e = (expr);                                                                     \
@@ -24,6 +25,11 @@ void set_last_error(const char* fmt, ...);
       ecamp::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
       return -2;                                                                                 \
     }                                                                                            \
+  } while (0)
+#define ECAMP_LAUNCHED()                                 \
+  do {                                                   \
+    ECAMP_CUDA_OK(cudaGetLastError());                   \
+    ecamp::count_launch();                               \
   } while (0)
 #define ECAMP_REQUIRE(cond, ...)                                                                 \
   do {                                                                                           \

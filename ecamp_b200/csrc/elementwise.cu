@@ -449,7 +449,7 @@ __global__ void permute_pe_grad_kernel(const float* __restrict__ dw_pqc, float* 
 
 }  // namespace
 
-#define LAUNCH_OK() ECAMP_CUDA_OK(cudaGetLastError())
+#define LAUNCH_OK() ECAMP_LAUNCHED()
 
 int random_masking(const float* noise, int B, int L, int len_keep, int32_t* ids_restore, int32_t* ids_keep,
                    float* mask, int64_t* ids_restore64, int64_t* ids_keep64, cudaStream_t st) {
@@ -567,7 +567,11 @@ int dropout_bwd_f32(float* g, size_t n, DropoutCfg drop, cudaStream_t st) {
 int bert_embeddings_bwd(const float* d_pre, const int64_t* ids, const int64_t* type_ids, int B, int T, int D,
                         float* d_word, float* d_type, float* d_pos, int accumulate, float* ws, cudaStream_t st) {
   const int M = B * T;
-  if (!accumulate) ECAMP_CUDA_OK(cudaMemsetAsync(d_word, 0, (size_t)30000 * D * sizeof(float), st));
+  if (!accumulate) {
+    // rows that no token of this batch touches (and positions >= T) must read as zero, not as stale gradients
+    ECAMP_CUDA_OK(cudaMemsetAsync(d_word, 0, (size_t)30000 * D * sizeof(float), st));
+    ECAMP_CUDA_OK(cudaMemsetAsync(d_pos, 0, (size_t)256 * D * sizeof(float), st));
+  }
   emb_word_bwd_kernel<<<M, D / 4, 0, st>>>(d_pre, ids, D, d_word);
   LAUNCH_OK();
   emb_pos_type_bwd_kernel<<<T, D / 4, 0, st>>>(d_pre, type_ids, B, T, D, d_pos, accumulate, ws);

@@ -16,6 +16,7 @@
 #include "gemm.cuh"
 
 #include <cuda.h>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -407,7 +408,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kfn<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, M, N, K, ea);
-  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_LAUNCHED();
   return 0;
 }
 
@@ -459,6 +460,9 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
 }
 
 // ---------------------------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 static thread_local char g_err[1024] = "";
 void set_last_error(const char* fmt, ...) {
   va_list ap;

@@ -173,7 +173,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
     ln_fwd_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, out_bf16, out_f32, mean, rstd);
   else
     ln_fwd_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, out_bf16, out_f32, mean, rstd);
-  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_LAUNCHED();
   return 0;
 }
 
@@ -187,10 +187,10 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
     ln_bwd_kernel<6><<<grid, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, partial_ws);
   else
     ln_bwd_kernel<4><<<grid, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, partial_ws);
-  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_LAUNCHED();
   if (dgamma && dbeta) {
     ln_bwd_finalize<<<(2 * D + 255) / 256, 256, 0, st>>>(partial_ws, grid, D, dgamma, dbeta, accumulate);
-    ECAMP_CUDA_OK(cudaGetLastError());
+    ECAMP_LAUNCHED();
   }
   return 0;
 }

@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(bf16* __restrict__ logits,
 
 }  // namespace
 
-#define LAUNCH_OK() ECAMP_CUDA_OK(cudaGetLastError())
+#define LAUNCH_OK() ECAMP_LAUNCHED()
 
 int sum_to_scalar(const float* x, size_t n, float scale, float* out, cudaStream_t st) {
   sum_to_scalar_kernel<<<1, 1024, 0, st>>>(x, n, scale, out);

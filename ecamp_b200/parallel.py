@@ -1,0 +1,86 @@
+"""Data-parallel step: one process per GPU, gradients averaged once per optimizer step.
+
+The reference wraps the model in stock DistributedDataParallel(find_unused_parameters=True) and, with
+accum_iter = 8 and no no_sync(), all-reduces on every micro-step (ECAMP/Pre-training/main_pretrain.py:135-153,249;
+SURVEY D10).  Here the native backward runs in stages that finish CONTIGUOUS ranges of one flat fp32 gradient
+buffer from the back (LM head first, patch-embed last), so a bucket is just a slice: when the stages of a
+bucket are done an event is recorded and the slice is all-reduced on a side stream (NCCL over NVLink /
+NVSwitch) while the remaining stages keep computing.  Averaging (1 / world) is folded into the fused AdamW.
+The path shards by samples with exactly this one exchange step; there is no other collective.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+
+def stage_ranges(lib):
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    out = []
+    for s in range(lib.ecamp_backward_stage_count()):
+        rc = lib.ecamp_backward_stage_range(s, ctypes.byref(lo), ctypes.byref(hi))
+        if rc != 0:
+            raise RuntimeError("ecamp_backward_stage_range failed")
+        out.append((lo.value, hi.value))
+    return out
+
+
+def plan_buckets(ranges, bucket_floats):
+    """Merge consecutive backward stages (whose ranges tile the buffer back to front) into buckets of at least
+    `bucket_floats`.  Returns [(last_stage, lo, hi)]: after `last_stage` has run, flat[lo:hi] is final."""
+    buckets, cur_hi, cur_lo = [], None, None
+    for s, (lo, hi) in enumerate(ranges):
+        if cur_hi is None:
+            cur_hi = hi
+        elif hi != cur_lo:
+            raise ValueError("backward stage ranges must be contiguous and descending")
+        cur_lo = lo
+        if cur_hi - cur_lo >= bucket_floats or s == len(ranges) - 1:
+            buckets.append((s, cur_lo, cur_hi))
+            cur_hi = None
+    return buckets
+
+
+def allreduce_flat(flat, buckets, group=None, after_stage=None):
+    """All-reduce (sum) `flat` bucket by bucket.  With `after_stage` given, only the buckets that end at that
+    stage are reduced (the overlapped path); otherwise all of them.  Returns the async work handles."""
+    works = []
+    for last, lo, hi in buckets:
+        if after_stage is None or last == after_stage:
+            works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    return works
+
+
+class DataParallelStep:
+    def __init__(self, model, optimizer, bucket_mb=64, group=None):
+        from . import _lib as L
+        self.model, self.optimizer, self.group = model, optimizer, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.buckets = plan_buckets(stage_ranges(L.lib()), int(bucket_mb * (1 << 20) // 4))
+        self.comm = torch.cuda.Stream() if self.world > 1 else None
+
+    def step(self, batch, loss_weights=(1.0, 1.0, 1.0), update=True):
+        """forward + backward (+ overlapped gradient all-reduce) (+ fused AdamW).  Returns the 3 local losses."""
+        if self.world == 1:
+            losses = self.model.forward_backward(batch, loss_weights)
+        else:
+            cur = torch.cuda.current_stream()
+            self.comm.wait_stream(cur)
+            ends = {b[0]: b for b in self.buckets}
+
+            def on_stage(stage, lo, hi):
+                b = ends.get(stage)
+                if b is None or not update:
+                    return
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self.comm.wait_event(ev)
+                with torch.cuda.stream(self.comm):
+                    dist.all_reduce(self.model.flat_grads()[b[1]:b[2]], op=dist.ReduceOp.SUM, group=self.group)
+
+            losses = self.model.forward_backward(batch, loss_weights, stage_callback=on_stage)
+            cur.wait_stream(self.comm)
+        if update:
+            self.optimizer.step(grad_scale=1.0 / self.world)
+            self.optimizer.zero_grad(set_to_none=True)
+        return losses

@@ -38,6 +38,8 @@ extern "C" {
 
 ECAMP_API int ecamp_abi_version(void);
 ECAMP_API const char* ecamp_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports the delta per timed region) */
+ECAMP_API int64_t ecamp_launch_count(void);
 
 /* ==========================================================================================
  * 1. Operators (each usable on its own; the parity tests call these)

@@ -1,362 +1,8 @@
-"""GPU diagnostic: operator-level and whole-step parity of libecamp_b200 against the oracle.
-Prints one JSON line per check and never stops at the first failure (use under `timeout`)."""
-import ctypes
-import json
-import math
+"""Runs every parity check of tests/parity_checks.py on the GPU, printing one JSON line per check."""
+import os
+import runpy
 import sys
-import traceback
 
-import torch
-import torch.nn.functional as F
-
-sys.path.insert(0, ".")
-from ecamp_b200 import _lib as L
-from ecamp_b200.model_ecamp import ecamp
-from oracle.ecamp_oracle import (ecamp_oracle, seeded_state_dict, synthetic_batch, random_masking_ids,
-                                 bicubic_downsample_2x)
-
-torch.backends.cuda.matmul.allow_tf32 = False
-torch.backends.cudnn.allow_tf32 = False
-dev = "cuda"
-lib = L.lib()
-results = []
-
-
-def report(name, ok, **kw):
-    results.append(ok)
-    print(json.dumps(dict(name=name, ok=bool(ok), **kw)), flush=True)
-
-
-def rel(a, b):
-    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-12)).item()
-
-
-def guard(fn):
-    def w():
-        try:
-            fn()
-        except Exception as e:  # noqa
-            report(fn.__name__, False, error=str(e)[:400], tb=traceback.format_exc()[-600:])
-    return w
-
-
-@guard
-def check_masking():
-    gold = json.load(open("tests/golden/golden_cases.json"))["ties"]
-    noise = torch.tensor(gold["noise_bits"], dtype=torch.int32).view(torch.float32).to(dev)
-    B = noise.shape[0]
-    idr = torch.empty(B, 196, dtype=torch.int64, device=dev)
-    idk = torch.empty(B, 49, dtype=torch.int64, device=dev)
-    mask = torch.empty(B, 196, device=dev)
-    scr = torch.empty(B * 196 + B * 49, dtype=torch.int32, device=dev)
-    L.check(lib.ecamp_random_masking(L.ptr(noise), B, 196, 49, L.ptr(idr), L.ptr(idk), L.ptr(mask), L.ptr(scr), L.cur_stream()), "mask")
-    ok = (idr.cpu().tolist() == gold["ids_restore"] and idk.cpu().tolist() == gold["ids_keep"]
-          and mask.int().cpu().tolist() == gold["mask"])
-    noise2 = torch.rand(64, 196, device=dev)
-    idr2 = torch.empty(64, 196, dtype=torch.int64, device=dev); idk2 = torch.empty(64, 19, dtype=torch.int64, device=dev)
-    mask2 = torch.empty(64, 196, device=dev); scr2 = torch.empty(64 * 196 + 64 * 19, dtype=torch.int32, device=dev)
-    L.check(lib.ecamp_random_masking(L.ptr(noise2), 64, 196, 19, L.ptr(idr2), L.ptr(idk2), L.ptr(mask2), L.ptr(scr2), L.cur_stream()), "mask")
-    r, k, m = random_masking_ids(noise2, 19)
-    ok2 = torch.equal(r, idr2) and torch.equal(k, idk2) and torch.equal(m, mask2)
-    report("random_masking", ok and ok2, ties_ok=ok, random_ok=ok2)
-
-
-@guard
-def check_resize():
-    big = torch.randn(3, 3, 448, 448, device=dev)
-    tgt = torch.empty(3, 196, 768, device=dev)
-    L.check(lib.ecamp_resize_patchify(L.ptr(big), 3, 448, L.ptr(tgt), L.cur_stream()), "resize")
-    ref = bicubic_downsample_2x(big)
-    ref_p = ref.reshape(3, 3, 14, 16, 14, 16)
-    ref_p = torch.einsum("nchpwq->nhwpqc", ref_p).reshape(3, 196, 768)
-    e = (tgt - ref_p).abs().max().item()
-    report("resize_patchify", e < 5e-6, max_abs=e)
-
-
-@guard
-def check_layernorm():
-    for D in (768, 512):
-        M = 1000
-        x = torch.randn(M, D, device=dev) * 2 + 0.5
-        g = torch.randn(D, device=dev); b = torch.randn(D, device=dev)
-        ob = torch.empty(M, D, dtype=torch.bfloat16, device=dev); of = torch.empty(M, D, device=dev)
-        mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
-        L.check(lib.ecamp_layernorm_fwd(L.ptr(x), L.ptr(g), L.ptr(b), ctypes.c_float(1e-6), M, D, L.ptr(ob), L.ptr(of), L.ptr(mean), L.ptr(rstd), L.cur_stream()), "ln")
-        xr = x.clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
-        ref = F.layer_norm(xr, (D,), gr, br, 1e-6)
-        e1 = (of - ref).abs().max().item()
-        dy = torch.randn(M, D, device=dev)
-        ref.backward(dy)
-        add = torch.randn(M, D, device=dev)
-        dx = torch.empty(M, D, device=dev); dxb = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
-        dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)
-        ws = torch.empty(lib.ecamp_layernorm_ws_floats(), device=dev)
-        L.check(lib.ecamp_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(g), M, D, L.ptr(add), L.ptr(dx), L.ptr(dxb), L.ptr(dg), L.ptr(db), 0, L.ptr(ws), L.cur_stream()), "lnb")
-        e2 = rel(dx - add, xr.grad); e3 = rel(dg, gr.grad); e4 = rel(db, br.grad)
-        report(f"layernorm_{D}", e1 < 1e-4 and e2 < 1e-4 and e3 < 1e-4 and e4 < 1e-4, fwd=e1, dx=e2, dgamma=e3, dbeta=e4)
-
-
-def attn_ref(q, k, v, key_mask, scale):
-    s = (q.float() @ k.float().transpose(-1, -2)) * scale
-    if key_mask is not None:
-        s = s + (1.0 - key_mask[:, None, None, :].float()) * torch.finfo(torch.float32).min
-    p = s.softmax(-1)
-    return p @ v.float()
-
-
-@guard
-def check_attention():
-    for (name, B, H, Sq, Sk, D, masked) in [("enc", 3, 12, 50, 50, 64, False), ("dec", 2, 16, 197, 197, 32, False),
-                                            ("bert", 3, 6, 128, 128, 128, True), ("bert256", 2, 6, 256, 256, 128, True),
-                                            ("cross", 3, 6, 128, 49, 128, False), ("odd", 2, 6, 37, 49, 128, True)]:
-        q = torch.randn(B, Sq, H * D, device=dev).to(torch.bfloat16)
-        k = torch.randn(B, Sk, H * D, device=dev).to(torch.bfloat16)
-        v = torch.randn(B, Sk, H * D, device=dev).to(torch.bfloat16)
-        km = None
-        if masked:
-            lens = torch.randint(Sk // 3, Sk + 1, (B,), device=dev)
-            km = (torch.arange(Sk, device=dev)[None, :] < lens[:, None]).long()
-        o = torch.empty(B, Sq, H * D, dtype=torch.bfloat16, device=dev)
-        lse = torch.empty(B, H, Sq, device=dev)
-        a = L.Attn()
-        a.q, a.k, a.v, a.o, a.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr()
-        a.ldq = a.ldk = a.ldv = a.ldo = H * D
-        a.key_mask = km.data_ptr() if km is not None else None
-        a.B, a.H, a.Sq, a.Sk, a.D = B, H, Sq, Sk, D
-        a.scale = 1.0 / math.sqrt(D)
-        L.check(lib.ecamp_attention_fwd(ctypes.byref(a), L.cur_stream()), "attn_fwd")
-        qr = q.float().view(B, Sq, H, D).transpose(1, 2).requires_grad_(True)
-        kr = k.float().view(B, Sk, H, D).transpose(1, 2).requires_grad_(True)
-        vr = v.float().view(B, Sk, H, D).transpose(1, 2).requires_grad_(True)
-        ref = attn_ref(qr, kr, vr, km, a.scale)
-        ref_flat = ref.transpose(1, 2).reshape(B, Sq, H * D)
-        e_f = rel(o.float(), ref_flat)
-        do = torch.randn(B, Sq, H * D, device=dev).to(torch.bfloat16)
-        ref_flat.backward(do.float())
-        dq = torch.zeros_like(q); dk = torch.zeros_like(k); dv = torch.zeros_like(v)
-        delta = torch.empty(B, H, Sq, device=dev)
-        a.d_o, a.ld_do, a.delta = do.data_ptr(), H * D, delta.data_ptr()
-        a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
-        a.lddq = a.lddk = a.lddv = H * D
-        L.check(lib.ecamp_attention_bwd(ctypes.byref(a), L.cur_stream()), "attn_bwd")
-        torch.cuda.synchronize()
-        e_q = rel(dq.float(), qr.grad.transpose(1, 2).reshape(B, Sq, H * D))
-        e_k = rel(dk.float(), kr.grad.transpose(1, 2).reshape(B, Sk, H * D))
-        e_v = rel(dv.float(), vr.grad.transpose(1, 2).reshape(B, Sk, H * D))
-        report(f"attention_{name}", max(e_f, e_q, e_k, e_v) < 2e-2, fwd=e_f, dq=e_q, dk=e_k, dv=e_v)
-    # dropout: statistics + forward/backward consistency through a finite difference on V (linear in V)
-    B, H, S, D = 2, 6, 128, 128
-    q = torch.randn(B, S, H * D, device=dev).to(torch.bfloat16); k = torch.randn_like(q); v = torch.randn_like(q)
-    o0 = torch.empty_like(q); o1 = torch.empty_like(q); lse = torch.empty(B, H, S, device=dev)
-    a = L.Attn()
-    a.q, a.k, a.v, a.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr()
-    a.ldq = a.ldk = a.ldv = a.ldo = H * D
-    a.B, a.H, a.Sq, a.Sk, a.D = B, H, S, S, D
-    a.scale = 1.0 / math.sqrt(D)
-    a.o = o0.data_ptr()
-    L.check(lib.ecamp_attention_fwd(ctypes.byref(a), L.cur_stream()), "attn")
-    a.o = o1.data_ptr(); a.drop_p = 0.1; a.seed = 42; a.site = 3
-    L.check(lib.ecamp_attention_fwd(ctypes.byref(a), L.cur_stream()), "attn")
-    o2 = torch.empty_like(q); a.o = o2.data_ptr()
-    L.check(lib.ecamp_attention_fwd(ctypes.byref(a), L.cur_stream()), "attn")
-    # backward with dropout: dV = Pdrop^T dO  => sum(dV * V) == sum(dO * O)
-    do = torch.randn_like(q); dq = torch.zeros_like(q); dk = torch.zeros_like(q); dv = torch.zeros_like(q)
-    delta = torch.empty(B, H, S, device=dev)
-    a.o = o1.data_ptr(); a.d_o, a.ld_do, a.delta = do.data_ptr(), H * D, delta.data_ptr()
-    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr(); a.lddq = a.lddk = a.lddv = H * D
-    L.check(lib.ecamp_attention_bwd(ctypes.byref(a), L.cur_stream()), "attn_bwd")
-    torch.cuda.synchronize()
-    lhs = (dv.float() * v.float()).sum().item(); rhs = (do.float() * o1.float()).sum().item()
-    report("attention_dropout", torch.equal(o1, o2) and not torch.equal(o0, o1) and abs(lhs - rhs) < 2e-2 * abs(rhs) + 1.0
-           and rel(o1.float(), o0.float()) < 0.6, deterministic=bool(torch.equal(o1, o2)), dv_identity=[lhs, rhs],
-           drift=rel(o1.float(), o0.float()))
-
-
-@guard
-def check_losses():
-    B = 3
-    orc = ecamp_oracle().to(dev)
-    pred = (torch.randn(B, 197, 768, device=dev) * 0.5).requires_grad_(True)
-    big = torch.randn(B, 3, 448, 448, device=dev)
-    imgs = bicubic_downsample_2x(big)
-    noise = torch.rand(B, 196, device=dev)
-    _, _, mask = random_masking_ids(noise, 49)
-    column = torch.tensor([0, 2, 1], device=dev); row = torch.tensor([2, 0, 1], device=dev)
-    for p in orc.super_res.parameters():
-        torch.nn.init.normal_(p, std=0.3)
-    mim_r, res_r = orc.forward_loss(imgs, big, pred[:, 1:], mask, column, row)
-    g = torch.tensor([0.7, 1.3, 1.0], device=dev)
-    (g[0] * mim_r + g[1] * res_r).backward()
-    tgt = torch.empty(B, 196, 768, device=dev)
-    L.check(lib.ecamp_resize_patchify(L.ptr(big), B, 448, L.ptr(tgt), L.cur_stream()), "resize")
-    loss = torch.zeros(2, device=dev)
-    ws = torch.empty(max(lib.ecamp_sr_ws_floats(B), B * 196), device=dev)
-    sr = orc.super_res
-    w1, b1, w2, b2 = sr.conv1.weight.detach().contiguous(), sr.conv1.bias.detach(), sr.conv2.weight.detach().contiguous(), sr.conv2.bias.detach()
-    pd = pred.detach().contiguous()
-    L.check(lib.ecamp_mim_loss(L.ptr(pd), L.ptr(tgt), L.ptr(mask), B, L.ptr(loss), L.ptr(ws), L.cur_stream()), "mim")
-    L.check(lib.ecamp_sr_loss_fwd(L.ptr(pd), L.ptr(big), L.ptr(column), L.ptr(row), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), B, ctypes.c_void_p(loss.data_ptr() + 4), L.ptr(ws), L.cur_stream()), "sr")
-    d_u = torch.empty(B, 3, 448, 448, device=dev); d_conv = torch.zeros(168, device=dev)
-    L.check(lib.ecamp_sr_loss_bwd(L.ptr(pd), L.ptr(big), L.ptr(column), L.ptr(row), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), B, ctypes.c_void_p(g.data_ptr() + 4), L.ptr(d_u), L.ptr(d_conv), 0, L.ptr(ws), L.cur_stream()), "srb")
-    d_pred = torch.empty(B, 197, 768, dtype=torch.bfloat16, device=dev)
-    L.check(lib.ecamp_pred_grad(L.ptr(pd), L.ptr(tgt), L.ptr(mask), L.ptr(d_u), L.ptr(g), B, L.ptr(d_pred), L.cur_stream()), "pg")
-    torch.cuda.synchronize()
-    e_m = abs(loss[0].item() - mim_r.item()) / mim_r.item(); e_r = abs(loss[1].item() - res_r.item()) / res_r.item()
-    ref_conv = torch.cat([sr.conv1.weight.grad.flatten(), sr.conv1.bias.grad, sr.conv2.weight.grad.flatten(), sr.conv2.bias.grad])
-    e_c = rel(d_conv, ref_conv); e_p = rel(d_pred.float(), pred.grad)
-    report("image_losses", e_m < 1e-5 and e_r < 1e-5 and e_c < 1e-4 and e_p < 5e-3, mim=e_m, res=e_r, conv_grad=e_c, d_pred=e_p,
-           cls_row_zero=bool((d_pred[:, 0] == 0).all().item()))
-
-
-@guard
-def check_ce():
-    rows, V = 300, 30000
-    logits = (torch.randn(rows, V, device=dev) * 2).to(torch.bfloat16)
-    labels = torch.randint(0, V, (rows,), device=dev); labels[5] = -100
-    w = torch.rand(rows, device=dev) + 0.05
-    g = torch.tensor([0.5], device=dev)
-    lr = logits.float().requires_grad_(True)
-    ce = F.cross_entropy(lr, labels, reduction="none")
-    (ce * w).sum().mul(0.5 / 1000).backward()
-    row_loss = torch.empty(rows, device=dev)
-    lg = logits.clone()
-    L.check(lib.ecamp_ce_rows(L.ptr(lg), V, rows, V, L.ptr(labels), L.ptr(w), L.ptr(row_loss), L.ptr(g), ctypes.c_float(1.0 / 1000), 1, L.cur_stream()), "ce")
-    torch.cuda.synchronize()
-    e1 = rel(row_loss, (ce * w).detach()); e2 = rel(lg.float(), lr.grad)
-    report("cross_entropy", e1 < 1e-4 and e2 < 1e-2, loss=e1, grad=e2)
-
-
-def build_pair(seed=0):
-    orc = ecamp_oracle().to(dev)
-    w = seeded_state_dict(orc, seed)
-    orc.load_state_dict(w)
-    orc.eval()
-    m = ecamp().to(dev)
-    m.load_state_dict(w)
-    return orc, m
-
-
-@guard
-def check_step():
-    gold = json.load(open("tests/golden/golden_cases.json"))["cases"]
-    orc, m = build_pair(0)
-    m.eval()
-    for case in gold[:2]:
-        B, T, seed = case["B"], case["T"], case["seed"]
-        b = synthetic_batch(B, T=T, seed=seed, device=dev)
-        for p in orc.parameters():
-            p.grad = None
-        lo = orc(b)
-        (lo[0] + lo[1] + lo[2]).backward()
-        m.zero_grad(set_to_none=True)
-        lm = m(b)
-        (lm[0] + lm[1] + lm[2]).backward()
-        torch.cuda.synchronize()
-        ids_ok = (m.last["ids_restore"].cpu().tolist() == case["ids_restore"] and m.last["ids_keep"].cpu().tolist() == case["ids_keep"])
-        le = [abs(lm[i].item() - lo[i].item()) / abs(lo[i].item()) for i in range(3)]
-        lg = [abs(lm[0].item() - case["mim_loss"]) / case["mim_loss"], abs(lm[1].item() - case["res_loss"]) / case["res_loss"],
-              abs(lm[2].item() - case["mlm_loss"]) / case["mlm_loss"]]
-        keep = 49
-        lat = m.debug_buffer("latent", (B, keep + 1, 768), torch.bfloat16).float()
-        pred = m.debug_buffer("pred", (B, 197, 768), torch.float32)[:, 1:]
-        e_lat = rel(lat, orc.last["latent"]); e_pred = rel(pred, orc.last["pred"])
-        report(f"step_forward_B{B}_T{T}", ids_ok and max(le) < 5e-3, ids_ok=ids_ok, loss_rel_vs_oracle=le, loss_rel_vs_golden=lg,
-               latent=e_lat, pred=e_pred, losses=[x.item() for x in lm])
-        go = dict(orc.named_parameters()); gm = dict(m.named_parameters())
-        errs = {}
-        for k, p in go.items():
-            if p.grad is None:
-                if gm[k].grad is not None:
-                    errs[k] = float("inf")
-                continue
-            if gm[k].grad is None:
-                errs[k] = float("nan")
-                continue
-            errs[k] = ((gm[k].grad.double() - p.grad.double()).norm() / p.grad.double().norm().clamp_min(1e-5)).item()
-        worst = sorted(errs.items(), key=lambda kv: -kv[1] if kv[1] == kv[1] else -1e9)[:12]
-        import statistics
-        med = statistics.median(errs.values())
-        report(f"step_backward_B{B}_T{T}", worst[0][1] < 0.08 and med < 0.03, median=med, worst=worst,
-               pooler_none=gm["bert_encoder.model.bert.pooler.dense.weight"].grad is None,
-               pad_row_zero=float(gm["bert_encoder.model.bert.embeddings.word_embeddings.weight"].grad[0].abs().max()))
-    # per-loss gradient routing: each loss alone
-    b = synthetic_batch(2, T=32, seed=1, device=dev)
-    for li in range(3):
-        for p in orc.parameters():
-            p.grad = None
-        orc(b)[li].backward()
-        m.zero_grad(set_to_none=True)
-        m(b)[li].backward()
-        go = dict(orc.named_parameters()); gm = dict(m.named_parameters())
-        errs = {}
-        for k, p in go.items():
-            if p.grad is None or p.grad.norm() == 0:
-                if gm[k].grad is not None and gm[k].grad.abs().max() > 1e-6:
-                    errs[k] = 1e9
-                continue
-            errs[k] = ((gm[k].grad.double() - p.grad.double()).norm() / p.grad.double().norm().clamp_min(1e-6)).item()
-        worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
-        report(f"step_backward_only_loss{li}", worst[0][1] < 0.1, worst=worst)
-    # fused path == autograd path
-    m.zero_grad(set_to_none=True)
-    l1 = m(b); (l1[0] + l1[1] + l1[2]).backward()
-    g1 = m.flat_grads().clone()
-    m.zero_grad(set_to_none=True)
-    l2 = m.forward_backward(b)
-    g2 = m.flat_grads().clone()
-    report("fused_equals_autograd", rel(g2, g1) < 1e-3 and rel(l2, torch.stack(list(l1)).detach()) < 1e-4, grads=rel(g2, g1),
-           losses=rel(l2, torch.stack(list(l1)).detach()))
-    # accumulation
-    l3 = m.forward_backward(b)
-    report("grad_accumulation", rel(m.flat_grads(), 2 * g2) < 1e-3, err=rel(m.flat_grads(), 2 * g2))
-    # 224-px positional form
-    b2 = synthetic_batch(2, T=32, big=False, seed=5, device=dev)
-    lo = orc(b2["image"], b2["ids"], b2["attention_mask"], b2["labels"], 0.75, type_ids=b2["type_ids"], weights=b2["weights"], noise=b2["noise"])
-    lm = m(b2["image"], b2["ids"], b2["attention_mask"], b2["labels"], 0.75, type_ids=b2["type_ids"], weights=b2["weights"], noise=b2["noise"])
-    le = [abs(lm[i].item() - lo[i].item()) / max(abs(lo[i].item()), 1e-9) for i in (0, 2)]
-    report("positional_224", max(le) < 5e-3 and lm[1].item() == 0.0, loss_rel=le)
-    # training mode with dropout: finite, different from eval
-    m.train()
-    m.zero_grad(set_to_none=True)
-    lt = m.forward_backward(b)
-    fin = bool(torch.isfinite(lt).all()) and bool(torch.isfinite(m.flat_grads()).all())
-    report("train_mode_dropout", fin and abs(lt[2].item() - l2[2].item()) > 1e-6, losses=lt.tolist())
-
-
-@guard
-def check_adamw():
-    orc, m = build_pair(1)
-    m.eval()
-    b = synthetic_batch(2, T=32, seed=1, device=dev)
-    ref = ecamp().to(dev)
-    ref.load_state_dict(m.state_dict())
-    m.zero_grad(set_to_none=True)
-    m.forward_backward(b)
-    named = dict(m.named_parameters()); rnamed = dict(ref.named_parameters())
-    decay, no_decay = [], []
-    for k, p in rnamed.items():
-        if not p.requires_grad:
-            continue
-        if named[k].grad is not None:
-            p.grad = named[k].grad.clone()
-        (no_decay if (p.dim() == 1 or k.endswith(".bias")) else decay).append(p)
-    opt = torch.optim.AdamW([dict(params=no_decay, weight_decay=0.0), dict(params=decay, weight_decay=0.05)], lr=1.5e-4, betas=(0.9, 0.95))
-    for step in (1, 2):
-        opt.step()
-        L.check(lib.ecamp_adamw_step(m._rt["ctx"], ctypes.c_float(1.5e-4), ctypes.c_float(0.9), ctypes.c_float(0.95), ctypes.c_float(1e-8),
-                                     ctypes.c_float(0.05), step, ctypes.c_float(1.0), L.cur_stream()), "adamw")
-    torch.cuda.synchronize()
-    worst = 0.0
-    for k, p in rnamed.items():
-        worst = max(worst, (named[k].detach() - p.detach()).abs().max().item())
-    pool_same = torch.equal(named["bert_encoder.model.bert.pooler.dense.weight"], rnamed["bert_encoder.model.bert.pooler.dense.weight"])
-    # shadows follow: forward after the fused step equals forward of the torch-stepped copy
-    l_m = m(b); l_r = ref(b)
-    report("adamw", worst < 1e-6 and pool_same and rel(torch.stack(list(l_m)), torch.stack(list(l_r))) < 1e-4, max_abs_param_diff=worst,
-           loss_after=[x.item() for x in l_m], loss_after_ref=[x.item() for x in l_r])
-
-
-for fn in (check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw):
-    fn()
-    torch.cuda.synchronize()
-print("ALL_OK" if all(results) else "SOME_FAILED")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "parity_checks.py"),
+               run_name="__main__")

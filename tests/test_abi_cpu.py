@@ -1,0 +1,94 @@
+"""The C-ABI shared library builds (cross-compiled for sm_100a), loads without a GPU and exports every
+symbol include/ecamp_b200.h declares; the host-side mirror of the reference module has the reference's
+state_dict layout and refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "ecamp_b200.h")).read()
+    return sorted(set(re.findall(r"ECAMP_API[^;(]*?\b(ecamp_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = built_lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ecamp_b200.h but not exported"
+    assert sorted(built_lib.SYMBOLS) == syms
+    assert lib.ecamp_abi_version() == 1
+
+
+def test_parameter_table_matches_reference_layout(built_lib):
+    lib = built_lib.lib()
+    lay = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_layout.json")))
+    n = lib.ecamp_param_count()
+    names = [lib.ecamp_param_name(i).decode() for i in range(n)]
+    assert n == 345 and len(set(names)) == n
+    # every trainable reference parameter except the dead pooler (bert_modeling.py:144) and the bias alias
+    expected = [k for k in lay["keys"] if k not in lay["frozen"] and "pooler" not in k and not k.endswith("decoder.bias")]
+    assert sorted(names) == sorted(expected)
+    off = 0
+    for i, k in enumerate(names):
+        numel = 1
+        for d in lay["keys"][k]:
+            numel *= d
+        assert lib.ecamp_param_numel(i) == numel
+        assert lib.ecamp_param_grad_offset(i) == off
+        off += numel
+        ndim = len(lay["keys"][k])
+        assert lib.ecamp_param_decay(i) == int(not (ndim == 1 or k.endswith(".bias")))  # timm add_weight_decay
+    assert lib.ecamp_grad_floats() == off == 183173080 - 2 * 0 - (768 * 768 + 768)
+    # backward stages tile the flat gradient buffer back to front
+    hi_prev = off
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    for s in range(lib.ecamp_backward_stage_count()):
+        assert lib.ecamp_backward_stage_range(s, ctypes.byref(lo), ctypes.byref(hi)) == 0
+        assert hi.value == hi_prev and lo.value < hi.value
+        hi_prev = lo.value
+    assert hi_prev == 0
+
+
+def test_error_convention(built_lib):
+    lib = built_lib.lib()
+    rc = lib.ecamp_ctx_set_workspace(None, None, ctypes.c_int64(0), None)
+    assert rc < 0 and b"null" in lib.ecamp_last_error()
+    ep = built_lib.Epilogue()
+    assert lib.ecamp_gemm_bf16(None, 0, 0, None, 0, 0, 1, 1, 1, ctypes.byref(ep), 0, None) < 0
+
+
+def test_module_layout_and_no_cpu_fallback(built_lib):
+    from ecamp_b200.model_ecamp import ecamp
+    torch.manual_seed(0)
+    m = ecamp(norm_pix_loss=True)  # the reference passes this flag (main_pretrain.py:233); it is a no-op there too
+    lay = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_layout.json")))
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(lay["keys"].keys())
+    assert all(list(v.shape) == lay["keys"][k] and v.dtype == torch.float32 for k, v in sd.items())
+    assert len(list(m.parameters())) == 349
+    assert sd["bert_encoder.model.cls.predictions.decoder.bias"].data_ptr() == sd["bert_encoder.model.cls.predictions.bias"].data_ptr()
+    assert sd["bert_encoder.model.cls.predictions.decoder.weight"].data_ptr() != sd["bert_encoder.model.bert.embeddings.word_embeddings.weight"].data_ptr()
+    assert not m.pos_embed.requires_grad and not m.decoder_pos_embed.requires_grad
+    # round trip through the oracle's layout (what misc.save_model / load_model do by key)
+    from oracle.ecamp_oracle import ecamp_oracle
+    o = ecamp_oracle()
+    assert torch.equal(o.pos_embed, m.pos_embed) and torch.equal(o.decoder_pos_embed, m.decoder_pos_embed)
+    missing, unexpected = o.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    batch = dict(image=torch.zeros(1, 3, 448, 448), ids=torch.zeros(1, 8, dtype=torch.long), labels=torch.zeros(1, 8, dtype=torch.long),
+                 attention_mask=torch.ones(1, 8, dtype=torch.long), type_ids=torch.zeros(1, 8, dtype=torch.long),
+                 weights=torch.ones(1, 8), column=torch.zeros(1, dtype=torch.long), row=torch.zeros(1, dtype=torch.long))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            m(batch)
+    with pytest.raises(ValueError):
+        from ecamp_b200.model_ecamp import ECAMP
+        ECAMP(embed_dim=384)
