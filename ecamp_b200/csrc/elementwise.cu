@@ -392,34 +392,38 @@ __global__ void emb_type_finalize_kernel(const float* __restrict__ type_ws, int 
 // ---------------------------------------------------------------------------------------------
 // bias gradients
 // ---------------------------------------------------------------------------------------------
-constexpr int kColsumChunks = 32;
+// out[n] = sum_m x[m, n]: CTA = 256 columns x one row chunk; each lane owns 8 consecutive columns (128-bit loads),
+// the 8 warps stride over the rows of the chunk; per-chunk partials are reduced by a second tiny kernel.
+constexpr int kColsumChunks = 64;
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int ld, int M, int N,
                                                      float* __restrict__ ws) {
-  __shared__ float2 red[8][32];
+  __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = blockIdx.x * 64 + lane * 2;
+  const int col = blockIdx.x * 256 + lane * 8;
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-  float2 acc = make_float2(0.f, 0.f);
-  if (col < N) {
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (col < N) {  // N % 8 == 0 checked on the host
     for (int r = r0 + warp; r < r1; r += 8) {
-      const uint32_t u = *reinterpret_cast<const uint32_t*>(x + (size_t)r * ld + col);
-      const float2 f = unpack_bf16x2(u);
-      acc.x += f.x;
-      acc.y += f.y;
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)r * ld + col);
+      float2 f;
+      f = unpack_bf16x2(u.x); acc[0] += f.x; acc[1] += f.y;
+      f = unpack_bf16x2(u.y); acc[2] += f.x; acc[3] += f.y;
+      f = unpack_bf16x2(u.z); acc[4] += f.x; acc[5] += f.y;
+      f = unpack_bf16x2(u.w); acc[6] += f.x; acc[7] += f.y;
     }
   }
-  red[warp][lane] = acc;
-  __syncthreads();
-  if (warp == 0 && col < N) {
-    float2 s = red[0][lane];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) {
-      s.x += red[w][lane].x;
-      s.y += red[w][lane].y;
-    }
-    ws[(size_t)blockIdx.y * N + col] = s.x;
-    if (col + 1 < N) ws[(size_t)blockIdx.y * N + col + 1] = s.y;
+  for (int k = 0; k < 8; ++k) red[warp][lane * 8 + k] = acc[k];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    ws[(size_t)blockIdx.y * N + c] = s;
   }
 }
 __global__ void colsum_finalize_kernel(const float* __restrict__ ws, int chunks, int N, float* __restrict__ out,
@@ -582,9 +586,12 @@ int bert_embeddings_bwd(const float* d_pre, const int64_t* ids, const int64_t* t
 }
 size_t colsum_ws_floats(int N) { return (size_t)kColsumChunks * N; }
 int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate, float* ws, cudaStream_t st) {
-  ECAMP_REQUIRE(ld % 2 == 0, "colsum: ld must be even");
-  const int chunks = M < kColsumChunks * 8 ? 1 : kColsumChunks;
-  dim3 grid((N + 63) / 64, chunks);
+  ECAMP_REQUIRE(ld % 8 == 0 && N % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                "colsum: pitch and width must be multiples of 8 elements, base 16-byte aligned");
+  int chunks = (M + 63) / 64;  // at least 64 rows per chunk
+  if (chunks > kColsumChunks) chunks = kColsumChunks;
+  if (chunks < 1) chunks = 1;
+  dim3 grid((N + 255) / 256, chunks);
   colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, ws);
   LAUNCH_OK();
   colsum_finalize_kernel<<<(N + 255) / 256, 256, 0, st>>>(ws, chunks, N, out, accumulate);

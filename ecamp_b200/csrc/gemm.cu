@@ -44,7 +44,26 @@ struct Cfg {
 struct EpiArgs {
   GemmEpilogue ep;
   int vec_ok;
+  int split_k;  // > 1: the contraction is split over `split_k` work units per tile, partials added with fp32 atomics
+  int kb_per;   // k-blocks per split
 };
+
+// split-K epilogue: out_f32[row, col0..col0+31] += v (the buffer was zeroed, or holds the running gradient)
+ECAMP_DEVINL void epilogue_atomic_row32(const EpiArgs& ea, const float (&v)[32], int row, int col0, int N) {
+  float* op = ea.ep.out_f32 + (size_t)row * ea.ep.ld_f32 + col0;
+  const int nvalid = min(32, N - col0);
+  if (ea.vec_ok && nvalid == 32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                   "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                   : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < nvalid) atomicAdd(op + i, v[i]);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // epilogue for one thread: one output row, 32 consecutive columns
@@ -193,6 +212,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
+  const int num_units = num_tiles * ea.split_k;  // work unit = (tile, k-split); unit % num_tiles = tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -223,9 +243,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit % num_tiles, ks = unit / num_tiles;
         const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = ks * ea.kb_per, kb1 = min(num_kb, kb0 + ea.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* a_dst = sA + stage * C::A_BYTES;
@@ -255,12 +277,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       if (lane == 0) {
+        const int ks = unit / num_tiles;
+        const int kb0 = ks * ea.kb_per, kb1 = min(num_kb, kb0 + ea.kb_per);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + stage * C::A_BYTES);
@@ -274,10 +298,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                         : umma_smem_desc_sw128(a_base + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_base + k * 2048, BK * 128, 1024)
                                         : umma_smem_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -291,7 +315,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     constexpr int HALF_N = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int tile = unit % num_tiles;
       const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -313,7 +338,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          epilogue_row32(ea, v, row, col0, N);
+          if (ea.split_k > 1) epilogue_atomic_row32(ea, v, row, col0, N);
+          else epilogue_row32(ea, v, row, col0, N);
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -380,21 +406,33 @@ int num_sms() {
   return n;
 }
 
-int pick_bn(int M, int N) {
+// Tile width and k-split minimising (waves) x (k-blocks per unit + fixed per-unit cost) x (cost per k-block).
+// split_k > 1 is only offered to plain fp32-output GEMMs (the weight gradients), whose output tiles are few
+// (e.g. 768 x 768 -> 18 tiles on 148 SMs) while the contraction (all rows of the batch) is long.
+void pick_config(int M, int N, int K, bool splittable, int force_bn, int* bn_out, int* split_out) {
   const int sms = num_sms();
   const int m_tiles = (M + BM - 1) / BM;
+  const int num_kb = (K + BK - 1) / BK;
   const int cand[3] = {256, 192, 128};
   const float eff[3] = {1.00f, 0.97f, 0.88f};  // smaller tiles put more shared-memory traffic behind each MMA
-  int best = 256;
+  const int splits[9] = {1, 2, 3, 4, 6, 8, 12, 16, 24};
   float best_cost = 1e30f;
+  *bn_out = 256;
+  *split_out = 1;
   for (int i = 0; i < 3; ++i) {
     const int bn = cand[i];
+    if (force_bn && bn != force_bn) continue;
     const int tiles = m_tiles * ((N + bn - 1) / bn);
-    const int waves = (tiles + sms - 1) / sms;
-    const float cost = (float)waves * (float)bn / eff[i];
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+    for (int j = 0; j < (splittable ? 9 : 1); ++j) {
+      const int sp = splits[j];
+      const int kb_per = (num_kb + sp - 1) / sp;
+      if (sp > 1 && (kb_per < 8 || (sp - 1) * kb_per >= num_kb)) continue;
+      const int waves = (tiles * sp + sms - 1) / sms;
+      const float fixed = sp > 1 ? 14.f : 6.f;  // pipeline fill + epilogue, in k-block units (atomics cost more)
+      const float cost = (float)waves * ((float)kb_per + fixed) * (float)bn / eff[i];
+      if (cost < best_cost) { best_cost = cost; *bn_out = bn; *split_out = sp; }
+    }
   }
-  return best;
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -405,7 +443,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
     ECAMP_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * ea.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kfn<<<grid, kThreads, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, M, N, K, ea);
   ECAMP_LAUNCHED();
@@ -430,8 +468,13 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
   if (ep.flags & GEMM_DROPOUT)
     ECAMP_REQUIRE(N % 4 == 0 && ep.drop_p >= 0.f && ep.drop_p < 1.f, "gemm: dropout needs N %% 4 == 0, 0 <= p < 1");
   if (ep.flags & GEMM_DGELU) ECAMP_REQUIRE(ep.aux_in != nullptr, "gemm: dGELU needs aux_in");
-  const int bn = force_bn ? force_bn : pick_bn(M, N);
-  ECAMP_REQUIRE(bn == 128 || bn == 192 || bn == 256, "gemm: unsupported tile N %d", bn);
+  ECAMP_REQUIRE(force_bn == 0 || force_bn == 128 || force_bn == 192 || force_bn == 256, "gemm: unsupported tile N %d",
+                force_bn);
+  const bool accumulate = ep.residual != nullptr && ep.residual == ep.out_f32 && ep.ld_res == ep.ld_f32;
+  const bool splittable = ep.out_f32 && !ep.out_bf16 && !ep.bias && ep.flags == 0 && !ep.aux_out &&
+                          (ep.residual == nullptr || accumulate);
+  int bn = 256, split_k = 1;
+  pick_config(M, N, K, splittable, force_bn, &bn, &split_k);
 
   CUtensorMap ta, tb;
   int rc;
@@ -446,6 +489,14 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
 
   EpiArgs ea;
   ea.ep = ep;
+  ea.split_k = split_k;
+  ea.kb_per = (((K + BK - 1) / BK) + split_k - 1) / split_k;
+  if (split_k > 1) {
+    ea.ep.residual = nullptr;  // partial sums are added atomically on top of the running gradient / zeros
+    if (!accumulate)
+      ECAMP_CUDA_OK(cudaMemset2DAsync(ep.out_f32, (size_t)ep.ld_f32 * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M,
+                                      stream));
+  }
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   ea.vec_ok = 1;
   if (ep.bias && !al16(ep.bias)) ea.vec_ok = 0;

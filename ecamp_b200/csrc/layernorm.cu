@@ -144,15 +144,23 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   }
 }
 
-__global__ void ln_bwd_finalize(const float* __restrict__ partial, int nblocks, int D, float* __restrict__ dgamma,
-                                float* __restrict__ dbeta, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * D) return;
+// one CTA per 32 columns of [dgamma | dbeta]; 8 warps stride over the per-CTA partial rows
+__global__ void __launch_bounds__(256) ln_bwd_finalize(const float* __restrict__ partial, int nblocks, int D,
+                                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                       int accumulate) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;  // 2 * D is a multiple of 32
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 2 * D + c];
-  float* dst = c < D ? dgamma + c : dbeta + (c - D);
-  if (dst == nullptr) return;
-  *dst = accumulate ? *dst + s : s;
+  for (int b = warp; b < nblocks; b += 8) s += partial[(size_t)b * 2 * D + c];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += red[w][lane];
+    float* dst = c < D ? dgamma + c : dbeta + (c - D);
+    *dst = accumulate ? *dst + s : s;
+  }
 }
 
 int bwd_blocks(int M) {
@@ -189,7 +197,7 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
     ln_bwd_kernel<4><<<grid, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, partial_ws);
   ECAMP_LAUNCHED();
   if (dgamma && dbeta) {
-    ln_bwd_finalize<<<(2 * D + 255) / 256, 256, 0, st>>>(partial_ws, grid, D, dgamma, dbeta, accumulate);
+    ln_bwd_finalize<<<2 * D / 32, 256, 0, st>>>(partial_ws, grid, D, dgamma, dbeta, accumulate);
     ECAMP_LAUNCHED();
   }
   return 0;
