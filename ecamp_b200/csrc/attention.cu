@@ -98,12 +98,18 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
   load_tile<D, LDS>(sQ, a.q + ((size_t)b * a.Sq + q0) * a.ldq + h * D, a.ldq, 64, min(64, a.Sq - q0), tid, 128);
   load_tile<D, LDS>(sK, a.k + (size_t)b * a.Sk * a.ldk + h * D, a.ldk, Skp, a.Sk, tid, 128);
   load_tile<D, LDS>(sV, a.v + (size_t)b * a.Sk * a.ldv + h * D, a.ldv, Skp, a.Sk, tid, 128);
+  // keys after the last attendable one contribute exactly zero: the key loop stops there (padding is a suffix)
+  __shared__ int s_kend;
+  if (tid == 0) s_kend = 0;
+  __syncthreads();
   for (int j = tid; j < Skp; j += 128) {
     bool ok = j < a.Sk;
     if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + j] != 0;
     sBias[j] = ok ? 0.f : -INFINITY;
+    if (ok) atomicMax(&s_kend, j + 1);
   }
   __syncthreads();
+  const int kend = (s_kend + 15) & ~15;
 
   uint32_t qf[D / 16][4];
 #pragma unroll
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
   const uint64_t bh = (uint64_t)b * a.H + h;
   const int row_g = q0 + warp * 16 + g;  // this thread's rows: row_g and row_g + 8
 
-  for (int kb = 0; kb < Skp; kb += 64) {
+  for (int kb = 0; kb < kend; kb += 64) {
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
     for (int kt = 0; kt < D / 16; ++kt) {
 #pragma unroll
       for (int jp = 0; jp < 4; ++jp) {
-        if (kb + jp * 16 < Skp) {
+        if (kb + jp * 16 < kend) {
           uint32_t bf[4];
           load_b_frag_nk<LDS>(bf, sK, kb + jp * 16, kt * 16, lane);
           mma_bf16_16816(s[2 * jp], qf[kt], bf[0], bf[1]);
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int col = kb + j * 8 + t4 * 2 + (e & 1);
-        const float bias = col < Skp ? sBias[col] : -INFINITY;
+        const float bias = col < kend ? sBias[col] : -INFINITY;
         s[j][e] = s[j][e] * a.scale + bias;
         bm[e >> 1] = fmaxf(bm[e >> 1], s[j][e]);
       }
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
     // O += P V
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      if (kb + kk * 16 < Skp) {
+      if (kb + kk * 16 < kend) {
         uint32_t pa[4];
         pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
         pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
@@ -260,6 +266,9 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
   const bf16* gV = a.v + (size_t)b * a.Sk * a.ldv + h * D;
   const bf16* gdO = a.d_o + (size_t)b * a.Sq * a.ld_do + h * D;
   const int rvalid = min(64, Sr - r0);
+  __shared__ int s_cend;
+  if (tid == 0) s_cend = TR ? Scp : 0;
+  __syncthreads();
   if (!TR) {
     load_tile<D, LDS>(sR1, gQ + (size_t)r0 * a.ldq, a.ldq, 64, rvalid, tid, 128);
     load_tile<D, LDS>(sR2, gdO + (size_t)r0 * a.ld_do, a.ld_do, 64, rvalid, tid, 128);
@@ -269,6 +278,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
       bool ok = j < Sc;
       if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + j] != 0;
       sColA[j] = ok ? 0.f : -INFINITY;
+      if (ok) atomicMax(&s_cend, j + 1);
     }
   } else {
     load_tile<D, LDS>(sR1, gK + (size_t)r0 * a.ldk, a.ldk, 64, rvalid, tid, 128);
@@ -281,6 +291,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
     }
   }
   __syncthreads();
+  const int cend = TR ? Scp : ((s_cend + 15) & ~15);  // dQ pass: keys after the last attendable one are skipped
 
   // per-row statistics / validity for this thread's two rows
   const int row_g = r0 + warp * 16 + g;
@@ -296,6 +307,19 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
       if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + row] != 0;
       row_a[r] = ok ? 0.f : -INFINITY;  // key bias
       row_b[r] = 0.f;
+    }
+  }
+
+  if (TR) {
+    const int any_valid = __syncthreads_or((row_a[0] == 0.f || row_a[1] == 0.f) ? 1 : 0);
+    if (!any_valid) {
+      for (int idx = tid; idx < rvalid * (D / 8); idx += 128) {
+        const int r = idx / (D / 8), c8 = idx % (D / 8);
+        const size_t row = (size_t)b * a.Sk + r0 + r;
+        *reinterpret_cast<uint4*>(a.dk + row * a.lddk + h * D + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(a.dv + row * a.lddv + h * D + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      return;
     }
   }
 
@@ -317,7 +341,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
   float dsum[2] = {0.f, 0.f};
 #pragma unroll 1
   for (int pass = TR ? 1 : 0; pass < 2; ++pass) {
-  for (int cb = 0; cb < Scp; cb += CB) {
+  for (int cb = 0; cb < cend; cb += CB) {
     float s[NT][4], dp[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -331,7 +355,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
       load_a_frag<LDS>(a2, sR2, warp * 16, kt * 16, lane);
 #pragma unroll
       for (int jp = 0; jp < NT / 2; ++jp) {
-        if (cb + jp * 16 < Scp) {
+        if (cb + jp * 16 < cend) {
           uint32_t bf[4];
           load_b_frag_nk<LDS>(bf, sC1, cb + jp * 16, kt * 16, lane);
           mma_bf16_16816(s[2 * jp], a1, bf[0], bf[1]);
@@ -349,7 +373,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
       for (int e = 0; e < 4; ++e) {
         const int col = cb + j * 8 + t4 * 2 + (e & 1);
         const int r = e >> 1;
-        const bool cin = col < Scp;
+        const bool cin = col < cend;
         float lse, delta, bias;
         if (!TR) {
           lse = row_a[r]; delta = row_b[r]; bias = cin ? sColA[col] : -INFINITY;
@@ -375,7 +399,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
     // out1 += dS . C1 ; (TR) out2 += Pdrop . C2
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
-      if (cb + kk * 16 < Scp) {
+      if (cb + kk * 16 < cend) {
         uint32_t da[4], pa[4];
         da[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
         da[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);

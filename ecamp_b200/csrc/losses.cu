@@ -42,6 +42,9 @@ __global__ void __launch_bounds__(1024) sum_to_scalar_kernel(const float* __rest
 struct SrWeights {
   float w1[81], b1[3], w2[81], b2[3];
 };
+// The 168 conv parameters live in constant memory (copied device-to-device on the stream before each launch) so
+// that every unrolled FMA takes its weight straight from the constant bank instead of a shared-memory load.
+__constant__ SrWeights c_sr;
 
 ECAMP_DEVINL float pred_pixel(const float* __restrict__ pred_b, int c, int y, int x) {
   // pred_b: [197, 768] of one sample, row 0 = cls; unpatchify 'nhwpqc->nchpwq' (model_ecamp.py:153-165)
@@ -59,8 +62,8 @@ ECAMP_DEVINL void bilinear_src(int Y, int& y0, int& y1, float& lam) {
 //   sU: (OUT+4)^2 x 3 up-sampled input, origin (Y0-2, X0-2), zero outside the image (conv zero padding)
 //   sH: (OUT+2)^2 x 3 relu(conv1), origin (Y0-1, X0-1), zero outside the image
 template <int OUT>
-ECAMP_DEVINL void sr_forward_region(const float* __restrict__ pred_b, const SrWeights& w, int Y0, int X0, float* sU,
-                                    float* sH) {
+ECAMP_DEVINL void sr_forward_region(const float* __restrict__ pred_b, int Y0, int X0, float* sU, float* sH) {
+  const SrWeights& w = c_sr;
   constexpr int UW = OUT + 4, HW = OUT + 2;
   for (int i = threadIdx.x; i < UW * UW; i += blockDim.x) {
     const int uy = i / UW, ux = i % UW;
@@ -112,7 +115,8 @@ ECAMP_DEVINL void sr_forward_region(const float* __restrict__ pred_b, const SrWe
 
 // pre-activation output of the head at region pixel (oy, ox): conv2(h1) + b2 + u
 template <int OUT>
-ECAMP_DEVINL void sr_out_pixel(const SrWeights& w, const float* sU, const float* sH, int oy, int ox, float (&o)[3]) {
+ECAMP_DEVINL void sr_out_pixel(const float* sU, const float* sH, int oy, int ox, float (&o)[3]) {
+  const SrWeights& w = c_sr;
   constexpr int UW = OUT + 4, HW = OUT + 2;
   o[0] = w.b2[0] + sU[(oy + 2) * UW + ox + 2];
   o[1] = w.b2[1] + sU[UW * UW + (oy + 2) * UW + ox + 2];
@@ -130,18 +134,6 @@ ECAMP_DEVINL void sr_out_pixel(const SrWeights& w, const float* sU, const float*
       }
 }
 
-ECAMP_DEVINL void load_sr_weights(SrWeights* sw, const float* w1, const float* b1, const float* w2, const float* b2) {
-  for (int i = threadIdx.x; i < 81; i += blockDim.x) {
-    sw->w1[i] = w1[i];
-    sw->w2[i] = w2[i];
-  }
-  if (threadIdx.x < 3) {
-    sw->b1[threadIdx.x] = b1[threadIdx.x];
-    sw->b2[threadIdx.x] = b2[threadIdx.x];
-  }
-  __syncthreads();
-}
-
 // window of sample b in 32-px tiles: rows [c0, c1), cols [r0, r1) (model_ecamp.py:207-208: slices clip at 14)
 ECAMP_DEVINL void sr_window(const int64_t* column, const int64_t* row, int b, int& c0, int& c1, int& r0, int& r1) {
   const long long c = column[b], r = row[b];
@@ -153,10 +145,8 @@ ECAMP_DEVINL void sr_window(const int64_t* column, const int64_t* row, int b, in
 
 __global__ void __launch_bounds__(256) sr_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ big,
                                                      const int64_t* __restrict__ column,
-                                                     const int64_t* __restrict__ row, const float* w1, const float* b1,
-                                                     const float* w2, const float* b2, float* __restrict__ ws) {
+                                                     const int64_t* __restrict__ row, float* __restrict__ ws) {
   constexpr int OUT = 32, UW = OUT + 4, HW = OUT + 2;
-  __shared__ SrWeights sw;
   __shared__ float sU[3 * UW * UW];
   __shared__ float sH[3 * HW * HW];
   __shared__ float red[32];
@@ -168,15 +158,14 @@ __global__ void __launch_bounds__(256) sr_fwd_kernel(const float* __restrict__ p
     if (threadIdx.x == 0) ws[blockIdx.x] = 0.f;
     return;
   }
-  load_sr_weights(&sw, w1, b1, w2, b2);
   const float* pred_b = pred + (size_t)b * 197 * PD;
   const int Y0 = ty * 32, X0 = tx * 32;
-  sr_forward_region<OUT>(pred_b, sw, Y0, X0, sU, sH);
+  sr_forward_region<OUT>(pred_b, Y0, X0, sU, sH);
   float s = 0.f;
   for (int i = threadIdx.x; i < OUT * OUT; i += blockDim.x) {
     const int oy = i / OUT, ox = i % OUT;
     float o[3];
-    sr_out_pixel<OUT>(sw, sU, sH, oy, ox, o);
+    sr_out_pixel<OUT>(sU, sH, oy, ox, o);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float d = fmaxf(o[c], 0.f) - big[(((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox];
@@ -191,8 +180,7 @@ __global__ void __launch_bounds__(256) sr_fwd_kernel(const float* __restrict__ p
 constexpr int SR_BWD_SMEM_FLOATS = 3 * (40 * 40 + 38 * 38 + 36 * 36 + 34 * 34);
 __global__ void __launch_bounds__(256) sr_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ big,
                                                      const int64_t* __restrict__ column,
-                                                     const int64_t* __restrict__ row, const float* w1, const float* b1,
-                                                     const float* w2, const float* b2, int B,
+                                                     const int64_t* __restrict__ row, int B,
                                                      const float* __restrict__ g_res, float* __restrict__ d_u,
                                                      float* __restrict__ ws) {
   constexpr int OUT = 36, UW = 40, HW = 38, OW = 36, GW = 34;
@@ -201,8 +189,8 @@ __global__ void __launch_bounds__(256) sr_bwd_kernel(const float* __restrict__ p
   float* sH = sU + 3 * UW * UW;
   float* sDO = sH + 3 * HW * HW;
   float* sDH = sDO + 3 * OW * OW;
-  __shared__ SrWeights sw;
   __shared__ float redw[8][84];
+  const SrWeights& sw = c_sr;
   const int tile = blockIdx.x % (GRID * GRID), b = blockIdx.x / (GRID * GRID);
   const int ty = tile / GRID, tx = tile % GRID;
   const int Y0 = ty * 32, X0 = tx * 32;  // origin of the owned 32x32 region
@@ -221,9 +209,8 @@ __global__ void __launch_bounds__(256) sr_bwd_kernel(const float* __restrict__ p
     for (int i = threadIdx.x; i < 168; i += blockDim.x) ws_t[i] = 0.f;
     return;
   }
-  load_sr_weights(&sw, w1, b1, w2, b2);
   const float* pred_b = pred + (size_t)b * 197 * PD;
-  sr_forward_region<OUT>(pred_b, sw, Y0 - 2, X0 - 2, sU, sH);
+  sr_forward_region<OUT>(pred_b, Y0 - 2, X0 - 2, sU, sH);
   const float gscale = 2.0f * (*g_res) / ((float)B * 3.f * BIG * BIG);
 
   // d_out (pre-ReLU) on the 36x36 region with origin (Y0-2, X0-2)
@@ -233,7 +220,7 @@ __global__ void __launch_bounds__(256) sr_bwd_kernel(const float* __restrict__ p
     float d[3] = {0.f, 0.f, 0.f};
     if (Y >= wy0 && Y < wy1 && X >= wx0 && X < wx1) {  // inside the window (hence inside the image)
       float o[3];
-      sr_out_pixel<OUT>(sw, sU, sH, oy, ox, o);
+      sr_out_pixel<OUT>(sU, sH, oy, ox, o);
 #pragma unroll
       for (int c = 0; c < 3; ++c)
         d[c] = o[c] > 0.f ? gscale * (o[c] - big[(((size_t)b * 3 + c) * BIG + Y) * BIG + X]) : 0.f;
@@ -503,10 +490,21 @@ int mim_loss_fwd(const float* pred, int rows_per_batch, const float* tgt, const 
 
 size_t sr_ws_floats(int B) { return (size_t)B * GRID * GRID * 168; }
 
+static int upload_sr_weights(const float* w1, const float* b1, const float* w2, const float* b2, cudaStream_t st) {
+  static SrWeights* dev = nullptr;
+  if (!dev) ECAMP_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&dev), c_sr));
+  ECAMP_CUDA_OK(cudaMemcpyAsync(dev->w1, w1, 81 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ECAMP_CUDA_OK(cudaMemcpyAsync(dev->b1, b1, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ECAMP_CUDA_OK(cudaMemcpyAsync(dev->w2, w2, 81 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ECAMP_CUDA_OK(cudaMemcpyAsync(dev->b2, b2, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 int sr_loss_fwd(const float* pred, const float* big, const int64_t* column, const int64_t* row, const float* w1,
                 const float* b1, const float* w2, const float* b2, int B, float* loss_out, float* ws,
                 cudaStream_t st) {
-  sr_fwd_kernel<<<B * GRID * GRID, 256, 0, st>>>(pred, big, column, row, w1, b1, w2, b2, ws);
+  if (int rc = upload_sr_weights(w1, b1, w2, b2, st)) return rc;
+  sr_fwd_kernel<<<B * GRID * GRID, 256, 0, st>>>(pred, big, column, row, ws);
   LAUNCH_OK();
   return sum_to_scalar(ws, (size_t)B * GRID * GRID, 1.0f / ((float)B * 3.f * BIG * BIG), loss_out, st);
 }
@@ -520,8 +518,9 @@ int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, cons
                                        SR_BWD_SMEM_FLOATS * (int)sizeof(float)));
     attr = true;
   }
-  sr_bwd_kernel<<<B * GRID * GRID, 256, SR_BWD_SMEM_FLOATS * sizeof(float), st>>>(pred, big, column, row, w1, b1, w2,
-                                                                                   b2, B, g_res, d_u, ws);
+  if (int rc = upload_sr_weights(w1, b1, w2, b2, st)) return rc;
+  sr_bwd_kernel<<<B * GRID * GRID, 256, SR_BWD_SMEM_FLOATS * sizeof(float), st>>>(pred, big, column, row, B, g_res,
+                                                                                   d_u, ws);
   LAUNCH_OK();
   sr_wgrad_finalize_kernel<<<168, 256, 0, st>>>(ws, B * GRID * GRID, d_conv, accumulate);
   LAUNCH_OK();

@@ -49,6 +49,13 @@ for bn in (128, 192, 256):
     run_case("mn_mn", 256, 2 * bn, 512, True, True, bn)
     run_case("mn_k", 256, 2 * bn, 512, True, False, bn)
     run_case("mn_mn_tails", 200, 304, 136, True, True, bn)
+# split-K candidates (fp32-only outputs with few tiles and a long contraction)
+for rep in range(3):
+    run_case("splitk_dgrad_small_m", 100, 768, 3072, False, True, 0)
+    run_case("splitk_dgrad_394", 394, 512, 2048, False, True, 0)
+    run_case("splitk_wgrad_768", 768, 768, 32768, True, True, 0)
+    run_case("splitk_wgrad_3072", 3072, 768, 12800, True, True, 0)
+    run_case("splitk_wgrad_tail", 768, 1536, 12544 + 37, True, True, 0)
 run_case("many_tiles", 12800, 768, 768, False, False, 0)
 run_case("vocab_like", 1024, 30000, 768, False, False, 0)
 run_case("dgrad_vocab", 512, 768, 30000, False, True, 0)

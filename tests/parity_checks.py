@@ -342,6 +342,21 @@ def check_step():
     g2 = m.flat_grads().clone()
     report("fused_equals_autograd", rel(g2, g1) < 1e-3 and rel(l2, torch.stack(list(l1)).detach()) < 1e-4, grads=rel(g2, g1),
            losses=rel(l2, torch.stack(list(l1)).detach()))
+    # run-to-run reproducibility of the fused path (fp32 atomics in split-K GEMMs and the word-embedding scatter
+    # reorder sums: tiny differences are expected, anything above 1e-5 per tensor points at a race)
+    m.zero_grad(set_to_none=True)
+    m.forward_backward(b)
+    g3 = m.flat_grads().clone()
+    rt = m._rt
+    diffs = []
+    for k, off, n in zip(rt["names"], rt["goff"], rt["numel"]):
+        a_, b_ = g2[off:off + n], g3[off:off + n]
+        d = (a_ - b_).norm().item() / max(a_.norm().item(), 1e-12)
+        if d > 0:
+            diffs.append((d, k))
+    diffs.sort(reverse=True)
+    report("run_to_run", (not diffs) or diffs[0][0] < 1e-5, n_differing=len(diffs), worst=diffs[:8])
+    g2 = g3
     # accumulation
     l3 = m.forward_backward(b)
     report("grad_accumulation", rel(m.flat_grads(), 2 * g2) < 1e-3, err=rel(m.flat_grads(), 2 * g2))
