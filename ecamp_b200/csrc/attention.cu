@@ -459,6 +459,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
   }
 }
 
+constexpr int kMaxDynSmem = 226 * 1024;  // 227 KB per CTA minus the kernels' static shared variables
 size_t fwd_smem(int D, int Sk) {
   const int LDS = D + 8, Skp = (Sk + 15) & ~15;
   return (size_t)(64 + 2 * Skp) * LDS * 2 + (size_t)Skp * 4;
@@ -476,7 +477,7 @@ int check_args(const AttnArgs& a, bool bwd) {
   ECAMP_REQUIRE(a.drop.p >= 0.f && a.drop.p < 1.f, "attention: dropout p out of range");
   const size_t sm = bwd ? (bwd_smem(a.D, a.Sk) > bwd_smem(a.D, a.Sq) ? bwd_smem(a.D, a.Sk) : bwd_smem(a.D, a.Sq))
                         : fwd_smem(a.D, a.Sk);
-  ECAMP_REQUIRE(sm <= 227 * 1024, "attention: sequence too long for the single-pass kernel (smem %zu B)", sm);
+  ECAMP_REQUIRE(sm <= (size_t)kMaxDynSmem, "attention: sequence too long for the single-pass kernel (smem %zu B)", sm);
   if (bwd) {
     ECAMP_REQUIRE(a.d_o && a.delta && a.lse && a.dq && a.dk && a.dv, "attention_bwd: missing pointers");
     ECAMP_REQUIRE(a.ld_do % 8 == 0 && a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0,
@@ -488,7 +489,7 @@ int check_args(const AttnArgs& a, bool bwd) {
 template <int D>
 int launch_fwd(const AttnArgs& a, cudaStream_t st) {
   const size_t sm = fwd_smem(D, a.Sk);
-  ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   dim3 grid((a.Sq + 63) / 64, a.H, a.B);
   attn_fwd_kernel<D><<<grid, 128, sm, st>>>(a);
   ECAMP_LAUNCHED();
@@ -497,9 +498,9 @@ int launch_fwd(const AttnArgs& a, cudaStream_t st) {
 template <int D>
 int launch_bwd(const AttnArgs& a, cudaStream_t st) {
   ECAMP_CUDA_OK(
-      cudaFuncSetAttribute(attn_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      cudaFuncSetAttribute(attn_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   ECAMP_CUDA_OK(
-      cudaFuncSetAttribute(attn_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      cudaFuncSetAttribute(attn_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   dim3 gq((a.Sq + 63) / 64, a.H, a.B);
   attn_bwd_kernel<D, false><<<gq, 128, bwd_smem(D, a.Sk), st>>>(a);
   ECAMP_LAUNCHED();

@@ -394,7 +394,7 @@ __global__ void emb_type_finalize_kernel(const float* __restrict__ type_ws, int 
 // ---------------------------------------------------------------------------------------------
 // out[n] = sum_m x[m, n]: CTA = 256 columns x one row chunk; each lane owns 8 consecutive columns (128-bit loads),
 // the 8 warps stride over the rows of the chunk; per-chunk partials are reduced by a second tiny kernel.
-constexpr int kColsumChunks = 64;
+constexpr int kColsumMaxWsFloats = 1 << 22;  // per-chunk partials: chunks * N floats
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int ld, int M, int N,
                                                      float* __restrict__ ws) {
   __shared__ float red[8][256];
@@ -406,8 +406,23 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (col < N) {  // N % 8 == 0 checked on the host
-    for (int r = r0 + warp; r < r1; r += 8) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)r * ld + col);
+    const bf16* base = x + col;
+    int r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {  // four independent 128-bit loads in flight per lane
+      uint4 u[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) u[i] = *reinterpret_cast<const uint4*>(base + (size_t)(r + 8 * i) * ld);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f;
+        f = unpack_bf16x2(u[i].x); acc[0] += f.x; acc[1] += f.y;
+        f = unpack_bf16x2(u[i].y); acc[2] += f.x; acc[3] += f.y;
+        f = unpack_bf16x2(u[i].z); acc[4] += f.x; acc[5] += f.y;
+        f = unpack_bf16x2(u[i].w); acc[6] += f.x; acc[7] += f.y;
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t)r * ld);
       float2 f;
       f = unpack_bf16x2(u.x); acc[0] += f.x; acc[1] += f.y;
       f = unpack_bf16x2(u.y); acc[2] += f.x; acc[3] += f.y;
@@ -426,13 +441,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
     ws[(size_t)blockIdx.y * N + c] = s;
   }
 }
-__global__ void colsum_finalize_kernel(const float* __restrict__ ws, int chunks, int N, float* __restrict__ out,
-                                       int accumulate) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// one CTA per 32 columns; the 8 warps stride over the chunk partials
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ ws, int chunks, int N,
+                                                              float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int c = 0; c < chunks; ++c) s += ws[(size_t)c * N + n];
-  out[n] = accumulate ? out[n] + s : s;
+  if (n < N)
+    for (int c = warp; c < chunks; c += 8) s += ws[(size_t)c * N + n];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += red[w][lane];
+    out[n] = accumulate ? out[n] + s : s;
+  }
 }
 
 __global__ void scale_f32_kernel(float* __restrict__ x, const float* __restrict__ scale, size_t n) {
@@ -584,17 +608,18 @@ int bert_embeddings_bwd(const float* d_pre, const int64_t* ids, const int64_t* t
   LAUNCH_OK();
   return 0;
 }
-size_t colsum_ws_floats(int N) { return (size_t)kColsumChunks * N; }
+size_t colsum_ws_floats(int N) { return (size_t)kColsumMaxWsFloats > (size_t)N ? (size_t)kColsumMaxWsFloats : (size_t)N; }
 int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate, float* ws, cudaStream_t st) {
   ECAMP_REQUIRE(ld % 8 == 0 && N % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
                 "colsum: pitch and width must be multiples of 8 elements, base 16-byte aligned");
-  int chunks = (M + 63) / 64;  // at least 64 rows per chunk
-  if (chunks > kColsumChunks) chunks = kColsumChunks;
+  int chunks = (M + 127) / 128;  // 128 rows per CTA: ~600-1500 CTAs for the shapes of the step
+  if (chunks > 512) chunks = 512;
+  if ((long long)chunks * N > kColsumMaxWsFloats) chunks = kColsumMaxWsFloats / N;
   if (chunks < 1) chunks = 1;
   dim3 grid((N + 255) / 256, chunks);
   colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, ws);
   LAUNCH_OK();
-  colsum_finalize_kernel<<<(N + 255) / 256, 256, 0, st>>>(ws, chunks, N, out, accumulate);
+  colsum_finalize_kernel<<<(N + 31) / 32, 256, 0, st>>>(ws, chunks, N, out, accumulate);
   LAUNCH_OK();
   return 0;
 }
