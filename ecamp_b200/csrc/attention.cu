@@ -51,17 +51,23 @@ ECAMP_DEVINL void load_b_frag_kn(uint32_t (&r)[4], const bf16* tile, int k0, int
   ldsm_x4_t(r, smem_u32(p));
 }
 
-// cooperative copy of `rows` rows (zero-filled from `valid` on) of width D from global (row pitch ld) to smem
+// cooperative asynchronous copy of `rows` rows (zero-filled from `valid` on) of width D from global (row pitch ld)
+// to shared memory: every 16-byte chunk is one cp.async, so all of a thread's loads are in flight at once
+// (a plain load/store loop kept one load in flight per thread and dominated the kernels: long-scoreboard stalls).
 template <int D, int LDS>
 ECAMP_DEVINL void load_tile(bf16* dst, const bf16* src, int ld, int rows, int valid, int tid, int nthreads) {
   constexpr int CPR = D / 8;
   for (int idx = tid; idx < rows * CPR; idx += nthreads) {
     const int r = idx / CPR, c = idx % CPR;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < valid) v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld + c * 8);
-    *reinterpret_cast<uint4*>(dst + (size_t)r * LDS + c * 8) = v;
+    const bool ok = r < valid;
+    const bf16* g = src + (size_t)(ok ? r : 0) * ld + c * 8;
+    const uint32_t sz = ok ? 16u : 0u;  // src-size 0 -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + (size_t)r * LDS + c * 8)), "l"(g),
+                 "r"(sz)
+                 : "memory");
   }
 }
+ECAMP_DEVINL void load_tile_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 ECAMP_DEVINL float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -108,6 +114,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
     sBias[j] = ok ? 0.f : -INFINITY;
     if (ok) atomicMax(&s_kend, j + 1);
   }
+  load_tile_wait();
   __syncthreads();
   const int kend = (s_kend + 15) & ~15;
 
@@ -290,6 +297,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
       sColB[i] = i < Sc ? a.delta[bh * a.Sq + i] : 0.f;
     }
   }
+  load_tile_wait();
   __syncthreads();
   const int cend = TR ? Scp : ((s_cend + 15) & ~15);  // dQ pass: keys after the last attendable one are skipped
 

@@ -58,6 +58,31 @@ ECAMP_DEVINL void bilinear_src(int Y, int& y0, int& y1, float& lam) {
   lam = src - (float)y0;
 }
 
+// 3x3 convolution over the 3 planes of a shared-memory region for a strip of 4 horizontally adjacent outputs:
+// 6 shared loads feed 36 FMAs (weights come from the constant bank).
+//   FLIP = false (forward):    acc[o][p] += w[o][i][ky][kx] * in[i][y0 + ky][x0 + p + kx]
+//   FLIP = true  (transposed): acc[i][p] += w[o][i][ky][kx] * in[o][y0 + 2 - ky][x0 + p + 2 - kx]
+template <int W, int PLANE, bool FLIP>
+ECAMP_DEVINL void conv3_strip4(const float* in, int y0, int x0, const float* wt, float (&acc)[3][4]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const float* r = in + a * PLANE + (y0 + (FLIP ? 2 - ky : ky)) * W + x0;
+      float v[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) v[j] = r[j];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float w = FLIP ? wt[(a * 3 + c) * 9 + ky * 3 + kx] : wt[(c * 3 + a) * 9 + ky * 3 + kx];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[c][q] += w * v[q + (FLIP ? 2 - kx : kx)];
+        }
+    }
+}
+
 // Forward of the SR head on an OUT x OUT output region whose top-left output pixel is (Y0, X0):
 //   sU: (OUT+4)^2 x 3 up-sampled input, origin (Y0-2, X0-2), zero outside the image (conv zero padding)
 //   sH: (OUT+2)^2 x 3 relu(conv1), origin (Y0-1, X0-1), zero outside the image
@@ -87,51 +112,39 @@ ECAMP_DEVINL void sr_forward_region(const float* __restrict__ pred_b, int Y0, in
     sU[2 * UW * UW + i] = v2;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < HW * HW; i += blockDim.x) {
-    const int hy = i / HW, hx = i % HW;
-    const int Y = Y0 - 1 + hy, X = X0 - 1 + hx;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (Y >= 0 && Y < BIG && X >= 0 && X < BIG) {
-      a0 = w.b1[0]; a1 = w.b1[1]; a2 = w.b1[2];
+  constexpr int HS = (HW + 3) / 4;
+  for (int t = threadIdx.x; t < HW * HS; t += blockDim.x) {
+    const int hy = t / HS, hx0 = (t % HS) * 4;
+    float acc[3][4];
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+      for (int q = 0; q < 4; ++q) acc[c][q] = w.b1[c];
+    conv3_strip4<UW, UW * UW, false>(sU, hy, hx0, w.w1, acc);
+    const int Y = Y0 - 1 + hy;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float u = sU[ci * UW * UW + (hy + ky) * UW + hx + kx];
-            a0 += w.w1[(0 * 3 + ci) * 9 + ky * 3 + kx] * u;
-            a1 += w.w1[(1 * 3 + ci) * 9 + ky * 3 + kx] * u;
-            a2 += w.w1[(2 * 3 + ci) * 9 + ky * 3 + kx] * u;
-          }
-      a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f);
+    for (int q = 0; q < 4; ++q) {
+      const int hx = hx0 + q, X = X0 - 1 + hx;
+      if (hx < HW) {
+        const bool in_img = Y >= 0 && Y < BIG && X >= 0 && X < BIG;  // outside: conv2's zero padding
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sH[c * HW * HW + hy * HW + hx] = in_img ? fmaxf(acc[c][q], 0.f) : 0.f;
+      }
     }
-    sH[i] = a0;
-    sH[HW * HW + i] = a1;
-    sH[2 * HW * HW + i] = a2;
   }
   __syncthreads();
 }
 
-// pre-activation output of the head at region pixel (oy, ox): conv2(h1) + b2 + u
+// pre-activation outputs of the head for the strip (oy, ox0 .. ox0+3): conv2(h1) + b2 + u
 template <int OUT>
-ECAMP_DEVINL void sr_out_pixel(const float* sU, const float* sH, int oy, int ox, float (&o)[3]) {
+ECAMP_DEVINL void sr_out_strip(const float* sU, const float* sH, int oy, int ox0, float (&o)[3][4]) {
   const SrWeights& w = c_sr;
   constexpr int UW = OUT + 4, HW = OUT + 2;
-  o[0] = w.b2[0] + sU[(oy + 2) * UW + ox + 2];
-  o[1] = w.b2[1] + sU[UW * UW + (oy + 2) * UW + ox + 2];
-  o[2] = w.b2[2] + sU[2 * UW * UW + (oy + 2) * UW + ox + 2];
 #pragma unroll
-  for (int ci = 0; ci < 3; ++ci)
+  for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float hv = sH[ci * HW * HW + (oy + ky) * HW + ox + kx];
-        o[0] += w.w2[(0 * 3 + ci) * 9 + ky * 3 + kx] * hv;
-        o[1] += w.w2[(1 * 3 + ci) * 9 + ky * 3 + kx] * hv;
-        o[2] += w.w2[(2 * 3 + ci) * 9 + ky * 3 + kx] * hv;
-      }
+    for (int q = 0; q < 4; ++q) o[c][q] = w.b2[c] + sU[c * UW * UW + (oy + 2) * UW + ox0 + q + 2];
+  conv3_strip4<HW, HW * HW, false>(sH, oy, ox0, w.w2, o);
 }
 
 // window of sample b in 32-px tiles: rows [c0, c1), cols [r0, r1) (model_ecamp.py:207-208: slices clip at 14)
@@ -147,8 +160,8 @@ __global__ void __launch_bounds__(256) sr_fwd_kernel(const float* __restrict__ p
                                                      const int64_t* __restrict__ column,
                                                      const int64_t* __restrict__ row, float* __restrict__ ws) {
   constexpr int OUT = 32, UW = OUT + 4, HW = OUT + 2;
-  __shared__ float sU[3 * UW * UW];
-  __shared__ float sH[3 * HW * HW];
+  __shared__ float sU[3 * UW * UW + 8];  // +8: strips may read (and discard) a few floats past a row end
+  __shared__ float sH[3 * HW * HW + 8];
   __shared__ float red[32];
   const int tile = blockIdx.x % (GRID * GRID), b = blockIdx.x / (GRID * GRID);
   const int ty = tile / GRID, tx = tile % GRID;
@@ -162,14 +175,16 @@ __global__ void __launch_bounds__(256) sr_fwd_kernel(const float* __restrict__ p
   const int Y0 = ty * 32, X0 = tx * 32;
   sr_forward_region<OUT>(pred_b, Y0, X0, sU, sH);
   float s = 0.f;
-  for (int i = threadIdx.x; i < OUT * OUT; i += blockDim.x) {
-    const int oy = i / OUT, ox = i % OUT;
-    float o[3];
-    sr_out_pixel<OUT>(sU, sH, oy, ox, o);
+  for (int t = threadIdx.x; t < OUT * (OUT / 4); t += blockDim.x) {
+    const int oy = t / (OUT / 4), ox0 = (t % (OUT / 4)) * 4;
+    float o[3][4];
+    sr_out_strip<OUT>(sU, sH, oy, ox0, o);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float d = fmaxf(o[c], 0.f) - big[(((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox];
-      s += d * d;
+      const float4 tg = *reinterpret_cast<const float4*>(big + (((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox0);
+      const float d0 = fmaxf(o[c][0], 0.f) - tg.x, d1 = fmaxf(o[c][1], 0.f) - tg.y;
+      const float d2 = fmaxf(o[c][2], 0.f) - tg.z, d3 = fmaxf(o[c][3], 0.f) - tg.w;
+      s += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
     }
   }
   s = block_sum(s, red);
@@ -177,7 +192,7 @@ __global__ void __launch_bounds__(256) sr_fwd_kernel(const float* __restrict__ p
 }
 
 // backward: one CTA per 32x32 tile of d_u.  Dynamic smem layout: U 40^2x3 | H 38^2x3 | dOut 36^2x3 | dH 34^2x3
-constexpr int SR_BWD_SMEM_FLOATS = 3 * (40 * 40 + 38 * 38 + 36 * 36 + 34 * 34);
+constexpr int SR_BWD_SMEM_FLOATS = 3 * (40 * 40 + 38 * 38 + 36 * 36 + 34 * 34) + 8;
 __global__ void __launch_bounds__(256) sr_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ big,
                                                      const int64_t* __restrict__ column,
                                                      const int64_t* __restrict__ row, int B,
@@ -214,69 +229,62 @@ __global__ void __launch_bounds__(256) sr_bwd_kernel(const float* __restrict__ p
   const float gscale = 2.0f * (*g_res) / ((float)B * 3.f * BIG * BIG);
 
   // d_out (pre-ReLU) on the 36x36 region with origin (Y0-2, X0-2)
-  for (int i = threadIdx.x; i < OW * OW; i += blockDim.x) {
-    const int oy = i / OW, ox = i % OW;
-    const int Y = Y0 - 2 + oy, X = X0 - 2 + ox;
-    float d[3] = {0.f, 0.f, 0.f};
-    if (Y >= wy0 && Y < wy1 && X >= wx0 && X < wx1) {  // inside the window (hence inside the image)
-      float o[3];
-      sr_out_pixel<OUT>(sU, sH, oy, ox, o);
+  for (int t = threadIdx.x; t < OW * (OW / 4); t += blockDim.x) {
+    const int oy = t / (OW / 4), ox0 = (t % (OW / 4)) * 4;
+    const int Y = Y0 - 2 + oy;
+    float o[3][4];
+    sr_out_strip<OUT>(sU, sH, oy, ox0, o);
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        d[c] = o[c] > 0.f ? gscale * (o[c] - big[(((size_t)b * 3 + c) * BIG + Y) * BIG + X]) : 0.f;
+    for (int q = 0; q < 4; ++q) {
+      const int X = X0 - 2 + ox0 + q;
+      const bool in_win = Y >= wy0 && Y < wy1 && X >= wx0 && X < wx1;  // inside the window (hence inside the image)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float d = 0.f;
+        if (in_win && o[c][q] > 0.f) d = gscale * (o[c][q] - big[(((size_t)b * 3 + c) * BIG + Y) * BIG + X]);
+        sDO[c * OW * OW + oy * OW + ox0 + q] = d;
+      }
     }
-    sDO[i] = d[0];
-    sDO[OW * OW + i] = d[1];
-    sDO[2 * OW * OW + i] = d[2];
   }
   __syncthreads();
-  // d_h1 (pre-ReLU) on the 34x34 region with origin (Y0-1, X0-1)
-  for (int i = threadIdx.x; i < GW * GW; i += blockDim.x) {
-    const int gy = i / GW, gx = i % GW;
-    const int Y = Y0 - 1 + gy, X = X0 - 1 + gx;
-    float d[3] = {0.f, 0.f, 0.f};
-    if (Y >= 0 && Y < BIG && X >= 0 && X < BIG) {
-      // H region coords of (Y, X): (gy + 2, gx + 2); dOut region coords of (Y - ky + 1, X - kx + 1): (gy + 2 - ky, gx + 2 - kx)
+  // d_h1 (pre-ReLU) on the 34x34 region with origin (Y0-1, X0-1):
+  //   dH(Yh, Xh)[ci] = relu'(h1) * sum w2[co][ci][ky][kx] * dOut(Yh - ky + 1, Xh - kx + 1)[co]; region coords of dOut: (gy + 2 - ky, gx + 2 - kx)
+  constexpr int GS = (GW + 3) / 4;
+  for (int t = threadIdx.x; t < GW * GS; t += blockDim.x) {
+    const int gy = t / GS, gx0 = (t % GS) * 4;
+    float d[3][4];
 #pragma unroll
-      for (int co = 0; co < 3; ++co)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+      for (int q = 0; q < 4; ++q) d[c][q] = 0.f;
+    conv3_strip4<OW, OW * OW, true>(sDO, gy, gx0, sw.w2, d);
+    const int Y = Y0 - 1 + gy;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float g = sDO[co * OW * OW + (gy + 2 - ky) * OW + gx + 2 - kx];
-            d[0] += sw.w2[(co * 3 + 0) * 9 + ky * 3 + kx] * g;
-            d[1] += sw.w2[(co * 3 + 1) * 9 + ky * 3 + kx] * g;
-            d[2] += sw.w2[(co * 3 + 2) * 9 + ky * 3 + kx] * g;
-          }
+    for (int q = 0; q < 4; ++q) {
+      const int gx = gx0 + q, X = X0 - 1 + gx;
+      if (gx < GW) {
+        const bool in_img = Y >= 0 && Y < BIG && X >= 0 && X < BIG;
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        if (!(sH[c * HW * HW + (gy + 2) * HW + gx + 2] > 0.f)) d[c] = 0.f;
+        for (int c = 0; c < 3; ++c)
+          sDH[c * GW * GW + gy * GW + gx] = (in_img && sH[c * HW * HW + (gy + 2) * HW + gx + 2] > 0.f) ? d[c][q] : 0.f;
+      }
     }
-    sDH[i] = d[0];
-    sDH[GW * GW + i] = d[1];
-    sDH[2 * GW * GW + i] = d[2];
   }
   __syncthreads();
   // d_u on the owned 32x32 region: skip path + conv1^T
-  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
-    const int oy = i >> 5, ox = i & 31;
-    float d[3];
+  for (int t = threadIdx.x; t < 32 * 8; t += blockDim.x) {
+    const int oy = t >> 3, ox0 = (t & 7) * 4;
+    float d[3][4];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) d[c] = sDO[c * OW * OW + (oy + 2) * OW + ox + 2];
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int co = 0; co < 3; ++co)
+      for (int q = 0; q < 4; ++q) d[c][q] = sDO[c * OW * OW + (oy + 2) * OW + ox0 + q + 2];
+    // dH region coords of (Y - ky + 1, X - kx + 1) with (Y, X) = (Y0 + oy, X0 + ox): (oy + 2 - ky, ox + 2 - kx)
+    conv3_strip4<GW, GW * GW, true>(sDH, oy, ox0, sw.w1, d);
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          // dH region coords of (Y - ky + 1, X - kx + 1) with (Y, X) = (Y0 + oy, X0 + ox): (oy + 2 - ky, ox + 2 - kx)
-          const float g = sDH[co * GW * GW + (oy + 2 - ky) * GW + ox + 2 - kx];
-          d[0] += sw.w1[(co * 3 + 0) * 9 + ky * 3 + kx] * g;
-          d[1] += sw.w1[(co * 3 + 1) * 9 + ky * 3 + kx] * g;
-          d[2] += sw.w1[(co * 3 + 2) * 9 + ky * 3 + kx] * g;
-        }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) d_u[(((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox] = d[c];
+    for (int c = 0; c < 3; ++c)
+      *reinterpret_cast<float4*>(d_u + (((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox0) =
+          make_float4(d[c][0], d[c][1], d[c][2], d[c][3]);
   }
   // conv weight gradients over the OWNED 32x32 pixels only (each pixel is owned by exactly one tile)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
