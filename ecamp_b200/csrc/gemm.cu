@@ -19,6 +19,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -355,6 +356,188 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster own a 256 x BN tile.  Each CTA stages its own
+// 128 rows of A and HALF of the B tile, so per MMA every SM pulls two thirds of the bytes of the 1-CTA kernel through
+// L2 and the shared-memory ring holds 6-8 stages instead of 4-6 (the 1-CTA kernel measured ~43 % tensor-pipe activity,
+// limited by operand delivery).  The leader (even) CTA issues every MMA; TMA completions of both CTAs are credited
+// to the leader's "full" barrier; MMA commits are multicast to both CTAs' "empty" / "accumulator full" barriers; the
+// epilogue warps of both CTAs (each draining its own 128 TMEM lanes) arrive on the leader's "accumulator empty".
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct Cfg2 {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 6 : ((BN == 192) ? 7 : 8);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
+                         int N, int K, EpiArgs ea) {
+  using C = Cfg2<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int HB = BN / 2;  // B rows staged by each CTA
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * C::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair = (int)cluster_id_x();
+  const int num_pairs = (int)(gridDim.x >> 1);
+  const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+  const int num_units = num_tiles * ea.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = pair; unit < num_units; unit += num_pairs) {
+        const int tile = unit % num_tiles, ks = unit / num_tiles;
+        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        const int kb0 = ks * ea.kb_per, kb1 = min(num_kb, kb0 + ea.kb_per);
+        const int m0 = m_blk * 2 * BM + (int)rank * BM;
+        const int n0 = n_blk * BN + (int)rank * HB;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * C::A_BYTES;
+          uint8_t* b_dst = sB + stage * C::B_BYTES;
+          if (!A_MN) {
+            tma_load_2d_2sm(a_dst, &tma_a, &full_bar[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d_2sm(a_dst + j * (BK * 128), &tma_a, &full_bar[stage], m0 + j * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(b_dst, &tma_b, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < HB / 64; ++j)
+              tma_load_2d_2sm(b_dst + j * (BK * 128), &tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int unit = pair; unit < num_units; unit += num_pairs) {
+        const int ks = unit / num_tiles;
+        const int kb0 = ks * ea.kb_per, kb1 = min(num_kb, kb0 + ea.kb_per);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * C::A_BYTES);
+          const uint32_t b_base = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? umma_smem_desc_sw128(a_base + k * 2048, BK * 128, 1024)
+                                        : umma_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_base + k * 2048, BK * 128, 1024)
+                                        : umma_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (kb == kb1 - 1) umma_commit_2sm(&tmem_full[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int q = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
+    constexpr int HALF_N = BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = pair; unit < num_units; unit += num_pairs) {
+      const int tile = unit % num_tiles;
+      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < HALF_N / 32; ++c) {
+        const int tcol = acc * BN + half * HALF_N + c * 32;
+        const int col0 = n_blk * BN + half * HALF_N + c * 32;
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tcol, raw);
+        tmem_ld_wait();
+        if (c == HALF_N / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's MMA warp owns the hand-back
+        }
+        if (row < M && col0 < N) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          if (ea.split_k > 1) epilogue_atomic_row32(ea, v, row, col0, N);
+          else epilogue_row32(ea, v, row, col0, N);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody may exit (or free TMEM) while the peer can still signal / read it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -395,6 +578,13 @@ int make_tmap(CUtensorMap* map, const bf16* ptr, uint64_t inner, uint64_t outer,
   return 0;
 }
 
+// 0 = automatic (CTA pairs whenever the problem has more than one 128-row tile), 1 = single-CTA kernel only,
+// 2 = CTA-pair kernel always.  ECAMP_GEMM_CTA_PAIR overrides the default; ecamp_gemm_set_cta_pair() at run time.
+int g_cta_pair_mode = [] {
+  const char* e = getenv("ECAMP_GEMM_CTA_PAIR");
+  return e ? atoi(e) : 0;
+}();
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -409,9 +599,10 @@ int num_sms() {
 // Tile width and k-split minimising (waves) x (k-blocks per unit + fixed per-unit cost) x (cost per k-block).
 // split_k > 1 is only offered to plain fp32-output GEMMs (the weight gradients), whose output tiles are few
 // (e.g. 768 x 768 -> 18 tiles on 148 SMs) while the contraction (all rows of the batch) is long.
-void pick_config(int M, int N, int K, bool splittable, int force_bn, int* bn_out, int* split_out) {
-  const int sms = num_sms();
-  const int m_tiles = (M + BM - 1) / BM;
+void pick_config(int M, int N, int K, bool splittable, int force_bn, bool cta2, bool b_mn, int* bn_out,
+                 int* split_out) {
+  const int sms = cta2 ? num_sms() / 2 : num_sms();            // schedulable units: CTA pairs or CTAs
+  const int m_tiles = cta2 ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
   const int num_kb = (K + BK - 1) / BK;
   const int cand[3] = {256, 192, 128};
   const float eff[3] = {1.00f, 0.97f, 0.88f};  // smaller tiles put more shared-memory traffic behind each MMA
@@ -422,6 +613,7 @@ void pick_config(int M, int N, int K, bool splittable, int force_bn, int* bn_out
   for (int i = 0; i < 3; ++i) {
     const int bn = cand[i];
     if (force_bn && bn != force_bn) continue;
+    if (cta2 && b_mn && bn == 192) continue;  // each CTA stages BN/2 columns of an MN-major B in 64-wide groups
     const int tiles = m_tiles * ((N + bn - 1) / bn);
     for (int j = 0; j < (splittable ? 9 : 1); ++j) {
       const int sp = splits[j];
@@ -450,6 +642,43 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
   return 0;
 }
 
+template <int BN, bool A_MN, bool B_MN>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
+  auto kfn = gemm_tcgen05_2cta_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int units = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN) * ea.split_k;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = units < max_pairs ? units : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg2<BN>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ECAMP_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, ta, tb, M, N, K, ea));
+  ECAMP_LAUNCHED();
+  return 0;
+}
+
+template <int BN>
+int launch_major2(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+                  const EpiArgs& ea, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2<BN, false, false>(ta, tb, M, N, K, ea, st);
+  if (!a_mn && b_mn) return launch2<BN, false, true>(ta, tb, M, N, K, ea, st);
+  if (a_mn && b_mn) return launch2<BN, true, true>(ta, tb, M, N, K, ea, st);
+  return launch2<BN, true, false>(ta, tb, M, N, K, ea, st);
+}
+
 template <int BN>
 int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                  const EpiArgs& ea, cudaStream_t st) {
@@ -474,7 +703,9 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
   const bool splittable = ep.out_f32 && !ep.out_bf16 && !ep.bias && ep.flags == 0 && !ep.aux_out &&
                           (ep.residual == nullptr || accumulate);
   int bn = 256, split_k = 1;
-  pick_config(M, N, K, splittable, force_bn, &bn, &split_k);
+  const bool cta2 = g_cta_pair_mode == 2 || (g_cta_pair_mode == 0 && M > BM);
+  pick_config(M, N, K, splittable, force_bn, cta2, b_mn != 0, &bn, &split_k);
+  ECAMP_REQUIRE(!(cta2 && b_mn && bn == 192), "gemm: tile N 192 is not available to the CTA-pair kernel with an MN-major B");
 
   CUtensorMap ta, tb;
   int rc;
@@ -484,7 +715,7 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
             : make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM);
   if (rc) return rc;
   rc = b_mn ? make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK)
-            : make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)bn);
+            : make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)(cta2 ? bn / 2 : bn));
   if (rc) return rc;
 
   EpiArgs ea;
@@ -505,12 +736,18 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
   if (ep.out_f32 && (ep.ld_f32 % 4 != 0 || !al16(ep.out_f32))) ea.vec_ok = 0;
   if (ep.out_bf16 && (ep.ld_bf16 % 8 != 0 || !al16(ep.out_bf16))) ea.vec_ok = 0;
 
+  if (cta2) {
+    if (bn == 256) return launch_major2<256>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
+    if (bn == 192) return launch_major2<192>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
+    return launch_major2<128>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
+  }
   if (bn == 256) return launch_major<256>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
   if (bn == 192) return launch_major<192>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
   return launch_major<128>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
+void set_cta_pair_mode(int mode) { g_cta_pair_mode = mode; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }

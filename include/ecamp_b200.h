@@ -72,6 +72,8 @@ typedef struct ecamp_epilogue {
 } ecamp_epilogue;
 /* D[M,N] = epilogue(A . B^T).  a_mn / b_mn = 0: operand stored [rows, contraction] (contraction
  * contiguous); = 1: stored [contraction, rows].  tile_n = 0 lets the library choose. */
+/* 0 = automatic, 1 = single-CTA tcgen05 kernel only, 2 = CTA-pair (cta_group::2) kernel always (testing knob) */
+ECAMP_API void ecamp_gemm_set_cta_pair(int32_t mode);
 ECAMP_API int ecamp_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int32_t ldb, int32_t b_mn,
                               int32_t M, int32_t N, int32_t K, const ecamp_epilogue* ep, int32_t tile_n, void* stream);
 

@@ -11,6 +11,9 @@ from ecamp_b200 import _lib as L
 
 torch.manual_seed(0)
 dev = "cuda"
+MODE = int(sys.argv[1]) if len(sys.argv) > 1 else 0   # 0 auto, 1 single-CTA kernel, 2 CTA-pair kernel
+L.lib().ecamp_gemm_set_cta_pair(MODE)
+print(json.dumps(dict(cta_pair_mode=MODE)), flush=True)
 results = []
 
 
@@ -42,6 +45,10 @@ def run_case(name, M, N, K, a_mn, b_mn, tile_n, **kw):
 
 
 for bn in (128, 192, 256):
+    if MODE == 2 and bn == 192:
+        for (nm, a_, b_) in (("kk", False, False), ("mn_k", True, False)):
+            run_case(nm + "_192_pair", 512, 384, 512, a_, b_, bn)
+        continue
     run_case("kk_single_kblock", 128, bn, 64, False, False, bn)
     run_case("kk_multi_k", 256, 2 * bn, 512, False, False, bn)
     run_case("kk_tails", 200, 300, 136, False, False, bn)
