@@ -580,9 +580,12 @@ int make_tmap(CUtensorMap* map, const bf16* ptr, uint64_t inner, uint64_t outer,
 
 // 0 = automatic (CTA pairs whenever the problem has more than one 128-row tile), 1 = single-CTA kernel only,
 // 2 = CTA-pair kernel always.  ECAMP_GEMM_CTA_PAIR overrides the default; ecamp_gemm_set_cta_pair() at run time.
+// Default 1: measured on B200 (profiles/r01_gemm_pair_vs_single.log) the pair kernel is bit-correct but not faster
+// than the single-CTA kernel on this step's shapes (-3 % .. +1 % at K = 768, +5 % at 8192^3, slower for MN-major B),
+// so operand delivery through L2 is not what limits the single-CTA kernel; it stays selectable for further tuning.
 int g_cta_pair_mode = [] {
   const char* e = getenv("ECAMP_GEMM_CTA_PAIR");
-  return e ? atoi(e) : 0;
+  return e ? atoi(e) : 1;
 }();
 
 int num_sms() {
