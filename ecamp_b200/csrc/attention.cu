@@ -11,6 +11,8 @@
 // "dK/dV" walks query blocks for a key tile (the transposed problem); no atomics, deterministic.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace ecamp {
 namespace {
 
@@ -520,14 +522,27 @@ int launch_bwd(const AttnArgs& a, cudaStream_t st) {
 
 }  // namespace
 
+// tcgen05 kernels (attention_tc.cu)
+bool attention_tc_fwd_supported(const AttnArgs& a);
+bool attention_tc_bwd_supported(const AttnArgs& a);
+int attention_tc_fwd(const AttnArgs& a, cudaStream_t st);
+int attention_tc_bwd(const AttnArgs& a, cudaStream_t st);
+static int g_attn_tc = [] {
+  const char* e = getenv("ECAMP_ATTN_TC");
+  return e ? atoi(e) : 1;
+}();
+void set_attention_tc(int on) { g_attn_tc = on; }
+
 int attention_fwd(const AttnArgs& a, cudaStream_t st) {
   if (int rc = check_args(a, false)) return rc;
+  if (g_attn_tc && attention_tc_fwd_supported(a)) return attention_tc_fwd(a, st);
   if (a.D == 32) return launch_fwd<32>(a, st);
   if (a.D == 64) return launch_fwd<64>(a, st);
   return launch_fwd<128>(a, st);
 }
 int attention_bwd(const AttnArgs& a, cudaStream_t st) {
   if (int rc = check_args(a, true)) return rc;
+  if (g_attn_tc && attention_tc_bwd_supported(a)) return attention_tc_bwd(a, st);
   if (a.D == 32) return launch_bwd<32>(a, st);
   if (a.D == 64) return launch_bwd<64>(a, st);
   return launch_bwd<128>(a, st);

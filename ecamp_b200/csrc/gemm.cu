@@ -693,6 +693,11 @@ int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& t
 
 }  // namespace
 
+int make_tmap_bf16(void* map, const bf16* ptr, unsigned long long inner, unsigned long long outer,
+                   unsigned long long pitch_elems, unsigned box_outer) {
+  return make_tmap(static_cast<CUtensorMap*>(map), ptr, inner, outer, pitch_elems, box_outer);
+}
+
 int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
               const GemmEpilogue& ep, int force_bn, cudaStream_t stream) {
   ECAMP_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem %d x %d x %d", M, N, K);

@@ -35,4 +35,9 @@ struct GemmEpilogue {
 int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
               const GemmEpilogue& ep, int force_bn, cudaStream_t stream);
 
+// 2-D TMA descriptor (128-byte swizzle, box = [box_outer rows, 64 elements]) over a row-major bf16 matrix;
+// `map` points to a CUtensorMap (kept opaque here so that callers need not include <cuda.h>).
+int make_tmap_bf16(void* map, const bf16* ptr, unsigned long long inner, unsigned long long outer,
+                   unsigned long long pitch_elems, unsigned box_outer);
+
 }  // namespace ecamp

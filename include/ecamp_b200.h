@@ -115,6 +115,8 @@ typedef struct ecamp_attn {
   void *dq, *dk, *dv;         /* backward outputs, bf16 */
   int32_t lddq, lddk, lddv;
 } ecamp_attn;
+/* 1 (default): head_dim 64 / 128 problems that fit use the tcgen05 / TMEM kernels; 0: always the mma.sync kernels */
+ECAMP_API void ecamp_attention_set_tcgen05(int32_t on);
 ECAMP_API int ecamp_attention_fwd(const ecamp_attn* a, void* stream);
 ECAMP_API int ecamp_attention_bwd(const ecamp_attn* a, void* stream);
 

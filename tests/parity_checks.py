@@ -147,6 +147,13 @@ def attn_ref(q, k, v, key_mask, scale):
 
 @guard
 def check_attention():
+    for tc in (1, 0):   # 1: tcgen05 / TMEM kernels where the shape fits; 0: mma.sync kernels everywhere
+        lib.ecamp_attention_set_tcgen05(tc)
+        _check_attention("tcgen05" if tc else "mma")
+    lib.ecamp_attention_set_tcgen05(1)
+
+
+def _check_attention(tag):
     for (name, B, H, Sq, Sk, D, masked) in [("enc", 3, 12, 50, 50, 64, False), ("dec", 2, 16, 197, 197, 32, False),
                                             ("bert", 3, 6, 128, 128, 128, True), ("bert256", 2, 6, 256, 256, 128, True),
                                             ("cross", 3, 6, 128, 49, 128, False), ("odd", 2, 6, 37, 49, 128, True)]:
@@ -184,7 +191,7 @@ def check_attention():
         e_q = rel(dq.float(), qr.grad.transpose(1, 2).reshape(B, Sq, H * D))
         e_k = rel(dk.float(), kr.grad.transpose(1, 2).reshape(B, Sk, H * D))
         e_v = rel(dv.float(), vr.grad.transpose(1, 2).reshape(B, Sk, H * D))
-        report(f"attention_{name}", max(e_f, e_q, e_k, e_v) < 2e-2, fwd=e_f, dq=e_q, dk=e_k, dv=e_v)
+        report(f"attention_{name}_{tag}", max(e_f, e_q, e_k, e_v) < 2e-2, fwd=e_f, dq=e_q, dk=e_k, dv=e_v)
     # dropout: statistics + forward/backward consistency through a finite difference on V (linear in V)
     B, H, S, D = 2, 6, 128, 128
     q = torch.randn(B, S, H * D, device=dev).to(torch.bfloat16); k = torch.randn_like(q); v = torch.randn_like(q)
@@ -208,7 +215,7 @@ def check_attention():
     L.check(lib.ecamp_attention_bwd(ctypes.byref(a), L.cur_stream()), "attn_bwd")
     torch.cuda.synchronize()
     lhs = (dv.float() * v.float()).sum().item(); rhs = (do.float() * o1.float()).sum().item()
-    report("attention_dropout", torch.equal(o1, o2) and not torch.equal(o0, o1) and abs(lhs - rhs) < 2e-2 * abs(rhs) + 1.0
+    report(f"attention_dropout_{tag}", torch.equal(o1, o2) and not torch.equal(o0, o1) and abs(lhs - rhs) < 2e-2 * abs(rhs) + 1.0
            and rel(o1.float(), o0.float()) < 0.6, deterministic=bool(torch.equal(o1, o2)), dv_identity=[lhs, rhs],
            drift=rel(o1.float(), o0.float()))
 
