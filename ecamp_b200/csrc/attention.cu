@@ -80,10 +80,11 @@ ECAMP_DEVINL float quad_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-// keep-decision of attention-probability dropout for (query i, key j) of head-instance bh
-ECAMP_DEVINL bool attn_keep(const Philox& ph, uint32_t thr, uint64_t site, uint64_t bh, int Sq, int Sk, int i, int j) {
-  const uint64_t idx = (bh * (uint64_t)Sq + (uint64_t)i) * (uint64_t)Sk + (uint64_t)j;
-  return philox_word(ph, idx, site) >= thr;
+// keep-decision of attention-probability dropout for (query i, key j) of head-instance bh: the same 16-bit-per-
+// element Philox stream as the tcgen05 kernels (attention_tc.cu), so forward and backward may use either family
+ECAMP_DEVINL bool attn_keep(const Philox& ph, uint32_t thr16, uint64_t site, uint64_t bh, int Sq, int Sk, int i, int j) {
+  const uint32_t m = philox_keep8(ph, bh * (uint64_t)Sq + (uint64_t)i, (Sk + 7) >> 3, j >> 3, site, thr16);
+  return (m >> (j & 7)) & 1u;
 }
 
 // =============================================================================================
@@ -130,8 +131,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 
   const Philox ph(a.drop.seed);
-  const uint32_t thr = dropout_threshold(a.drop.p);
-  const float keep_scale = a.drop.p > 0.f ? 1.0f / (1.0f - a.drop.p) : 1.0f;
+  const uint32_t thr = dropout_threshold16(a.drop.p);
+  const float keep_scale = a.drop.p > 0.f ? dropout_keep_scale16(thr) : 1.0f;
   const uint64_t bh = (uint64_t)b * a.H + h;
   const int row_g = q0 + warp * 16 + g;  // this thread's rows: row_g and row_g + 8
 
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
   for (int j = 0; j < (TR ? D / 8 : 1); ++j) acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f;
 
   const Philox ph(a.drop.seed);
-  const uint32_t thr = dropout_threshold(a.drop.p);
-  const float keep_scale = a.drop.p > 0.f ? 1.0f / (1.0f - a.drop.p) : 1.0f;
+  const uint32_t thr = dropout_threshold16(a.drop.p);
+  const float keep_scale = a.drop.p > 0.f ? dropout_keep_scale16(thr) : 1.0f;
 
   // The dQ kernel runs two passes over the key blocks: pass 0 accumulates delta_i = sum_j P_ij dP_ij in fp32 from
   // the SAME P / dP that pass 1 uses for dS = P (dP - delta), so the cancellation inside (dP - delta) is exact

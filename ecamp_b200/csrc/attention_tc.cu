@@ -19,11 +19,6 @@ namespace {
 constexpr int kRows = 128;            // query rows per CTA = TMEM lanes
 constexpr int kAtomBytes = 128 * 128;  // one 64-column atom of a 128-row K-major tile
 
-ECAMP_DEVINL bool tc_keep(const Philox& ph, uint32_t thr, uint64_t site, uint64_t bh, int Sq, int Sk, int i, int j) {
-  const uint64_t idx = (bh * (uint64_t)Sq + (uint64_t)i) * (uint64_t)Sk + (uint64_t)j;
-  return philox_word(ph, idx, site) >= thr;
-}
-
 // store 8 consecutive bf16 (columns c8*8 .. c8*8+7 of row r) into a K-major, 128B-swizzled [128 x ncols] tile
 ECAMP_DEVINL void st_swizzled8(uint8_t* tile, int r, int c8, const float (&v)[8]) {
   const int atom = c8 >> 3, chunk = c8 & 7;
@@ -136,8 +131,10 @@ __global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant_
     }
     const float m_use = (m == -INFINITY) ? 0.f : m;
     const Philox ph(a.drop.seed);
-    const uint32_t thr = dropout_threshold(a.drop.p);
-    const float keep_scale = a.drop.p > 0.f ? 1.0f / (1.0f - a.drop.p) : 1.0f;
+    const uint32_t thr = dropout_threshold16(a.drop.p);
+    const float keep_scale = dropout_keep_scale16(thr);
+    const bool use_drop = a.drop.p > 0.f;
+    const int kgroups = (a.Sk + 7) >> 3;
     float l = 0.f;
     for (int c = 0; c < nchunk; ++c) {
       uint32_t raw[32];
@@ -148,13 +145,13 @@ __global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant_
         const int col0 = c * 32 + g8 * 8;
         if (col0 < Skp) {
           float pv[8];
+          const uint32_t keep = use_drop ? philox_keep8(ph, bh * a.Sq + qi, kgroups, col0 >> 3, a.drop.site, thr) : 0xFFu;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int col = col0 + i;
-            float p = exp2f(__uint_as_float(raw[g8 * 8 + i]) * sl2 + sBias[col] - m_use);
+            const float p = exp2f(__uint_as_float(raw[g8 * 8 + i]) * sl2 + sBias[col] - m_use);
             l += p;
-            if (a.drop.p > 0.f) p = tc_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, qi, col) ? p * keep_scale : 0.f;
-            pv[i] = p;
+            pv[i] = ((keep >> i) & 1u) ? (use_drop ? p * keep_scale : p) : 0.f;
           }
           st_swizzled8(sP, r, col0 >> 3, pv);
         }
@@ -296,8 +293,10 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
     const bool qvalid = r < a.Sq;
     const float lse = qvalid ? a.lse[bh * a.Sq + r] : INFINITY;  // +inf -> P = 0 for padded query rows
     const Philox ph(a.drop.seed);
-    const uint32_t thr = dropout_threshold(a.drop.p);
-    const float keep_scale = a.drop.p > 0.f ? 1.0f / (1.0f - a.drop.p) : 1.0f;
+    const uint32_t thr = dropout_threshold16(a.drop.p);
+    const bool use_drop = a.drop.p > 0.f;
+    const float keep_scale = use_drop ? dropout_keep_scale16(thr) : 1.0f;
+    const int kgroups = (a.Sk + 7) >> 3;
     mbar_wait(bar_s, 0);
     tc_fence_after();
     // pass 1: delta = sum_j P_ij dPeff_ij (exact fp32, same P / dP as pass 2)
@@ -309,12 +308,15 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
       tmem_ld_32x32(tdP + lane_base + c * 32, rp);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int col = c * 32 + i;
-        const float p = __expf(__uint_as_float(rs[i]) * a.scale + sBias[col] - lse);
-        float dpe = __uint_as_float(rp[i]);
-        if (a.drop.p > 0.f) dpe = tc_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, r, col) ? dpe * keep_scale : 0.f;
-        delta += p * dpe;
+      for (int g8 = 0; g8 < 4; ++g8) {
+        const uint32_t keep = use_drop ? philox_keep8(ph, bh * a.Sq + r, kgroups, c * 4 + g8, a.drop.site, thr) : 0xFFu;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int col = c * 32 + g8 * 8 + i;
+          const float p = __expf(__uint_as_float(rs[g8 * 8 + i]) * a.scale + sBias[col] - lse);
+          const float dpe = ((keep >> i) & 1u) ? __uint_as_float(rp[g8 * 8 + i]) * keep_scale : 0.f;
+          delta += p * dpe;
+        }
       }
     }
     if (qvalid && a.delta) a.delta[bh * a.Sq + r] = delta;
@@ -328,18 +330,14 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {
         float pv[8], dv[8];
+        const uint32_t keep = use_drop ? philox_keep8(ph, bh * a.Sq + r, kgroups, c * 4 + g8, a.drop.site, thr) : 0xFFu;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int col = c * 32 + g8 * 8 + i;
           const float p = __expf(__uint_as_float(rs[g8 * 8 + i]) * a.scale + sBias[col] - lse);
-          float dpe = __uint_as_float(rp[g8 * 8 + i]);
-          float pd = p;
-          if (a.drop.p > 0.f) {
-            const bool keep = tc_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, r, col);
-            dpe = keep ? dpe * keep_scale : 0.f;
-            pd = keep ? p * keep_scale : 0.f;
-          }
-          pv[i] = pd;
+          const bool kp = (keep >> i) & 1u;
+          const float dpe = kp ? __uint_as_float(rp[g8 * 8 + i]) * keep_scale : 0.f;
+          pv[i] = kp ? p * keep_scale : 0.f;
           dv[i] = p * (dpe - delta) * a.scale;
         }
         st_swizzled8(sP, r, c * 4 + g8, pv);

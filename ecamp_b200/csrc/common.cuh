@@ -301,6 +301,26 @@ ECAMP_DEVINL uint32_t philox_word(const Philox& ph, uint64_t idx, uint64_t strea
   return w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w));
 }
 
+// Attention-probability dropout draws 16 bits per element: one Philox call decides 8 consecutive keys of one query
+// (per-element calls made the attention kernels RNG-bound).  p is quantised to thr16 / 65536.
+ECAMP_DEVINL uint32_t dropout_threshold16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+ECAMP_DEVINL float dropout_keep_scale16(uint32_t thr16) { return 65536.0f / (65536.0f - (float)thr16); }
+// bit k of the result = keep element 8 * group + k of row `row_id` (row_id enumerates (batch, head, query))
+ECAMP_DEVINL uint32_t philox_keep8(const Philox& ph, uint64_t row_id, int groups_per_row, int group, uint64_t site,
+                                   uint32_t thr16) {
+  const uint4 r = ph(row_id * (uint64_t)groups_per_row + (uint64_t)group, site);
+  uint32_t m = 0;
+  m |= ((r.x & 0xFFFFu) >= thr16) ? 1u : 0u;
+  m |= ((r.x >> 16) >= thr16) ? 2u : 0u;
+  m |= ((r.y & 0xFFFFu) >= thr16) ? 4u : 0u;
+  m |= ((r.y >> 16) >= thr16) ? 8u : 0u;
+  m |= ((r.z & 0xFFFFu) >= thr16) ? 16u : 0u;
+  m |= ((r.z >> 16) >= thr16) ? 32u : 0u;
+  m |= ((r.w & 0xFFFFu) >= thr16) ? 64u : 0u;
+  m |= ((r.w >> 16) >= thr16) ? 128u : 0u;
+  return m;
+}
+
 // ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------
