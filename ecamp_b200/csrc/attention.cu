@@ -90,7 +90,7 @@ ECAMP_DEVINL bool attn_keep(const Philox& ph, uint32_t thr16, uint64_t site, uin
 // =============================================================================================
 // forward
 // =============================================================================================
-template <int D>
+template <int D, bool DROP>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
   constexpr int LDS = D + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
       for (int e = 0; e < 4; ++e) {
         float p = __expf(s[j][e] - m_use[e >> 1]);
         l_run[e >> 1] += p;
-        if (a.drop.p > 0.f) {
+        if (DROP) {
           const int col = kb + j * 8 + t4 * 2 + (e & 1);
           const int row = row_g + (e >> 1) * 8;
           p = attn_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, row, col) ? p * keep_scale : 0.f;
@@ -250,7 +250,7 @@ __global__ void attn_delta_kernel(AttnArgs a) {
 //            TR = true : rows = keys    (R1 = K, R2 = V),  columns = queries (C1 = Q, C2 = dO);
 //                        out1 = dK = dS^T Q, out2 = dV = Pdrop^T dO.
 // =============================================================================================
-template <int D, bool TR>
+template <int D, bool TR, bool DROP>
 __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
   constexpr int LDS = D + 8;
   constexpr int CB = TR ? 32 : 64;  // column block
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
         float p = __expf(s[j][e] * a.scale + bias - lse);  // masked / padded -> exp(-inf) = 0
         float dpe = dp[j][e];
         float pd = p;
-        if (a.drop.p > 0.f) {
+        if (DROP) {
           const int row = row_g + r * 8;
           const int qi = TR ? col : row, kj = TR ? row : col;
           const bool keep = attn_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, qi, kj);
@@ -500,24 +500,36 @@ int check_args(const AttnArgs& a, bool bwd) {
 template <int D>
 int launch_fwd(const AttnArgs& a, cudaStream_t st) {
   const size_t sm = fwd_smem(D, a.Sk);
-  ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   dim3 grid((a.Sq + 63) / 64, a.H, a.B);
-  attn_fwd_kernel<D><<<grid, 128, sm, st>>>(a);
+  if (a.drop.p > 0.f) {
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    attn_fwd_kernel<D, true><<<grid, 128, sm, st>>>(a);
+  } else {
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    attn_fwd_kernel<D, false><<<grid, 128, sm, st>>>(a);
+  }
   ECAMP_LAUNCHED();
   return 0;
 }
 template <int D>
 int launch_bwd(const AttnArgs& a, cudaStream_t st) {
-  ECAMP_CUDA_OK(
-      cudaFuncSetAttribute(attn_bwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  ECAMP_CUDA_OK(
-      cudaFuncSetAttribute(attn_bwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   dim3 gq((a.Sq + 63) / 64, a.H, a.B);
-  attn_bwd_kernel<D, false><<<gq, 128, bwd_smem(D, a.Sk), st>>>(a);
-  ECAMP_LAUNCHED();
   dim3 gk((a.Sk + 63) / 64, a.H, a.B);
-  attn_bwd_kernel<D, true><<<gk, 128, bwd_smem(D, a.Sq), st>>>(a);
-  ECAMP_LAUNCHED();
+  if (a.drop.p > 0.f) {
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    attn_bwd_kernel<D, false, true><<<gq, 128, bwd_smem(D, a.Sk), st>>>(a);
+    ECAMP_LAUNCHED();
+    attn_bwd_kernel<D, true, true><<<gk, 128, bwd_smem(D, a.Sq), st>>>(a);
+    ECAMP_LAUNCHED();
+  } else {
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<D, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    attn_bwd_kernel<D, false, false><<<gq, 128, bwd_smem(D, a.Sk), st>>>(a);
+    ECAMP_LAUNCHED();
+    attn_bwd_kernel<D, true, false><<<gk, 128, bwd_smem(D, a.Sq), st>>>(a);
+    ECAMP_LAUNCHED();
+  }
   return 0;
 }
 

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant_
 // backward (Sq <= 128, Sk <= 128): one CTA per (batch, head) produces dQ, dK and dV
 // =============================================================================================
 template <int D>
-__global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant__ TcMaps maps, AttnArgs a) {
+__global__ void __launch_bounds__(288) attn_tc_bwd_kernel(const __grid_constant__ TcMaps maps, AttnArgs a) {
   constexpr int ATOMS = D / 64;
   constexpr int TILE = ATOMS * kAtomBytes;  // a [128 x D] bf16 tile
   extern __shared__ uint8_t smem_raw[];
@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
   uint8_t* sP = sV + TILE;                  // [128 q x 128 keys] bf16 = 2 atoms (dropped probabilities)
   uint8_t* sdS = sP + 2 * kAtomBytes;       // [128 q x 128 keys] bf16
   float* sBias = reinterpret_cast<float*>(sdS + 2 * kAtomBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 128);
+  float* sDelta = sBias + 128;  // [2][128] partial row sums of the two column halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
   uint64_t *bar_ld = bars, *bar_s = bars + 1, *bar_p = bars + 2, *bar_g = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
@@ -217,10 +218,10 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
   const uint64_t bh = (uint64_t)b * a.H + h;
 
   if (tid == 0) {
-    mbar_init(bar_ld, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_g, 1);
+    mbar_init(bar_ld, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_g, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tdP = tmem + 128, tdK = tmem + 256;  // dQ re-uses tS, dV re-uses tdP
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_ld, 4u * TILE);
 #pragma unroll
@@ -288,8 +289,10 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
       umma_commit(bar_g);
     }
   } else {
-    const int r = tid;  // query row for the softmax part, key row for the dK / dV epilogue
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    // 8 warps: warp w serves TMEM lane quarter (w & 3) and column half (w >> 2), i.e. two threads share a row
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;  // query row for the softmax part, key row for the dK / dV epilogue
+    const uint32_t lane_base = ((uint32_t)(quarter * 32)) << 16;
     const bool qvalid = r < a.Sq;
     const float lse = qvalid ? a.lse[bh * a.Sq + r] : INFINITY;  // +inf -> P = 0 for padded query rows
     const Philox ph(a.drop.seed);
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
     // pass 1: delta = sum_j P_ij dPeff_ij (exact fp32, same P / dP as pass 2)
     float delta = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 2 * half; c < 2 * half + 2; ++c) {
       uint32_t rs[32], rp[32];
       tmem_ld_32x32(tS + lane_base + c * 32, rs);
       tmem_ld_32x32(tdP + lane_base + c * 32, rp);
@@ -319,10 +322,13 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
         }
       }
     }
-    if (qvalid && a.delta) a.delta[bh * a.Sq + r] = delta;
+    sDelta[half * 128 + r] = delta;
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 256 softmax threads only
+    delta = sDelta[r] + sDelta[128 + r];
+    if (half == 0 && qvalid && a.delta) a.delta[bh * a.Sq + r] = delta;
     // pass 2: Pdrop and dS = P (dPeff - delta) scale -> shared memory (bf16, swizzled K-major [q, key])
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 2 * half; c < 2 * half + 2; ++c) {
       uint32_t rs[32], rp[32];
       tmem_ld_32x32(tS + lane_base + c * 32, rs);
       tmem_ld_32x32(tdP + lane_base + c * 32, rp);
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
       bf16* base = which == 0 ? a.dq + ((size_t)b * a.Sq + r) * a.lddq
                               : (which == 1 ? a.dk + ((size_t)b * a.Sk + r) * a.lddk : a.dv + ((size_t)b * a.Sk + r) * a.lddv);
 #pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {
         uint32_t raw[32];
         tmem_ld_32x32(tsrc + lane_base + c * 32, raw);
         tmem_ld_wait();
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(160) attn_tc_bwd_kernel(const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -425,14 +431,14 @@ int launch_tc_bwd(const AttnArgs& a, cudaStream_t st) {
   TcMaps maps;
   if (int rc = build_maps(a, true, kRows, &maps)) return rc;
   constexpr int ATOMS = D / 64;
-  const size_t smem = 4 * (size_t)ATOMS * kAtomBytes + 4 * (size_t)kAtomBytes + 128 * 4 + 64 + 1024;
+  const size_t smem = 4 * (size_t)ATOMS * kAtomBytes + 4 * (size_t)kAtomBytes + 384 * 4 + 64 + 1024;
   static bool attr = false;
   if (!attr) {
     ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr = true;
   }
   dim3 grid(a.H, a.B);
-  attn_tc_bwd_kernel<D><<<grid, 160, smem, st>>>(maps, a);
+  attn_tc_bwd_kernel<D><<<grid, 288, smem, st>>>(maps, a);
   ECAMP_LAUNCHED();
   return 0;
 }
@@ -453,6 +459,8 @@ bool attention_tc_fwd_supported(const AttnArgs& a) {
 }
 bool attention_tc_bwd_supported(const AttnArgs& a) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  // the ViT encoder (50 x 50, head_dim 64) wastes most of a 128 x 128 tile: measured slower than the mma.sync kernels
+  if (a.D == 64 && a.Sq <= 64 && a.Sk <= 64) return false;
   return tc_layout_ok(a) && a.Sq <= 128 && a.Sk <= 128 && a.ld_do % 8 == 0 && a.lddq % 8 == 0 && a.lddk % 8 == 0 &&
          a.lddv % 8 == 0 && al(a.d_o) && al(a.dq) && al(a.dk) && al(a.dv);
 }
