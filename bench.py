@@ -92,6 +92,7 @@ def gemm_roofline(B, T, peak_tflops):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tot_flops = tot_ms = 0.0
     launches = 0
+    per_shape = []
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed(fn, reps=3):
@@ -120,11 +121,13 @@ def gemm_roofline(B, T, peak_tflops):
         tot_flops += 3 * fl * scale * count
         tot_ms += (t_f + t_d + t_w) * scale * count
         launches += 3 * count * int(round(scale))
+        per_shape.append(dict(rows=rows, out=n_out, inp=n_in, count=count, fwd_tflops=round(fl / t_f / 1e9, 0),
+                              dgrad_tflops=round(fl / t_d / 1e9, 0), wgrad_tflops=round(fl / t_w / 1e9, 0)))
         del x, w, dy, y, dx, dw
     achieved = tot_flops / (tot_ms * 1e-3) / 1e12
     return dict(bound="tensor", achieved=round(achieved, 1), peak=peak_tflops, unit="TFLOP/s", frac=round(achieved / peak_tflops, 4),
                 traffic=None, kernel="gemm_tcgen05_kernel (all Linear fwd/dgrad/wgrad launches of one step)",
-                flops_per_step=tot_flops, gemm_ms_per_step=round(tot_ms, 3), launches_per_step=launches)
+                flops_per_step=tot_flops, gemm_ms_per_step=round(tot_ms, 3), launches_per_step=launches, shapes=per_shape)
 
 
 def cpu_baseline(T):
