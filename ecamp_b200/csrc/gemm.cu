@@ -39,7 +39,7 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 192) ? 5 : 6);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 2048 /*bias x2*/ + 1024 /*alignment slack*/;
 };
 
 struct EpiArgs {
@@ -69,12 +69,21 @@ ECAMP_DEVINL void epilogue_atomic_row32(const EpiArgs& ea, const float (&v)[32],
 // ---------------------------------------------------------------------------------------------
 // epilogue for one thread: one output row, 32 consecutive columns
 // ---------------------------------------------------------------------------------------------
-ECAMP_DEVINL void epilogue_row32(const EpiArgs& ea, float (&v)[32], int row, int col0, int N) {
+// `sbias` (optional): this tile's bias staged in shared memory, pointing at column col0; `pre_res` (optional): the
+// residual of this row / chunk already fetched into registers (both hide global-load latency from the epilogue).
+ECAMP_DEVINL void epilogue_row32(const EpiArgs& ea, float (&v)[32], int row, int col0, int N,
+                                 const float* sbias = nullptr, const float4* pre_res = nullptr) {
   const GemmEpilogue& ep = ea.ep;
   const bool full = ea.vec_ok && (col0 + 32 <= N);
   const int nvalid = min(32, N - col0);
 
-  if (ep.bias) {
+  if (ep.bias && sbias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = reinterpret_cast<const float4*>(sbias)[i];
+      v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+  } else if (ep.bias) {
     if (full) {
       const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
@@ -144,7 +153,12 @@ ECAMP_DEVINL void epilogue_row32(const EpiArgs& ea, float (&v)[32], int row, int
       v[4 * i + 3] = (r.w >= thr) ? v[4 * i + 3] * scale : 0.f;
     }
   }
-  if (ep.residual) {
+  if (ep.residual && pre_res && full) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[4 * i + 0] += pre_res[i].x; v[4 * i + 1] += pre_res[i].y; v[4 * i + 2] += pre_res[i].z; v[4 * i + 3] += pre_res[i].w;
+    }
+  } else if (ep.residual) {
     const float* rp = ep.residual + (size_t)row * ep.ld_res + col0;
     if (full) {
 #pragma unroll
@@ -206,6 +220,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256);  // [2][256], one per accumulator stage
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -319,15 +334,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int tile = unit % num_tiles;
       const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool plain = ea.split_k == 1;
+      // stage this tile's bias in shared memory while the accumulator is still being produced
+      float* sb = s_bias + acc * 256;
+      if (plain && ea.ep.bias) {
+        const int t = threadIdx.x - kEpiWarp0 * 32;
+        const int col = n_blk * BN + t;
+        if (t < BN) sb[t] = col < N ? __ldg(ea.ep.bias + col) : 0.f;
+      }
+      // residual of the first chunk, fetched before waiting for the accumulator
+      const bool pre = plain && ea.ep.residual != nullptr && ea.vec_ok && row < M;
+      float4 rcur[8];
+      if (pre) {
+        const int col0 = n_blk * BN + half * HALF_N;
+        if (col0 + 32 <= N) {
+          const float4* rp = reinterpret_cast<const float4*>(ea.ep.residual + (size_t)row * ea.ep.ld_res + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rcur[i] = rp[i];
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only: s_bias[acc] is complete
 #pragma unroll 1
       for (int c = 0; c < HALF_N / 32; ++c) {
         const int tcol = acc * BN + half * HALF_N + c * 32;
         const int col0 = n_blk * BN + half * HALF_N + c * 32;
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tcol, raw);
+        float4 rnext[8];
+        if (pre && c + 1 < HALF_N / 32 && col0 + 64 <= N) {  // next chunk's residual in flight during this chunk
+          const float4* rp = reinterpret_cast<const float4*>(ea.ep.residual + (size_t)row * ea.ep.ld_res + col0 + 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rnext[i] = rp[i];
+        }
         tmem_ld_wait();
         if (c == HALF_N / 32 - 1) {
           // all of this warp's TMEM reads for the tile are done: hand the accumulator stage back
@@ -339,9 +380,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          if (ea.split_k > 1) epilogue_atomic_row32(ea, v, row, col0, N);
-          else epilogue_row32(ea, v, row, col0, N);
+          if (!plain) epilogue_atomic_row32(ea, v, row, col0, N);
+          else epilogue_row32(ea, v, row, col0, N, ea.ep.bias ? sb + half * HALF_N + c * 32 : nullptr, pre ? rcur : nullptr);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
