@@ -167,7 +167,7 @@ ECAMP_DEVINL void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
       "{\n"
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
@@ -246,29 +246,50 @@ ECAMP_DEVINL bool elect_one() {
 // ---------------------------------------------------------------------------------------------
 // math
 // ---------------------------------------------------------------------------------------------
-// Exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.26 rational form of erf (|error| <= 1.5e-7, far below the
-// bf16 rounding of the stored result): one ex2 + one rcp + 7 FMAs instead of the ~40-instruction erff, because the
-// fused GEMM epilogues (bias -> GELU, dGELU) were issue-bound on it.  e = exp(-x^2 / 2) is shared between the erf
-// tail and the normal pdf of the derivative.
-ECAMP_DEVINL float erf_tail_poly(float z /* >= 0 */) {
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  return p * t;  // erf(z) = 1 - this * exp(-z^2)
+// Exact-erf GELU, x * Phi(x), with Phi evaluated as a logistic function of an odd polynomial:
+//   Phi(x) = 1 / (1 + exp(-2 u(x))),  u(x) = x (c1 + c3 x^2 + c5 x^4 + c7 x^6),  |x| clamped to 6,
+// the form tanh-GELU uses, but with the polynomial re-fitted (two more terms) to the normal CDF itself:
+// |Phi error| <= 7e-6, |GELU error| <= 2.5e-5, |GELU' error| <= 6e-5 over all x (checked in float32 against
+// scipy's erf) - far below the bf16 rounding of the stored activation.  Cost: 2 MUFU (ex2, rcp) + 7 FMA-pipe
+// instructions; the fused GEMM epilogues were bound by the ~25 instructions of the erf form they replaced
+// (measured: fc1 forward 663 -> 1112 TFLOP/s with the epilogue math removed).
+ECAMP_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-ECAMP_DEVINL float gelu_erf(float x) {
-  const float e = exp2f(-0.72134752044448170f * x * x);  // exp(-x^2 / 2)
-  const float tail = erf_tail_poly(fabsf(x) * 0.70710678118654752f) * e;
-  const float cdf = x >= 0.f ? 1.0f - 0.5f * tail : 0.5f * tail;  // Phi(x)
-  return x * cdf;
+ECAMP_DEVINL float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+// coefficients of -2 log2(e) u(x) / x
+#define ECAMP_PHI_K1 (-2.3020227f)     // -2 log2(e) * 0.7978202620075527
+#define ECAMP_PHI_K3 (-0.10545136f)    // -2 log2(e) * 0.03654665804906016
+#define ECAMP_PHI_K5 (5.6107155e-4f)   // -2 log2(e) * -1.9445258094679608e-4
+#define ECAMP_PHI_K7 (3.9495544e-5f)   // -2 log2(e) * -1.3688112480251091e-5
+ECAMP_DEVINL float normal_cdf(float x) {
+  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
+  const float t = xc * xc;
+  float p = fmaf(ECAMP_PHI_K7, t, ECAMP_PHI_K5);
+  p = fmaf(p, t, ECAMP_PHI_K3);
+  p = fmaf(p, t, ECAMP_PHI_K1);
+  return rcp_approx(1.0f + ex2_approx(xc * p));
+}
+ECAMP_DEVINL float gelu_erf(float x) { return x * normal_cdf(x); }
+// d/dx [x Phi(x)] = Phi + x Phi', with Phi' taken from the same approximation: Phi (1 - Phi) 2 u'(x)
 ECAMP_DEVINL float gelu_erf_grad(float x) {
-  const float e = exp2f(-0.72134752044448170f * x * x);
-  const float tail = erf_tail_poly(fabsf(x) * 0.70710678118654752f) * e;
-  const float cdf = x >= 0.f ? 1.0f - 0.5f * tail : 0.5f * tail;
-  return fmaf(x * 0.3989422804014327f, e, cdf);
+  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
+  const float t = xc * xc;
+  float p = fmaf(ECAMP_PHI_K7, t, ECAMP_PHI_K5);
+  p = fmaf(p, t, ECAMP_PHI_K3);
+  p = fmaf(p, t, ECAMP_PHI_K1);
+  const float s = rcp_approx(1.0f + ex2_approx(xc * p));
+  // 2 u'(x) = 2 (c1 + 3 c3 t + 5 c5 t^2 + 7 c7 t^3)
+  float d = fmaf(-1.9163357e-4f, t, -1.9445258e-3f);
+  d = fmaf(d, t, 0.21927995f);
+  d = fmaf(d, t, 1.5956405f);
+  return fmaf(x * d, fmaf(-s, s, s), s);
 }
 
 // Philox4x32-10: counter-based, so forward and backward regenerate identical dropout masks from

@@ -29,8 +29,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span
-constexpr int kThreads = 384;
-constexpr int kEpiWarp0 = 4;
+constexpr int kThreads = 352;  // 11 warps: 65536 / 352 leaves 184 registers per thread for the epilogue
+constexpr int kEpiWarp0 = 3;
 constexpr int kNumEpiWarps = 8;
 
 template <int BN>
@@ -38,168 +38,323 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 192) ? 5 : 6);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 2048 /*bias x2*/ + 1024 /*alignment slack*/;
+  static constexpr int STAGES = (BN == 128) ? 6 : 4;
+  static constexpr int EPI_BYTES = kNumEpiWarps * 4096;  // one 32 x 32 fp32 transpose tile per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget of one CTA exceeded");
 };
 
 struct EpiArgs {
   GemmEpilogue ep;
   int vec_ok;
+  int mode;     // EpiMode
   int split_k;  // > 1: the contraction is split over `split_k` work units per tile, partials added with fp32 atomics
   int kb_per;   // k-blocks per split
+  int dbg;      // development: 1 = the epilogue only drains TMEM (no transpose / math / stores)
 };
 
-// split-K epilogue: out_f32[row, col0..col0+31] += v (the buffer was zeroed, or holds the running gradient)
-ECAMP_DEVINL void epilogue_atomic_row32(const EpiArgs& ea, const float (&v)[32], int row, int col0, int N) {
-  float* op = ea.ep.out_f32 + (size_t)row * ea.ep.ld_f32 + col0;
-  const int nvalid = min(32, N - col0);
-  if (ea.vec_ok && nvalid == 32) {
+// ---------------------------------------------------------------------------------------------
+// epilogue.  The accumulator arrives from TMEM with one ROW per thread (tcgen05.ld 32x32b); writing global memory in
+// that layout touches 32 different 128-byte lines per warp instruction, and the LSU wavefront rate (one line per
+// ~2 cycles) then bounds the whole GEMM (measured: 550-750 TFLOP/s on the fp32-residual shapes).  Each epilogue warp
+// therefore transposes its 32 x 32 chunk through a private 4 KB swizzled shared-memory tile and works in the
+// COALESCED layout: in step i (0..7) lane l owns row 4 i + l / 8, columns 4 (l % 8) .. +3, so a warp instruction
+// covers 4 rows x 128 contiguous bytes (fp32) or 4 x 64 bytes (bf16).
+// ---------------------------------------------------------------------------------------------
+// The epilogue is specialised (inside one kernel, selected once per tile) for the operator combinations the step
+// uses; anything else takes the generic path, which tests every flag per element group.  With only two epilogue
+// warps per scheduler the per-element branches of the generic path are latency, not throughput, so they matter.
+enum EpiMode : int {
+  EM_GENERIC = 0,
+  EM_BF16,          // (+bias) -> bf16
+  EM_GELU,          // +bias -> bf16 pre-activation to aux_out -> GELU -> bf16
+  EM_DGELU,         // * GELU'(aux_in) -> bf16
+  EM_F32,           // (+bias) -> fp32
+  EM_F32_RES,       // (+bias) + fp32 residual -> fp32
+  EM_F32_RES_DROP,  // (+bias) -> dropout -> + fp32 residual -> fp32
+  EM_ATOMIC,        // split-K partial: fp32 vector reduction into out_f32
+};
+
+// scalar fall-back for one element (unaligned operands or a column tail that is not a multiple of 4)
+ECAMP_DEVINL void epi_scalar(const EpiArgs& ea, float v, int row, int col, int N) {
+  const GemmEpilogue& ep = ea.ep;
+  if (ea.split_k != 1) { atomicAdd(ep.out_f32 + (size_t)row * ep.ld_f32 + col, v); return; }
+  if (ep.bias) v += __ldg(ep.bias + col);
+  if (ep.flags & GEMM_GELU) {
+    v = bf2f(f2bf(v));
+    if (ep.aux_out) ep.aux_out[(size_t)row * ep.ld_aux + col] = f2bf(v);
+    v = gelu_erf(v);
+  }
+  if (ep.flags & GEMM_DGELU) v *= gelu_erf_grad(bf2f(ep.aux_in[(size_t)row * ep.ld_aux + col]));
+  if (ep.flags & GEMM_DROPOUT) {
+    const Philox ph(ep.seed);
+    const uint32_t w = philox_word(ph, (uint64_t)row * (uint64_t)N + (uint64_t)col, ep.stream);
+    v = (w >= dropout_threshold(ep.drop_p)) ? v * (1.0f / (1.0f - ep.drop_p)) : 0.f;
+  }
+  if (ep.residual) v += ep.residual[(size_t)row * ep.ld_res + col];
+  if (ep.out_f32) ep.out_f32[(size_t)row * ep.ld_f32 + col] = v;
+  if (ep.out_bf16) ep.out_bf16[(size_t)row * ep.ld_bf16 + col] = f2bf(v);
+}
+
+ECAMP_DEVINL float4 dropout4(const GemmEpilogue& ep, float4 v, int row, int col, int N) {
+  const Philox ph(ep.seed);
+  const uint32_t thr = dropout_threshold(ep.drop_p);
+  const float scale = 1.0f / (1.0f - ep.drop_p);
+  const uint64_t base = (uint64_t)row * (uint64_t)N + (uint64_t)col;  // N % 4 == 0 checked on the host
+  const uint4 r = ph(base >> 2, ep.stream);
+  v.x = (r.x >= thr) ? v.x * scale : 0.f;
+  v.y = (r.y >= thr) ? v.y * scale : 0.f;
+  v.z = (r.z >= thr) ? v.z * scale : 0.f;
+  v.w = (r.w >= thr) ? v.w * scale : 0.f;
+  return v;
+}
+ECAMP_DEVINL uint2 pack4(const float4& v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+  return u;
+}
+
+// generic: one thread, 4 consecutive columns of one row, every operator tested at run time
+ECAMP_DEVINL void epi_vec4_generic(const EpiArgs& ea, float4 v, int row, int col, int N, const float4& bias4) {
+  const GemmEpilogue& ep = ea.ep;
+  if (!ea.vec_ok || col + 4 > N) {
+    const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
-                   "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
-                   : "memory");
-  } else {
+    for (int j = 0; j < 4; ++j)
+      if (col + j < N) epi_scalar(ea, e[j], row, col + j, N);
+    return;
+  }
+  if (ea.split_k != 1) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ep.out_f32 + (size_t)row * ep.ld_f32 + col),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+    return;
+  }
+  v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+  if (ep.flags & GEMM_GELU) {
+    const uint2 u = pack4(v);
+    if (ep.aux_out) *reinterpret_cast<uint2*>(ep.aux_out + (size_t)row * ep.ld_aux + col) = u;
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    v.x = gelu_erf(a.x); v.y = gelu_erf(a.y); v.z = gelu_erf(b.x); v.w = gelu_erf(b.y);
+  }
+  if (ep.flags & GEMM_DGELU) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(ep.aux_in + (size_t)row * ep.ld_aux + col));
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    v.x *= gelu_erf_grad(a.x); v.y *= gelu_erf_grad(a.y); v.z *= gelu_erf_grad(b.x); v.w *= gelu_erf_grad(b.y);
+  }
+  if (ep.flags & GEMM_DROPOUT) v = dropout4(ep, v, row, col, N);
+  if (ep.residual) {
+    const float4 r = *reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ld_res + col);
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  }
+  if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ld_f32 + col) = v;
+  if (ep.out_bf16) *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ld_bf16 + col) = pack4(v);
+}
+
+// what a specialised mode prefetches one chunk ahead (one 16-byte register slot per step)
+template <int MODE>
+ECAMP_DEVINL void epi_prefetch(const GemmEpilogue& ep, int row0, int col, int M, int N, uint4 (&p)[8]) {
+  if (MODE != EM_F32_RES && MODE != EM_F32_RES_DROP && MODE != EM_DGELU) return;
+  if (col >= N) return;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < nvalid) atomicAdd(op + i, v[i]);
+  for (int i = 0; i < 8; ++i) {
+    const int row = row0 + 4 * i;
+    if (row < M) {
+      if (MODE == EM_DGELU) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(ep.aux_in + (size_t)row * ep.ld_aux + col));
+        p[i].x = u.x; p[i].y = u.y;
+      } else {
+        p[i] = *reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ld_res + col);
+      }
+    }
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// epilogue for one thread: one output row, 32 consecutive columns
-// ---------------------------------------------------------------------------------------------
-// `sbias` (optional): this tile's bias staged in shared memory, pointing at column col0; `pre_res` (optional): the
-// residual of this row / chunk already fetched into registers (both hide global-load latency from the epilogue).
-ECAMP_DEVINL void epilogue_row32(const EpiArgs& ea, float (&v)[32], int row, int col0, int N,
-                                 const float* sbias = nullptr, const float4* pre_res = nullptr) {
-  const GemmEpilogue& ep = ea.ep;
-  const bool full = ea.vec_ok && (col0 + 32 <= N);
-  const int nvalid = min(32, N - col0);
+// The epilogue of one warp for one accumulator stage: TMEM lane quarter at `taddr`, columns [ncol0, ncol0 + HALF_N) of
+// the tile whose first output row (of this quarter) is m0.  `stage4k` is the warp's private 4 KB transpose tile.
+// Arrives on `tmem_empty` as soon as the last TMEM read has landed.
+ECAMP_DEVINL void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+ECAMP_DEVINL float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
-  if (ep.bias && sbias) {
+// Pull the epilogue operand (fp32 residual or bf16 dGELU pre-activation) of a 32-row x HALF_N-column region into L2:
+// issued one tile ahead, so that the register prefetch of epi_prefetch (one chunk ahead) only ever pays L2 latency.
+template <int HALF_N, int MODE>
+ECAMP_DEVINL void epi_prefetch_l2(const GemmEpilogue& ep, int m0, int ncol0, int M, int N, int lane) {
+  if (MODE != EM_F32_RES && MODE != EM_F32_RES_DROP && MODE != EM_DGELU) return;
+  constexpr int ROW_BYTES = HALF_N * (MODE == EM_DGELU ? 2 : 4);
+  constexpr int LINES = (ROW_BYTES + 127) / 128;  // 128-byte lines per row of the region
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 b = reinterpret_cast<const float4*>(sbias)[i];
-      v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-    }
-  } else if (ep.bias) {
-    if (full) {
-      const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 b = __ldg(bp + i);
-        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nvalid) v[i] += __ldg(ep.bias + col0 + i);
+  for (int j = 0; j < LINES; ++j) {
+    const int row = m0 + lane;
+    const int col = ncol0 + j * (MODE == EM_DGELU ? 64 : 32);
+    if (row < M && col < N && col < ncol0 + HALF_N) {
+      const void* p = MODE == EM_DGELU ? static_cast<const void*>(ep.aux_in + (size_t)row * ep.ld_aux + col)
+                                       : static_cast<const void*>(ep.residual + (size_t)row * ep.ld_res + col);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
   }
-  if (ep.flags & GEMM_GELU) {
-    // the reference applies GELU to the half-precision Linear output; keep forward and backward
-    // consistent by activating the rounded value that is saved for backward
+}
+
+template <int HALF_N, int MODE>
+ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int ncol0, int M, int N, float* stage4k,
+                                int lane, uint64_t* tmem_full, uint32_t full_phase, uint64_t* tmem_empty,
+                                bool remote_empty, int next_m0, int next_ncol0) {
+  constexpr int NCH = HALF_N / 32;
+  const GemmEpilogue& ep = ea.ep;
+  const int sub = lane >> 3, u = lane & 7;  // coalesced layout: step i -> row 4 i + sub, 16-byte unit u
+  const bool vbias = MODE != EM_ATOMIC && MODE != EM_DGELU && ea.split_k == 1 && ep.bias && ea.vec_ok;
+  const int row0 = m0 + sub;
+  const uint32_t stage_addr = smem_u32(stage4k);  // explicit shared-space accesses (the generic pointer compiled to LD.E / ST.E)
+  uint4 pcur[8], pnext[8];
+  epi_prefetch<MODE>(ep, row0, ncol0 + 4 * u, M, N, pcur);  // in flight while the accumulator is still being produced
+  if (next_m0 >= 0) epi_prefetch_l2<HALF_N, MODE>(ep, next_m0, next_ncol0, M, N, lane);
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), bias_next = bias4;
+  if (vbias && ncol0 + 4 * u + 4 <= N) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + ncol0 + 4 * u));
+  mbar_wait(tmem_full, full_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t raw[32];
+    tmem_ld_32x32(taddr + (uint32_t)(c * 32), raw);
+    const int col = ncol0 + c * 32 + 4 * u;
+    if (vbias && c + 1 < NCH && col + 36 <= N) bias_next = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 32));
+    tmem_ld_wait();
+    if (c == NCH - 1) {
+      // all of this warp's TMEM reads for the tile are done: hand the accumulator stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (remote_empty) mbar_arrive_cluster(tmem_empty, 0);
+        else mbar_arrive(tmem_empty);
+      }
+    }
+    if (ea.dbg == 1) continue;
+    // transpose: thread = row `lane` writes its 8 16-byte units, unit j at physical slot j ^ (lane & 7)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = bf2f(f2bf(v[i]));
-    if (ep.aux_out) {
-      bf16* ap = ep.aux_out + (size_t)row * ep.ld_aux + col0;
-      if (full) {
+    for (int j = 0; j < 8; ++j)
+      sts128(stage_addr + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), raw[4 * j], raw[4 * j + 1], raw[4 * j + 2],
+             raw[4 * j + 3]);
+    if (c + 1 < NCH) epi_prefetch<MODE>(ep, row0, col + 32, M, N, pnext);  // next chunk's operand in flight from here
+    __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-          u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-          reinterpret_cast<uint4*>(ap)[i] = u;
+    for (int hb = 0; hb < 2; ++hb) {  // two batches of four steps keep the live registers below the 168 available
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = 4 * (4 * hb + k) + sub;
+        v[k] = lds128(stage_addr + (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)));
+      }
+      if (MODE == EM_GENERIC) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = row0 + 4 * (4 * hb + k);
+          if (row < M && col < N) epi_vec4_generic(ea, v[k], row, col, N, bias4);
         }
-      } else {
+      } else if (col < N) {  // specialised modes require N % 4 == 0 and 16-byte aligned operands (host-checked)
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < nvalid) ap[i] = f2bf(v[i]);
+        for (int k = 0; k < 4; ++k) {
+          const int i = 4 * hb + k;
+          const int row = row0 + 4 * i;
+          if (row < M) {
+            float4 x = v[k];
+            if (MODE == EM_ATOMIC) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ep.out_f32 + (size_t)row * ep.ld_f32 + col),
+                           "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
+                           : "memory");
+              continue;
+            }
+            if (MODE != EM_DGELU) { x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w; }
+            if (MODE == EM_GELU) {
+              const uint2 pk = pack4(x);
+              *reinterpret_cast<uint2*>(ep.aux_out + (size_t)row * ep.ld_aux + col) = pk;
+              const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
+              x.x = gelu_erf(a.x); x.y = gelu_erf(a.y); x.z = gelu_erf(b.x); x.w = gelu_erf(b.y);
+            }
+            if (MODE == EM_DGELU) {
+              const float2 a = unpack_bf16x2(pcur[i].x), b = unpack_bf16x2(pcur[i].y);
+              x.x *= gelu_erf_grad(a.x); x.y *= gelu_erf_grad(a.y); x.z *= gelu_erf_grad(b.x); x.w *= gelu_erf_grad(b.y);
+            }
+            if (MODE == EM_F32_RES_DROP) x = dropout4(ep, x, row, col, N);
+            if (MODE == EM_F32_RES || MODE == EM_F32_RES_DROP) {
+              x.x += __uint_as_float(pcur[i].x); x.y += __uint_as_float(pcur[i].y);
+              x.z += __uint_as_float(pcur[i].z); x.w += __uint_as_float(pcur[i].w);
+            }
+            if (MODE == EM_F32 || MODE == EM_F32_RES || MODE == EM_F32_RES_DROP)
+              *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ld_f32 + col) = x;
+            else
+              *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ld_bf16 + col) = pack4(x);
+          }
+        }
       }
     }
+    __syncwarp();
+    if (MODE == EM_F32_RES || MODE == EM_F32_RES_DROP || MODE == EM_DGELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-  }
-  if (ep.flags & GEMM_DGELU) {
-    const bf16* ap = ep.aux_in + (size_t)row * ep.ld_aux + col0;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(ap) + i);
-        float2 f;
-        f = unpack_bf16x2(u.x); v[8 * i + 0] *= gelu_erf_grad(f.x); v[8 * i + 1] *= gelu_erf_grad(f.y);
-        f = unpack_bf16x2(u.y); v[8 * i + 2] *= gelu_erf_grad(f.x); v[8 * i + 3] *= gelu_erf_grad(f.y);
-        f = unpack_bf16x2(u.z); v[8 * i + 4] *= gelu_erf_grad(f.x); v[8 * i + 5] *= gelu_erf_grad(f.y);
-        f = unpack_bf16x2(u.w); v[8 * i + 6] *= gelu_erf_grad(f.x); v[8 * i + 7] *= gelu_erf_grad(f.y);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nvalid) v[i] *= gelu_erf_grad(bf2f(ap[i]));
+      for (int i = 0; i < 8; ++i) pcur[i] = pnext[i];
     }
+    bias4 = bias_next;
   }
-  if (ep.flags & GEMM_DROPOUT) {
-    const Philox ph(ep.seed);
-    const uint32_t thr = dropout_threshold(ep.drop_p);
-    const float scale = 1.0f / (1.0f - ep.drop_p);
-    const uint64_t base = (uint64_t)row * (uint64_t)N + (uint64_t)col0;  // N % 4 == 0 checked on the host
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint4 r = ph((base >> 2) + i, ep.stream);
-      v[4 * i + 0] = (r.x >= thr) ? v[4 * i + 0] * scale : 0.f;
-      v[4 * i + 1] = (r.y >= thr) ? v[4 * i + 1] * scale : 0.f;
-      v[4 * i + 2] = (r.z >= thr) ? v[4 * i + 2] * scale : 0.f;
-      v[4 * i + 3] = (r.w >= thr) ? v[4 * i + 3] * scale : 0.f;
-    }
+}
+
+// The whole persistent epilogue loop of one warp, specialised per mode (the switch sits OUTSIDE the tile loop so that
+// every mode is an independent region for the register allocator).  Work unit u covers tile u % num_tiles; the first
+// output row of the CTA's 128-row slab is (tile % m_tiles) * m_stride + m_off.
+template <int BN, int MODE>
+ECAMP_DEVINL void epilogue_loop(const EpiArgs& ea, uint32_t tmem_base, int q, int half, int unit0, int unit_step,
+                                int num_units, int num_tiles, int m_tiles, int m_stride, int m_off, int M, int N,
+                                float* stage4k, int lane, uint64_t* tmem_full, uint64_t* tmem_empty, bool remote_empty) {
+  constexpr int HALF_N = BN / 2;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  if (unit0 < num_units) {  // the first tile's operand: nobody prefetched it one tile ahead
+    const int tile = unit0 % num_tiles;
+    epi_prefetch_l2<HALF_N, MODE>(ea.ep, (tile % m_tiles) * m_stride + m_off + q * 32, (tile / m_tiles) * BN + half * HALF_N,
+                                  M, N, lane);
   }
-  if (ep.residual && pre_res && full) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      v[4 * i + 0] += pre_res[i].x; v[4 * i + 1] += pre_res[i].y; v[4 * i + 2] += pre_res[i].z; v[4 * i + 3] += pre_res[i].w;
+  for (int unit = unit0; unit < num_units; unit += unit_step) {
+    const int tile = unit % num_tiles;
+    const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+    int next_m0 = -1, next_ncol0 = 0;
+    if (unit + unit_step < num_units) {
+      const int nt = (unit + unit_step) % num_tiles;
+      next_m0 = (nt % m_tiles) * m_stride + m_off + q * 32;
+      next_ncol0 = (nt / m_tiles) * BN + half * HALF_N;
     }
-  } else if (ep.residual) {
-    const float* rp = ep.residual + (size_t)row * ep.ld_res + col0;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 r = reinterpret_cast<const float4*>(rp)[i];
-        v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nvalid) v[i] += rp[i];
-    }
+    epilogue_warp<HALF_N, MODE>(ea, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N),
+                                m_blk * m_stride + m_off + q * 32, n_blk * BN + half * HALF_N, M, N, stage4k, lane,
+                                &tmem_full[acc], acc_phase, &tmem_empty[acc], remote_empty, next_m0, next_ncol0);
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
-  if (ep.out_f32) {
-    float* op = ep.out_f32 + (size_t)row * ep.ld_f32 + col0;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        reinterpret_cast<float4*>(op)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nvalid) op[i] = v[i];
-    }
+}
+template <int BN>
+ECAMP_DEVINL void epilogue_dispatch(const EpiArgs& ea, uint32_t tmem_base, int q, int half, int unit0, int unit_step,
+                                    int num_units, int num_tiles, int m_tiles, int m_stride, int m_off, int M, int N,
+                                    float* stage4k, int lane, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                    bool remote_empty) {
+#define ECAMP_EPI_CASE(MODE_)                                                                                        \
+  case MODE_:                                                                                                         \
+    epilogue_loop<BN, MODE_>(ea, tmem_base, q, half, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride, m_off, \
+                             M, N, stage4k, lane, tmem_full, tmem_empty, remote_empty);                               \
+    break;
+  switch (ea.mode) {
+    ECAMP_EPI_CASE(EM_BF16)
+    ECAMP_EPI_CASE(EM_GELU)
+    ECAMP_EPI_CASE(EM_DGELU)
+    ECAMP_EPI_CASE(EM_F32)
+    ECAMP_EPI_CASE(EM_F32_RES)
+    ECAMP_EPI_CASE(EM_F32_RES_DROP)
+    ECAMP_EPI_CASE(EM_ATOMIC)
+    default:
+      epilogue_loop<BN, EM_GENERIC>(ea, tmem_base, q, half, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride,
+                                    m_off, M, N, stage4k, lane, tmem_full, tmem_empty, remote_empty);
   }
-  if (ep.out_bf16) {
-    bf16* op = ep.out_bf16 + (size_t)row * ep.ld_bf16 + col0;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-        reinterpret_cast<uint4*>(op)[i] = u;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nvalid) op[i] = f2bf(v[i]);
-    }
-  }
+#undef ECAMP_EPI_CASE
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -215,12 +370,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * C::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  float* s_epi = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256);  // [2][256], one per accumulator stage
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -262,7 +417,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int tile = unit % num_tiles, ks = unit / num_tiles;
         const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
-        const int kb0 = ks * ea.kb_per, kb1 = min(num_kb, kb0 + ea.kb_per);
+        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_kb, kb0 + ea.kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
@@ -296,7 +451,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       if (lane == 0) {
         const int ks = unit / num_tiles;
-        const int kb0 = ks * ea.kb_per, kb1 = min(num_kb, kb0 + ea.kb_per);
+        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_kb, kb0 + ea.kb_per);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -328,66 +483,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // ===================== epilogue =====================
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns
-    constexpr int HALF_N = BN / 2;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      const int tile = unit % num_tiles;
-      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
-      const int row = m_blk * BM + q * 32 + lane;
-      const bool plain = ea.split_k == 1;
-      // stage this tile's bias in shared memory while the accumulator is still being produced
-      float* sb = s_bias + acc * 256;
-      if (plain && ea.ep.bias) {
-        const int t = threadIdx.x - kEpiWarp0 * 32;
-        const int col = n_blk * BN + t;
-        if (t < BN) sb[t] = col < N ? __ldg(ea.ep.bias + col) : 0.f;
-      }
-      // residual of the first chunk, fetched before waiting for the accumulator
-      const bool pre = plain && ea.ep.residual != nullptr && ea.vec_ok && row < M;
-      float4 rcur[8];
-      if (pre) {
-        const int col0 = n_blk * BN + half * HALF_N;
-        if (col0 + 32 <= N) {
-          const float4* rp = reinterpret_cast<const float4*>(ea.ep.residual + (size_t)row * ea.ep.ld_res + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rcur[i] = rp[i];
-        }
-      }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only: s_bias[acc] is complete
-#pragma unroll 1
-      for (int c = 0; c < HALF_N / 32; ++c) {
-        const int tcol = acc * BN + half * HALF_N + c * 32;
-        const int col0 = n_blk * BN + half * HALF_N + c * 32;
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tcol, raw);
-        float4 rnext[8];
-        if (pre && c + 1 < HALF_N / 32 && col0 + 64 <= N) {  // next chunk's residual in flight during this chunk
-          const float4* rp = reinterpret_cast<const float4*>(ea.ep.residual + (size_t)row * ea.ep.ld_res + col0 + 32);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rnext[i] = rp[i];
-        }
-        tmem_ld_wait();
-        if (c == HALF_N / 32 - 1) {
-          // all of this warp's TMEM reads for the tile are done: hand the accumulator stage back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        if (row < M && col0 < N) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          if (!plain) epilogue_atomic_row32(ea, v, row, col0, N);
-          else epilogue_row32(ea, v, row, col0, N, ea.ep.bias ? sb + half * HALF_N + c * 32 : nullptr, pre ? rcur : nullptr);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
+    float* stage4k = s_epi + (warp - kEpiWarp0) * 1024;
+    epilogue_dispatch<BN>(ea, tmem_base, q, half, blockIdx.x, gridDim.x, num_units, num_tiles, m_tiles, BM, 0, M, N, stage4k,
+                          lane, tmem_full, tmem_empty, false);
   }
 
   tc_fence_before();
@@ -411,8 +509,10 @@ struct Cfg2 {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 6 : ((BN == 192) ? 7 : 8);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int STAGES = (BN == 128) ? 8 : 6;
+  static constexpr int EPI_BYTES = kNumEpiWarps * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget of one CTA exceeded");
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -426,7 +526,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * C::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  float* s_epi = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -475,7 +576,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       for (int unit = pair; unit < num_units; unit += num_pairs) {
         const int tile = unit % num_tiles, ks = unit / num_tiles;
         const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
-        const int kb0 = ks * ea.kb_per, kb1 = min(num_kb, kb0 + ea.kb_per);
+        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_kb, kb0 + ea.kb_per);
         const int m0 = m_blk * 2 * BM + (int)rank * BM;
         const int n0 = n_blk * BN + (int)rank * HB;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -511,7 +612,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       uint32_t acc_phase = 0;
       for (int unit = pair; unit < num_units; unit += num_pairs) {
         const int ks = unit / num_tiles;
-        const int kb0 = ks * ea.kb_per, kb1 = min(num_kb, kb0 + ea.kb_per);
+        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_kb, kb0 + ea.kb_per);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -539,37 +640,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int q = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
-    constexpr int HALF_N = BN / 2;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int unit = pair; unit < num_units; unit += num_pairs) {
-      const int tile = unit % num_tiles;
-      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < HALF_N / 32; ++c) {
-        const int tcol = acc * BN + half * HALF_N + c * 32;
-        const int col0 = n_blk * BN + half * HALF_N + c * 32;
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tcol, raw);
-        tmem_ld_wait();
-        if (c == HALF_N / 32 - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's MMA warp owns the hand-back
-        }
-        if (row < M && col0 < N) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          if (ea.split_k > 1) epilogue_atomic_row32(ea, v, row, col0, N);
-          else epilogue_row32(ea, v, row, col0, N);
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
+    float* stage4k = s_epi + (warp - kEpiWarp0) * 1024;
+    // the leader's MMA warp owns the accumulator hand-back: both CTAs arrive on ITS barrier
+    epilogue_dispatch<BN>(ea, tmem_base, q, half, pair, num_pairs, num_units, num_tiles, m_tiles, 2 * BM, (int)rank * BM, M,
+                          N, stage4k, lane, tmem_full, tmem_empty, true);
   }
 
   tc_fence_before();
@@ -623,12 +697,18 @@ int make_tmap(CUtensorMap* map, const bf16* ptr, uint64_t inner, uint64_t outer,
 
 // 0 = automatic (CTA pairs whenever the problem has more than one 128-row tile), 1 = single-CTA kernel only,
 // 2 = CTA-pair kernel always.  ECAMP_GEMM_CTA_PAIR overrides the default; ecamp_gemm_set_cta_pair() at run time.
-// Default 1: measured on B200 (profiles/r01_gemm_pair_vs_single.log) the pair kernel is bit-correct but not faster
-// than the single-CTA kernel on this step's shapes (-3 % .. +1 % at K = 768, +5 % at 8192^3, slower for MN-major B),
-// so operand delivery through L2 is not what limits the single-CTA kernel; it stays selectable for further tuning.
+// Default 0: once the epilogue stopped being the bound (coalesced stores through the shared-memory transpose), the
+// pair kernel - each SM pulls 2/3 of the operand bytes of the single-CTA kernel through L2 - is faster on every shape
+// of the step (profiles/r01c_gemm_tile_sweep.log: 8192^3 1411 vs 1289 TFLOP/s, BERT qkv 1222 vs 1020).
 int g_cta_pair_mode = [] {
   const char* e = getenv("ECAMP_GEMM_CTA_PAIR");
-  return e ? atoi(e) : 1;
+  return e ? atoi(e) : 0;
+}();
+
+// tests: route every GEMM through the generic (run-time checked) epilogue
+int g_force_generic_epilogue = [] {
+  const char* e = getenv("ECAMP_GEMM_GENERIC_EPILOGUE");
+  return e ? atoi(e) : 0;
 }();
 
 int num_sms() {
@@ -651,7 +731,10 @@ void pick_config(int M, int N, int K, bool splittable, int force_bn, bool cta2, 
   const int m_tiles = cta2 ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
   const int num_kb = (K + BK - 1) / BK;
   const int cand[3] = {256, 192, 128};
-  const float eff[3] = {1.00f, 0.97f, 0.88f};  // smaller tiles put more shared-memory traffic behind each MMA
+  // narrower tiles move more operand bytes through L2 and shared memory per MMA; measured on B200 at 8192^3
+  // (profiles/r01c_gemm_tile_sweep.log): pair kernel 1411 / 1152 / 754 TFLOP/s, single-CTA kernel 1289 / 1061 / ~800
+  const float eff1[3] = {1.00f, 0.85f, 0.65f}, eff2[3] = {1.00f, 0.82f, 0.55f};
+  const float* eff = cta2 ? eff2 : eff1;
   const int splits[9] = {1, 2, 3, 4, 6, 8, 12, 16, 24};
   float best_cost = 1e30f;
   *bn_out = 256;
@@ -787,6 +870,24 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
   if (ep.out_f32 && (ep.ld_f32 % 4 != 0 || !al16(ep.out_f32))) ea.vec_ok = 0;
   if (ep.out_bf16 && (ep.ld_bf16 % 8 != 0 || !al16(ep.out_bf16))) ea.vec_ok = 0;
 
+  ea.mode = EM_GENERIC;
+  if (ea.vec_ok && N % 4 == 0) {
+    const bool only_bf16 = ep.out_bf16 && !ep.out_f32, only_f32 = ep.out_f32 && !ep.out_bf16;
+    if (split_k > 1) ea.mode = EM_ATOMIC;
+    else if (ep.flags == 0 && !ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_BF16;
+    else if (ep.flags == GEMM_GELU && ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_GELU;
+    else if (ep.flags == GEMM_DGELU && !ep.bias && !ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_DGELU;
+    else if (ep.flags == 0 && !ep.aux_out && !ep.residual && only_f32) ea.mode = EM_F32;
+    else if (ep.flags == 0 && !ep.aux_out && ep.residual && only_f32) ea.mode = EM_F32_RES;
+    else if (ep.flags == GEMM_DROPOUT && !ep.aux_out && ep.residual && only_f32) ea.mode = EM_F32_RES_DROP;
+  }
+  if (g_force_generic_epilogue) ea.mode = EM_GENERIC;
+  static const int dbg = getenv("ECAMP_GEMM_DBG") ? atoi(getenv("ECAMP_GEMM_DBG")) : 0;
+  ea.dbg = dbg;
+
+#ifdef ECAMP_EPI_ONLY_MODE
+  return launch<256, false, false>(ta, tb, M, N, K, ea, stream);
+#endif
   if (cta2) {
     if (bn == 256) return launch_major2<256>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
     if (bn == 192) return launch_major2<192>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
