@@ -29,6 +29,7 @@ class Epilogue(ctypes.Structure):
         ("drop_p", ctypes.c_float),
         ("seed", ctypes.c_uint64),
         ("site", ctypes.c_uint64),
+        ("colsum_out", ctypes.c_void_p),
     ]
 
 
@@ -108,7 +109,7 @@ def cur_stream():
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, bias=None, aux_in=None, aux_out=None,
-         residual=None, out_f32=None, out_bf16=None, flags=0, drop_p=0.0, seed=0, site=0, tile_n=0):
+         residual=None, out_f32=None, out_bf16=None, flags=0, drop_p=0.0, seed=0, site=0, tile_n=0, colsum_out=None):
     """D = epilogue(A . B^T) on the tcgen05 kernel.  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn)."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(-1) == 1 and b.stride(-1) == 1
     if M is None:
@@ -128,6 +129,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, bias=None, aux
     ep.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
     ep.ld_bf16 = out_bf16.stride(0) if out_bf16 is not None else 0
     ep.flags, ep.drop_p, ep.seed, ep.site = flags, drop_p, seed, site
+    ep.colsum_out = colsum_out.data_ptr() if colsum_out is not None else None
     rc = lib().ecamp_gemm_bf16(ptr(a), ctypes.c_int32(a.stride(0)), ctypes.c_int32(int(a_mn)), ptr(b),
                                ctypes.c_int32(b.stride(0)), ctypes.c_int32(int(b_mn)), ctypes.c_int32(M),
                                ctypes.c_int32(N), ctypes.c_int32(K), ctypes.byref(ep), ctypes.c_int32(tile_n),

@@ -65,6 +65,7 @@ int ecamp_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int
   e.drop_p = ep->drop_p;
   e.seed = ep->seed;
   e.stream = ep->site;
+  e.colsum_out = ep->colsum_out;
   return gemm_bf16(static_cast<const bf16*>(A), lda, a_mn, static_cast<const bf16*>(B), ldb, b_mn, M, N, K, e, tile_n,
                    S(stream));
 }
@@ -88,9 +89,9 @@ int ecamp_layernorm_fwd(const float* x, const float* gamma, const float* beta, f
 }
 int ecamp_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                         int32_t M, int32_t D, const float* addend, float* dx_f32, void* dx_bf16, float* dgamma,
-                        float* dbeta, int32_t accumulate, float* ws, void* stream) {
+                        float* dbeta, float* colsum_out, int32_t accumulate, float* /*ws*/, void* stream) {
   return layernorm_bwd(dy, x, mean, rstd, gamma, M, D, addend, dx_f32, static_cast<bf16*>(dx_bf16), DropoutCfg(),
-                       dgamma, dbeta, accumulate, ws, S(stream));
+                       dgamma, dbeta, colsum_out, accumulate, S(stream));
 }
 size_t ecamp_layernorm_ws_floats(void) { return layernorm_bwd_ws_floats(768); }
 

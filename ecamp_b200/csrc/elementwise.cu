@@ -394,9 +394,8 @@ __global__ void emb_type_finalize_kernel(const float* __restrict__ type_ws, int 
 // ---------------------------------------------------------------------------------------------
 // out[n] = sum_m x[m, n]: CTA = 256 columns x one row chunk; each lane owns 8 consecutive columns (128-bit loads),
 // the 8 warps stride over the rows of the chunk; per-chunk partials are reduced by a second tiny kernel.
-constexpr int kColsumMaxWsFloats = 1 << 22;  // per-chunk partials: chunks * N floats
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int ld, int M, int N,
-                                                     float* __restrict__ ws) {
+                                                     float* __restrict__ out) {
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -438,27 +437,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    ws[(size_t)blockIdx.y * N + c] = s;
+    atomicAdd(out + c, s);  // one add per row chunk and column (the destination starts from zero / the running gradient)
   }
 }
-// one CTA per 32 columns; the 8 warps stride over the chunk partials
-__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ ws, int chunks, int N,
-                                                              float* __restrict__ out, int accumulate) {
-  __shared__ float red[8][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + lane;
-  float s = 0.f;
-  if (n < N)
-    for (int c = warp; c < chunks; c += 8) s += ws[(size_t)c * N + n];
-  red[warp][lane] = s;
-  __syncthreads();
-  if (warp == 0 && n < N) {
-#pragma unroll
-    for (int w = 1; w < 8; ++w) s += red[w][lane];
-    out[n] = accumulate ? out[n] + s : s;
-  }
-}
-
 __global__ void scale_f32_kernel(float* __restrict__ x, const float* __restrict__ scale, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] *= *scale;
@@ -608,18 +589,16 @@ int bert_embeddings_bwd(const float* d_pre, const int64_t* ids, const int64_t* t
   LAUNCH_OK();
   return 0;
 }
-size_t colsum_ws_floats(int N) { return (size_t)kColsumMaxWsFloats > (size_t)N ? (size_t)kColsumMaxWsFloats : (size_t)N; }
-int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate, float* ws, cudaStream_t st) {
+size_t colsum_ws_floats(int) { return 64; }  // the column sums are added with atomics: no partials workspace any more
+int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate, float* /*ws*/, cudaStream_t st) {
   ECAMP_REQUIRE(ld % 8 == 0 && N % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
                 "colsum: pitch and width must be multiples of 8 elements, base 16-byte aligned");
   int chunks = (M + 127) / 128;  // 128 rows per CTA: ~600-1500 CTAs for the shapes of the step
   if (chunks > 512) chunks = 512;
-  if ((long long)chunks * N > kColsumMaxWsFloats) chunks = kColsumMaxWsFloats / N;
   if (chunks < 1) chunks = 1;
+  if (!accumulate) ECAMP_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
   dim3 grid((N + 255) / 256, chunks);
-  colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, ws);
-  LAUNCH_OK();
-  colsum_finalize_kernel<<<(N + 31) / 32, 256, 0, st>>>(ws, chunks, N, out, accumulate);
+  colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, out);
   LAUNCH_OK();
   return 0;
 }

@@ -94,6 +94,7 @@ ECAMP_DEVINL void epi_scalar(const EpiArgs& ea, float v, int row, int col, int N
   if (ep.residual) v += ep.residual[(size_t)row * ep.ld_res + col];
   if (ep.out_f32) ep.out_f32[(size_t)row * ep.ld_f32 + col] = v;
   if (ep.out_bf16) ep.out_bf16[(size_t)row * ep.ld_bf16 + col] = f2bf(v);
+  if (ep.colsum_out) atomicAdd(ep.colsum_out + col, bf2f(f2bf(v)));
 }
 
 ECAMP_DEVINL float4 dropout4(const GemmEpilogue& ep, float4 v, int row, int col, int N) {
@@ -149,6 +150,12 @@ ECAMP_DEVINL void epi_vec4_generic(const EpiArgs& ea, float4 v, int row, int col
   }
   if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ld_f32 + col) = v;
   if (ep.out_bf16) *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ld_bf16 + col) = pack4(v);
+  if (ep.colsum_out) {
+    const uint2 pk = pack4(v);
+    const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
+    atomicAdd(ep.colsum_out + col, a.x); atomicAdd(ep.colsum_out + col + 1, a.y);
+    atomicAdd(ep.colsum_out + col + 2, b.x); atomicAdd(ep.colsum_out + col + 3, b.y);
+  }
 }
 
 // what a specialised mode prefetches one chunk ahead (one 16-byte register slot per step)
@@ -242,6 +249,7 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
              raw[4 * j + 3]);
     if (c + 1 < NCH) epi_prefetch<MODE>(ep, row0, col + 32, M, N, pnext);  // next chunk's operand in flight from here
     __syncwarp();
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // EM_DGELU: column sums of this chunk's emitted values
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {  // two batches of four steps keep the live registers below the 168 available
       float4 v[4];
@@ -287,11 +295,32 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
             }
             if (MODE == EM_F32 || MODE == EM_F32_RES || MODE == EM_F32_RES_DROP)
               *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ld_f32 + col) = x;
-            else
-              *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ld_bf16 + col) = pack4(x);
+            else {
+              const uint2 pk = pack4(x);
+              *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ld_bf16 + col) = pk;
+              if (MODE == EM_DGELU) {
+                const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
+                csum.x += a.x; csum.y += a.y; csum.z += b.x; csum.w += b.y;
+              }
+            }
           }
         }
       }
+    }
+    if (MODE == EM_DGELU && ep.colsum_out) {
+      // lanes l, l ^ 8, l ^ 16, l ^ 24 hold the same four columns (different rows): fold them, then one vector
+      // reduction per 4 columns and 32-row slab
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
+        csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+        csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
+        csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+      }
+      if (sub == 0 && col < N)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ep.colsum_out + col), "f"(csum.x), "f"(csum.y),
+                     "f"(csum.z), "f"(csum.w)
+                     : "memory");
     }
     __syncwarp();
     if (MODE == EM_F32_RES || MODE == EM_F32_RES_DROP || MODE == EM_DGELU) {
@@ -831,10 +860,13 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
   if (ep.flags & GEMM_DROPOUT)
     ECAMP_REQUIRE(N % 4 == 0 && ep.drop_p >= 0.f && ep.drop_p < 1.f, "gemm: dropout needs N %% 4 == 0, 0 <= p < 1");
   if (ep.flags & GEMM_DGELU) ECAMP_REQUIRE(ep.aux_in != nullptr, "gemm: dGELU needs aux_in");
+  if (ep.colsum_out)
+    ECAMP_REQUIRE(ep.out_bf16 && (reinterpret_cast<uintptr_t>(ep.colsum_out) & 15) == 0,
+                  "gemm: colsum_out needs a bf16 output and a 16-byte aligned destination");
   ECAMP_REQUIRE(force_bn == 0 || force_bn == 128 || force_bn == 192 || force_bn == 256, "gemm: unsupported tile N %d",
                 force_bn);
   const bool accumulate = ep.residual != nullptr && ep.residual == ep.out_f32 && ep.ld_res == ep.ld_f32;
-  const bool splittable = ep.out_f32 && !ep.out_bf16 && !ep.bias && ep.flags == 0 && !ep.aux_out &&
+  const bool splittable = ep.out_f32 && !ep.out_bf16 && !ep.bias && ep.flags == 0 && !ep.aux_out && !ep.colsum_out &&
                           (ep.residual == nullptr || accumulate);
   int bn = 256, split_k = 1;
   const bool cta2 = g_cta_pair_mode == 2 || (g_cta_pair_mode == 0 && M > BM);
@@ -880,6 +912,7 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
     else if (ep.flags == 0 && !ep.aux_out && !ep.residual && only_f32) ea.mode = EM_F32;
     else if (ep.flags == 0 && !ep.aux_out && ep.residual && only_f32) ea.mode = EM_F32_RES;
     else if (ep.flags == GEMM_DROPOUT && !ep.aux_out && ep.residual && only_f32) ea.mode = EM_F32_RES_DROP;
+    if (ep.colsum_out && ea.mode != EM_DGELU) ea.mode = EM_GENERIC;  // only the dGELU mode folds the column sums in
   }
   if (g_force_generic_epilogue) ea.mode = EM_GENERIC;
   static const int dbg = getenv("ECAMP_GEMM_DBG") ? atoi(getenv("ECAMP_GEMM_DBG")) : 0;

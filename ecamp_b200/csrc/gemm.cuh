@@ -21,6 +21,8 @@ struct GemmEpilogue {
   int ld_f32 = 0;
   bf16* out_bf16 = nullptr;
   int ld_bf16 = 0;
+  float* colsum_out = nullptr;      // [N] fp32: += column sums of the emitted values (atomics; the bias gradient of the
+                                    // Linear that consumes this output).  Only with out_bf16, not with split-K.
   int flags = 0;
   float drop_p = 0.f;
   unsigned long long seed = 0, stream = 0;

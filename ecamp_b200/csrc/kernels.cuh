@@ -18,7 +18,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
 // dgamma/dbeta partials are reduced and ADDED to dgamma/dbeta when accumulate != 0, else stored.
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
                   int D, const float* addend, float* dx_f32, bf16* dx_bf16, DropoutCfg drop, float* dgamma,
-                  float* dbeta, int accumulate, float* partial_ws, cudaStream_t st);
+                  float* dbeta, float* colsum_out, int accumulate, cudaStream_t st);
 size_t layernorm_bwd_ws_floats(int D);
 
 // ---- elementwise.cu ---------------------------------------------------------------------------

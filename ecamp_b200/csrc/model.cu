@@ -416,7 +416,8 @@ int lin_fwd(Ctx* c, const bf16* x, int ldx, int M, const bf16* W, int N, int K, 
 int lin_dgrad(Ctx* c, const bf16* dy, int ld_dy, int M, const bf16* W, int N, int K, GemmEpilogue ep) {
   return gemm_bf16(dy, ld_dy, 0, W, K, 1, M, K, N, ep, 0, c->st);
 }
-// dW[N, K] (+)= dy[M, N]^T x[M, K];  db[N] (+)= colsum(dy)
+// dW[N, K] (+)= dy[M, N]^T x[M, K];  db[N] += colsum(dy)  (bias / LayerNorm gradients are zeroed by zero_small_grads at
+// the start of a non-accumulating backward and only ever added to)
 int lin_wgrad(Ctx* c, const bf16* dy, int ld_dy, const bf16* x, int ldx, int M, int N, int K, float* dW, float* db,
               int acc) {
   GemmEpilogue ep;
@@ -424,7 +425,8 @@ int lin_wgrad(Ctx* c, const bf16* dy, int ld_dy, const bf16* x, int ldx, int M, 
   ep.ld_f32 = K;
   if (acc) { ep.residual = dW; ep.ld_res = K; }
   RC(gemm_bf16(dy, ld_dy, 1, x, ldx, 1, N, K, M, ep, 0, c->st));
-  if (db) RC(colsum_bf16(dy, ld_dy, M, N, db, acc, c->colsum_ws, c->st));
+  // db == nullptr: the kernel that produced dy already folded the bias gradient in (LayerNorm backward, dGELU epilogue)
+  if (db) RC(colsum_bf16(dy, ld_dy, M, N, db, 1, c->colsum_ws, c->st));
   return 0;
 }
 GemmEpilogue ep_bias_bf16(const float* bias, bf16* out, int ld) {
@@ -467,19 +469,20 @@ int vit_block_bwd(Ctx* c, VitStack& s, int l) {
   VitAct& a = s.a[l];
   const int pb = s.pbase + l * VIT_BLOCK_PARAMS, M = s.M, D = s.D, B = c->sh.B, acc = c->acc;
   // fc2
-  RC(lin_wgrad(c, c->gX, D, a.act, s.hid, M, D, s.hid, c->Gp(pb + 10), c->Gp(pb + 11), acc));
+  RC(lin_wgrad(c, c->gX, D, a.act, s.hid, M, D, s.hid, c->Gp(pb + 10), nullptr, acc));  // bias: by the producer of gX
   GemmEpilogue e2;
   e2.flags = GEMM_DGELU; e2.aux_in = a.pre; e2.ld_aux = s.hid; e2.out_bf16 = c->dA; e2.ld_bf16 = s.hid;
+  e2.colsum_out = c->Gp(pb + 9);  // fc1 bias gradient = column sums of dA
   RC(lin_dgrad(c, c->gX, D, M, c->W(pb + 10), D, s.hid, e2));
   // fc1
-  RC(lin_wgrad(c, c->dA, s.hid, a.ln2, D, M, s.hid, D, c->Gp(pb + 8), c->Gp(pb + 9), acc));
+  RC(lin_wgrad(c, c->dA, s.hid, a.ln2, D, M, s.hid, D, c->Gp(pb + 8), nullptr, acc));
   GemmEpilogue e1;
   e1.out_f32 = c->dH; e1.ld_f32 = D;
   RC(lin_dgrad(c, c->dA, s.hid, M, c->W(pb + 8), s.hid, D, e1));
   RC(layernorm_bwd(c->dH, a.x_mid, a.mean2, a.rstd2, c->P(pb + 6), M, D, c->dX, c->dX, c->gX, DropoutCfg(),
-                   c->Gp(pb + 6), c->Gp(pb + 7), acc, c->ln_ws, c->st));
+                   c->Gp(pb + 6), c->Gp(pb + 7), c->Gp(pb + 5) /* proj bias */, 1, c->st));
   // proj
-  RC(lin_wgrad(c, c->gX, D, a.ao, D, M, D, D, c->Gp(pb + 4), c->Gp(pb + 5), acc));
+  RC(lin_wgrad(c, c->gX, D, a.ao, D, M, D, D, c->Gp(pb + 4), nullptr, acc));
   GemmEpilogue ep;
   ep.out_bf16 = c->dAO; ep.ld_bf16 = D;
   RC(lin_dgrad(c, c->gX, D, M, c->W(pb + 4), D, D, ep));
@@ -493,8 +496,9 @@ int vit_block_bwd(Ctx* c, VitStack& s, int l) {
   GemmEpilogue eq;
   eq.out_f32 = c->dH; eq.ld_f32 = D;
   RC(lin_dgrad(c, c->dQKV, 3 * D, M, c->W(pb + 2), 3 * D, D, eq));
+  // the bf16 gradient emitted here is the dY of the PREVIOUS block's fc2: its bias gradient is folded in
   RC(layernorm_bwd(c->dH, a.x_in, a.mean1, a.rstd1, c->P(pb + 0), M, D, c->dX, c->dX, c->gX, DropoutCfg(),
-                   c->Gp(pb + 0), c->Gp(pb + 1), acc, c->ln_ws, c->st));
+                   c->Gp(pb + 0), c->Gp(pb + 1), l > 0 ? c->Gp(pb - VIT_BLOCK_PARAMS + 11) : nullptr, 1, c->st));
   return 0;
 }
 
@@ -519,8 +523,8 @@ int bert_attn_half_fwd(Ctx* c, BertAct& a, int pb, const bf16* h_in, const float
 int bert_attn_half_bwd(Ctx* c, BertAct& a, int pb, unsigned long long site) {
   const int Mt = c->sh.B * c->sh.T, B = c->sh.B, T = c->sh.T, acc = c->acc;
   RC(layernorm_bwd(c->dX, a.s1, a.mean1, a.rstd1, c->P(pb + 8), Mt, 768, nullptr, c->dX, c->gX, c->drop(site + 1),
-                   c->Gp(pb + 8), c->Gp(pb + 9), acc, c->ln_ws, c->st));
-  RC(lin_wgrad(c, c->gX, 768, a.ao, 768, Mt, 768, 768, c->Gp(pb + 6), c->Gp(pb + 7), acc));
+                   c->Gp(pb + 8), c->Gp(pb + 9), c->Gp(pb + 7) /* attention.output.dense bias */, 1, c->st));
+  RC(lin_wgrad(c, c->gX, 768, a.ao, 768, Mt, 768, 768, c->Gp(pb + 6), nullptr, acc));
   GemmEpilogue ep;
   ep.out_bf16 = c->dAO; ep.ld_bf16 = 768;
   RC(lin_dgrad(c, c->gX, 768, Mt, c->W(pb + 6), 768, 768, ep));
@@ -554,12 +558,13 @@ int bert_ffn_half_fwd(Ctx* c, BertAct& a, int pi, const bf16* x, const float* x_
 int bert_ffn_half_bwd(Ctx* c, BertAct& a, int pi, const bf16* x, unsigned long long site) {
   const int Mt = c->sh.B * c->sh.T, acc = c->acc;
   RC(layernorm_bwd(c->dX, a.s2, a.mean2, a.rstd2, c->P(pi + 4), Mt, 768, nullptr, c->dX, c->gX, c->drop(site),
-                   c->Gp(pi + 4), c->Gp(pi + 5), acc, c->ln_ws, c->st));
-  RC(lin_wgrad(c, c->gX, 768, a.act, BHID, Mt, 768, BHID, c->Gp(pi + 2), c->Gp(pi + 3), acc));
+                   c->Gp(pi + 4), c->Gp(pi + 5), c->Gp(pi + 3) /* output.dense bias */, 1, c->st));
+  RC(lin_wgrad(c, c->gX, 768, a.act, BHID, Mt, 768, BHID, c->Gp(pi + 2), nullptr, acc));
   GemmEpilogue e2;
   e2.flags = GEMM_DGELU; e2.aux_in = a.pre; e2.ld_aux = BHID; e2.out_bf16 = c->dA; e2.ld_bf16 = BHID;
+  e2.colsum_out = c->Gp(pi + 1);  // intermediate.dense bias gradient
   RC(lin_dgrad(c, c->gX, 768, Mt, c->W(pi + 2), 768, BHID, e2));
-  RC(lin_wgrad(c, c->dA, BHID, x, 768, Mt, BHID, 768, c->Gp(pi), c->Gp(pi + 1), acc));
+  RC(lin_wgrad(c, c->dA, BHID, x, 768, Mt, BHID, 768, c->Gp(pi), nullptr, acc));
   GemmEpilogue e1;
   e1.residual = c->dX; e1.ld_res = 768; e1.out_f32 = c->dX; e1.ld_f32 = 768;
   RC(lin_dgrad(c, c->dA, BHID, Mt, c->W(pi), BHID, 768, e1));
@@ -622,7 +627,7 @@ int lm_transform_bwd(Ctx* c) {  // in: dTL.  out: c->dX = d(bert output)
   const int Mt = c->sh.B * c->sh.T, acc = c->acc;
   const int pt = param_index("bert_encoder.model.cls.predictions.transform.dense.weight");
   RC(layernorm_bwd(c->dTL, c->t_act, c->t_mean, c->t_rstd, c->P(pt + 2), Mt, 768, nullptr, c->dTL, nullptr,
-                   DropoutCfg(), c->Gp(pt + 2), c->Gp(pt + 3), acc, c->ln_ws, c->st));
+                   DropoutCfg(), c->Gp(pt + 2), c->Gp(pt + 3), nullptr, 1, c->st));
   RC(gelu_bwd_bf16(c->dTL, c->t_pre, c->gX, (size_t)Mt * 768, c->st));
   RC(lin_wgrad(c, c->gX, 768, c->layers[BL - 1].h_out, 768, Mt, 768, 768, c->Gp(pt), c->Gp(pt + 1), acc));
   GemmEpilogue e;
@@ -709,8 +714,8 @@ int text_front_bwd(Ctx* c) {
   RC(bert_ffn_half_bwd(c, a, f.inter, c->f_a2, 14));  // dX = d(a2)
   // out_layer
   RC(layernorm_bwd(c->dX, c->f_s_ol, c->f_mean_ol, c->f_rstd_ol, c->P(f.ol + 2), Mt, 768, nullptr, c->dX, c->gX,
-                   c->drop(13), c->Gp(f.ol + 2), c->Gp(f.ol + 3), acc, c->ln_ws, c->st));
-  RC(lin_wgrad(c, c->gX, 768, c->f_oc2, 768, Mt, 768, 768, c->Gp(f.ol), c->Gp(f.ol + 1), acc));
+                   c->drop(13), c->Gp(f.ol + 2), c->Gp(f.ol + 3), c->Gp(f.ol + 1) /* out_layer.dense bias */, 1, c->st));
+  RC(lin_wgrad(c, c->gX, 768, c->f_oc2, 768, Mt, 768, 768, c->Gp(f.ol), nullptr, acc));
   GemmEpilogue eoc;
   eoc.out_bf16 = c->dAO; eoc.ld_bf16 = 768;
   RC(lin_dgrad(c, c->gX, 768, Mt, c->W(f.ol), 768, 768, eoc));  // dAO = d(oc2) = d(oc)
@@ -746,7 +751,7 @@ int text_front_bwd(Ctx* c) {
   // embeddings: dropout -> LN -> tables
   RC(dropout_bwd_f32(c->dX, (size_t)Mt * 768, c->drop(1), c->st));
   RC(layernorm_bwd(c->dX, c->emb_pre, c->emb_mean, c->emb_rstd, c->P(pe + 3), Mt, 768, nullptr, c->dX, nullptr,
-                   DropoutCfg(), c->Gp(pe + 3), c->Gp(pe + 4), acc, c->ln_ws, c->st));
+                   DropoutCfg(), c->Gp(pe + 3), c->Gp(pe + 4), nullptr, 1, c->st));
   RC(bert_embeddings_bwd(c->dX, c->batch.ids, c->batch.type_ids, B, T, 768, c->Gp(pe), c->Gp(pe + 2), c->Gp(pe + 1),
                          acc, c->misc_ws, c->st));
   return 0;
@@ -858,6 +863,43 @@ int backward_stage_range(int stage, long long* g_begin, long long* g_end) {
 }
 
 namespace {
+// every gradient tensor of at most kSmallGrad elements (all biases, LayerNorm weights, cls / mask tokens, the SR
+// convolutions, token-type embeddings, the 30000-entry vocabulary bias): contiguous runs of the flat buffer are merged
+constexpr long long kSmallGrad = 32768;
+struct ZeroRuns {
+  static constexpr int kMax = 160;
+  long long off[kMax];
+  int n[kMax];
+  int count;
+};
+__global__ void zero_runs_kernel(float* __restrict__ g, const ZeroRuns runs) {
+  const int r = blockIdx.x;
+  float* p = g + runs.off[r];
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < runs.n[r]; i += gridDim.y * blockDim.x) p[i] = 0.f;
+}
+int zero_small_grads(Ctx* c) {
+  static ZeroRuns runs = [] {
+    ZeroRuns z;
+    z.count = 0;
+    const auto& s = param_specs();
+    size_t i = 0;
+    while (i < s.size()) {
+      if (s[i].numel > kSmallGrad) { ++i; continue; }
+      size_t j = i;
+      long long n = 0;
+      while (j < s.size() && s[j].numel <= kSmallGrad) { n += s[j].numel; ++j; }
+      if (z.count < ZeroRuns::kMax) { z.off[z.count] = s[i].g_off; z.n[z.count] = (int)n; }
+      ++z.count;
+      i = j;
+    }
+    return z;
+  }();
+  ECAMP_REQUIRE(runs.count <= ZeroRuns::kMax, "zero_small_grads: %d runs exceed the table", runs.count);
+  zero_runs_kernel<<<dim3(runs.count, 4), 256, 0, c->st>>>(c->G, runs);
+  ECAMP_LAUNCHED();
+  return 0;
+}
+
 int run_stage(Ctx* c, int stage) {
   const int B = c->sh.B, keep = c->sh.keep, Me = B * (keep + 1), Mi = B * keep, Md = B * 197, acc = c->acc;
   if (stage == 0) {
@@ -880,7 +922,8 @@ int run_stage(Ctx* c, int stage) {
     e.out_f32 = c->dH; e.ld_f32 = DD;
     RC(lin_dgrad(c, c->gX, PDIM, Md, c->W(pn + 2), PDIM, DD, e));
     RC(layernorm_bwd(c->dH, c->dec.x_out, c->mean_dn, c->rstd_dn, c->P(pn), Md, DD, nullptr, c->dX, c->gX,
-                     DropoutCfg(), c->Gp(pn), c->Gp(pn + 1), acc, c->ln_ws, c->st));
+                     DropoutCfg(), c->Gp(pn), c->Gp(pn + 1),
+                     c->Gp(c->dec.pbase + (DL - 1) * VIT_BLOCK_PARAMS + 11) /* last decoder block's fc2 bias */, 1, c->st));
   } else if (stage <= 12) {
     RC(vit_block_bwd(c, c->dec, 12 - stage));
   } else if (stage == 13) {
@@ -895,7 +938,8 @@ int run_stage(Ctx* c, int stage) {
   } else if (stage == 14) {
     const int pn = param_index("norm.weight");
     RC(layernorm_bwd(c->dLat, c->enc.x_out, c->mean_n, c->rstd_n, c->P(pn), Me, E, nullptr, c->dX, c->gX, DropoutCfg(),
-                     c->Gp(pn), c->Gp(pn + 1), acc, c->ln_ws, c->st));
+                     c->Gp(pn), c->Gp(pn + 1),
+                     c->Gp(c->enc.pbase + (EL - 1) * VIT_BLOCK_PARAMS + 11) /* last encoder block's fc2 bias */, 1, c->st));
   } else if (stage <= 26) {
     RC(vit_block_bwd(c, c->enc, 26 - stage));
   } else {
@@ -905,7 +949,7 @@ int run_stage(Ctx* c, int stage) {
     e.out_f32 = c->dw_pe; e.ld_f32 = PDIM;
     RC(gemm_bf16(d_pe, E, 1, c->a_pe, PDIM, 1, E, PDIM, Mi, e, 0, c->st));
     RC(permute_pe_weight_grad(c->dw_pe, c->Gp(0), acc, c->st));
-    RC(colsum_bf16(d_pe, E, Mi, E, c->Gp(1), acc, c->colsum_ws, c->st));
+    RC(colsum_bf16(d_pe, E, Mi, E, c->Gp(1), 1, c->colsum_ws, c->st));
   }
   return 0;
 }
@@ -915,6 +959,9 @@ int ctx_backward(Ctx* c, const float* g3, int accumulate, int stage, cudaStream_
   ECAMP_REQUIRE(c->bound && c->planned && c->losses, "backward: no forward has been run");
   ECAMP_REQUIRE(g3 != nullptr, "backward: null upstream gradient");
   c->g3 = g3; c->acc = accumulate; c->st = st;
+  // bias / LayerNorm / token gradients are accumulated with atomics by the kernels that produce their operands:
+  // a non-accumulating backward zeroes them once, before the first stage
+  if (!accumulate && stage <= 0) RC(zero_small_grads(c));
   if (stage >= 0) return run_stage(c, stage);
   for (int s = 0; s < backward_stage_count(); ++s) RC(run_stage(c, s));
   return 0;

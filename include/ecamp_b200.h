@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ECAMP_ABI_VERSION 1
+#define ECAMP_ABI_VERSION 2
 #if defined(__GNUC__)
 #define ECAMP_API __attribute__((visibility("default")))
 #else
@@ -69,6 +69,8 @@ typedef struct ecamp_epilogue {
   float drop_p;
   uint64_t seed;
   uint64_t site;
+  float* colsum_out;     /* fp32 [N] or NULL: += column sums of the emitted bf16 values (atomic adds): the bias
+                          * gradient of the Linear that consumes out_bf16.  Needs out_bf16; excludes split-K.   */
 } ecamp_epilogue;
 /* D[M,N] = epilogue(A . B^T).  a_mn / b_mn = 0: operand stored [rows, contraction] (contraction
  * contiguous); = 1: stored [contraction, rows].  tile_n = 0 lets the library choose. */
@@ -90,10 +92,13 @@ ECAMP_API int ecamp_resize_patchify(const float* big, int32_t B, int32_t side_in
 /* LayerNorm forward / backward (fp32 in, bf16 and/or fp32 out). */
 ECAMP_API int ecamp_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int32_t M,
                                   int32_t D, void* out_bf16, float* out_f32, float* mean, float* rstd, void* stream);
+/* dgamma / dbeta / colsum_out (each may be NULL) are ADDED to with atomics; accumulate == 0 zeroes them first.
+ * colsum_out [D] = column sums of dx_bf16 (the bias gradient of the Linear that produced the LayerNorm input's
+ * branch).  ws is unused since ABI 2 (kept so that callers need not change their allocation code). */
 ECAMP_API int ecamp_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
                                   const float* gamma, int32_t M, int32_t D, const float* addend, float* dx_f32,
-                                  void* dx_bf16, float* dgamma, float* dbeta, int32_t accumulate,
-                                  float* ws /* ecamp_layernorm_ws_floats() */, void* stream);
+                                  void* dx_bf16, float* dgamma, float* dbeta, float* colsum_out, int32_t accumulate,
+                                  float* ws /* unused */, void* stream);
 ECAMP_API size_t ecamp_layernorm_ws_floats(void);
 
 /* fused attention (timm Attention; HF BertSelfAttention eager path incl. key-padding mask and

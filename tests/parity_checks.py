@@ -130,11 +130,16 @@ def check_layernorm():
         ref.backward(dy)
         add = torch.randn(M, D, device=dev)
         dx = torch.empty(M, D, device=dev); dxb = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
-        dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)
-        ws = torch.empty(lib.ecamp_layernorm_ws_floats(), device=dev)
-        L.check(lib.ecamp_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(g), M, D, L.ptr(add), L.ptr(dx), L.ptr(dxb), L.ptr(dg), L.ptr(db), 0, L.ptr(ws), L.cur_stream()), "lnb")
+        dg = torch.full((D,), 7.0, device=dev); db = torch.full((D,), -3.0, device=dev)   # accumulate = 0 must overwrite
+        cs = torch.full((D,), 5.0, device=dev)
+        L.check(lib.ecamp_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(g), M, D, L.ptr(add), L.ptr(dx), L.ptr(dxb), L.ptr(dg), L.ptr(db), L.ptr(cs), 0, None, L.cur_stream()), "lnb")
         e2 = rel(dx - add, xr.grad); e3 = rel(dg, gr.grad); e4 = rel(db, br.grad)
-        report(f"layernorm_{D}", e1 < 1e-4 and e2 < 1e-4 and e3 < 1e-4 and e4 < 1e-4, fwd=e1, dx=e2, dgamma=e3, dbeta=e4)
+        e5 = rel(cs, dxb.float().sum(0)); e6 = rel(dxb.float(), dx)
+        # accumulate = 1 adds on top of the running values
+        L.check(lib.ecamp_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(g), M, D, L.ptr(add), L.ptr(dx), L.ptr(dxb), L.ptr(dg), L.ptr(db), None, 1, None, L.cur_stream()), "lnb")
+        e7 = rel(dg, 2 * gr.grad)
+        report(f"layernorm_{D}", e1 < 1e-4 and e2 < 1e-4 and e3 < 1e-4 and e4 < 1e-4 and e5 < 1e-4 and e6 < 5e-3 and e7 < 1e-4,
+               fwd=e1, dx=e2, dgamma=e3, dbeta=e4, colsum=e5, bf16=e6, accumulate=e7)
 
 
 def attn_ref(q, k, v, key_mask, scale):
