@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace ecamp {
 namespace {
@@ -22,6 +23,14 @@ ECAMP_DEVINL void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t
       "{%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// first k-step of an accumulation: C = 0 comes from the zero register instead of 4 cleared accumulator registers
+ECAMP_DEVINL void mma_bf16_16816_z(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%10, %10, %10, %10};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
 }
 ECAMP_DEVINL void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -90,36 +99,54 @@ ECAMP_DEVINL bool attn_keep(const Philox& ph, uint32_t thr16, uint64_t site, uin
 // =============================================================================================
 // forward
 // =============================================================================================
-template <int D, bool DROP>
-__global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
+// The kernels are bound by the element-wise work on the score tile, not by the tensor pipe (ncu: issue slots 75-80 %
+// busy, tensor pipe 26 %), so that part is kept to ~5 instructions per score: one FMNMX for the running maximum on
+// the RAW score (the scale is positive), one FFMA that folds scale * log2(e) and the maximum into the ex2 argument,
+// ex2, one FADD for the row sum and half a pack.  Key masks / the ragged tail are only tested in the 16-column group
+// that contains them, fully padded groups and fully padded 16-row warp slices are skipped.
+ECAMP_DEVINL float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// NW warps of 16 query rows per CTA; the whole K / V of the head is staged once per CTA, so NW is chosen to cover all
+// queries of a head when they fit (decoder: 13 warps for S = 197) - with 64-row CTAs K / V were re-read 4 times
+// through L2, which bounded the kernel.
+template <int D, int NW, bool DROP>
+__global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
+  constexpr int RT = NW * 16, NT_ = NW * 32;
   constexpr int LDS = D + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int Skp = (a.Sk + 15) & ~15;
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
-  bf16* sK = sQ + 64 * LDS;
+  bf16* sK = sQ + RT * LDS;
   bf16* sV = sK + (size_t)Skp * LDS;
   float* sBias = reinterpret_cast<float*>(sV + (size_t)Skp * LDS);  // additive key mask: 0 or -inf
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * RT, h = blockIdx.y, b = blockIdx.z;
   const int g = lane >> 2, t4 = lane & 3;
 
-  load_tile<D, LDS>(sQ, a.q + ((size_t)b * a.Sq + q0) * a.ldq + h * D, a.ldq, 64, min(64, a.Sq - q0), tid, 128);
-  load_tile<D, LDS>(sK, a.k + (size_t)b * a.Sk * a.ldk + h * D, a.ldk, Skp, a.Sk, tid, 128);
-  load_tile<D, LDS>(sV, a.v + (size_t)b * a.Sk * a.ldv + h * D, a.ldv, Skp, a.Sk, tid, 128);
+  load_tile<D, LDS>(sQ, a.q + ((size_t)b * a.Sq + q0) * a.ldq + h * D, a.ldq, RT, min(RT, a.Sq - q0), tid, NT_);
+  load_tile<D, LDS>(sK, a.k + (size_t)b * a.Sk * a.ldk + h * D, a.ldk, Skp, a.Sk, tid, NT_);
+  load_tile<D, LDS>(sV, a.v + (size_t)b * a.Sk * a.ldv + h * D, a.ldv, Skp, a.Sk, tid, NT_);
   // keys after the last attendable one contribute exactly zero: the key loop stops there (padding is a suffix)
-  __shared__ int s_kend;
-  if (tid == 0) s_kend = 0;
+  __shared__ int s_kend, s_kfull;
+  if (tid == 0) { s_kend = 0; s_kfull = Skp; }
   __syncthreads();
-  for (int j = tid; j < Skp; j += 128) {
+  for (int j = tid; j < Skp; j += NT_) {
     bool ok = j < a.Sk;
     if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + j] != 0;
     sBias[j] = ok ? 0.f : -INFINITY;
     if (ok) atomicMax(&s_kend, j + 1);
+    else atomicMin(&s_kfull, j);
   }
   load_tile_wait();
   __syncthreads();
   const int kend = (s_kend + 15) & ~15;
+  const int kfull = s_kfull & ~15;  // every key below this index is attendable: no per-element test needed there
+  if (q0 + warp * 16 >= a.Sq) return;  // this warp's 16 query rows are all padding (no block-wide barrier follows)
 
   uint32_t qf[D / 16][4];
 #pragma unroll
@@ -128,7 +155,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
   float o[D / 8][4];
 #pragma unroll
   for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};  // running maximum of the RAW scores, row sums
+  const float sl2 = a.scale * 1.4426950408889634f;
 
   const Philox ph(a.drop.seed);
   const uint32_t thr = dropout_threshold16(a.drop.p);
@@ -152,24 +180,32 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
         }
       }
     }
-    // scale + mask, block row-max
+    // mask (only in 16-column groups that contain a masked / padded key), block row-max of the raw scores
     float bm[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int jp = 0; jp < 4; ++jp) {
+      const int c0 = kb + jp * 16;
+      if (c0 < kend) {
+        if (c0 + 16 > kfull) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = kb + j * 8 + t4 * 2 + (e & 1);
-        const float bias = col < kend ? sBias[col] : -INFINITY;
-        s[j][e] = s[j][e] * a.scale + bias;
-        bm[e >> 1] = fmaxf(bm[e >> 1], s[j][e]);
+          for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[2 * jp + jj][e] += sBias[c0 + jj * 8 + t4 * 2 + (e & 1)];
+        }
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          bm[0] = fmaxf(bm[0], fmaxf(s[2 * jp + jj][0], s[2 * jp + jj][1]));
+          bm[1] = fmaxf(bm[1], fmaxf(s[2 * jp + jj][2], s[2 * jp + jj][3]));
+        }
       }
     }
-    float corr[2], m_use[2];
+    float corr[2], m_sc[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const float m_new = fmaxf(m_run[r], quad_max(bm[r]));
-      m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
-      corr[r] = __expf(m_run[r] - m_use[r]);  // m_run = -inf -> 0
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      corr[r] = ex2f((m_run[r] - m_use) * sl2);  // m_run = -inf -> 0
+      m_sc[r] = m_use * sl2;
       m_run[r] = m_new;
       l_run[r] *= corr[r];
     }
@@ -179,17 +215,23 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
       o[j][2] *= corr[1]; o[j][3] *= corr[1];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int jp = 0; jp < 4; ++jp) {
+      if (kb + jp * 16 < kend) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float p = __expf(s[j][e] - m_use[e >> 1]);
-        l_run[e >> 1] += p;
-        if (DROP) {
-          const int col = kb + j * 8 + t4 * 2 + (e & 1);
-          const int row = row_g + (e >> 1) * 8;
-          p = attn_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, row, col) ? p * keep_scale : 0.f;
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = 2 * jp + jj;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float p = ex2f(fmaf(s[j][e], sl2, -m_sc[e >> 1]));  // masked: -inf -> 0
+            l_run[e >> 1] += p;
+            if (DROP) {
+              const int col = kb + j * 8 + t4 * 2 + (e & 1);
+              const int row = row_g + (e >> 1) * 8;
+              p = attn_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, row, col) ? p * keep_scale : 0.f;
+            }
+            s[j][e] = p;
+          }
         }
-        s[j][e] = p;
       }
     }
     // O += P V
@@ -222,7 +264,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
       for (int j = 0; j < D / 8; ++j)
         *reinterpret_cast<uint32_t*>(orow + j * 8 + t4 * 2) = pack_bf16x2(o[j][2 * r] * inv, o[j][2 * r + 1] * inv);
-      if (t4 == 0 && a.lse) a.lse[(bh * a.Sq) + row] = (l > 0.f) ? m_run[r] + __logf(l) : -INFINITY;
+      if (t4 == 0 && a.lse) a.lse[(bh * a.Sq) + row] = (l > 0.f) ? m_run[r] * a.scale + __logf(l) : -INFINITY;
     }
   }
 }
@@ -250,68 +292,29 @@ __global__ void attn_delta_kernel(AttnArgs a) {
 //            TR = true : rows = keys    (R1 = K, R2 = V),  columns = queries (C1 = Q, C2 = dO);
 //                        out1 = dK = dS^T Q, out2 = dV = Pdrop^T dO.
 // =============================================================================================
-template <int D, bool TR, bool DROP>
-__global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
+// The backward of one row tile (NW * 16 rows starting at r0) against all columns, operands already in shared memory.
+// Returns (block-uniformly) true when the tile was fully masked and has been zero-filled.
+template <int D, bool TR, bool DROP, int NW>
+ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf16* sR2, const bf16* sC1, const bf16* sC2,
+                                   const float* sColA, const float* sColB, int r0, int cend, int cfull, int b, int h) {
   constexpr int LDS = D + 8;
   constexpr int CB = TR ? 32 : 64;  // column block
   constexpr int NT = CB / 8;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
   const int Sr = TR ? a.Sk : a.Sq;  // row-side length
-  const int Sc = TR ? a.Sq : a.Sk;  // column-side length
-  const int Scp = (Sc + 15) & ~15;
-  bf16* sR1 = reinterpret_cast<bf16*>(smem_raw);
-  bf16* sR2 = sR1 + 64 * LDS;
-  bf16* sC1 = sR2 + 64 * LDS;
-  bf16* sC2 = sC1 + (size_t)Scp * LDS;
-  float* sColA = reinterpret_cast<float*>(sC2 + (size_t)Scp * LDS);  // !TR: key bias (0/-inf); TR: lse per query
-  float* sColB = sColA + Scp;                                        // TR: delta per query
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
   const int g = lane >> 2, t4 = lane & 3;
   const uint64_t bh = (uint64_t)b * a.H + h;
-
-  const bf16* gQ = a.q + (size_t)b * a.Sq * a.ldq + h * D;
-  const bf16* gK = a.k + (size_t)b * a.Sk * a.ldk + h * D;
-  const bf16* gV = a.v + (size_t)b * a.Sk * a.ldv + h * D;
-  const bf16* gdO = a.d_o + (size_t)b * a.Sq * a.ld_do + h * D;
-  const int rvalid = min(64, Sr - r0);
-  __shared__ int s_cend;
-  if (tid == 0) s_cend = TR ? Scp : 0;
-  __syncthreads();
-  if (!TR) {
-    load_tile<D, LDS>(sR1, gQ + (size_t)r0 * a.ldq, a.ldq, 64, rvalid, tid, 128);
-    load_tile<D, LDS>(sR2, gdO + (size_t)r0 * a.ld_do, a.ld_do, 64, rvalid, tid, 128);
-    load_tile<D, LDS>(sC1, gK, a.ldk, Scp, Sc, tid, 128);
-    load_tile<D, LDS>(sC2, gV, a.ldv, Scp, Sc, tid, 128);
-    for (int j = tid; j < Scp; j += 128) {
-      bool ok = j < Sc;
-      if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + j] != 0;
-      sColA[j] = ok ? 0.f : -INFINITY;
-      if (ok) atomicMax(&s_cend, j + 1);
-    }
-  } else {
-    load_tile<D, LDS>(sR1, gK + (size_t)r0 * a.ldk, a.ldk, 64, rvalid, tid, 128);
-    load_tile<D, LDS>(sR2, gV + (size_t)r0 * a.ldv, a.ldv, 64, rvalid, tid, 128);
-    load_tile<D, LDS>(sC1, gQ, a.ldq, Scp, Sc, tid, 128);
-    load_tile<D, LDS>(sC2, gdO, a.ld_do, Scp, Sc, tid, 128);
-    for (int i = tid; i < Scp; i += 128) {
-      sColA[i] = i < Sc ? a.lse[bh * a.Sq + i] : INFINITY;  // +inf -> p = 0 for padded queries
-      sColB[i] = i < Sc ? a.delta[bh * a.Sq + i] : 0.f;
-    }
-  }
-  load_tile_wait();
-  __syncthreads();
-  const int cend = TR ? Scp : ((s_cend + 15) & ~15);  // dQ pass: keys after the last attendable one are skipped
-
+  const float sl2 = a.scale * 1.4426950408889634f;
+  const int rvalid = min(NW * 16, Sr - r0);
   // per-row statistics / validity for this thread's two rows
   const int row_g = r0 + warp * 16 + g;
-  float row_a[2], row_b[2];
+  float row_a[2], row_b[2];  // !TR: -lse * log2(e), delta;  TR: key bias (0 / -inf), unused
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int row = row_g + r * 8;
     if (!TR) {
-      row_a[r] = row < Sr ? a.lse[bh * a.Sq + row] : INFINITY;
+      row_a[r] = row < Sr ? -a.lse[bh * a.Sq + row] * 1.4426950408889634f : -INFINITY;  // lse = -inf (fully masked row) -> +inf
+      if (row < Sr && a.lse[bh * a.Sq + row] == -INFINITY) row_a[r] = -INFINITY;          // ... which must still give p = 0
       row_b[r] = 0.f;  // delta: produced by pass 0 below
     } else {
       bool ok = row < Sr;
@@ -324,15 +327,16 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
   if (TR) {
     const int any_valid = __syncthreads_or((row_a[0] == 0.f || row_a[1] == 0.f) ? 1 : 0);
     if (!any_valid) {
-      for (int idx = tid; idx < rvalid * (D / 8); idx += 128) {
+      for (int idx = tid; idx < rvalid * (D / 8); idx += NW * 32) {
         const int r = idx / (D / 8), c8 = idx % (D / 8);
         const size_t row = (size_t)b * a.Sk + r0 + r;
         *reinterpret_cast<uint4*>(a.dk + row * a.lddk + h * D + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(a.dv + row * a.lddv + h * D + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
       }
-      return;
+      return true;  // block-uniform: nothing else to do for this row tile
     }
   }
+  if (r0 + warp * 16 >= Sr) return false;  // this warp's 16 rows are all padding
 
   float acc1[D / 8][4];
   float acc2[TR ? D / 8 : 1][4];
@@ -349,6 +353,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
   // the SAME P / dP that pass 1 uses for dS = P (dP - delta), so the cancellation inside (dP - delta) is exact
   // (computing delta from the bf16-rounded O, FlashAttention-style, loses it when attention is near-uniform).
   // delta is also published for the dK/dV kernel, which runs afterwards on the same stream.
+  // Element-wise work per score: p = ex2(s * scale*log2e + (bias) - lse*log2e) (one FFMA + ex2; the bias only in
+  // 16-column groups that contain a masked / padded key), then pass 0: one FFMA; pass 1: FADD + 2 FMUL + packs.
   float dsum[2] = {0.f, 0.f};
 #pragma unroll 1
   for (int pass = TR ? 1 : 0; pass < 2; ++pass) {
@@ -377,33 +383,46 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
         }
       }
     }
-    // p = exp(scale * s + key_bias - lse); ds = p * (dp_eff - delta) * scale
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
+    for (int jp = 0; jp < NT / 2; ++jp) {
+      const int c0 = cb + jp * 16;
+      if (c0 < cend) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = cb + j * 8 + t4 * 2 + (e & 1);
-        const int r = e >> 1;
-        const bool cin = col < cend;
-        float lse, delta, bias;
-        if (!TR) {
-          lse = row_a[r]; delta = row_b[r]; bias = cin ? sColA[col] : -INFINITY;
-        } else {
-          lse = cin ? sColA[col] : INFINITY; delta = cin ? sColB[col] : 0.f; bias = row_a[r];
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = 2 * jp + jj;
+          const int colb = c0 + jj * 8 + t4 * 2;  // this thread's two columns of the 8-wide n-tile: colb, colb + 1
+          float ce[2], cd[2];                     // per-column exponent offset / delta
+          if (!TR) {
+            ce[0] = ce[1] = 0.f;
+            if (c0 + 16 > cfull) { ce[0] = sColA[colb]; ce[1] = sColA[colb + 1]; }
+            cd[0] = cd[1] = 0.f;
+          } else {
+            const float2 la = *reinterpret_cast<const float2*>(sColA + colb);
+            const float2 de = *reinterpret_cast<const float2*>(sColB + colb);
+            ce[0] = la.x; ce[1] = la.y; cd[0] = de.x; cd[1] = de.y;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = e >> 1, cc = e & 1;
+            // !TR: exponent = s*sl2 + key_bias - lse2(row);  TR: s*sl2 + key_bias(row) - lse2(col)
+            const float p = ex2f(fmaf(s[j][e], sl2, ce[cc] + row_a[r]));  // masked / padded -> ex2(-inf) = 0
+            float dpe = dp[j][e];
+            float pd = p;
+            if (DROP) {
+              const int row = row_g + r * 8, col = colb + cc;
+              const int qi = TR ? col : row, kj = TR ? row : col;
+              const bool keep = attn_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, qi, kj);
+              dpe = keep ? dpe * keep_scale : 0.f;
+              pd = keep ? p * keep_scale : 0.f;
+            }
+            if (!TR && pass == 0) {
+              dsum[r] = fmaf(p, dpe, dsum[r]);
+            } else {
+              s[j][e] = (p * a.scale) * (dpe - (TR ? cd[cc] : row_b[r]));  // dS
+              dp[j][e] = pd;                                                // dropped probabilities (only used when TR)
+            }
+          }
         }
-        float p = __expf(s[j][e] * a.scale + bias - lse);  // masked / padded -> exp(-inf) = 0
-        float dpe = dp[j][e];
-        float pd = p;
-        if (DROP) {
-          const int row = row_g + r * 8;
-          const int qi = TR ? col : row, kj = TR ? row : col;
-          const bool keep = attn_keep(ph, thr, a.drop.site, bh, a.Sq, a.Sk, qi, kj);
-          dpe = keep ? dpe * keep_scale : 0.f;
-          pd = keep ? p * keep_scale : 0.f;
-        }
-        if (pass == 0) dsum[r] += p * dpe;
-        s[j][e] = p * (dpe - delta) * a.scale;  // dS
-        dp[j][e] = pd;                          // dropped probabilities (only used when TR)
       }
     }
     if (pass == 0) continue;
@@ -468,17 +487,120 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
       }
     }
   }
+  return false;
+}
+
+// stand-alone kernels: TR = false produces dQ (+ delta), TR = true produces dK / dV; one CTA per 64-row tile
+template <int D, bool TR, bool DROP>
+__global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
+  constexpr int LDS = D + 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int Sr = TR ? a.Sk : a.Sq;  // row-side length
+  const int Sc = TR ? a.Sq : a.Sk;  // column-side length
+  const int Scp = (Sc + 15) & ~15;
+  bf16* sR1 = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sR2 = sR1 + 64 * LDS;
+  bf16* sC1 = sR2 + 64 * LDS;
+  bf16* sC2 = sC1 + (size_t)Scp * LDS;
+  float* sColA = reinterpret_cast<float*>(sC2 + (size_t)Scp * LDS);  // !TR: key bias (0/-inf); TR: -lse * log2(e) per query
+  float* sColB = sColA + Scp;                                        // TR: delta per query
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const uint64_t bh = (uint64_t)b * a.H + h;
+  const bf16* gQ = a.q + (size_t)b * a.Sq * a.ldq + h * D;
+  const bf16* gK = a.k + (size_t)b * a.Sk * a.ldk + h * D;
+  const bf16* gV = a.v + (size_t)b * a.Sk * a.ldv + h * D;
+  const bf16* gdO = a.d_o + (size_t)b * a.Sq * a.ld_do + h * D;
+  const int rvalid = min(64, Sr - r0);
+  __shared__ int s_cend, s_cfull;
+  if (tid == 0) { s_cend = TR ? Scp : 0; s_cfull = Scp; }
+  __syncthreads();
+  if (!TR) {
+    load_tile<D, LDS>(sR1, gQ + (size_t)r0 * a.ldq, a.ldq, 64, rvalid, tid, 128);
+    load_tile<D, LDS>(sR2, gdO + (size_t)r0 * a.ld_do, a.ld_do, 64, rvalid, tid, 128);
+    load_tile<D, LDS>(sC1, gK, a.ldk, Scp, Sc, tid, 128);
+    load_tile<D, LDS>(sC2, gV, a.ldv, Scp, Sc, tid, 128);
+    for (int j = tid; j < Scp; j += 128) {
+      bool ok = j < Sc;
+      if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + j] != 0;
+      sColA[j] = ok ? 0.f : -INFINITY;
+      if (ok) atomicMax(&s_cend, j + 1);
+      else atomicMin(&s_cfull, j);
+    }
+  } else {
+    load_tile<D, LDS>(sR1, gK + (size_t)r0 * a.ldk, a.ldk, 64, rvalid, tid, 128);
+    load_tile<D, LDS>(sR2, gV + (size_t)r0 * a.ldv, a.ldv, 64, rvalid, tid, 128);
+    load_tile<D, LDS>(sC1, gQ, a.ldq, Scp, Sc, tid, 128);
+    load_tile<D, LDS>(sC2, gdO, a.ld_do, Scp, Sc, tid, 128);
+    for (int i = tid; i < Scp; i += 128) {
+      const float l = i < Sc ? a.lse[bh * a.Sq + i] : -INFINITY;  // -inf: padded / fully masked query row -> p = 0
+      sColA[i] = l == -INFINITY ? -INFINITY : -l * 1.4426950408889634f;
+      sColB[i] = i < Sc ? a.delta[bh * a.Sq + i] : 0.f;
+    }
+  }
+  load_tile_wait();
+  __syncthreads();
+  const int cend = TR ? Scp : ((s_cend + 15) & ~15);  // dQ pass: keys after the last attendable one are skipped
+  const int cfull = TR ? Scp : (s_cfull & ~15);       // dQ pass: columns below this need no mask test
+  attn_bwd_compute<D, TR, DROP, 4>(a, sR1, sR2, sC1, sC2, sColA, sColB, r0, cend, cfull, b, h);
+}
+
+// merged kernel: ONE CTA per (batch, head) with all of Q, dO, K, V (<= NW * 16 rows each) staged once; first the dQ
+// problem (rows = queries), then - delta handed over through global memory, block-local - the transposed dK / dV
+// problem (rows = keys) on the same tiles.  The two stand-alone kernels re-read K, V / Q, dO for every 64-row tile
+// (8 x the bytes through L2 for the decoder's 197 x 197 heads), which is what bounded them.
+template <int D, int NW, bool DROP>
+__global__ void __launch_bounds__(NW * 32) attn_bwd_merged_kernel(AttnArgs a) {
+  constexpr int LDS = D + 8, RT = NW * 16, NT_ = NW * 32;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sdO = sQ + RT * LDS;
+  bf16* sK = sdO + RT * LDS;
+  bf16* sV = sK + RT * LDS;
+  float* sColA = reinterpret_cast<float*>(sV + RT * LDS);
+  float* sColB = sColA + RT;
+  const int tid = threadIdx.x;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const uint64_t bh = (uint64_t)b * a.H + h;
+  const int Skp = (a.Sk + 15) & ~15, Sqp = (a.Sq + 15) & ~15;
+  __shared__ int s_cend, s_cfull;
+  if (tid == 0) { s_cend = 0; s_cfull = Skp; }
+  __syncthreads();
+  load_tile<D, LDS>(sQ, a.q + (size_t)b * a.Sq * a.ldq + h * D, a.ldq, RT, a.Sq, tid, NT_);
+  load_tile<D, LDS>(sdO, a.d_o + (size_t)b * a.Sq * a.ld_do + h * D, a.ld_do, RT, a.Sq, tid, NT_);
+  load_tile<D, LDS>(sK, a.k + (size_t)b * a.Sk * a.ldk + h * D, a.ldk, RT, a.Sk, tid, NT_);
+  load_tile<D, LDS>(sV, a.v + (size_t)b * a.Sk * a.ldv + h * D, a.ldv, RT, a.Sk, tid, NT_);
+  for (int j = tid; j < Skp; j += NT_) {
+    bool ok = j < a.Sk;
+    if (ok && a.key_mask) ok = a.key_mask[(size_t)b * a.Sk + j] != 0;
+    sColA[j] = ok ? 0.f : -INFINITY;
+    if (ok) atomicMax(&s_cend, j + 1);
+    else atomicMin(&s_cfull, j);
+  }
+  load_tile_wait();
+  __syncthreads();
+  attn_bwd_compute<D, false, DROP, NW>(a, sQ, sdO, sK, sV, sColA, sColB, 0, (s_cend + 15) & ~15, s_cfull & ~15, b, h);
+  __syncthreads();  // delta of every query row of this head is in global memory (written by this CTA); sColA is free
+  for (int i = tid; i < Sqp; i += NT_) {
+    const float l = i < a.Sq ? a.lse[bh * a.Sq + i] : -INFINITY;
+    sColA[i] = l == -INFINITY ? -INFINITY : -l * 1.4426950408889634f;
+    sColB[i] = i < a.Sq ? a.delta[bh * a.Sq + i] : 0.f;
+  }
+  __syncthreads();
+  attn_bwd_compute<D, true, DROP, NW>(a, sK, sV, sQ, sdO, sColA, sColB, 0, Sqp, Sqp, b, h);
 }
 
 constexpr int kMaxDynSmem = 226 * 1024;  // 227 KB per CTA minus the kernels' static shared variables
-size_t fwd_smem(int D, int Sk) {
+size_t fwd_smem(int D, int Sk, int rows = 64) {
   const int LDS = D + 8, Skp = (Sk + 15) & ~15;
-  return (size_t)(64 + 2 * Skp) * LDS * 2 + (size_t)Skp * 4;
+  return (size_t)(rows + 2 * Skp) * LDS * 2 + (size_t)Skp * 4;
 }
 size_t bwd_smem(int D, int Sc) {
   const int LDS = D + 8, Scp = (Sc + 15) & ~15;
   return (size_t)(128 + 2 * Scp) * LDS * 2 + (size_t)Scp * 8;
 }
+constexpr int kBigNW = 13;  // 13 warps x 16 rows = 208 rows: one CTA covers a whole decoder head (S = 197)
+size_t merged_smem(int D) { return (size_t)4 * kBigNW * 16 * (D + 8) * 2 + (size_t)kBigNW * 16 * 8; }
 
 int check_args(const AttnArgs& a, bool bwd) {
   ECAMP_REQUIRE(a.D == 32 || a.D == 64 || a.D == 128, "attention: head_dim must be 32, 64 or 128 (got %d)", a.D);
@@ -497,22 +619,43 @@ int check_args(const AttnArgs& a, bool bwd) {
   return 0;
 }
 
-template <int D>
-int launch_fwd(const AttnArgs& a, cudaStream_t st) {
-  const size_t sm = fwd_smem(D, a.Sk);
-  dim3 grid((a.Sq + 63) / 64, a.H, a.B);
+template <int D, int NW>
+int launch_fwd_nw(const AttnArgs& a, cudaStream_t st) {
+  const size_t sm = fwd_smem(D, a.Sk, NW * 16);
+  dim3 grid((a.Sq + NW * 16 - 1) / (NW * 16), a.H, a.B);
   if (a.drop.p > 0.f) {
-    ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    attn_fwd_kernel<D, true><<<grid, 128, sm, st>>>(a);
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    attn_fwd_kernel<D, NW, true><<<grid, NW * 32, sm, st>>>(a);
   } else {
-    ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    attn_fwd_kernel<D, false><<<grid, 128, sm, st>>>(a);
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    attn_fwd_kernel<D, NW, false><<<grid, NW * 32, sm, st>>>(a);
   }
   ECAMP_LAUNCHED();
   return 0;
 }
 template <int D>
+int launch_fwd(const AttnArgs& a, cudaStream_t st) {
+  // head_dim 32 (ViT decoder): one CTA per head when all its queries fit in 13 warps
+  static const int big = getenv("ECAMP_ATTN_BIG") ? atoi(getenv("ECAMP_ATTN_BIG")) : 0;  // measured slower (1 CTA / SM)
+  if (big && D == 32 && a.Sq > 64 && a.Sq <= kBigNW * 16 && fwd_smem(D, a.Sk, kBigNW * 16) <= (size_t)kMaxDynSmem)
+    return launch_fwd_nw<32, kBigNW>(a, st);
+  return launch_fwd_nw<D, 4>(a, st);
+}
+template <int D>
 int launch_bwd(const AttnArgs& a, cudaStream_t st) {
+  static const int big = getenv("ECAMP_ATTN_BIG") ? atoi(getenv("ECAMP_ATTN_BIG")) : 0;  // measured slower (1 CTA / SM)
+  if (big && D == 32 && a.Sq <= kBigNW * 16 && a.Sk <= kBigNW * 16 && (a.Sq > 64 || a.Sk > 64)) {
+    dim3 grid(a.H, a.B);
+    if (a.drop.p > 0.f) {
+      ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_merged_kernel<32, kBigNW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      attn_bwd_merged_kernel<32, kBigNW, true><<<grid, kBigNW * 32, merged_smem(32), st>>>(a);
+    } else {
+      ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_merged_kernel<32, kBigNW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      attn_bwd_merged_kernel<32, kBigNW, false><<<grid, kBigNW * 32, merged_smem(32), st>>>(a);
+    }
+    ECAMP_LAUNCHED();
+    return 0;
+  }
   dim3 gq((a.Sq + 63) / 64, a.H, a.B);
   dim3 gk((a.Sk + 63) / 64, a.H, a.B);
   if (a.drop.p > 0.f) {
@@ -548,7 +691,9 @@ void set_attention_tc(int on) { g_attn_tc = on; }
 
 int attention_fwd(const AttnArgs& a, cudaStream_t st) {
   if (int rc = check_args(a, false)) return rc;
-  if (g_attn_tc && attention_tc_fwd_supported(a)) return attention_tc_fwd(a, st);
+  // measured (scripts/attn_time.py): ViT encoder heads (50 x 50, head_dim 64) 27 us on the mma.sync kernel, 39 us on tcgen05
+  const bool small64 = a.D == 64 && a.Sq <= 64 && a.Sk <= 64;
+  if (g_attn_tc && !small64 && attention_tc_fwd_supported(a)) return attention_tc_fwd(a, st);
   if (a.D == 32) return launch_fwd<32>(a, st);
   if (a.D == 64) return launch_fwd<64>(a, st);
   return launch_fwd<128>(a, st);

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) sr_fwd_kernel(const float* __restrict__ p
 
 // backward: one CTA per 32x32 tile of d_u.  Dynamic smem layout: U 40^2x3 | H 38^2x3 | dOut 36^2x3 | dH 34^2x3
 constexpr int SR_BWD_SMEM_FLOATS = 3 * (40 * 40 + 38 * 38 + 36 * 36 + 34 * 34) + 8;
-__global__ void __launch_bounds__(256) sr_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ big,
+__global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ big,
                                                      const int64_t* __restrict__ column,
                                                      const int64_t* __restrict__ row, int B,
                                                      const float* __restrict__ g_res, float* __restrict__ d_u,
@@ -286,55 +286,64 @@ __global__ void __launch_bounds__(256) sr_bwd_kernel(const float* __restrict__ p
       *reinterpret_cast<float4*>(d_u + (((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox0) =
           make_float4(d[c][0], d[c][1], d[c][2], d[c][3]);
   }
-  // conv weight gradients over the OWNED 32x32 pixels only (each pixel is owned by exactly one tile)
+  // conv weight gradients over the OWNED 32x32 pixels only (each pixel is owned by exactly one tile): every thread
+  // takes one strip of 4 horizontally adjacent pixels (6 shared loads feed the 36 products of a (ci, ky) row), then
+  // the 84 per-thread sums are reduced across the warp with a halving butterfly (31 shuffles per 32 values instead
+  // of 5 per value) and across the 8 warps through shared memory.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int soy = threadIdx.x >> 3, sox0 = (threadIdx.x & 7) * 4;
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
-    float acc[84];
+    float acc[96];
 #pragma unroll
-    for (int k = 0; k < 84; ++k) acc[k] = 0.f;
-    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
-      const int oy = i >> 5, ox = i & 31;
-      if (which == 0) {
-        // conv2: d_w2[co][ci][ky][kx] += dOut(Y, X)[co] * H(Y + ky - 1, X + kx - 1)[ci]
-        float g[3];
+    for (int k = 0; k < 96; ++k) acc[k] = 0.f;
+    // which == 0: conv2: d_w2[co][ci][ky][kx] += dOut(Y, X)[co] * H(Y + ky - 1, X + kx - 1)[ci]
+    // which == 1: conv1: d_w1[co][ci][ky][kx] += dH(Y, X)[co]   * U(Y + ky - 1, X + kx - 1)[ci]
+    const float* gsrc = which == 0 ? sDO : sDH;
+    const int gW = which == 0 ? OW : GW, goff = which == 0 ? 2 : 1;
+    const float* isrc = which == 0 ? sH : sU;
+    const int iW = which == 0 ? HW : UW, ioff = which == 0 ? 2 : 3;
+    float g[3][4];
 #pragma unroll
-        for (int co = 0; co < 3; ++co) g[co] = sDO[co * OW * OW + (oy + 2) * OW + ox + 2];
+    for (int co = 0; co < 3; ++co)
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
+      for (int q = 0; q < 4; ++q) g[co][q] = gsrc[co * gW * gW + (soy + goff) * gW + sox0 + goff + q];
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+    for (int co = 0; co < 3; ++co) acc[81 + co] = (g[co][0] + g[co][1]) + (g[co][2] + g[co][3]);
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const float hv = sH[ci * HW * HW + (oy + 2 + ky) * HW + ox + 2 + kx];
+    for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-              for (int co = 0; co < 3; ++co) acc[(co * 3 + ci) * 9 + ky * 3 + kx] += g[co] * hv;
-            }
+      for (int ky = 0; ky < 3; ++ky) {
+        const float* r = isrc + ci * iW * iW + (soy + ioff + ky) * iW + sox0 + ioff;
+        float v[6];
 #pragma unroll
-        for (int co = 0; co < 3; ++co) acc[81 + co] += g[co];
-      } else {
-        // conv1: d_w1[co][ci][ky][kx] += dH(Y, X)[co] * U(Y + ky - 1, X + kx - 1)[ci]
-        float g[3];
+        for (int j = 0; j < 6; ++j) v[j] = r[j];
 #pragma unroll
-        for (int co = 0; co < 3; ++co) g[co] = sDH[co * GW * GW + (oy + 1) * GW + ox + 1];
+        for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const float uv = sU[ci * UW * UW + (oy + 3 + ky) * UW + ox + 3 + kx];
-#pragma unroll
-              for (int co = 0; co < 3; ++co) acc[(co * 3 + ci) * 9 + ky * 3 + kx] += g[co] * uv;
-            }
-#pragma unroll
-        for (int co = 0; co < 3; ++co) acc[81 + co] += g[co];
+          for (int co = 0; co < 3; ++co) {
+            float s = g[co][0] * v[kx];
+            s = fmaf(g[co][1], v[kx + 1], s);
+            s = fmaf(g[co][2], v[kx + 2], s);
+            s = fmaf(g[co][3], v[kx + 3], s);
+            acc[(co * 3 + ci) * 9 + ky * 3 + kx] = s;
+          }
       }
-    }
+    // butterfly: after the step with distance d a lane keeps the half of its values selected by (lane & d), so
+    // that in the end lane l holds the warp total of value l (three groups of 32 values)
 #pragma unroll
-    for (int k = 0; k < 84; ++k) {
-      const float v = warp_sum(acc[k]);
-      if (lane == 0) redw[warp][k] = v;
+    for (int grp = 0; grp < 3; ++grp) {
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        const bool up = (lane & d) != 0;
+#pragma unroll
+        for (int i = 0; i < d; ++i) {
+          const float lo = acc[grp * 32 + i], hi = acc[grp * 32 + i + d];
+          const float send = up ? lo : hi, keep = up ? hi : lo;
+          acc[grp * 32 + i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+        }
+      }
+      if (grp * 32 + lane < 84) redw[warp][grp * 32 + lane] = acc[grp * 32];
     }
     __syncthreads();
     if (threadIdx.x < 84) {
