@@ -29,9 +29,25 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span
-constexpr int kThreads = 352;  // 11 warps: 65536 / 352 leaves 184 registers per thread for the epilogue
+// Warps 0-2: TMA producer, MMA issuer, TMEM allocator; then kNumEpiWarps epilogue warps (8: two per TMEM lane quarter,
+// each draining half of the tile's columns in 32-column chunks; or 16: four per quarter, 16-column chunks, <= 96
+// registers).  Measured on B200 (profiles/r01c_gemm_epilogue_study.md): both configurations run the GELU / dGELU /
+// residual epilogues at the same speed, and so does a build whose epilogue skips its global stores - the fused
+// epilogues are bound by SHARED-MEMORY bandwidth (operand reads of the MMAs + TMA writes + the transpose tile), not
+// by issue slots or by the stores, so the 8-warp configuration (fewer instructions per element) is kept.
+#ifndef ECAMP_NEPI
+#define ECAMP_NEPI 8
+#endif
+constexpr int kNumEpiWarps = ECAMP_NEPI;           // 8 or 16
 constexpr int kEpiWarp0 = 3;
-constexpr int kNumEpiWarps = 8;
+constexpr int kThreads = (kEpiWarp0 + kNumEpiWarps) * 32;
+constexpr int kCW = kNumEpiWarps == 16 ? 16 : 32;  // chunk width (columns per tcgen05.ld / transpose)
+constexpr int kSlices = kNumEpiWarps / 4;          // column slices of a tile (one per group of 4 epilogue warps)
+constexpr int kLPR = kCW / 4;                      // lanes per row in the coalesced layout (16 bytes each)
+constexpr int kRPS = 32 / kLPR;                    // rows per step
+constexpr int kSteps = 32 / kRPS;                  // steps per chunk (= kLPR)
+constexpr int kStageFloats = 32 * kCW;             // transpose tile of one warp
+
 
 template <int BN>
 struct Cfg {
@@ -39,7 +55,7 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 128) ? 6 : 4;
-  static constexpr int EPI_BYTES = kNumEpiWarps * 4096;  // one 32 x 32 fp32 transpose tile per epilogue warp
+  static constexpr int EPI_BYTES = kNumEpiWarps * kStageFloats * 4;  // one 32 x kCW fp32 transpose tile per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget of one CTA exceeded");
 };
@@ -160,12 +176,12 @@ ECAMP_DEVINL void epi_vec4_generic(const EpiArgs& ea, float4 v, int row, int col
 
 // what a specialised mode prefetches one chunk ahead (one 16-byte register slot per step)
 template <int MODE>
-ECAMP_DEVINL void epi_prefetch(const GemmEpilogue& ep, int row0, int col, int M, int N, uint4 (&p)[8]) {
+ECAMP_DEVINL void epi_prefetch(const GemmEpilogue& ep, int row0, int col, int M, int N, uint4 (&p)[kSteps]) {
   if (MODE != EM_F32_RES && MODE != EM_F32_RES_DROP && MODE != EM_DGELU) return;
   if (col >= N) return;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = row0 + 4 * i;
+  for (int i = 0; i < kSteps; ++i) {
+    const int row = row0 + kRPS * i;
     if (row < M) {
       if (MODE == EM_DGELU) {
         const uint2 u = __ldg(reinterpret_cast<const uint2*>(ep.aux_in + (size_t)row * ep.ld_aux + col));
@@ -177,9 +193,6 @@ ECAMP_DEVINL void epi_prefetch(const GemmEpilogue& ep, int row0, int col, int M,
   }
 }
 
-// The epilogue of one warp for one accumulator stage: TMEM lane quarter at `taddr`, columns [ncol0, ncol0 + HALF_N) of
-// the tile whose first output row (of this quarter) is m0.  `stage4k` is the warp's private 4 KB transpose tile.
-// Arrives on `tmem_empty` as soon as the last TMEM read has landed.
 ECAMP_DEVINL void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -188,19 +201,22 @@ ECAMP_DEVINL float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// swizzle of the transpose tile: 16-byte unit `unit` of row `r` lives at unit ^ swz(r), which makes both the
+// row-per-thread stores and the coalesced-layout loads conflict-free (rows are kCW * 4 = 128 or 64 bytes)
+ECAMP_DEVINL int epi_swz(int r) { return kCW == 32 ? (r & 7) : ((r >> 1) & 3); }
 
-// Pull the epilogue operand (fp32 residual or bf16 dGELU pre-activation) of a 32-row x HALF_N-column region into L2:
+// Pull the epilogue operand (fp32 residual or bf16 dGELU pre-activation) of a 32-row x COLS-column region into L2:
 // issued one tile ahead, so that the register prefetch of epi_prefetch (one chunk ahead) only ever pays L2 latency.
-template <int HALF_N, int MODE>
+template <int COLS, int MODE>
 ECAMP_DEVINL void epi_prefetch_l2(const GemmEpilogue& ep, int m0, int ncol0, int M, int N, int lane) {
   if (MODE != EM_F32_RES && MODE != EM_F32_RES_DROP && MODE != EM_DGELU) return;
-  constexpr int ROW_BYTES = HALF_N * (MODE == EM_DGELU ? 2 : 4);
+  constexpr int ROW_BYTES = COLS * (MODE == EM_DGELU ? 2 : 4);
   constexpr int LINES = (ROW_BYTES + 127) / 128;  // 128-byte lines per row of the region
 #pragma unroll
   for (int j = 0; j < LINES; ++j) {
     const int row = m0 + lane;
     const int col = ncol0 + j * (MODE == EM_DGELU ? 64 : 32);
-    if (row < M && col < N && col < ncol0 + HALF_N) {
+    if (row < M && col < N && col < ncol0 + COLS) {
       const void* p = MODE == EM_DGELU ? static_cast<const void*>(ep.aux_in + (size_t)row * ep.ld_aux + col)
                                        : static_cast<const void*>(ep.residual + (size_t)row * ep.ld_res + col);
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -208,29 +224,34 @@ ECAMP_DEVINL void epi_prefetch_l2(const GemmEpilogue& ep, int m0, int ncol0, int
   }
 }
 
-template <int HALF_N, int MODE>
-ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int ncol0, int M, int N, float* stage4k,
+// The epilogue of one warp for one accumulator stage: TMEM lane quarter at `taddr`, columns [ncol0, ncol0 + COLS) of
+// the tile whose first output row (of this quarter) is m0.  `stage` is the warp's private transpose tile.
+// Arrives on `tmem_empty` as soon as the last TMEM read has landed.
+template <int COLS, int MODE>
+ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int ncol0, int M, int N, float* stage,
                                 int lane, uint64_t* tmem_full, uint32_t full_phase, uint64_t* tmem_empty,
                                 bool remote_empty, int next_m0, int next_ncol0) {
-  constexpr int NCH = HALF_N / 32;
+  constexpr int NCH = COLS / kCW;
+  static_assert(COLS % kCW == 0, "column slice must be whole chunks");
   const GemmEpilogue& ep = ea.ep;
-  const int sub = lane >> 3, u = lane & 7;  // coalesced layout: step i -> row 4 i + sub, 16-byte unit u
+  const int sub = lane / kLPR, u = lane % kLPR;  // coalesced layout: step i -> row kRPS i + sub, 16-byte unit u
   const bool vbias = MODE != EM_ATOMIC && MODE != EM_DGELU && ea.split_k == 1 && ep.bias && ea.vec_ok;
   const int row0 = m0 + sub;
-  const uint32_t stage_addr = smem_u32(stage4k);  // explicit shared-space accesses (the generic pointer compiled to LD.E / ST.E)
-  uint4 pcur[8], pnext[8];
+  const uint32_t stage_addr = smem_u32(stage);  // explicit shared-space accesses (a generic pointer compiled to LD.E / ST.E)
+  uint4 pcur[kSteps], pnext[kSteps];
   epi_prefetch<MODE>(ep, row0, ncol0 + 4 * u, M, N, pcur);  // in flight while the accumulator is still being produced
-  if (next_m0 >= 0) epi_prefetch_l2<HALF_N, MODE>(ep, next_m0, next_ncol0, M, N, lane);
+  if (next_m0 >= 0) epi_prefetch_l2<COLS, MODE>(ep, next_m0, next_ncol0, M, N, lane);
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), bias_next = bias4;
   if (vbias && ncol0 + 4 * u + 4 <= N) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + ncol0 + 4 * u));
   mbar_wait(tmem_full, full_phase);
   tc_fence_after();
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
-    uint32_t raw[32];
-    tmem_ld_32x32(taddr + (uint32_t)(c * 32), raw);
-    const int col = ncol0 + c * 32 + 4 * u;
-    if (vbias && c + 1 < NCH && col + 36 <= N) bias_next = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 32));
+    uint32_t raw[kCW];
+    if (kCW == 32) tmem_ld_32x32(taddr + (uint32_t)(c * kCW), reinterpret_cast<uint32_t(&)[32]>(raw));
+    else tmem_ld_32x16(taddr + (uint32_t)(c * kCW), reinterpret_cast<uint32_t(&)[16]>(raw));
+    const int col = ncol0 + c * kCW + 4 * u;
+    if (vbias && c + 1 < NCH && col + kCW + 4 <= N) bias_next = __ldg(reinterpret_cast<const float4*>(ep.bias + col + kCW));
     tmem_ld_wait();
     if (c == NCH - 1) {
       // all of this warp's TMEM reads for the tile are done: hand the accumulator stage back
@@ -242,33 +263,34 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
       }
     }
     if (ea.dbg == 1) continue;
-    // transpose: thread = row `lane` writes its 8 16-byte units, unit j at physical slot j ^ (lane & 7)
+    // transpose: thread = row `lane` writes its kLPR 16-byte units, unit j at physical slot j ^ swz(lane)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      sts128(stage_addr + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), raw[4 * j], raw[4 * j + 1], raw[4 * j + 2],
-             raw[4 * j + 3]);
-    if (c + 1 < NCH) epi_prefetch<MODE>(ep, row0, col + 32, M, N, pnext);  // next chunk's operand in flight from here
+    for (int j = 0; j < kLPR; ++j)
+      sts128(stage_addr + (uint32_t)(lane * (kCW * 4) + ((j ^ epi_swz(lane)) << 4)), raw[4 * j], raw[4 * j + 1],
+             raw[4 * j + 2], raw[4 * j + 3]);
+    if (c + 1 < NCH) epi_prefetch<MODE>(ep, row0, col + kCW, M, N, pnext);  // next chunk's operand in flight from here
     __syncwarp();
     float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // EM_DGELU: column sums of this chunk's emitted values
+    constexpr int BATCH = kSteps < 4 ? kSteps : 4;   // steps per batch: keeps the live registers bounded
 #pragma unroll
-    for (int hb = 0; hb < 2; ++hb) {  // two batches of four steps keep the live registers below the 168 available
-      float4 v[4];
+    for (int hb = 0; hb < kSteps / BATCH; ++hb) {
+      float4 v[BATCH];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = 4 * (4 * hb + k) + sub;
-        v[k] = lds128(stage_addr + (uint32_t)(r * 128 + ((u ^ (r & 7)) << 4)));
+      for (int k = 0; k < BATCH; ++k) {
+        const int r = kRPS * (BATCH * hb + k) + sub;
+        v[k] = lds128(stage_addr + (uint32_t)(r * (kCW * 4) + ((u ^ epi_swz(r)) << 4)));
       }
       if (MODE == EM_GENERIC) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int row = row0 + 4 * (4 * hb + k);
+        for (int k = 0; k < BATCH; ++k) {
+          const int row = row0 + kRPS * (BATCH * hb + k);
           if (row < M && col < N) epi_vec4_generic(ea, v[k], row, col, N, bias4);
         }
       } else if (col < N) {  // specialised modes require N % 4 == 0 and 16-byte aligned operands (host-checked)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = 4 * hb + k;
-          const int row = row0 + 4 * i;
+        for (int k = 0; k < BATCH; ++k) {
+          const int i = BATCH * hb + k;
+          const int row = row0 + kRPS * i;
           if (row < M) {
             float4 x = v[k];
             if (MODE == EM_ATOMIC) {
@@ -280,7 +302,7 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
             if (MODE != EM_DGELU) { x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w; }
             if (MODE == EM_GELU) {
               const uint2 pk = pack4(x);
-              *reinterpret_cast<uint2*>(ep.aux_out + (size_t)row * ep.ld_aux + col) = pk;
+              if (ea.dbg != 3 || x.x == 123.456f) *reinterpret_cast<uint2*>(ep.aux_out + (size_t)row * ep.ld_aux + col) = pk;
               const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
               x.x = gelu_erf(a.x); x.y = gelu_erf(a.y); x.z = gelu_erf(b.x); x.w = gelu_erf(b.y);
             }
@@ -293,11 +315,11 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
               x.x += __uint_as_float(pcur[i].x); x.y += __uint_as_float(pcur[i].y);
               x.z += __uint_as_float(pcur[i].z); x.w += __uint_as_float(pcur[i].w);
             }
-            if (MODE == EM_F32 || MODE == EM_F32_RES || MODE == EM_F32_RES_DROP)
-              *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ld_f32 + col) = x;
-            else {
+            if (MODE == EM_F32 || MODE == EM_F32_RES || MODE == EM_F32_RES_DROP) {
+              if (ea.dbg != 3 || x.x == 123.456f) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ld_f32 + col) = x;
+            } else {
               const uint2 pk = pack4(x);
-              *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ld_bf16 + col) = pk;
+              if (ea.dbg != 3 || x.x == 123.456f) *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ld_bf16 + col) = pk;
               if (MODE == EM_DGELU) {
                 const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
                 csum.x += a.x; csum.y += a.y; csum.z += b.x; csum.w += b.y;
@@ -308,10 +330,10 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
       }
     }
     if (MODE == EM_DGELU && ep.colsum_out) {
-      // lanes l, l ^ 8, l ^ 16, l ^ 24 hold the same four columns (different rows): fold them, then one vector
+      // lanes that differ only in `sub` hold the same four columns (different rows): fold them, then one vector
       // reduction per 4 columns and 32-row slab
 #pragma unroll
-      for (int o = 8; o <= 16; o <<= 1) {
+      for (int o = kLPR; o <= 16; o <<= 1) {
         csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
         csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
         csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
@@ -325,7 +347,7 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
     __syncwarp();
     if (MODE == EM_F32_RES || MODE == EM_F32_RES_DROP || MODE == EM_DGELU) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pcur[i] = pnext[i];
+      for (int i = 0; i < kSteps; ++i) pcur[i] = pnext[i];
     }
     bias4 = bias_next;
   }
@@ -335,16 +357,16 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
 // every mode is an independent region for the register allocator).  Work unit u covers tile u % num_tiles; the first
 // output row of the CTA's 128-row slab is (tile % m_tiles) * m_stride + m_off.
 template <int BN, int MODE>
-ECAMP_DEVINL void epilogue_loop(const EpiArgs& ea, uint32_t tmem_base, int q, int half, int unit0, int unit_step,
+ECAMP_DEVINL void epilogue_loop(const EpiArgs& ea, uint32_t tmem_base, int q, int slice, int unit0, int unit_step,
                                 int num_units, int num_tiles, int m_tiles, int m_stride, int m_off, int M, int N,
-                                float* stage4k, int lane, uint64_t* tmem_full, uint64_t* tmem_empty, bool remote_empty) {
-  constexpr int HALF_N = BN / 2;
+                                float* stage, int lane, uint64_t* tmem_full, uint64_t* tmem_empty, bool remote_empty) {
+  constexpr int COLS = BN / kSlices;
   int acc = 0;
   uint32_t acc_phase = 0;
   if (unit0 < num_units) {  // the first tile's operand: nobody prefetched it one tile ahead
     const int tile = unit0 % num_tiles;
-    epi_prefetch_l2<HALF_N, MODE>(ea.ep, (tile % m_tiles) * m_stride + m_off + q * 32, (tile / m_tiles) * BN + half * HALF_N,
-                                  M, N, lane);
+    epi_prefetch_l2<COLS, MODE>(ea.ep, (tile % m_tiles) * m_stride + m_off + q * 32, (tile / m_tiles) * BN + slice * COLS,
+                                M, N, lane);
   }
   for (int unit = unit0; unit < num_units; unit += unit_step) {
     const int tile = unit % num_tiles;
@@ -353,23 +375,23 @@ ECAMP_DEVINL void epilogue_loop(const EpiArgs& ea, uint32_t tmem_base, int q, in
     if (unit + unit_step < num_units) {
       const int nt = (unit + unit_step) % num_tiles;
       next_m0 = (nt % m_tiles) * m_stride + m_off + q * 32;
-      next_ncol0 = (nt / m_tiles) * BN + half * HALF_N;
+      next_ncol0 = (nt / m_tiles) * BN + slice * COLS;
     }
-    epilogue_warp<HALF_N, MODE>(ea, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N),
-                                m_blk * m_stride + m_off + q * 32, n_blk * BN + half * HALF_N, M, N, stage4k, lane,
-                                &tmem_full[acc], acc_phase, &tmem_empty[acc], remote_empty, next_m0, next_ncol0);
+    epilogue_warp<COLS, MODE>(ea, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slice * COLS),
+                              m_blk * m_stride + m_off + q * 32, n_blk * BN + slice * COLS, M, N, stage, lane,
+                              &tmem_full[acc], acc_phase, &tmem_empty[acc], remote_empty, next_m0, next_ncol0);
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
 }
 template <int BN>
-ECAMP_DEVINL void epilogue_dispatch(const EpiArgs& ea, uint32_t tmem_base, int q, int half, int unit0, int unit_step,
+ECAMP_DEVINL void epilogue_dispatch(const EpiArgs& ea, uint32_t tmem_base, int q, int slice, int unit0, int unit_step,
                                     int num_units, int num_tiles, int m_tiles, int m_stride, int m_off, int M, int N,
-                                    float* stage4k, int lane, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                    float* stage, int lane, uint64_t* tmem_full, uint64_t* tmem_empty,
                                     bool remote_empty) {
 #define ECAMP_EPI_CASE(MODE_)                                                                                        \
   case MODE_:                                                                                                         \
-    epilogue_loop<BN, MODE_>(ea, tmem_base, q, half, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride, m_off, \
-                             M, N, stage4k, lane, tmem_full, tmem_empty, remote_empty);                               \
+    epilogue_loop<BN, MODE_>(ea, tmem_base, q, slice, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride, m_off, \
+                             M, N, stage, lane, tmem_full, tmem_empty, remote_empty);                               \
     break;
   switch (ea.mode) {
     ECAMP_EPI_CASE(EM_BF16)
@@ -380,8 +402,8 @@ ECAMP_DEVINL void epilogue_dispatch(const EpiArgs& ea, uint32_t tmem_base, int q
     ECAMP_EPI_CASE(EM_F32_RES_DROP)
     ECAMP_EPI_CASE(EM_ATOMIC)
     default:
-      epilogue_loop<BN, EM_GENERIC>(ea, tmem_base, q, half, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride,
-                                    m_off, M, N, stage4k, lane, tmem_full, tmem_empty, remote_empty);
+      epilogue_loop<BN, EM_GENERIC>(ea, tmem_base, q, slice, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride,
+                                    m_off, M, N, stage, lane, tmem_full, tmem_empty, remote_empty);
   }
 #undef ECAMP_EPI_CASE
 }
@@ -511,8 +533,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns
-    float* stage4k = s_epi + (warp - kEpiWarp0) * 1024;
+    const int half = (warp - kEpiWarp0) >> 2;  // which column slice of the tile
+    float* stage4k = s_epi + (warp - kEpiWarp0) * kStageFloats;
     epilogue_dispatch<BN>(ea, tmem_base, q, half, blockIdx.x, gridDim.x, num_units, num_tiles, m_tiles, BM, 0, M, N, stage4k,
                           lane, tmem_full, tmem_empty, false);
   }
@@ -539,7 +561,7 @@ struct Cfg2 {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 128) ? 8 : 6;
-  static constexpr int EPI_BYTES = kNumEpiWarps * 4096;
+  static constexpr int EPI_BYTES = kNumEpiWarps * kStageFloats * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget of one CTA exceeded");
 };
@@ -669,7 +691,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int q = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
-    float* stage4k = s_epi + (warp - kEpiWarp0) * 1024;
+    float* stage4k = s_epi + (warp - kEpiWarp0) * kStageFloats;
     // the leader's MMA warp owns the accumulator hand-back: both CTAs arrive on ITS barrier
     epilogue_dispatch<BN>(ea, tmem_base, q, half, pair, num_pairs, num_units, num_tiles, m_tiles, 2 * BM, (int)rank * BM, M,
                           N, stage4k, lane, tmem_full, tmem_empty, true);
