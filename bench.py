@@ -78,17 +78,29 @@ def to_device(batch, dev, stream=None):
 
 
 def gemm_roofline(B, T, peak_tflops):
-    """Time every distinct GEMM shape of the step through the C ABI (CUDA events on the launching stream, L2 flushed
-    between launches) and return achieved TFLOP/s over all tcgen05 GEMM launches of one step."""
+    """Time every GEMM of the step through the C ABI WITH THE EPILOGUE THE STEP USES for it (CUDA events on the launching
+    stream, L2 flushed between launches) and return achieved TFLOP/s over all tcgen05 GEMM launches of one step.
+    Per Linear: (rows, out, in, count, forward epilogue, dgrad epilogue or None); the weight gradient is always a plain
+    fp32 store (split-K atomics where the library chooses them)."""
     from ecamp_b200 import _lib as L
     dev = "cuda"
     Me, Mi, Md, Mt = B * 50, B * 49, B * 197, B * T
-    lin = []  # (rows, out, in, count)
-    lin += [(Mi, 768, 768, 1)]
-    lin += [(Me, 2304, 768, 12), (Me, 768, 768, 12), (Me, 3072, 768, 12), (Me, 768, 3072, 12)]
-    lin += [(Me, 512, 768, 1), (Md, 1536, 512, 4), (Md, 512, 512, 4), (Md, 2048, 512, 4), (Md, 512, 2048, 4), (Md, 768, 512, 1)]
-    lin += [(Me, 768, 768, 1), (Mt, 2304, 768, 7), (Mt, 768, 768, 7 + 2 + 1), (Mi, 1536, 768, 1), (Mt, 1536, 768, 7), (Mt, 768, 1536, 7)]
-    lin += [(Mt, 30000, 768, 1)]
+    lin = [
+        (Mi, 768, 768, 1, "f32", None),                       # patch embed (49 kept patches); no input gradient
+        (Me, 2304, 768, 12, "bf16", "f32"), (Me, 768, 768, 12, "res", "bf16"),          # encoder qkv, proj
+        (Me, 3072, 768, 12, "gelu", "f32"), (Me, 768, 3072, 12, "res", "dgelu"),        # encoder fc1, fc2
+        (Me, 512, 768, 1, "bf16", "res"),                                               # decoder_embed
+        (Md, 1536, 512, 4, "bf16", "f32"), (Md, 512, 512, 4, "res", "bf16"),            # decoder qkv, proj
+        (Md, 2048, 512, 4, "gelu", "f32"), (Md, 512, 2048, 4, "res", "dgelu"),          # decoder fc1, fc2
+        (Md, 768, 512, 1, "f32", "f32"),                                                # decoder_pred
+        (Me, 768, 768, 1, "bf16", "f32"),                                               # bert_mlp
+        (Mt, 2304, 768, 7, "bf16", "res"),                                              # BERT / fusion q|k|v
+        (Mt, 768, 768, 8, "res_drop", "bf16"),                                          # attention.output.dense x7, out_layer.dense
+        (Mt, 768, 768, 1, "bf16", "res"), (Mt, 768, 768, 1, "gelu", "f32"),             # cross query; LM-head transform
+        (Mi, 1536, 768, 1, "bf16", "bf16"),                                             # cross key|value
+        (Mt, 1536, 768, 7, "gelu", "res"), (Mt, 768, 1536, 7, "res_drop", "dgelu"),     # BERT intermediate, output
+        (Mt, 30000, 768, 1, "bf16", "f32"),                                             # vocabulary projection (row chunks)
+    ]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tot_flops = tot_ms = 0.0
     launches = 0
@@ -105,28 +117,58 @@ def gemm_roofline(B, T, peak_tflops):
             ms.append(s.elapsed_time(e))
         return statistics.median(ms)
 
-    for rows, n_out, n_in, count in lin:
+    def epilogue(kind, rows, n):
+        kw = {}
+        if kind in ("bf16", "gelu", "dgelu"):
+            kw["out_bf16"] = torch.empty(rows, n, dtype=torch.bfloat16, device=dev)
+        else:
+            kw["out_f32"] = torch.empty(rows, n, dtype=torch.float32, device=dev)
+        if kind in ("bf16", "gelu", "res", "res_drop", "f32"):
+            kw["bias"] = torch.zeros(n, device=dev)
+        if kind == "gelu":
+            kw["aux_out"] = torch.empty(rows, n, dtype=torch.bfloat16, device=dev); kw["flags"] = L.GEMM_GELU
+        if kind == "dgelu":
+            kw["aux_in"] = torch.randn(rows, n, device=dev).to(torch.bfloat16); kw["flags"] = L.GEMM_DGELU
+            kw["colsum_out"] = torch.zeros(n, device=dev); kw.pop("bias", None)
+        if kind in ("res", "res_drop"):
+            kw["residual"] = torch.randn(rows, n, device=dev)
+        if kind == "res_drop":
+            kw["flags"] = L.GEMM_DROPOUT; kw["drop_p"] = 0.1; kw["seed"] = 1; kw["site"] = 1
+        return kw
+
+    for rows, n_out, n_in, count, k_f, k_d in lin:
         r = min(rows, 8192) if n_out == 30000 else rows          # the vocabulary projection runs in row chunks
         scale = rows / r
         x = torch.randn(r, n_in, device=dev).to(torch.bfloat16)
         w = torch.randn(n_out, n_in, device=dev).to(torch.bfloat16)
         dy = torch.randn(r, n_out, device=dev).to(torch.bfloat16)
-        y = torch.empty(r, n_out, dtype=torch.bfloat16, device=dev)
-        dx = torch.empty(r, n_in, dtype=torch.bfloat16, device=dev)
         dw = torch.empty(n_out, n_in, dtype=torch.float32, device=dev)
-        t_f = timed(lambda: L.gemm(x, w, out_bf16=y))
-        t_d = timed(lambda: L.gemm(dy, w, b_mn=True, M=r, N=n_in, K=n_out, out_bf16=dx))
+        kf = epilogue(k_f, r, n_out)
+        t_f = timed(lambda: L.gemm(x, w, **kf))
+        del kf
+        t_d = 0.0
+        if k_d is not None:
+            kd = epilogue(k_d, r, n_in)
+            kd.pop("bias", None)
+            t_d = timed(lambda: L.gemm(dy, w, b_mn=True, M=r, N=n_in, K=n_out, **kd))
+            del kd
         t_w = timed(lambda: L.gemm(dy, x, a_mn=True, b_mn=True, M=n_out, N=n_in, K=r, out_f32=dw))
         fl = 2.0 * r * n_out * n_in
-        tot_flops += 3 * fl * scale * count
+        n_g = 3 if k_d is not None else 2
+        tot_flops += n_g * fl * scale * count
         tot_ms += (t_f + t_d + t_w) * scale * count
-        launches += 3 * count * int(round(scale))
-        per_shape.append(dict(rows=rows, out=n_out, inp=n_in, count=count, fwd_tflops=round(fl / t_f / 1e9, 0),
-                              dgrad_tflops=round(fl / t_d / 1e9, 0), wgrad_tflops=round(fl / t_w / 1e9, 0)))
-        del x, w, dy, y, dx, dw
+        launches += n_g * count * int(round(scale))
+        per_shape.append(dict(rows=rows, out=n_out, inp=n_in, count=count, fwd=k_f, dgrad=k_d, fwd_tflops=round(fl / t_f / 1e9, 0),
+                              dgrad_tflops=round(fl / t_d / 1e9, 0) if k_d else None, wgrad_tflops=round(fl / t_w / 1e9, 0)))
+        del x, w, dy, dw
     achieved = tot_flops / (tot_ms * 1e-3) / 1e12
+    traffic = None
+    try:  # DRAM bytes per GEMM launch from the committed ncu capture of one step (profiles/, see r01c_ncu_summary.md)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01c_ncu_gemm_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
     return dict(bound="tensor", achieved=round(achieved, 1), peak=peak_tflops, unit="TFLOP/s", frac=round(achieved / peak_tflops, 4),
-                traffic=None, kernel="gemm_tcgen05_kernel (all Linear fwd/dgrad/wgrad launches of one step)",
+                traffic=traffic, kernel="gemm_tcgen05_2cta_kernel (every Linear forward / dgrad / wgrad launch of one step, with the step's fused epilogues)",
                 flops_per_step=tot_flops, gemm_ms_per_step=round(tot_ms, 3), launches_per_step=launches, shapes=per_shape)
 
 

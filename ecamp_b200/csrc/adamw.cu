@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict
                                                     const Chunk* __restrict__ chunks, float lr, float beta1,
                                                     float beta2, float eps, float wd, float bc1, float bc2_sqrt,
                                                     float grad_scale) {
+  ECAMP_PDL_ENTRY();
   const Chunk ch = chunks[blockIdx.x];
   const AdamTensor t = table[ch.tensor];
   const float decay = t.decay ? 1.0f - lr * wd : 1.0f;
@@ -131,18 +132,18 @@ int adamw_step(const void* dev_table, const void* dev_chunks, long long n_chunks
   if (n_chunks <= 0) return 0;
   const float bc1 = 1.0f - (float)pow((double)beta1, (double)step);
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-  adamw_kernel<true><<<(unsigned)n_chunks, 256, 0, st>>>(static_cast<const AdamTensor*>(dev_table),
+  ECAMP_CUDA_OK(launch_pdl(adamw_kernel<true>, (unsigned)n_chunks, 256, 0, st, static_cast<const AdamTensor*>(dev_table),
                                                          static_cast<const Chunk*>(dev_chunks), lr, beta1, beta2,
-                                                         eps, wd, bc1, bc2_sqrt, grad_scale);
+                                                         eps, wd, bc1, bc2_sqrt, grad_scale));
   ECAMP_LAUNCHED();
   return 0;
 }
 
 int refresh_shadows(const void* dev_table, const void* dev_chunks, long long n_chunks, cudaStream_t st) {
   if (n_chunks <= 0) return 0;
-  adamw_kernel<false><<<(unsigned)n_chunks, 256, 0, st>>>(static_cast<const AdamTensor*>(dev_table),
+  ECAMP_CUDA_OK(launch_pdl(adamw_kernel<false>, (unsigned)n_chunks, 256, 0, st, static_cast<const AdamTensor*>(dev_table),
                                                           static_cast<const Chunk*>(dev_chunks), 0.f, 0.f, 0.f, 0.f,
-                                                          0.f, 1.f, 1.f, 1.f);
+                                                          0.f, 1.f, 1.f, 1.f));
   ECAMP_LAUNCHED();
   return 0;
 }

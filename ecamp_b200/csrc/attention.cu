@@ -115,6 +115,7 @@ ECAMP_DEVINL float ex2f(float x) {
 // through L2, which bounded the kernel.
 template <int D, int NW, bool DROP>
 __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
+  ECAMP_PDL_ENTRY();
   constexpr int RT = NW * 16, NT_ = NW * 32;
   constexpr int LDS = D + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
 
 // delta[b, h, i] = sum_d dO[i, d] * O[i, d]; one warp per (b, h, i)
 __global__ void attn_delta_kernel(AttnArgs a) {
+  ECAMP_PDL_ENTRY();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int total = a.B * a.H * a.Sq;
   if (gw >= total) return;
@@ -493,6 +495,7 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
 // stand-alone kernels: TR = false produces dQ (+ delta), TR = true produces dK / dV; one CTA per 64-row tile
 template <int D, bool TR, bool DROP>
 __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
+  ECAMP_PDL_ENTRY();
   constexpr int LDS = D + 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int Sr = TR ? a.Sk : a.Sq;  // row-side length
@@ -551,6 +554,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
 // (8 x the bytes through L2 for the decoder's 197 x 197 heads), which is what bounded them.
 template <int D, int NW, bool DROP>
 __global__ void __launch_bounds__(NW * 32) attn_bwd_merged_kernel(AttnArgs a) {
+  ECAMP_PDL_ENTRY();
   constexpr int LDS = D + 8, RT = NW * 16, NT_ = NW * 32;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
@@ -625,10 +629,10 @@ int launch_fwd_nw(const AttnArgs& a, cudaStream_t st) {
   dim3 grid((a.Sq + NW * 16 - 1) / (NW * 16), a.H, a.B);
   if (a.drop.p > 0.f) {
     ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    attn_fwd_kernel<D, NW, true><<<grid, NW * 32, sm, st>>>(a);
+    ECAMP_CUDA_OK(launch_pdl(attn_fwd_kernel<D, NW, true>, grid, NW * 32, sm, st, a));
   } else {
     ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<D, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    attn_fwd_kernel<D, NW, false><<<grid, NW * 32, sm, st>>>(a);
+    ECAMP_CUDA_OK(launch_pdl(attn_fwd_kernel<D, NW, false>, grid, NW * 32, sm, st, a));
   }
   ECAMP_LAUNCHED();
   return 0;
@@ -643,15 +647,30 @@ int launch_fwd(const AttnArgs& a, cudaStream_t st) {
 }
 template <int D>
 int launch_bwd(const AttnArgs& a, cudaStream_t st) {
+  static const int small_merged = getenv("ECAMP_ATTN_SMALL_MERGED") ? atoi(getenv("ECAMP_ATTN_SMALL_MERGED")) : 1;
+  if (small_merged && D <= 64 && a.Sq <= 64 && a.Sk <= 64) {
+    // ViT encoder heads (50 x 50): dQ and dK/dV in ONE 128-thread CTA per head - one staging of Q, dO, K, V, one launch
+    dim3 grid(a.H, a.B);
+    const size_t sm = (size_t)4 * 64 * (D + 8) * 2 + 64 * 8;
+    if (a.drop.p > 0.f) {
+      ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_merged_kernel<D, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      ECAMP_CUDA_OK(launch_pdl(attn_bwd_merged_kernel<D, 4, true>, grid, 128, sm, st, a));
+    } else {
+      ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_merged_kernel<D, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      ECAMP_CUDA_OK(launch_pdl(attn_bwd_merged_kernel<D, 4, false>, grid, 128, sm, st, a));
+    }
+    ECAMP_LAUNCHED();
+    return 0;
+  }
   static const int big = getenv("ECAMP_ATTN_BIG") ? atoi(getenv("ECAMP_ATTN_BIG")) : 0;  // measured slower (1 CTA / SM)
   if (big && D == 32 && a.Sq <= kBigNW * 16 && a.Sk <= kBigNW * 16 && (a.Sq > 64 || a.Sk > 64)) {
     dim3 grid(a.H, a.B);
     if (a.drop.p > 0.f) {
       ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_merged_kernel<32, kBigNW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-      attn_bwd_merged_kernel<32, kBigNW, true><<<grid, kBigNW * 32, merged_smem(32), st>>>(a);
+      ECAMP_CUDA_OK(launch_pdl(attn_bwd_merged_kernel<32, kBigNW, true>, grid, kBigNW * 32, merged_smem(32), st, a));
     } else {
       ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_merged_kernel<32, kBigNW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-      attn_bwd_merged_kernel<32, kBigNW, false><<<grid, kBigNW * 32, merged_smem(32), st>>>(a);
+      ECAMP_CUDA_OK(launch_pdl(attn_bwd_merged_kernel<32, kBigNW, false>, grid, kBigNW * 32, merged_smem(32), st, a));
     }
     ECAMP_LAUNCHED();
     return 0;
@@ -661,16 +680,16 @@ int launch_bwd(const AttnArgs& a, cudaStream_t st) {
   if (a.drop.p > 0.f) {
     ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    attn_bwd_kernel<D, false, true><<<gq, 128, bwd_smem(D, a.Sk), st>>>(a);
+    ECAMP_CUDA_OK(launch_pdl(attn_bwd_kernel<D, false, true>, gq, 128, bwd_smem(D, a.Sk), st, a));
     ECAMP_LAUNCHED();
-    attn_bwd_kernel<D, true, true><<<gk, 128, bwd_smem(D, a.Sq), st>>>(a);
+    ECAMP_CUDA_OK(launch_pdl(attn_bwd_kernel<D, true, true>, gk, 128, bwd_smem(D, a.Sq), st, a));
     ECAMP_LAUNCHED();
   } else {
     ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<D, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    attn_bwd_kernel<D, false, false><<<gq, 128, bwd_smem(D, a.Sk), st>>>(a);
+    ECAMP_CUDA_OK(launch_pdl(attn_bwd_kernel<D, false, false>, gq, 128, bwd_smem(D, a.Sk), st, a));
     ECAMP_LAUNCHED();
-    attn_bwd_kernel<D, true, false><<<gk, 128, bwd_smem(D, a.Sq), st>>>(a);
+    ECAMP_CUDA_OK(launch_pdl(attn_bwd_kernel<D, true, false>, gk, 128, bwd_smem(D, a.Sq), st, a));
     ECAMP_LAUNCHED();
   }
   return 0;

@@ -37,6 +37,7 @@ struct TcMaps {
 // =============================================================================================
 template <int D>
 __global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, AttnArgs a, int tmem_cols) {
+  ECAMP_PDL_ENTRY();
   constexpr int ATOMS = D / 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant_
 // =============================================================================================
 template <int D>
 __global__ void __launch_bounds__(288) attn_tc_bwd_kernel(const __grid_constant__ TcMaps maps, AttnArgs a) {
+  ECAMP_PDL_ENTRY();
   constexpr int ATOMS = D / 64;
   constexpr int TILE = ATOMS * kAtomBytes;  // a [128 x D] bf16 tile
   extern __shared__ uint8_t smem_raw[];
@@ -421,7 +423,7 @@ int launch_tc_fwd(const AttnArgs& a, cudaStream_t st) {
   }
   ECAMP_REQUIRE(smem <= 226 * 1024, "attention (tcgen05): shared memory %zu B too large", smem);
   dim3 grid((a.Sq + kRows - 1) / kRows, a.H, a.B);
-  attn_tc_fwd_kernel<D><<<grid, 160, smem, st>>>(maps, a, tmem_cols);
+  ECAMP_CUDA_OK(launch_pdl(attn_tc_fwd_kernel<D>, grid, 160, smem, st, maps, a, tmem_cols));
   ECAMP_LAUNCHED();
   return 0;
 }
@@ -438,7 +440,7 @@ int launch_tc_bwd(const AttnArgs& a, cudaStream_t st) {
     attr = true;
   }
   dim3 grid(a.H, a.B);
-  attn_tc_bwd_kernel<D><<<grid, 288, smem, st>>>(maps, a);
+  ECAMP_CUDA_OK(launch_pdl(attn_tc_bwd_kernel<D>, grid, 288, smem, st, maps, a));
   ECAMP_LAUNCHED();
   return 0;
 }

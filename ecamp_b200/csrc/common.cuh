@@ -40,6 +40,37 @@ void count_launch();  // every kernel launch of the library is counted (ecamp_la
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch: every kernel of the library is launched with the "programmatic stream
+// serialization" attribute and starts with ECAMP_PDL_ENTRY(): griddepcontrol.wait (all prerequisite grids have
+// completed, their writes are visible) followed by griddepcontrol.launch_dependents (once every CTA of this grid has
+// got that far the NEXT kernel's CTAs may become resident and sit in their own wait).  Launch latency and the next
+// kernel's prologue then overlap with this kernel's tail instead of following it (the step has ~600 launches).
+// A kernel launched without the attribute executes both as no-ops.  Nothing before the wait may touch global memory.
+// ---------------------------------------------------------------------------------------------
+ECAMP_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+ECAMP_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define ECAMP_PDL_ENTRY()             \
+  do {                                \
+    ecamp::pdl_wait();                \
+    ecamp::pdl_launch_dependents();   \
+  } while (0)
+int pdl_enabled();  // ECAMP_PDL=0 turns the launch attribute off (gemm.cu)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // shared-memory address / mbarrier
 // ---------------------------------------------------------------------------------------------
 ECAMP_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -15,6 +15,7 @@ __global__ void random_masking_kernel(const float* __restrict__ noise, int L, in
                                       int32_t* __restrict__ ids_restore, int32_t* __restrict__ ids_keep,
                                       float* __restrict__ mask, int64_t* __restrict__ ids_restore64,
                                       int64_t* __restrict__ ids_keep64) {
+  ECAMP_PDL_ENTRY();
   extern __shared__ float s_noise[];
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < L; i += blockDim.x) s_noise[i] = noise[(size_t)b * L + i];
@@ -44,6 +45,7 @@ __global__ void random_masking_kernel(const float* __restrict__ noise, int L, in
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(224) resize_patchify_kernel(const float* __restrict__ big, int Hin,
                                                               float* __restrict__ tgt) {
+  ECAMP_PDL_ENTRY();
   const int y = blockIdx.x % 224, b = blockIdx.x / 224;
   const int x = threadIdx.x;
   const float w[4] = {-0.09375f, 0.59375f, 0.59375f, -0.09375f};
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(224) resize_patchify_kernel(const float* __res
 }
 
 __global__ void __launch_bounds__(224) patchify224_kernel(const float* __restrict__ imgs, float* __restrict__ tgt) {
+  ECAMP_PDL_ENTRY();
   const int y = blockIdx.x % 224, b = blockIdx.x / 224;
   const int x = threadIdx.x;
   const int hy = y >> 4, p = y & 15, wx = x >> 4, q = x & 15;
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(224) patchify224_kernel(const float* __restric
 // one block per output row, D/4 threads
 __global__ void gather_patches_kernel(const float* __restrict__ tgt, const int32_t* __restrict__ ids_keep, int L,
                                       int keep, int PD, bf16* __restrict__ out) {
+  ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / keep;
   const int src_l = ids_keep[r];
   const float4 v = reinterpret_cast<const float4*>(tgt + ((size_t)b * L + src_l) * PD)[threadIdx.x];
@@ -92,6 +96,7 @@ __global__ void gather_patches_kernel(const float* __restrict__ tgt, const int32
 __global__ void assemble_enc_kernel(const float* __restrict__ pe, const float* __restrict__ cls,
                                     const float* __restrict__ pos, const int32_t* __restrict__ ids_keep, int keep,
                                     int D, float* __restrict__ x0) {
+  ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / (keep + 1), s = r % (keep + 1);
   const int c4 = threadIdx.x;
   float4 a, p;
@@ -106,6 +111,7 @@ __global__ void assemble_enc_kernel(const float* __restrict__ pe, const float* _
 }
 
 __global__ void assemble_enc_bwd_kernel(const float* __restrict__ dx0, int keep, int D, bf16* __restrict__ d_pe) {
+  ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / keep, j = r % keep;
   const float4 v = reinterpret_cast<const float4*>(dx0 + ((size_t)b * (keep + 1) + 1 + j) * D)[threadIdx.x];
   uint2 u;
@@ -117,6 +123,7 @@ __global__ void assemble_enc_bwd_kernel(const float* __restrict__ dx0, int keep,
 // out[d] (+)= sum_b x[b * stride + d]
 __global__ void strided_rowsum_kernel(const float* __restrict__ x, int B, size_t stride, int D,
                                       float* __restrict__ out, int accumulate) {
+  ECAMP_PDL_ENTRY();
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   float s = 0.f;
@@ -127,6 +134,7 @@ __global__ void strided_rowsum_kernel(const float* __restrict__ x, int B, size_t
 __global__ void assemble_dec_kernel(const bf16* __restrict__ e, const float* __restrict__ mask_token,
                                     const float* __restrict__ dpos, const int32_t* __restrict__ ids_restore, int L,
                                     int keep, int D, float* __restrict__ xd) {
+  ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / (L + 1), t = r % (L + 1);
   const int c4 = threadIdx.x;
   float4 a;
@@ -152,6 +160,7 @@ __global__ void assemble_dec_kernel(const bf16* __restrict__ e, const float* __r
 
 __global__ void assemble_dec_bwd_kernel(const float* __restrict__ dxd, const int32_t* __restrict__ ids_restore, int L,
                                         int keep, int D, bf16* __restrict__ d_e) {
+  ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / (L + 1), t = r % (L + 1);
   int dst = -1;
   if (t == 0) {
@@ -171,6 +180,7 @@ __global__ void assemble_dec_bwd_kernel(const float* __restrict__ dxd, const int
 // ws[b, d] = sum over masked positions l of dxd[b, 1 + l, d]
 __global__ void mask_token_grad_kernel(const float* __restrict__ dxd, const int32_t* __restrict__ ids_restore, int L,
                                        int keep, int D, float* __restrict__ ws) {
+  ECAMP_PDL_ENTRY();
   const int b = blockIdx.x;
   const int c4 = threadIdx.x;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -185,6 +195,7 @@ __global__ void mask_token_grad_kernel(const float* __restrict__ dxd, const int3
 
 __global__ void split_latent_gap_kernel(const bf16* __restrict__ lat2, int keep, int D, bf16* __restrict__ img_tok,
                                         bf16* __restrict__ gap) {
+  ECAMP_PDL_ENTRY();
   const int b = blockIdx.x, c4 = threadIdx.x;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int j = 0; j < keep; ++j) {
@@ -202,6 +213,7 @@ __global__ void split_latent_gap_kernel(const bf16* __restrict__ lat2, int keep,
 
 __global__ void split_latent_gap_bwd_kernel(const bf16* __restrict__ d_img_tok, const bf16* __restrict__ d_gap,
                                             int keep, int D, bf16* __restrict__ d_lat2) {
+  ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / (keep + 1), s = r % (keep + 1);
   const int c4 = threadIdx.x;
   uint2 o = make_uint2(0u, 0u);
@@ -217,6 +229,7 @@ __global__ void split_latent_gap_bwd_kernel(const bf16* __restrict__ d_img_tok, 
 }
 
 __global__ void add_batch_rowvec_kernel(bf16* __restrict__ y, const bf16* __restrict__ vec, int T, int D) {
+  ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / T, c4 = threadIdx.x;
   uint2 u = reinterpret_cast<uint2*>(y + (size_t)r * D)[c4];
   const uint2 g = reinterpret_cast<const uint2*>(vec + (size_t)b * D)[c4];
@@ -228,6 +241,7 @@ __global__ void add_batch_rowvec_kernel(bf16* __restrict__ y, const bf16* __rest
 
 __global__ void add_batch_rowvec_oop_kernel(const bf16* __restrict__ x, const bf16* __restrict__ vec, int T, int D,
                                             bf16* __restrict__ y) {
+  ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / T, c4 = threadIdx.x;
   uint2 u = reinterpret_cast<const uint2*>(x + (size_t)r * D)[c4];
   const uint2 g = reinterpret_cast<const uint2*>(vec + (size_t)b * D)[c4];
@@ -239,11 +253,13 @@ __global__ void add_batch_rowvec_oop_kernel(const bf16* __restrict__ x, const bf
 
 __global__ void gelu_bwd_bf16_kernel(const float* __restrict__ d, const bf16* __restrict__ pre, bf16* __restrict__ out,
                                      size_t n) {
+  ECAMP_PDL_ENTRY();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = f2bf(d[i] * gelu_erf_grad(bf2f(pre[i])));
 }
 
 __global__ void batch_colsum_kernel(const bf16* __restrict__ x, int T, int D, bf16* __restrict__ out) {
+  ECAMP_PDL_ENTRY();
   const int b = blockIdx.x, c4 = threadIdx.x;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = 0; t < T; ++t) {
@@ -266,6 +282,7 @@ __global__ void __launch_bounds__(256) bert_emb_fwd_kernel(
     const float* __restrict__ beta, float eps, int M, int T, DropoutCfg drop, float* __restrict__ pre,
     float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ out_bf16,
     float* __restrict__ out_f32) {
+  ECAMP_PDL_ENTRY();
   constexpr int NV = 6, D = 768;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * 8 + warp;
@@ -327,6 +344,7 @@ __global__ void __launch_bounds__(256) bert_emb_fwd_kernel(
 
 // in-place dropout backward on an fp32 gradient (embedding-output dropout site)
 __global__ void dropout_bwd_f32_kernel(float* __restrict__ g, size_t n4, DropoutCfg drop) {
+  ECAMP_PDL_ENTRY();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const Philox ph(drop.seed);
@@ -341,24 +359,45 @@ __global__ void dropout_bwd_f32_kernel(float* __restrict__ g, size_t n4, Dropout
   reinterpret_cast<float4*>(g)[i] = v;
 }
 
-// word-embedding gradient: scatter-add rows (padding_idx = 0 receives nothing)
-__global__ void emb_word_bwd_kernel(const float* __restrict__ d_pre, const int64_t* __restrict__ ids, int D,
-                                    float* __restrict__ d_word) {
-  const int row = blockIdx.x;
-  const long long id = ids[row];
-  if (id == 0) return;
-  const float4 v = reinterpret_cast<const float4*>(d_pre + (size_t)row * D)[threadIdx.x];
-  float* dst = d_word + (size_t)id * D + threadIdx.x * 4;
-  atomicAdd(dst + 0, v.x);
-  atomicAdd(dst + 1, v.y);
-  atomicAdd(dst + 2, v.z);
-  atomicAdd(dst + 3, v.w);
+// word-embedding gradient: scatter-add rows (padding_idx = 0 receives nothing).  The special tokens [CLS] = 2,
+// [MASK] = 3, [SEP] = 4 (ECAMP/Pre-training/module/pretrain_datasets.py:23-24) appear in every report - [MASK] on ~45 % of the
+// positions - and their rows serialise in the L2 atomic unit, so each CTA first folds its kEmbRows rows of those ids in
+// registers and adds them once; all other rows go out as 16-byte vector reductions.
+constexpr int kEmbRows = 64;
+__global__ void __launch_bounds__(192) emb_word_bwd_kernel(const float* __restrict__ d_pre, const int64_t* __restrict__ ids,
+                                                           int M, int D, float* __restrict__ d_word) {
+  ECAMP_PDL_ENTRY();
+  const int r0 = blockIdx.x * kEmbRows, r1 = min(M, r0 + kEmbRows);
+  float4 hot[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) hot[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = r0; row < r1; ++row) {
+    const long long id = ids[row];
+    if (id == 0) continue;
+    const float4 v = reinterpret_cast<const float4*>(d_pre + (size_t)row * D)[threadIdx.x];
+    if (id >= 2 && id <= 4) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (id == 2 + k) { hot[k].x += v.x; hot[k].y += v.y; hot[k].z += v.z; hot[k].w += v.w; }
+    } else {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d_word + (size_t)id * D + threadIdx.x * 4), "f"(v.x),
+                   "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (hot[k].x != 0.f || hot[k].y != 0.f || hot[k].z != 0.f || hot[k].w != 0.f)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d_word + (size_t)(2 + k) * D + threadIdx.x * 4),
+                   "f"(hot[k].x), "f"(hot[k].y), "f"(hot[k].z), "f"(hot[k].w)
+                   : "memory");
 }
 
 // one block per position t: position gradient (sum over batch) and per-type partial sums
 __global__ void emb_pos_type_bwd_kernel(const float* __restrict__ d_pre, const int64_t* __restrict__ type_ids, int B,
                                         int T, int D, float* __restrict__ d_pos, int accumulate,
                                         float* __restrict__ type_ws) {
+  ECAMP_PDL_ENTRY();
   const int t = blockIdx.x, c4 = threadIdx.x;
   float4 ap = make_float4(0.f, 0.f, 0.f, 0.f), a1 = ap;
   for (int b = 0; b < B; ++b) {
@@ -382,6 +421,7 @@ __global__ void emb_pos_type_bwd_kernel(const float* __restrict__ d_pre, const i
 
 __global__ void emb_type_finalize_kernel(const float* __restrict__ type_ws, int T, int D, float* __restrict__ d_type,
                                          int accumulate) {
+  ECAMP_PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over 2*D
   if (i >= 2 * D) return;
   float s = 0.f;
@@ -396,6 +436,7 @@ __global__ void emb_type_finalize_kernel(const float* __restrict__ type_ws, int 
 // the 8 warps stride over the rows of the chunk; per-chunk partials are reduced by a second tiny kernel.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int ld, int M, int N,
                                                      float* __restrict__ out) {
+  ECAMP_PDL_ENTRY();
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -441,14 +482,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   }
 }
 __global__ void scale_f32_kernel(float* __restrict__ x, const float* __restrict__ scale, size_t n) {
+  ECAMP_PDL_ENTRY();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] *= *scale;
 }
 __global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n) {
+  ECAMP_PDL_ENTRY();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = f2bf(x[i]);
 }
 __global__ void permute_pe_grad_kernel(const float* __restrict__ dw_pqc, float* __restrict__ grad_cpq, int accumulate) {
+  ECAMP_PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // canonical index n*768 + c*256 + pq
   if (i >= 768 * 768) return;
   const int n = i / 768, k = i % 768, c = k / 256, pq = k % 256;
@@ -465,8 +509,8 @@ int random_masking(const float* noise, int B, int L, int len_keep, int32_t* ids_
   ECAMP_REQUIRE(L > 0 && L <= 4096 && len_keep >= 0 && len_keep <= L, "random_masking: bad L %d / len_keep %d", L,
                 len_keep);
   if (B <= 0) return 0;
-  random_masking_kernel<<<B, 256, L * sizeof(float), st>>>(noise, L, len_keep, ids_restore, ids_keep, mask,
-                                                           ids_restore64, ids_keep64);
+  ECAMP_CUDA_OK(launch_pdl(random_masking_kernel, B, 256, L * sizeof(float), st, noise, L, len_keep, ids_restore, ids_keep, mask,
+                                                           ids_restore64, ids_keep64));
   LAUNCH_OK();
   return 0;
 }
@@ -474,84 +518,84 @@ int random_masking(const float* noise, int B, int L, int len_keep, int32_t* ids_
 int resize_bicubic_patchify(const float* big, int B, int Hin, float* tgt, cudaStream_t st) {
   ECAMP_REQUIRE(Hin == 448, "resize: only 448 -> 224 is on the reference path (got %d)", Hin);
   if (B <= 0) return 0;
-  resize_patchify_kernel<<<B * 224, 224, 0, st>>>(big, Hin, tgt);
+  ECAMP_CUDA_OK(launch_pdl(resize_patchify_kernel, B * 224, 224, 0, st, big, Hin, tgt));
   LAUNCH_OK();
   return 0;
 }
 int patchify224(const float* imgs, int B, float* tgt, cudaStream_t st) {
   if (B <= 0) return 0;
-  patchify224_kernel<<<B * 224, 224, 0, st>>>(imgs, tgt);
+  ECAMP_CUDA_OK(launch_pdl(patchify224_kernel, B * 224, 224, 0, st, imgs, tgt));
   LAUNCH_OK();
   return 0;
 }
 int gather_patches(const float* tgt, const int32_t* ids_keep, int B, int L, int keep, int PD, bf16* out,
                    cudaStream_t st) {
   if (B * keep <= 0) return 0;
-  gather_patches_kernel<<<B * keep, PD / 4, 0, st>>>(tgt, ids_keep, L, keep, PD, out);
+  ECAMP_CUDA_OK(launch_pdl(gather_patches_kernel, B * keep, PD / 4, 0, st, tgt, ids_keep, L, keep, PD, out));
   LAUNCH_OK();
   return 0;
 }
 int assemble_encoder_input(const float* pe, const float* cls, const float* pos, const int32_t* ids_keep, int B,
                            int keep, int D, float* x0, cudaStream_t st) {
-  assemble_enc_kernel<<<B * (keep + 1), D / 4, 0, st>>>(pe, cls, pos, ids_keep, keep, D, x0);
+  ECAMP_CUDA_OK(launch_pdl(assemble_enc_kernel, B * (keep + 1), D / 4, 0, st, pe, cls, pos, ids_keep, keep, D, x0));
   LAUNCH_OK();
   return 0;
 }
 int assemble_encoder_input_bwd(const float* dx0, int B, int keep, int D, bf16* d_pe, float* d_cls, int accumulate,
                                cudaStream_t st) {
   if (keep > 0) {
-    assemble_enc_bwd_kernel<<<B * keep, D / 4, 0, st>>>(dx0, keep, D, d_pe);
+    ECAMP_CUDA_OK(launch_pdl(assemble_enc_bwd_kernel, B * keep, D / 4, 0, st, dx0, keep, D, d_pe));
     LAUNCH_OK();
   }
-  strided_rowsum_kernel<<<(D + 127) / 128, 128, 0, st>>>(dx0, B, (size_t)(keep + 1) * D, D, d_cls, accumulate);
+  ECAMP_CUDA_OK(launch_pdl(strided_rowsum_kernel, (D + 127) / 128, 128, 0, st, dx0, B, (size_t)(keep + 1) * D, D, d_cls, accumulate));
   LAUNCH_OK();
   return 0;
 }
 int assemble_decoder_input(const bf16* e, const float* mask_token, const float* dpos, const int32_t* ids_restore,
                            int B, int L, int keep, int D, float* xd, cudaStream_t st) {
-  assemble_dec_kernel<<<B * (L + 1), D / 4, 0, st>>>(e, mask_token, dpos, ids_restore, L, keep, D, xd);
+  ECAMP_CUDA_OK(launch_pdl(assemble_dec_kernel, B * (L + 1), D / 4, 0, st, e, mask_token, dpos, ids_restore, L, keep, D, xd));
   LAUNCH_OK();
   return 0;
 }
 int assemble_decoder_input_bwd(const float* dxd, const int32_t* ids_restore, int B, int L, int keep, int D, bf16* d_e,
                                float* d_mask_token, int accumulate, float* ws, cudaStream_t st) {
-  assemble_dec_bwd_kernel<<<B * (L + 1), D / 4, 0, st>>>(dxd, ids_restore, L, keep, D, d_e);
+  ECAMP_CUDA_OK(launch_pdl(assemble_dec_bwd_kernel, B * (L + 1), D / 4, 0, st, dxd, ids_restore, L, keep, D, d_e));
   LAUNCH_OK();
-  mask_token_grad_kernel<<<B, D / 4, 0, st>>>(dxd, ids_restore, L, keep, D, ws);
+  ECAMP_CUDA_OK(launch_pdl(mask_token_grad_kernel, B, D / 4, 0, st, dxd, ids_restore, L, keep, D, ws));
   LAUNCH_OK();
-  strided_rowsum_kernel<<<(D + 127) / 128, 128, 0, st>>>(ws, B, (size_t)D, D, d_mask_token, accumulate);
+  ECAMP_CUDA_OK(launch_pdl(strided_rowsum_kernel, (D + 127) / 128, 128, 0, st, ws, B, (size_t)D, D, d_mask_token, accumulate));
   LAUNCH_OK();
   return 0;
 }
 int split_latent_gap(const bf16* lat2, int B, int keep, int D, bf16* img_tok, bf16* gap, cudaStream_t st) {
-  split_latent_gap_kernel<<<B, D / 4, 0, st>>>(lat2, keep, D, img_tok, gap);
+  ECAMP_CUDA_OK(launch_pdl(split_latent_gap_kernel, B, D / 4, 0, st, lat2, keep, D, img_tok, gap));
   LAUNCH_OK();
   return 0;
 }
 int split_latent_gap_bwd(const bf16* d_img_tok, const bf16* d_gap, int B, int keep, int D, bf16* d_lat2,
                          cudaStream_t st) {
-  split_latent_gap_bwd_kernel<<<B * (keep + 1), D / 4, 0, st>>>(d_img_tok, d_gap, keep, D, d_lat2);
+  ECAMP_CUDA_OK(launch_pdl(split_latent_gap_bwd_kernel, B * (keep + 1), D / 4, 0, st, d_img_tok, d_gap, keep, D, d_lat2));
   LAUNCH_OK();
   return 0;
 }
 int add_batch_rowvec(bf16* y, const bf16* vec, int B, int T, int D, cudaStream_t st) {
-  add_batch_rowvec_kernel<<<B * T, D / 4, 0, st>>>(y, vec, T, D);
+  ECAMP_CUDA_OK(launch_pdl(add_batch_rowvec_kernel, B * T, D / 4, 0, st, y, vec, T, D));
   LAUNCH_OK();
   return 0;
 }
 int add_batch_rowvec_oop(const bf16* x, const bf16* vec, int B, int T, int D, bf16* y, cudaStream_t st) {
-  add_batch_rowvec_oop_kernel<<<B * T, D / 4, 0, st>>>(x, vec, T, D, y);
+  ECAMP_CUDA_OK(launch_pdl(add_batch_rowvec_oop_kernel, B * T, D / 4, 0, st, x, vec, T, D, y));
   LAUNCH_OK();
   return 0;
 }
 int gelu_bwd_bf16(const float* d, const bf16* pre, bf16* out, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
-  gelu_bwd_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, pre, out, n);
+  ECAMP_CUDA_OK(launch_pdl(gelu_bwd_bf16_kernel, (unsigned)((n + 255) / 256), 256, 0, st, d, pre, out, n));
   LAUNCH_OK();
   return 0;
 }
 int batch_colsum(const bf16* x, int B, int T, int D, bf16* out, cudaStream_t st) {
-  batch_colsum_kernel<<<B, D / 4, 0, st>>>(x, T, D, out);
+  ECAMP_CUDA_OK(launch_pdl(batch_colsum_kernel, B, D / 4, 0, st, x, T, D, out));
   LAUNCH_OK();
   return 0;
 }
@@ -561,15 +605,15 @@ int bert_embeddings_fwd(const int64_t* ids, const int64_t* type_ids, const float
                         cudaStream_t st) {
   ECAMP_REQUIRE(D == 768, "bert embeddings: hidden size must be 768");
   const int M = B * T;
-  bert_emb_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, type_ids, word, type, pos, gamma, beta, eps, M, T, drop, pre,
-                                                   mean, rstd, out_bf16, out_f32);
+  ECAMP_CUDA_OK(launch_pdl(bert_emb_fwd_kernel, (M + 7) / 8, 256, 0, st, ids, type_ids, word, type, pos, gamma, beta, eps, M, T, drop, pre,
+                                                   mean, rstd, out_bf16, out_f32));
   LAUNCH_OK();
   return 0;
 }
 int dropout_bwd_f32(float* g, size_t n, DropoutCfg drop, cudaStream_t st) {
   if (drop.p <= 0.f || n == 0) return 0;
   const size_t n4 = n / 4;
-  dropout_bwd_f32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(g, n4, drop);
+  ECAMP_CUDA_OK(launch_pdl(dropout_bwd_f32_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, g, n4, drop));
   LAUNCH_OK();
   return 0;
 }
@@ -581,11 +625,11 @@ int bert_embeddings_bwd(const float* d_pre, const int64_t* ids, const int64_t* t
     ECAMP_CUDA_OK(cudaMemsetAsync(d_word, 0, (size_t)30000 * D * sizeof(float), st));
     ECAMP_CUDA_OK(cudaMemsetAsync(d_pos, 0, (size_t)256 * D * sizeof(float), st));
   }
-  emb_word_bwd_kernel<<<M, D / 4, 0, st>>>(d_pre, ids, D, d_word);
+  ECAMP_CUDA_OK(launch_pdl(emb_word_bwd_kernel, (M + kEmbRows - 1) / kEmbRows, D / 4, 0, st, d_pre, ids, M, D, d_word));
   LAUNCH_OK();
-  emb_pos_type_bwd_kernel<<<T, D / 4, 0, st>>>(d_pre, type_ids, B, T, D, d_pos, accumulate, ws);
+  ECAMP_CUDA_OK(launch_pdl(emb_pos_type_bwd_kernel, T, D / 4, 0, st, d_pre, type_ids, B, T, D, d_pos, accumulate, ws));
   LAUNCH_OK();
-  emb_type_finalize_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(ws, T, D, d_type, accumulate);
+  ECAMP_CUDA_OK(launch_pdl(emb_type_finalize_kernel, (2 * D + 255) / 256, 256, 0, st, ws, T, D, d_type, accumulate));
   LAUNCH_OK();
   return 0;
 }
@@ -598,24 +642,24 @@ int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate,
   if (chunks < 1) chunks = 1;
   if (!accumulate) ECAMP_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
   dim3 grid((N + 255) / 256, chunks);
-  colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, out);
+  ECAMP_CUDA_OK(launch_pdl(colsum_kernel, grid, 256, 0, st, x, ld, M, N, out));
   LAUNCH_OK();
   return 0;
 }
 int scale_f32(float* x, const float* scale_dev, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
-  scale_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, scale_dev, n);
+  ECAMP_CUDA_OK(launch_pdl(scale_f32_kernel, (unsigned)((n + 255) / 256), 256, 0, st, x, scale_dev, n));
   LAUNCH_OK();
   return 0;
 }
 int cast_f32_to_bf16(const float* x, bf16* y, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
-  cast_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n);
+  ECAMP_CUDA_OK(launch_pdl(cast_bf16_kernel, (unsigned)((n + 255) / 256), 256, 0, st, x, y, n));
   LAUNCH_OK();
   return 0;
 }
 int permute_pe_weight_grad(const float* dw_pqc, float* grad_cpq, int accumulate, cudaStream_t st) {
-  permute_pe_grad_kernel<<<(768 * 768 + 255) / 256, 256, 0, st>>>(dw_pqc, grad_cpq, accumulate);
+  ECAMP_CUDA_OK(launch_pdl(permute_pe_grad_kernel, (768 * 768 + 255) / 256, 256, 0, st, dw_pqc, grad_cpq, accumulate));
   LAUNCH_OK();
   return 0;
 }

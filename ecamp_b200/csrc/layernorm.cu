@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
                                                      const float* __restrict__ beta, float eps, int M,
                                                      bf16* __restrict__ out_bf16, float* __restrict__ out_f32,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  ECAMP_PDL_ENTRY();
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * kRowsPerBlock + warp;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 6) ln_bwd_kernel(const float* 
                                                      bf16* __restrict__ dx_bf16, DropoutCfg drop,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      float* __restrict__ colsum_out) {
+  ECAMP_PDL_ENTRY();
   constexpr int D = NV * 128;
   constexpr int NA = COLSUM ? 3 : 2;
   extern __shared__ __align__(16) float sm_ln[];
@@ -186,7 +188,7 @@ int launch_ln_bwd(const float* dy, const float* x, const float* mean, const floa
     ECAMP_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  kfn<<<bwd_blocks(M), kBwdWarps * 32, smem, st>>>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out);
+  ECAMP_CUDA_OK(launch_pdl(kfn, bwd_blocks(M), kBwdWarps * 32, smem, st, dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out));
   ECAMP_LAUNCHED();
   return 0;
 }
@@ -201,9 +203,9 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
   if (M <= 0) return 0;
   const int grid = (M + kRowsPerBlock - 1) / kRowsPerBlock;
   if (D == 768)
-    ln_fwd_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, out_bf16, out_f32, mean, rstd);
+    ECAMP_CUDA_OK(launch_pdl(ln_fwd_kernel<6>, grid, 256, 0, st, x, gamma, beta, eps, M, out_bf16, out_f32, mean, rstd));
   else
-    ln_fwd_kernel<4><<<grid, 256, 0, st>>>(x, gamma, beta, eps, M, out_bf16, out_f32, mean, rstd);
+    ECAMP_CUDA_OK(launch_pdl(ln_fwd_kernel<4>, grid, 256, 0, st, x, gamma, beta, eps, M, out_bf16, out_f32, mean, rstd));
   ECAMP_LAUNCHED();
   return 0;
 }

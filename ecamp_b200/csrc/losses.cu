@@ -14,6 +14,7 @@ constexpr int IMG = 224, BIG = 448, GRID = 14, PATCH = 16, PD = 768;
 __global__ void __launch_bounds__(192) mim_rows_kernel(const float* __restrict__ pred, int rows_per_batch,
                                                        const float* __restrict__ tgt, const float* __restrict__ mask,
                                                        int L, float* __restrict__ ws) {
+  ECAMP_PDL_ENTRY();
   __shared__ float red[32];
   const int r = blockIdx.x, b = r / L, l = r % L;
   float s = 0.f;
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(192) mim_rows_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(1024) sum_to_scalar_kernel(const float* __restrict__ x, size_t n, float scale,
                                                              float* __restrict__ out) {
+  ECAMP_PDL_ENTRY();
   __shared__ float red[32];
   float s = 0.f;
   for (size_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
@@ -159,6 +161,7 @@ ECAMP_DEVINL void sr_window(const int64_t* column, const int64_t* row, int b, in
 __global__ void __launch_bounds__(256) sr_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ big,
                                                      const int64_t* __restrict__ column,
                                                      const int64_t* __restrict__ row, float* __restrict__ ws) {
+  ECAMP_PDL_ENTRY();
   constexpr int OUT = 32, UW = OUT + 4, HW = OUT + 2;
   __shared__ float sU[3 * UW * UW + 8];  // +8: strips may read (and discard) a few floats past a row end
   __shared__ float sH[3 * HW * HW + 8];
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
                                                      const int64_t* __restrict__ row, int B,
                                                      const float* __restrict__ g_res, float* __restrict__ d_u,
                                                      float* __restrict__ ws) {
+  ECAMP_PDL_ENTRY();
   constexpr int OUT = 36, UW = 40, HW = 38, OW = 36, GW = 34;
   extern __shared__ float sm[];
   float* sU = sm;
@@ -359,6 +363,7 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) sr_wgrad_finalize_kernel(const float* __restrict__ ws, int ntiles,
                                                                 float* __restrict__ d_conv, int accumulate) {
+  ECAMP_PDL_ENTRY();
   __shared__ float red[32];
   const int k = blockIdx.x;  // 0..167
   float s = 0.f;
@@ -370,10 +375,21 @@ __global__ void __launch_bounds__(256) sr_wgrad_finalize_kernel(const float* __r
 // ---------------------------------------------------------------------------------------------
 // d_pred (bf16, the dY operand of decoder_pred's dgrad / wgrad)
 // ---------------------------------------------------------------------------------------------
+// weights of the transposed x2 bilinear up-sampling (align_corners = False) for source index y: the taps are the
+// up-sampled rows 2y-1, 2y, 2y+1, 2y+2 with weights .25 .75 .75 .25; at the image border the up-sampling clamps its
+// source index, which moves the missing tap's weight onto the border pixel itself
+ECAMP_DEVINL void bilinear_t_weights(int y, float (&w)[4]) {
+  w[0] = 0.25f; w[1] = 0.75f; w[2] = 0.75f; w[3] = 0.25f;
+  if (y == 0) { w[0] = 0.f; w[1] = 1.0f; }
+  if (y == IMG - 1) { w[2] = 1.0f; w[3] = 0.f; }
+}
 __global__ void __launch_bounds__(256) pred_grad_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
                                                         const float* __restrict__ mask, const float* __restrict__ d_u,
                                                         const float* __restrict__ g_mim, int B,
                                                         bf16* __restrict__ d_pred) {
+  ECAMP_PDL_ENTRY();
+  constexpr int RW = 34;  // 16 source pixels x 2 + one halo pixel on each side, in the up-sampled grid
+  __shared__ float sdu[3 * RW * RW];
   const int r = blockIdx.x, b = r / 197, t = r % 197;
   bf16* out = d_pred + (size_t)r * PD;
   if (t == 0) {
@@ -383,33 +399,30 @@ __global__ void __launch_bounds__(256) pred_grad_kernel(const float* __restrict_
   const int l = t - 1, hy = l / GRID, wx = l % GRID;
   const float m = mask[(size_t)b * 196 + l];
   const float gm = m != 0.f ? 2.0f * (*g_mim) / ((float)B * 3.f * IMG * IMG) : 0.f;
+  if (d_u) {
+    // stage the (34 x 34) x 3 neighbourhood of this patch of d_u (zero outside the image: those taps have weight 0)
+    const int Y0 = 2 * hy * PATCH - 1, X0 = 2 * wx * PATCH - 1;
+    for (int i = threadIdx.x; i < 3 * RW * RW; i += blockDim.x) {
+      const int c = i / (RW * RW), rem = i % (RW * RW), yy = rem / RW, xx = rem % RW;
+      const int Y = Y0 + yy, X = X0 + xx;
+      sdu[i] = (Y >= 0 && Y < BIG && X >= 0 && X < BIG) ? d_u[(((size_t)b * 3 + c) * BIG + Y) * BIG + X] : 0.f;
+    }
+    __syncthreads();
+  }
   for (int e = threadIdx.x; e < PD; e += blockDim.x) {
     float g = 0.f;
     if (gm != 0.f) g = gm * (pred[(size_t)r * PD + e] - tgt[((size_t)b * 196 + l) * PD + e]);
     if (d_u) {
       const int c = e % 3, pq = e / 3, p = pq >> 4, q = pq & 15;
-      const int y = hy * PATCH + p, x = wx * PATCH + q;
-      const float* du = d_u + ((size_t)b * 3 + c) * BIG * BIG;
+      float wy[4], wxx[4];
+      bilinear_t_weights(hy * PATCH + p, wy);
+      bilinear_t_weights(wx * PATCH + q, wxx);
+      const float* s0 = sdu + c * RW * RW + (2 * p) * RW + 2 * q;  // local row of up-sampled row 2y-1, column 2x-1
       float acc = 0.f;
 #pragma unroll
-      for (int dy = -1; dy <= 2; ++dy) {
-        const int Y = 2 * y + dy;
-        if (Y < 0 || Y >= BIG) continue;
-        int y0, y1;
-        float ly;
-        bilinear_src(Y, y0, y1, ly);
-        const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
-        if (wy == 0.f) continue;
-#pragma unroll
-        for (int dx = -1; dx <= 2; ++dx) {
-          const int X = 2 * x + dx;
-          if (X < 0 || X >= BIG) continue;
-          int x0, x1;
-          float lx;
-          bilinear_src(X, x0, x1, lx);
-          const float wxx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
-          if (wxx != 0.f) acc += wy * wxx * du[(size_t)Y * BIG + X];
-        }
+      for (int a = 0; a < 4; ++a) {
+        const float* sr = s0 + a * RW;
+        acc = fmaf(wy[a], fmaf(wxx[0], sr[0], fmaf(wxx[1], sr[1], fmaf(wxx[2], sr[2], wxx[3] * sr[3]))), acc);
       }
       g += acc;
     }
@@ -425,6 +438,7 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(bf16* __restrict__ logits,
                                                       const float* __restrict__ weights, float* __restrict__ row_loss,
                                                       const float* __restrict__ g_mlm, float inv_total,
                                                       int write_grad) {
+  ECAMP_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t ce_smem[];
   bf16* srow = reinterpret_cast<bf16*>(ce_smem);
   __shared__ float red[32];
@@ -449,23 +463,15 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(bf16* __restrict__ logits,
   mx = red[0];
 #pragma unroll
   for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
-  float se = 0.f;
-  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-    const uint4 u = reinterpret_cast<const uint4*>(srow)[i];
-    float2 f;
-    f = unpack_bf16x2(u.x); se += __expf(f.x - mx) + __expf(f.y - mx);
-    f = unpack_bf16x2(u.y); se += __expf(f.x - mx) + __expf(f.y - mx);
-    f = unpack_bf16x2(u.z); se += __expf(f.x - mx) + __expf(f.y - mx);
-    f = unpack_bf16x2(u.w); se += __expf(f.x - mx) + __expf(f.y - mx);
-  }
-  se = block_sum(se, red);
-  const float lse = mx + __logf(se);
+  // e_j = exp(z_j - max) is evaluated ONCE: summed in fp32 and kept (bf16, over the staged logit) for the gradient
+  // pass, which then is a scale and a pack (the kernel was bound by the two exps per logit; the gradient is stored
+  // in bf16 anyway)
   const long long label = labels[r];
   const bool valid = label >= 0 && label < V;  // CrossEntropyLoss ignore_index (-100) -> no loss, no gradient
-  const float w = weights[r];
-  if (threadIdx.x == 0) row_loss[r] = valid ? (lse - bf2f(srow[label])) * w : 0.f;
-  if (!write_grad) return;
-  const float coef = valid ? w * (*g_mlm) * inv_total : 0.f;
+  const float z_label = valid ? bf2f(srow[label]) : 0.f;
+  __syncthreads();  // every thread has read its label logit before the row is overwritten
+  float se = 0.f;
+  const float mx2 = mx * 1.4426950408889634f;
   for (int i = threadIdx.x; i < nv; i += blockDim.x) {
     const uint4 u = reinterpret_cast<const uint4*>(srow)[i];
     float v[8];
@@ -476,9 +482,35 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(bf16* __restrict__ logits,
     f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float p = __expf(v[k] - lse);
-      if (i * 8 + k == label) p -= 1.f;
-      v[k] = p * coef;
+      v[k] = ex2_approx(fmaf(v[k], 1.4426950408889634f, -mx2));
+      se += v[k];
+    }
+    if (write_grad) {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      reinterpret_cast<uint4*>(srow)[i] = o;
+    }
+  }
+  se = block_sum(se, red);
+  const float lse = mx + __logf(se);
+  const float w = weights[r];
+  if (threadIdx.x == 0) row_loss[r] = valid ? (lse - z_label) * w : 0.f;
+  if (!write_grad) return;
+  const float coef = valid ? w * (*g_mlm) * inv_total : 0.f;
+  const float pscale = coef / se;  // softmax_j * coef = e_j * coef / sum
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(srow)[i];
+    float v[8];
+    float2 f;
+    f = unpack_bf16x2(u.x); v[0] = f.x * pscale; v[1] = f.y * pscale;
+    f = unpack_bf16x2(u.y); v[2] = f.x * pscale; v[3] = f.y * pscale;
+    f = unpack_bf16x2(u.z); v[4] = f.x * pscale; v[5] = f.y * pscale;
+    f = unpack_bf16x2(u.w); v[6] = f.x * pscale; v[7] = f.y * pscale;
+    if ((long long)i == (label >> 3) && valid) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k == (int)(label & 7)) v[k] -= coef;
     }
     uint4 o;
     o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
@@ -492,7 +524,7 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(bf16* __restrict__ logits,
 #define LAUNCH_OK() ECAMP_LAUNCHED()
 
 int sum_to_scalar(const float* x, size_t n, float scale, float* out, cudaStream_t st) {
-  sum_to_scalar_kernel<<<1, 1024, 0, st>>>(x, n, scale, out);
+  ECAMP_CUDA_OK(launch_pdl(sum_to_scalar_kernel, 1, 1024, 0, st, x, n, scale, out));
   LAUNCH_OK();
   return 0;
 }
@@ -500,7 +532,7 @@ int sum_to_scalar(const float* x, size_t n, float scale, float* out, cudaStream_
 int mim_loss_fwd(const float* pred, int rows_per_batch, const float* tgt, const float* mask, int B, int L, int pd,
                  float* loss_out, float* ws, cudaStream_t st) {
   ECAMP_REQUIRE(pd == PD && L == 196, "mim loss: only 196 patches x 768 supported");
-  mim_rows_kernel<<<B * L, 192, 0, st>>>(pred, rows_per_batch, tgt, mask, L, ws);
+  ECAMP_CUDA_OK(launch_pdl(mim_rows_kernel, B * L, 192, 0, st, pred, rows_per_batch, tgt, mask, L, ws));
   LAUNCH_OK();
   return sum_to_scalar(ws, (size_t)B * L, 1.0f / ((float)B * 3.f * IMG * IMG), loss_out, st);
 }
@@ -521,7 +553,7 @@ int sr_loss_fwd(const float* pred, const float* big, const int64_t* column, cons
                 const float* b1, const float* w2, const float* b2, int B, float* loss_out, float* ws,
                 cudaStream_t st) {
   if (int rc = upload_sr_weights(w1, b1, w2, b2, st)) return rc;
-  sr_fwd_kernel<<<B * GRID * GRID, 256, 0, st>>>(pred, big, column, row, ws);
+  ECAMP_CUDA_OK(launch_pdl(sr_fwd_kernel, B * GRID * GRID, 256, 0, st, pred, big, column, row, ws));
   LAUNCH_OK();
   return sum_to_scalar(ws, (size_t)B * GRID * GRID, 1.0f / ((float)B * 3.f * BIG * BIG), loss_out, st);
 }
@@ -536,17 +568,17 @@ int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, cons
     attr = true;
   }
   if (int rc = upload_sr_weights(w1, b1, w2, b2, st)) return rc;
-  sr_bwd_kernel<<<B * GRID * GRID, 256, SR_BWD_SMEM_FLOATS * sizeof(float), st>>>(pred, big, column, row, B, g_res,
-                                                                                   d_u, ws);
+  ECAMP_CUDA_OK(launch_pdl(sr_bwd_kernel, B * GRID * GRID, 256, SR_BWD_SMEM_FLOATS * sizeof(float), st, pred, big, column, row, B, g_res,
+                                                                                   d_u, ws));
   LAUNCH_OK();
-  sr_wgrad_finalize_kernel<<<168, 256, 0, st>>>(ws, B * GRID * GRID, d_conv, accumulate);
+  ECAMP_CUDA_OK(launch_pdl(sr_wgrad_finalize_kernel, 168, 256, 0, st, ws, B * GRID * GRID, d_conv, accumulate));
   LAUNCH_OK();
   return 0;
 }
 
 int pred_grad(const float* pred, const float* tgt, const float* mask, const float* d_u, const float* g_mim, int B,
               bf16* d_pred, cudaStream_t st) {
-  pred_grad_kernel<<<B * 197, 256, 0, st>>>(pred, tgt, mask, d_u, g_mim, B, d_pred);
+  ECAMP_CUDA_OK(launch_pdl(pred_grad_kernel, B * 197, 256, 0, st, pred, tgt, mask, d_u, g_mim, B, d_pred));
   LAUNCH_OK();
   return 0;
 }
@@ -561,8 +593,8 @@ int ce_chunk(bf16* logits, int ldl, int rows, int V, const int64_t* labels, cons
     ECAMP_CUDA_OK(cudaFuncSetAttribute(ce_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  ce_rows_kernel<<<rows, 256, (size_t)V * 2, st>>>(logits, ldl, V, labels, weights, row_loss, g_mlm, inv_total,
-                                                   write_grad);
+  ECAMP_CUDA_OK(launch_pdl(ce_rows_kernel, rows, 256, (size_t)V * 2, st, logits, ldl, V, labels, weights, row_loss, g_mlm, inv_total,
+                                                   write_grad));
   LAUNCH_OK();
   return 0;
 }

@@ -873,6 +873,7 @@ struct ZeroRuns {
   int count;
 };
 __global__ void zero_runs_kernel(float* __restrict__ g, const ZeroRuns runs) {
+  ECAMP_PDL_ENTRY();
   const int r = blockIdx.x;
   float* p = g + runs.off[r];
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < runs.n[r]; i += gridDim.y * blockDim.x) p[i] = 0.f;
@@ -895,7 +896,7 @@ int zero_small_grads(Ctx* c) {
     return z;
   }();
   ECAMP_REQUIRE(runs.count <= ZeroRuns::kMax, "zero_small_grads: %d runs exceed the table", runs.count);
-  zero_runs_kernel<<<dim3(runs.count, 4), 256, 0, c->st>>>(c->G, runs);
+  ECAMP_CUDA_OK(launch_pdl(zero_runs_kernel, dim3(runs.count, 4), 256, 0, c->st, c->G, runs));
   ECAMP_LAUNCHED();
   return 0;
 }
