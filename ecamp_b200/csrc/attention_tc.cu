@@ -28,6 +28,40 @@ ECAMP_DEVINL void st_swizzled8(uint8_t* tile, int r, int c8, const float (&v)[8]
   *reinterpret_cast<uint4*>(tile + atom * kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4)) = u;
 }
 
+// Coalesced store of a [32 rows x NC columns] bf16 block that a warp holds ONE ROW PER THREAD (the layout tcgen05.ld
+// delivers): written that way every store instruction touches 32 different lines; instead the block goes through a
+// swizzled shared-memory tile and leaves as whole row segments (NC = 64: 4 rows x 128 B per instruction).
+// `packed`: the thread's NC bf16 as NC / 2 words; `g0`: global address of (row 0 of the warp's 32 rows, column 0 of
+// the block); rows >= rows_valid are not written.  `stage`: 32 * NC * 2 bytes private to the warp.
+template <int NC>
+ECAMP_DEVINL void store_rows_coalesced(uint8_t* stage, const uint32_t (&packed)[NC / 2], int lane, bf16* g0, size_t ld,
+                                       int rows_valid) {
+  constexpr int NU = NC / 8;       // 16-byte units per row (8 or 4)
+  constexpr int RB = NC * 2;       // row bytes (128 or 64)
+  constexpr int RPS = 32 / NU;     // rows per step of the coalesced read-back
+  const uint32_t sbase = smem_u32(stage);
+  const int wswz = NC == 64 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+  for (int j = 0; j < NU; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)(lane * RB + ((j ^ wswz) << 4))),
+                 "r"(packed[4 * j]), "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
+                 : "memory");
+  __syncwarp();
+  const int sub = lane / NU, u = lane % NU;
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    const int r = RPS * i + sub;
+    const int rswz = NC == 64 ? (r & 7) : ((r >> 1) & 3);
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(sbase + (uint32_t)(r * RB + ((u ^ rswz) << 4)))
+                 : "memory");
+    if (r < rows_valid) *reinterpret_cast<uint4*>(g0 + (size_t)r * ld + u * 8) = v;
+  }
+  __syncwarp();
+}
+
 struct TcMaps {
   CUtensorMap q, k, v, d_o;
 };
@@ -165,23 +199,23 @@ __global__ void __launch_bounds__(160) attn_tc_fwd_kernel(const __grid_constant_
     mbar_wait(bar_o, 0);
     tc_fence_after();
     const float inv = l > 0.f ? 1.0f / l : 0.f;
+    // all MMAs have completed: the operand tiles are dead, their space stages the output (4 KB per warp)
+    uint8_t* stage = smem + warp * 4096;
+    const int rows_valid = a.Sq - (q0 + warp * 32);
+    bf16* g0 = a.o + ((size_t)b * a.Sq + q0 + warp * 32) * a.ldo + h * D;
 #pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
-      uint32_t raw[32];
-      tmem_ld_32x32(tO + lane_base + c * 32, raw);
-      tmem_ld_wait();
-      if (qi < a.Sq) {
-        bf16* orow = a.o + ((size_t)b * a.Sq + qi) * a.ldo + h * D + c * 32;
+    for (int c2 = 0; c2 < D / 64; ++c2) {
+      uint32_t packed[32];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(raw[8 * i + 0]) * inv, __uint_as_float(raw[8 * i + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(raw[8 * i + 2]) * inv, __uint_as_float(raw[8 * i + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(raw[8 * i + 4]) * inv, __uint_as_float(raw[8 * i + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(raw[8 * i + 6]) * inv, __uint_as_float(raw[8 * i + 7]) * inv);
-          reinterpret_cast<uint4*>(orow)[i] = u;
-        }
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tO + lane_base + (c2 * 2 + cc) * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          packed[cc * 16 + i] = pack_bf16x2(__uint_as_float(raw[2 * i]) * inv, __uint_as_float(raw[2 * i + 1]) * inv);
       }
+      store_rows_coalesced<64>(stage, packed, lane, g0 + c2 * 64, (size_t)a.ldo, rows_valid);
     }
     if (qi < a.Sq && a.lse) a.lse[bh * a.Sq + qi] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
   }
@@ -358,30 +392,27 @@ __global__ void __launch_bounds__(288) attn_tc_bwd_kernel(const __grid_constant_
     // epilogue: dQ rows are queries, dK / dV rows are keys
     mbar_wait(bar_g, 0);
     tc_fence_after();
+    // all MMAs have completed (bar_g): the operand tiles are dead, their space stages the outputs (4 KB per warp)
+    uint8_t* stage = smem + warp * 4096;
 #pragma unroll 1
     for (int which = 0; which < 3; ++which) {
       const uint32_t tsrc = which == 0 ? tS : (which == 1 ? tdK : tdP);
-      const bool ok = which == 0 ? (r < a.Sq) : (r < a.Sk);
-      bf16* base = which == 0 ? a.dq + ((size_t)b * a.Sq + r) * a.lddq
-                              : (which == 1 ? a.dk + ((size_t)b * a.Sk + r) * a.lddk : a.dv + ((size_t)b * a.Sk + r) * a.lddv);
-#pragma unroll 1
-      for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tsrc + lane_base + c * 32, raw);
-        tmem_ld_wait();
-        if (ok) {
-          bf16* orow = base + h * D + c * 32;
+      const int nrows = which == 0 ? a.Sq : a.Sk;
+      bf16* base = which == 0 ? a.dq + (size_t)b * a.Sq * a.lddq
+                              : (which == 1 ? a.dk + (size_t)b * a.Sk * a.lddk : a.dv + (size_t)b * a.Sk * a.lddv);
+      const size_t ld = which == 0 ? (size_t)a.lddq : (which == 1 ? (size_t)a.lddk : (size_t)a.lddv);
+      constexpr int NC = D / 2;  // columns per warp (two warps share a row): 64 or 32
+      uint32_t packed[NC / 2];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(raw[8 * i + 0]), __uint_as_float(raw[8 * i + 1]));
-            u.y = pack_bf16x2(__uint_as_float(raw[8 * i + 2]), __uint_as_float(raw[8 * i + 3]));
-            u.z = pack_bf16x2(__uint_as_float(raw[8 * i + 4]), __uint_as_float(raw[8 * i + 5]));
-            u.w = pack_bf16x2(__uint_as_float(raw[8 * i + 6]), __uint_as_float(raw[8 * i + 7]));
-            reinterpret_cast<uint4*>(orow)[i] = u;
-          }
-        }
+      for (int cc = 0; cc < NC / 32; ++cc) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tsrc + lane_base + (half * (NC / 32) + cc) * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) packed[cc * 16 + i] = pack_bf16x2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]));
       }
+      store_rows_coalesced<NC>(stage, packed, lane, base + (size_t)(quarter * 32) * ld + h * D + half * NC, ld,
+                               nrows - quarter * 32);
     }
   }
   tc_fence_before();

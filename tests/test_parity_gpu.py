@@ -15,7 +15,7 @@ def pc():
     return parity_checks
 
 
-@pytest.mark.parametrize("name", ["check_masking", "check_resize", "check_layernorm", "check_attention", "check_losses",
+@pytest.mark.parametrize("name", ["check_masking", "check_resize", "check_gemm", "check_layernorm", "check_attention", "check_losses",
                                   "check_ce", "check_step", "check_adamw"])
 def test_parity(pc, name, capsys):
     ok = pc.run_check(getattr(pc, name))
