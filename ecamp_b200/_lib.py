@@ -53,7 +53,8 @@ class Attn(ctypes.Structure):
                 ("seed", ctypes.c_uint64), ("site", ctypes.c_uint64),
                 ("d_o", ctypes.c_void_p), ("ld_do", ctypes.c_int32), ("delta", ctypes.c_void_p),
                 ("dq", ctypes.c_void_p), ("dk", ctypes.c_void_p), ("dv", ctypes.c_void_p),
-                ("lddq", ctypes.c_int32), ("lddk", ctypes.c_int32), ("lddv", ctypes.c_int32)]
+                ("lddq", ctypes.c_int32), ("lddk", ctypes.c_int32), ("lddv", ctypes.c_int32),
+                ("cs_q", ctypes.c_void_p), ("cs_k", ctypes.c_void_p), ("cs_v", ctypes.c_void_p)]
 
 
 # every symbol include/ecamp_b200.h declares (tests check that the library exports all of them)

@@ -30,6 +30,7 @@ AttnArgs to_args(const ecamp_attn* a) {
   r.d_o = static_cast<const bf16*>(a->d_o); r.ld_do = a->ld_do; r.delta = a->delta;
   r.dq = static_cast<bf16*>(a->dq); r.dk = static_cast<bf16*>(a->dk); r.dv = static_cast<bf16*>(a->dv);
   r.lddq = a->lddq; r.lddk = a->lddk; r.lddv = a->lddv;
+  r.cs_q = a->cs_q; r.cs_k = a->cs_k; r.cs_v = a->cs_v;
   return r;
 }
 Shape to_shape(const ecamp_shape* s) {

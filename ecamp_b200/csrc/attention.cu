@@ -468,6 +468,34 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
     }
   }  // passes
 
+  // bias gradients of the q / k / v projections: column sums of this warp's 16 rows (fp32 accumulators), one atomic
+  // per column and warp
+  {
+    float* cs1 = TR ? a.cs_k : a.cs_q;
+    float* cs2 = TR ? a.cs_v : nullptr;
+    if (cs1 || cs2) {
+      const bool v0 = row_g < Sr, v1 = row_g + 8 < Sr;
+#pragma unroll
+      for (int j = 0; j < D / 8; ++j) {
+        float c1a = (v0 ? acc1[j][0] : 0.f) + (v1 ? acc1[j][2] : 0.f), c1b = (v0 ? acc1[j][1] : 0.f) + (v1 ? acc1[j][3] : 0.f);
+        float c2a = 0.f, c2b = 0.f;
+        if (TR) {
+          c2a = (v0 ? acc2[TR ? j : 0][0] : 0.f) + (v1 ? acc2[TR ? j : 0][2] : 0.f);
+          c2b = (v0 ? acc2[TR ? j : 0][1] : 0.f) + (v1 ? acc2[TR ? j : 0][3] : 0.f);
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          c1a += __shfl_xor_sync(0xffffffffu, c1a, o); c1b += __shfl_xor_sync(0xffffffffu, c1b, o);
+          if (TR) { c2a += __shfl_xor_sync(0xffffffffu, c2a, o); c2b += __shfl_xor_sync(0xffffffffu, c2b, o); }
+        }
+        if (g == 0) {
+          const int col = h * D + j * 8 + t4 * 2;
+          if (cs1) { atomicAdd(cs1 + col, c1a); atomicAdd(cs1 + col + 1, c1b); }
+          if (TR && cs2) { atomicAdd(cs2 + col, c2a); atomicAdd(cs2 + col + 1, c2b); }
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int row = row_g + r * 8;

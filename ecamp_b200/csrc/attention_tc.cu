@@ -33,9 +33,10 @@ ECAMP_DEVINL void st_swizzled8(uint8_t* tile, int r, int c8, const float (&v)[8]
 // swizzled shared-memory tile and leaves as whole row segments (NC = 64: 4 rows x 128 B per instruction).
 // `packed`: the thread's NC bf16 as NC / 2 words; `g0`: global address of (row 0 of the warp's 32 rows, column 0 of
 // the block); rows >= rows_valid are not written.  `stage`: 32 * NC * 2 bytes private to the warp.
+// `colsum` (optional): += the column sums of the valid rows (fp32 atomics; 8 columns per lane group).
 template <int NC>
 ECAMP_DEVINL void store_rows_coalesced(uint8_t* stage, const uint32_t (&packed)[NC / 2], int lane, bf16* g0, size_t ld,
-                                       int rows_valid) {
+                                       int rows_valid, float* colsum = nullptr) {
   constexpr int NU = NC / 8;       // 16-byte units per row (8 or 4)
   constexpr int RB = NC * 2;       // row bytes (128 or 64)
   constexpr int RPS = 32 / NU;     // rows per step of the coalesced read-back
@@ -48,6 +49,7 @@ ECAMP_DEVINL void store_rows_coalesced(uint8_t* stage, const uint32_t (&packed)[
                  : "memory");
   __syncwarp();
   const int sub = lane / NU, u = lane % NU;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < NU; ++i) {
     const int r = RPS * i + sub;
@@ -57,7 +59,25 @@ ECAMP_DEVINL void store_rows_coalesced(uint8_t* stage, const uint32_t (&packed)[
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "r"(sbase + (uint32_t)(r * RB + ((u ^ rswz) << 4)))
                  : "memory");
-    if (r < rows_valid) *reinterpret_cast<uint4*>(g0 + (size_t)r * ld + u * 8) = v;
+    if (r < rows_valid) {
+      *reinterpret_cast<uint4*>(g0 + (size_t)r * ld + u * 8) = v;
+      float2 f;
+      f = unpack_bf16x2(v.x); cs[0] += f.x; cs[1] += f.y;
+      f = unpack_bf16x2(v.y); cs[2] += f.x; cs[3] += f.y;
+      f = unpack_bf16x2(v.z); cs[4] += f.x; cs[5] += f.y;
+      f = unpack_bf16x2(v.w); cs[6] += f.x; cs[7] += f.y;
+    }
+  }
+  if (colsum) {  // lanes that differ only in `sub` hold the same 8 columns
+#pragma unroll
+    for (int o = NU; o < 32; o <<= 1)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], o);
+    if (sub == 0) {
+      float* dst = colsum + u * 8;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
+    }
   }
   __syncwarp();
 }
@@ -411,8 +431,9 @@ __global__ void __launch_bounds__(288) attn_tc_bwd_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 16; ++i) packed[cc * 16 + i] = pack_bf16x2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]));
       }
+      float* cs = which == 0 ? a.cs_q : (which == 1 ? a.cs_k : a.cs_v);
       store_rows_coalesced<NC>(stage, packed, lane, base + (size_t)(quarter * 32) * ld + h * D + half * NC, ld,
-                               nrows - quarter * 32);
+                               nrows - quarter * 32, cs ? cs + h * D + half * NC : nullptr);
     }
   }
   tc_fence_before();

@@ -92,6 +92,9 @@ struct AttnArgs {
   float* delta = nullptr;  // [B, H, Sq] scratch
   bf16 *dq = nullptr, *dk = nullptr, *dv = nullptr;
   int lddq = 0, lddk = 0, lddv = 0;
+  // optional [H * D] fp32 each: += column sums over all (batch, position) rows of dq / dk / dv (atomic adds) = the bias
+  // gradients of the query / key / value projections, folded into the kernel that produces their operand
+  float *cs_q = nullptr, *cs_k = nullptr, *cs_v = nullptr;
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t st);
 int attention_bwd(const AttnArgs& a, cudaStream_t st);

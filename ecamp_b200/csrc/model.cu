@@ -490,9 +490,10 @@ int vit_block_bwd(Ctx* c, VitStack& s, int l) {
   at.d_o = c->dAO; at.ld_do = D; at.delta = c->delta;
   at.dq = c->dQKV; at.dk = c->dQKV + D; at.dv = c->dQKV + 2 * D;
   at.lddq = at.lddk = at.lddv = 3 * D;
+  at.cs_q = c->Gp(pb + 3); at.cs_k = c->Gp(pb + 3) + D; at.cs_v = c->Gp(pb + 3) + 2 * D;  // qkv bias gradient
   RC(attention_bwd(at, c->st));
   // qkv
-  RC(lin_wgrad(c, c->dQKV, 3 * D, a.ln1, D, M, 3 * D, D, c->Gp(pb + 2), c->Gp(pb + 3), acc));
+  RC(lin_wgrad(c, c->dQKV, 3 * D, a.ln1, D, M, 3 * D, D, c->Gp(pb + 2), nullptr, acc));
   GemmEpilogue eq;
   eq.out_f32 = c->dH; eq.ld_f32 = D;
   RC(lin_dgrad(c, c->dQKV, 3 * D, M, c->W(pb + 2), 3 * D, D, eq));
@@ -534,8 +535,9 @@ int bert_attn_half_bwd(Ctx* c, BertAct& a, int pb, unsigned long long site) {
   at.d_o = c->dAO; at.ld_do = 768; at.delta = c->delta;
   at.dq = c->dQKV; at.dk = c->dQKV + 768; at.dv = c->dQKV + 1536;
   at.lddq = at.lddk = at.lddv = 2304;
+  at.cs_q = c->Gp(pb + 3); at.cs_k = c->Gp(pb + 3) + 768; at.cs_v = c->Gp(pb + 3) + 1536;  // q | k | v bias gradients
   RC(attention_bwd(at, c->st));
-  RC(lin_wgrad(c, c->dQKV, 2304, a.h_in, 768, Mt, 2304, 768, c->Gp(pb + 0), c->Gp(pb + 3), acc));
+  RC(lin_wgrad(c, c->dQKV, 2304, a.h_in, 768, Mt, 2304, 768, c->Gp(pb + 0), nullptr, acc));
   GemmEpilogue eq;
   eq.residual = c->dX; eq.ld_res = 768; eq.out_f32 = c->dX; eq.ld_f32 = 768;
   RC(lin_dgrad(c, c->dQKV, 2304, Mt, c->W(pb + 0), 2304, 768, eq));
@@ -731,14 +733,15 @@ int text_front_bwd(Ctx* c) {
   at.drop = c->drop(12);
   at.d_o = c->dAO; at.ld_do = 768; at.delta = c->delta;
   at.dq = c->dQKV; at.lddq = 768; at.dk = d_kv; at.dv = d_kv + 768; at.lddk = at.lddv = 1536;
+  at.cs_q = c->Gp(f.cq + 1); at.cs_k = c->Gp(f.ckv + 2); at.cs_v = c->Gp(f.ckv + 2) + 768;  // cross q / k | v bias gradients
   RC(attention_bwd(at, c->st));
   // cross query: d(a1) = dQc Wcq + dX (residual of out_layer)
-  RC(lin_wgrad(c, c->dQKV, 768, a.a, 768, Mt, 768, 768, c->Gp(f.cq), c->Gp(f.cq + 1), acc));
+  RC(lin_wgrad(c, c->dQKV, 768, a.a, 768, Mt, 768, 768, c->Gp(f.cq), nullptr, acc));
   GemmEpilogue eq;
   eq.residual = c->dX; eq.ld_res = 768; eq.out_f32 = c->dX; eq.ld_f32 = 768;
   RC(lin_dgrad(c, c->dQKV, 768, Mt, c->W(f.cq), 768, 768, eq));
   // cross key/value -> image tokens
-  RC(lin_wgrad(c, d_kv, 1536, c->img_tok, 768, Mi, 1536, 768, c->Gp(f.ckv), c->Gp(f.ckv + 2), acc));
+  RC(lin_wgrad(c, d_kv, 1536, c->img_tok, 768, Mi, 1536, 768, c->Gp(f.ckv), nullptr, acc));
   RC(lin_dgrad(c, d_kv, 1536, Mi, c->W(f.ckv), 1536, 768, ep_bias_bf16(nullptr, d_img, 768)));
   // bert_mlp: latent gradient from the text branch (stored into dLat; the image decoder accumulates later)
   RC(split_latent_gap_bwd(d_img, d_gap, B, keep, 768, d_lat2, c->st));

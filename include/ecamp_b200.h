@@ -119,6 +119,8 @@ typedef struct ecamp_attn {
   float* delta;               /* backward scratch [B, H, Sq] */
   void *dq, *dk, *dv;         /* backward outputs, bf16 */
   int32_t lddq, lddk, lddv;
+  float *cs_q, *cs_k, *cs_v;  /* backward, each [H*D] fp32 or NULL: += column sums of dq / dk / dv over all rows (atomic
+                               * adds): the bias gradients of the q / k / v projections                                */
 } ecamp_attn;
 /* 1 (default): head_dim 64 / 128 problems that fit use the tcgen05 / TMEM kernels; 0: always the mma.sync kernels */
 ECAMP_API void ecamp_attention_set_tcgen05(int32_t on);

@@ -262,12 +262,19 @@ def _check_attention(tag):
         a.d_o, a.ld_do, a.delta = do.data_ptr(), H * D, delta.data_ptr()
         a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
         a.lddq = a.lddk = a.lddv = H * D
+        cs = torch.full((3, H * D), 2.0, device=dev)     # fused bias gradients: += column sums of dq / dk / dv
+        a.cs_q, a.cs_k, a.cs_v = cs[0].data_ptr(), cs[1].data_ptr(), cs[2].data_ptr()
         L.check(lib.ecamp_attention_bwd(ctypes.byref(a), L.cur_stream()), "attn_bwd")
         torch.cuda.synchronize()
         e_q = rel(dq.float(), qr.grad.transpose(1, 2).reshape(B, Sq, H * D))
         e_k = rel(dk.float(), kr.grad.transpose(1, 2).reshape(B, Sk, H * D))
         e_v = rel(dv.float(), vr.grad.transpose(1, 2).reshape(B, Sk, H * D))
-        report(f"attention_{name}_{tag}", max(e_f, e_q, e_k, e_v) < 2e-2, fwd=e_f, dq=e_q, dk=e_k, dv=e_v)
+        # (the key-bias gradient is mathematically zero - every row of dS sums to zero - so it is compared on the scale
+        #  of the summands, not of the sum)
+        def cs_err(got, t):
+            return ((got - t.float().sum((0, 1))).norm() / t.float().abs().sum((0, 1)).norm().clamp_min(1e-12)).item()
+        e_cs = max(cs_err(cs[0] - 2.0, dq), cs_err(cs[1] - 2.0, dk), cs_err(cs[2] - 2.0, dv))
+        report(f"attention_{name}_{tag}", max(e_f, e_q, e_k, e_v) < 2e-2 and e_cs < 2e-3, fwd=e_f, dq=e_q, dk=e_k, dv=e_v, colsum=e_cs)
     # dropout: statistics + forward/backward consistency through a finite difference on V (linear in V)
     B, H, S, D = 2, 6, 128, 128
     q = torch.randn(B, S, H * D, device=dev).to(torch.bfloat16); k = torch.randn_like(q); v = torch.randn_like(q)
