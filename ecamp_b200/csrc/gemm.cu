@@ -175,8 +175,10 @@ ECAMP_DEVINL void epi_vec4_generic(const EpiArgs& ea, float4 v, int row, int col
 }
 
 // what a specialised mode prefetches one chunk ahead (one 16-byte register slot per step)
+// (EM_DGELU needs 8 bytes per step, so a slot holds TWO chunks - `hi` selects the half - and the pre-activation is
+//  fetched two chunks ahead: that operand comes from HBM, one chunk of lead did not cover its latency)
 template <int MODE>
-ECAMP_DEVINL void epi_prefetch(const GemmEpilogue& ep, int row0, int col, int M, int N, uint4 (&p)[kSteps]) {
+ECAMP_DEVINL void epi_prefetch(const GemmEpilogue& ep, int row0, int col, int M, int N, uint4 (&p)[kSteps], bool hi = false) {
   if (MODE != EM_F32_RES && MODE != EM_F32_RES_DROP && MODE != EM_DGELU) return;
   if (col >= N) return;
 #pragma unroll
@@ -185,7 +187,8 @@ ECAMP_DEVINL void epi_prefetch(const GemmEpilogue& ep, int row0, int col, int M,
     if (row < M) {
       if (MODE == EM_DGELU) {
         const uint2 u = __ldg(reinterpret_cast<const uint2*>(ep.aux_in + (size_t)row * ep.ld_aux + col));
-        p[i].x = u.x; p[i].y = u.y;
+        if (hi) { p[i].z = u.x; p[i].w = u.y; }
+        else { p[i].x = u.x; p[i].y = u.y; }
       } else {
         p[i] = *reinterpret_cast<const uint4*>(ep.residual + (size_t)row * ep.ld_res + col);
       }
@@ -240,6 +243,7 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
   const uint32_t stage_addr = smem_u32(stage);  // explicit shared-space accesses (a generic pointer compiled to LD.E / ST.E)
   uint4 pcur[kSteps], pnext[kSteps];
   epi_prefetch<MODE>(ep, row0, ncol0 + 4 * u, M, N, pcur);  // in flight while the accumulator is still being produced
+  if (MODE == EM_DGELU && NCH > 1) epi_prefetch<MODE>(ep, row0, ncol0 + kCW + 4 * u, M, N, pcur, true);
   if (next_m0 >= 0) epi_prefetch_l2<COLS, MODE>(ep, next_m0, next_ncol0, M, N, lane);
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), bias_next = bias4;
   if (vbias && ncol0 + 4 * u + 4 <= N) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + ncol0 + 4 * u));
@@ -268,7 +272,11 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
     for (int j = 0; j < kLPR; ++j)
       sts128(stage_addr + (uint32_t)(lane * (kCW * 4) + ((j ^ epi_swz(lane)) << 4)), raw[4 * j], raw[4 * j + 1],
              raw[4 * j + 2], raw[4 * j + 3]);
-    if (c + 1 < NCH) epi_prefetch<MODE>(ep, row0, col + kCW, M, N, pnext);  // next chunk's operand in flight from here
+    if (MODE == EM_DGELU) {
+      if (c + 2 < NCH) epi_prefetch<MODE>(ep, row0, col + 2 * kCW, M, N, pnext);  // two chunks ahead
+    } else if (c + 1 < NCH) {
+      epi_prefetch<MODE>(ep, row0, col + kCW, M, N, pnext);  // next chunk's operand in flight from here
+    }
     __syncwarp();
     float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // EM_DGELU: column sums of this chunk's emitted values
     constexpr int BATCH = kSteps < 4 ? kSteps : 4;   // steps per batch: keeps the live registers bounded
@@ -342,9 +350,16 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
                      : "memory");
     }
     __syncwarp();
-    if (MODE == EM_F32_RES || MODE == EM_F32_RES_DROP || MODE == EM_DGELU) {
+    if (MODE == EM_F32_RES || MODE == EM_F32_RES_DROP) {
 #pragma unroll
       for (int i = 0; i < kSteps; ++i) pcur[i] = pnext[i];
+    }
+    if (MODE == EM_DGELU) {
+#pragma unroll
+      for (int i = 0; i < kSteps; ++i) {
+        pcur[i].x = pcur[i].z; pcur[i].y = pcur[i].w;    // chunk c + 1 becomes current
+        pcur[i].z = pnext[i].x; pcur[i].w = pnext[i].y;  // chunk c + 2 moves up
+      }
     }
     bias4 = bias_next;
   }

@@ -490,10 +490,11 @@ int vit_block_bwd(Ctx* c, VitStack& s, int l) {
   at.d_o = c->dAO; at.ld_do = D; at.delta = c->delta;
   at.dq = c->dQKV; at.dk = c->dQKV + D; at.dv = c->dQKV + 2 * D;
   at.lddq = at.lddk = at.lddv = 3 * D;
-  at.cs_q = c->Gp(pb + 3); at.cs_k = c->Gp(pb + 3) + D; at.cs_v = c->Gp(pb + 3) + 2 * D;  // qkv bias gradient
+  // (the qkv bias gradient stays with colsum_kernel here: folded into the mma.sync kernels it costs more in atomics -
+  //  +0.26 ms for the encoder, +0.16 ms for the decoder - than the 16 column-sum launches it saves, ~0.2 ms)
   RC(attention_bwd(at, c->st));
   // qkv
-  RC(lin_wgrad(c, c->dQKV, 3 * D, a.ln1, D, M, 3 * D, D, c->Gp(pb + 2), nullptr, acc));
+  RC(lin_wgrad(c, c->dQKV, 3 * D, a.ln1, D, M, 3 * D, D, c->Gp(pb + 2), c->Gp(pb + 3), acc));
   GemmEpilogue eq;
   eq.out_f32 = c->dH; eq.ld_f32 = D;
   RC(lin_dgrad(c, c->dQKV, 3 * D, M, c->W(pb + 2), 3 * D, D, eq));
