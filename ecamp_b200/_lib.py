@@ -43,6 +43,12 @@ class Batch(ctypes.Structure):
                                                "column", "row", "noise")]
 
 
+class ClsIO(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("image", "pos_embed", "fc_norm_w", "fc_norm_b", "head_w16", "head_b", "dp_scale",
+                                               "logits", "d_logits", "g_pos_embed", "g_fc_norm_w", "g_fc_norm_b", "g_head_w",
+                                               "g_head_b")]
+
+
 class Attn(ctypes.Structure):
     _fields_ = [("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("v", ctypes.c_void_p),
                 ("ldq", ctypes.c_int32), ("ldk", ctypes.c_int32), ("ldv", ctypes.c_int32),
@@ -67,7 +73,7 @@ SYMBOLS = [
     "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_ctx_create", "ecamp_ctx_destroy", "ecamp_ctx_bind",
     "ecamp_workspace_bytes", "ecamp_ctx_set_workspace", "ecamp_refresh_shadows", "ecamp_forward",
     "ecamp_backward_stage_count", "ecamp_backward_stage_range", "ecamp_backward", "ecamp_adamw_step",
-    "ecamp_debug_buffer",
+    "ecamp_debug_buffer", "ecamp_cls_workspace_bytes", "ecamp_cls_set_workspace", "ecamp_cls_forward", "ecamp_cls_backward",
 ]
 
 _lib = None
@@ -85,7 +91,8 @@ def lib():
         _lib.ecamp_abi_version.restype = ctypes.c_int
         _lib.ecamp_param_name.restype = ctypes.c_char_p
         for f in ("ecamp_param_numel", "ecamp_param_grad_offset", "ecamp_grad_floats", "ecamp_shadow_bytes",
-                  "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_workspace_bytes", "ecamp_launch_count"):
+                  "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_workspace_bytes", "ecamp_launch_count",
+                  "ecamp_cls_workspace_bytes"):
             getattr(_lib, f).restype = ctypes.c_int64
         for f in ("ecamp_layernorm_ws_floats", "ecamp_sr_ws_floats"):
             getattr(_lib, f).restype = ctypes.c_size_t

@@ -198,4 +198,27 @@ const void* ecamp_debug_buffer(ecamp_ctx* ctx, const char* name) {
   return (ctx && name) ? ctx_debug_ptr(ctx->impl, name) : nullptr;
 }
 
+// ---- fine-tune classification ---------------------------------------------------------------------------------
+static ClsIO to_cls(const ecamp_cls_io* io) {
+  ClsIO r;
+  r.image = io->image; r.pos_embed = io->pos_embed; r.fc_norm_w = io->fc_norm_w; r.fc_norm_b = io->fc_norm_b;
+  r.head_w16 = static_cast<const bf16*>(io->head_w16); r.head_b = io->head_b; r.dp_scale = io->dp_scale; r.logits = io->logits;
+  r.d_logits = io->d_logits; r.g_pos_embed = io->g_pos_embed; r.g_fc_norm_w = io->g_fc_norm_w; r.g_fc_norm_b = io->g_fc_norm_b;
+  r.g_head_w = io->g_head_w; r.g_head_b = io->g_head_b;
+  return r;
+}
+int64_t ecamp_cls_workspace_bytes(int32_t B) { return B > 0 ? (int64_t)cls_workspace_bytes(B) : 0; }
+int ecamp_cls_set_workspace(ecamp_ctx* ctx, void* ws, int64_t bytes, int32_t B) {
+  ECAMP_REQUIRE(ctx && ws, "ecamp_cls_set_workspace: null argument");
+  return ctx_set_cls_workspace(ctx->impl, ws, (size_t)bytes, B);
+}
+int ecamp_cls_forward(ecamp_ctx* ctx, const ecamp_cls_io* io, void* stream) {
+  ECAMP_REQUIRE(ctx && io, "ecamp_cls_forward: null argument");
+  return ctx_cls_forward(ctx->impl, to_cls(io), S(stream));
+}
+int ecamp_cls_backward(ecamp_ctx* ctx, const ecamp_cls_io* io, int32_t accumulate, void* stream) {
+  ECAMP_REQUIRE(ctx && io, "ecamp_cls_backward: null argument");
+  return ctx_cls_backward(ctx->impl, to_cls(io), accumulate, S(stream));
+}
+
 }  // extern "C"

@@ -481,6 +481,40 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
     atomicAdd(out + c, s);  // one add per row chunk and column (the destination starts from zero / the running gradient)
   }
 }
+__global__ void iota_mod_kernel(int32_t* __restrict__ out, size_t n, int mod) {
+  ECAMP_PDL_ENTRY();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)(i % (size_t)mod);
+}
+// x[b, 1:, :].mean(dim=1)   (models_vit.py:92); one CTA per sample, thread = 4 columns
+__global__ void mean_pool_kernel(const float* __restrict__ x, int S, int D, float* __restrict__ out) {
+  ECAMP_PDL_ENTRY();
+  const int b = blockIdx.x, c4 = threadIdx.x;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 1; t < S; ++t) {
+    const float4 v = reinterpret_cast<const float4*>(x + ((size_t)b * S + t) * D)[c4];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  const float inv = 1.0f / (float)(S - 1);
+  reinterpret_cast<float4*>(out + (size_t)b * D)[c4] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+}
+__global__ void mean_pool_bwd_kernel(const float* __restrict__ d_pooled, int S, int D, float* __restrict__ dx,
+                                     bf16* __restrict__ gx, const float* __restrict__ scale) {
+  ECAMP_PDL_ENTRY();
+  const int r = blockIdx.x, b = r / S, t = r % S, c4 = threadIdx.x;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t > 0) {
+    const float inv = 1.0f / (float)(S - 1);
+    const float4 d = reinterpret_cast<const float4*>(d_pooled + (size_t)b * D)[c4];
+    v = make_float4(d.x * inv, d.y * inv, d.z * inv, d.w * inv);
+  }
+  reinterpret_cast<float4*>(dx + (size_t)r * D)[c4] = v;
+  const float s = scale ? scale[b] : 1.0f;
+  uint2 u;
+  u.x = pack_bf16x2(v.x * s, v.y * s);
+  u.y = pack_bf16x2(v.z * s, v.w * s);
+  reinterpret_cast<uint2*>(gx + (size_t)r * D)[c4] = u;
+}
 __global__ void scale_f32_kernel(float* __restrict__ x, const float* __restrict__ scale, size_t n) {
   ECAMP_PDL_ENTRY();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -643,6 +677,29 @@ int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate,
   if (!accumulate) ECAMP_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
   dim3 grid((N + 255) / 256, chunks);
   ECAMP_CUDA_OK(launch_pdl(colsum_kernel, grid, 256, 0, st, x, ld, M, N, out));
+  LAUNCH_OK();
+  return 0;
+}
+int iota_mod_i32(int32_t* out, size_t n, int mod, cudaStream_t st) {
+  if (n == 0) return 0;
+  ECAMP_CUDA_OK(launch_pdl(iota_mod_kernel, (unsigned)((n + 255) / 256), 256, 0, st, out, n, mod));
+  LAUNCH_OK();
+  return 0;
+}
+int mean_pool_tokens(const float* x, int B, int S, int D, float* out, cudaStream_t st) {
+  ECAMP_REQUIRE(D % 4 == 0 && D / 4 <= 1024 && S > 1, "mean_pool: unsupported shape");
+  ECAMP_CUDA_OK(launch_pdl(mean_pool_kernel, B, D / 4, 0, st, x, S, D, out));
+  LAUNCH_OK();
+  return 0;
+}
+int mean_pool_tokens_bwd(const float* d_pooled, int B, int S, int D, float* dx, bf16* gx, const float* scale, cudaStream_t st) {
+  ECAMP_REQUIRE(D % 4 == 0 && D / 4 <= 1024 && S > 1, "mean_pool_bwd: unsupported shape");
+  ECAMP_CUDA_OK(launch_pdl(mean_pool_bwd_kernel, B * S, D / 4, 0, st, d_pooled, S, D, dx, gx, scale));
+  LAUNCH_OK();
+  return 0;
+}
+int strided_rowsum(const float* x, int B, size_t stride, int D, float* out, int accumulate, cudaStream_t st) {
+  ECAMP_CUDA_OK(launch_pdl(strided_rowsum_kernel, (D + 127) / 128, 128, 0, st, x, B, stride, D, out, accumulate));
   LAUNCH_OK();
   return 0;
 }

@@ -107,6 +107,7 @@ ECAMP_DEVINL void epi_scalar(const EpiArgs& ea, float v, int row, int col, int N
     const uint32_t w = philox_word(ph, (uint64_t)row * (uint64_t)N + (uint64_t)col, ep.stream);
     v = (w >= dropout_threshold(ep.drop_p)) ? v * (1.0f / (1.0f - ep.drop_p)) : 0.f;
   }
+  if (ep.row_scale) v *= __ldg(ep.row_scale + row / ep.rows_per_scale);
   if (ep.residual) v += ep.residual[(size_t)row * ep.ld_res + col];
   if (ep.out_f32) ep.out_f32[(size_t)row * ep.ld_f32 + col] = v;
   if (ep.out_bf16) ep.out_bf16[(size_t)row * ep.ld_bf16 + col] = f2bf(v);
@@ -160,6 +161,10 @@ ECAMP_DEVINL void epi_vec4_generic(const EpiArgs& ea, float4 v, int row, int col
     v.x *= gelu_erf_grad(a.x); v.y *= gelu_erf_grad(a.y); v.z *= gelu_erf_grad(b.x); v.w *= gelu_erf_grad(b.y);
   }
   if (ep.flags & GEMM_DROPOUT) v = dropout4(ep, v, row, col, N);
+  if (ep.row_scale) {
+    const float rs = __ldg(ep.row_scale + row / ep.rows_per_scale);
+    v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+  }
   if (ep.residual) {
     const float4 r = *reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ld_res + col);
     v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
@@ -319,6 +324,10 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
               x.x *= gelu_erf_grad(a.x); x.y *= gelu_erf_grad(a.y); x.z *= gelu_erf_grad(b.x); x.w *= gelu_erf_grad(b.y);
             }
             if (MODE == EM_F32_RES_DROP) x = dropout4(ep, x, row, col, N);
+            if (MODE == EM_F32_RES && ep.row_scale) {  // DropPath (fine-tune path only)
+              const float rs = __ldg(ep.row_scale + row / ep.rows_per_scale);
+              x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
+            }
             if (MODE == EM_F32_RES || MODE == EM_F32_RES_DROP) {
               x.x += __uint_as_float(pcur[i].x); x.y += __uint_as_float(pcur[i].y);
               x.z += __uint_as_float(pcur[i].z); x.w += __uint_as_float(pcur[i].w);
@@ -908,7 +917,7 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
   ECAMP_REQUIRE(force_bn == 0 || force_bn == 128 || force_bn == 192 || force_bn == 256, "gemm: unsupported tile N %d",
                 force_bn);
   const bool accumulate = ep.residual != nullptr && ep.residual == ep.out_f32 && ep.ld_res == ep.ld_f32;
-  const bool splittable = ep.out_f32 && !ep.out_bf16 && !ep.bias && ep.flags == 0 && !ep.aux_out && !ep.colsum_out &&
+  const bool splittable = ep.out_f32 && !ep.out_bf16 && !ep.bias && ep.flags == 0 && !ep.aux_out && !ep.colsum_out && !ep.row_scale &&
                           (ep.residual == nullptr || accumulate);
   int bn = 256, split_k = 1;
   const bool cta2 = g_cta_pair_mode == 2 || (g_cta_pair_mode == 0 && M > BM);
@@ -955,6 +964,7 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
     else if (ep.flags == 0 && !ep.aux_out && ep.residual && only_f32) ea.mode = EM_F32_RES;
     else if (ep.flags == GEMM_DROPOUT && !ep.aux_out && ep.residual && only_f32) ea.mode = EM_F32_RES_DROP;
     if (ep.colsum_out && ea.mode != EM_DGELU) ea.mode = EM_GENERIC;  // only the dGELU mode folds the column sums in
+    if (ep.row_scale && ea.mode != EM_F32_RES) ea.mode = EM_GENERIC;
   }
   if (g_force_generic_epilogue) ea.mode = EM_GENERIC;
   static const int dbg = getenv("ECAMP_GEMM_DBG") ? atoi(getenv("ECAMP_GEMM_DBG")) : 0;

@@ -23,6 +23,8 @@ struct GemmEpilogue {
   int ld_bf16 = 0;
   float* colsum_out = nullptr;      // [N] fp32: += column sums of the emitted values (atomics; the bias gradient of the
                                     // Linear that consumes this output).  Only with out_bf16, not with split-K.
+  const float* row_scale = nullptr;  // optional [M / rows_per_scale] fp32: v *= row_scale[m / rows_per_scale] before the
+  int rows_per_scale = 1;            // residual is added (timm DropPath: per-sample mask / keep_prob on the branch)
   int flags = 0;
   float drop_p = 0.f;
   unsigned long long seed = 0, stream = 0;

@@ -18,7 +18,8 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
 // dgamma/dbeta partials are reduced and ADDED to dgamma/dbeta when accumulate != 0, else stored.
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
                   int D, const float* addend, float* dx_f32, bf16* dx_bf16, DropoutCfg drop, float* dgamma,
-                  float* dbeta, float* colsum_out, int accumulate, cudaStream_t st);
+                  float* dbeta, float* colsum_out, int accumulate, cudaStream_t st, const float* out_row_scale = nullptr,
+                  int rows_per_scale = 1);
 size_t layernorm_bwd_ws_floats(int D);
 
 // ---- elementwise.cu ---------------------------------------------------------------------------
@@ -68,6 +69,12 @@ size_t colsum_ws_floats(int N);
 // y = dropout(x) elementwise on bf16 (used for the dropout behind LayerNorm-less sites), in place allowed
 int scale_f32(float* x, const float* scale_dev, size_t n, cudaStream_t st);
 int cast_f32_to_bf16(const float* x, bf16* y, size_t n, cudaStream_t st);
+// fine-tune classification helpers (FT/Classification/models_vit.py:78-98)
+int iota_mod_i32(int32_t* out, size_t n, int mod, cudaStream_t st);                      // out[i] = i % mod
+int mean_pool_tokens(const float* x, int B, int S, int D, float* out, cudaStream_t st);  // mean over tokens 1..S-1
+// dx[b, 0] = 0, dx[b, t >= 1] = d_pooled[b] / (S - 1); gx = bf16(dx * scale[b]) (scale may be null)
+int mean_pool_tokens_bwd(const float* d_pooled, int B, int S, int D, float* dx, bf16* gx, const float* scale, cudaStream_t st);
+int strided_rowsum(const float* x, int B, size_t stride, int D, float* out, int accumulate, cudaStream_t st);
 // patch-embed weight: canonical [768, (c, p, q)] <-> GEMM K-order [768, (p, q, c)]
 int permute_pe_weight_grad(const float* dw_pqc, float* grad_cpq, int accumulate, cudaStream_t st);
 // out = bf16(d * gelu'(pre))   (LM-head transform: dense -> GELU -> LayerNorm, bert_modeling.py:208)

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 6) ln_bwd_kernel(const float* 
                                                      const float* __restrict__ addend, float* __restrict__ dx_f32,
                                                      bf16* __restrict__ dx_bf16, DropoutCfg drop,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                     float* __restrict__ colsum_out) {
+                                                     float* __restrict__ colsum_out,
+                                                     const float* __restrict__ out_row_scale, int rows_per_scale) {
   ECAMP_PDL_ENTRY();
   constexpr int D = NV * 128;
   constexpr int NA = COLSUM ? 3 : 2;
@@ -140,6 +141,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 6) ln_bwd_kernel(const float* 
       }
       if (dx_f32) reinterpret_cast<float4*>(dx_f32 + (size_t)row * D)[c4] = r;
       if (dx_bf16) {
+        if (out_row_scale) {  // DropPath of the branch this gradient feeds (per-sample mask / keep_prob)
+          const float rs_ = __ldg(out_row_scale + row / rows_per_scale);
+          r.x *= rs_; r.y *= rs_; r.z *= rs_; r.w *= rs_;
+        }
         if (drop.p > 0.f) {
           const uint4 rnd = ph(((uint64_t)row * D + (uint64_t)c4 * 4) >> 2, drop.site);
           r.x = rnd.x >= thr ? r.x * keep_scale : 0.f;
@@ -179,7 +184,7 @@ int bwd_blocks(int M) {
 template <int NV, bool COLSUM>
 int launch_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
                   const float* addend, float* dx_f32, bf16* dx_bf16, DropoutCfg drop, float* dgamma, float* dbeta,
-                  float* colsum_out, cudaStream_t st) {
+                  float* colsum_out, cudaStream_t st, const float* out_row_scale, int rows_per_scale) {
   constexpr int D = NV * 128;
   constexpr size_t smem = (size_t)(D + kBwdWarps * (COLSUM ? 3 : 2) * D) * sizeof(float);
   auto kfn = ln_bwd_kernel<NV, COLSUM>;
@@ -188,7 +193,7 @@ int launch_ln_bwd(const float* dy, const float* x, const float* mean, const floa
     ECAMP_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  ECAMP_CUDA_OK(launch_pdl(kfn, bwd_blocks(M), kBwdWarps * 32, smem, st, dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out));
+  ECAMP_CUDA_OK(launch_pdl(kfn, bwd_blocks(M), kBwdWarps * 32, smem, st, dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out, out_row_scale, rows_per_scale));
   ECAMP_LAUNCHED();
   return 0;
 }
@@ -212,7 +217,8 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
 
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
                   int D, const float* addend, float* dx_f32, bf16* dx_bf16, DropoutCfg drop, float* dgamma,
-                  float* dbeta, float* colsum_out, int accumulate, cudaStream_t st) {
+                  float* dbeta, float* colsum_out, int accumulate, cudaStream_t st, const float* out_row_scale,
+                  int rows_per_scale) {
   ECAMP_REQUIRE(D == 768 || D == 512, "layernorm: D must be 512 or 768 (got %d)", D);
   ECAMP_REQUIRE(!colsum_out || dx_bf16, "layernorm_bwd: the column sum is taken over the bf16 output");
   if (M <= 0) return 0;
@@ -222,11 +228,11 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
     if (colsum_out) ECAMP_CUDA_OK(cudaMemsetAsync(colsum_out, 0, (size_t)D * sizeof(float), st));
   }
   if (D == 768) {
-    if (colsum_out) return launch_ln_bwd<6, true>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out, st);
-    return launch_ln_bwd<6, false>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, nullptr, st);
+    if (colsum_out) return launch_ln_bwd<6, true>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out, st, out_row_scale, rows_per_scale);
+    return launch_ln_bwd<6, false>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, nullptr, st, out_row_scale, rows_per_scale);
   }
-  if (colsum_out) return launch_ln_bwd<4, true>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out, st);
-  return launch_ln_bwd<4, false>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, nullptr, st);
+  if (colsum_out) return launch_ln_bwd<4, true>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out, st, out_row_scale, rows_per_scale);
+  return launch_ln_bwd<4, false>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, nullptr, st, out_row_scale, rows_per_scale);
 }
 
 }  // namespace ecamp

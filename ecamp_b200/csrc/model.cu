@@ -185,6 +185,17 @@ struct Ctx {
   int acc = 0;
   const float* g3 = nullptr;
   cudaStream_t st = 0;
+  // ---- fine-tune classification path (FT/Classification/models_vit.py): full 197-token encoder + pooled head ----
+  const float* dp = nullptr;  // DropPath scales [12 blocks][2 branches][B] (mask / keep_prob), null = none
+  int cls_B = 0;
+  bool cls_planned = false;
+  int32_t* cls_ids = nullptr;
+  float *cls_pooled = nullptr, *cls_mean = nullptr, *cls_rstd = nullptr, *cls_dpooled = nullptr, *cls_dfeat = nullptr;
+  bf16 *cls_feat = nullptr, *cls_dlogits = nullptr;
+  // per-sample DropPath scale of (block l, branch br) of the ENCODER stack, or null
+  const float* dps(const VitStack* s, int l, int br) const {
+    return (dp && s == &enc && l >= 0) ? dp + ((size_t)l * 2 + br) * sh.B : nullptr;
+  }
 
   float* P(int i) const { return p[i]; }
   float* Gp(int i) const { return G + param_specs()[i].g_off; }
@@ -454,6 +465,7 @@ int vit_block_fwd(Ctx* c, VitStack& s, int l, float* x_next) {
   RC(attention_fwd(self_attn_args(a.qkv, 3 * D, a.ao, a.lse, B, s.H, s.S, D / s.H), c->st));
   GemmEpilogue ep;
   ep.bias = c->P(pb + 5); ep.residual = a.x_in; ep.ld_res = D; ep.out_f32 = a.x_mid; ep.ld_f32 = D;
+  ep.row_scale = c->dps(&s, l, 0); ep.rows_per_scale = s.S;
   RC(lin_fwd(c, a.ao, D, M, c->W(pb + 4), D, D, ep));
   RC(layernorm_fwd(a.x_mid, c->P(pb + 6), c->P(pb + 7), 1e-6f, M, D, a.ln2, nullptr, a.mean2, a.rstd2, c->st));
   GemmEpilogue e1;
@@ -461,6 +473,7 @@ int vit_block_fwd(Ctx* c, VitStack& s, int l, float* x_next) {
   RC(lin_fwd(c, a.ln2, D, M, c->W(pb + 8), s.hid, D, e1));
   GemmEpilogue e2;
   e2.bias = c->P(pb + 11); e2.residual = a.x_mid; e2.ld_res = D; e2.out_f32 = x_next; e2.ld_f32 = D;
+  e2.row_scale = c->dps(&s, l, 1); e2.rows_per_scale = s.S;
   RC(lin_fwd(c, a.act, s.hid, M, c->W(pb + 10), D, s.hid, e2));
   return 0;
 }
@@ -480,7 +493,7 @@ int vit_block_bwd(Ctx* c, VitStack& s, int l) {
   e1.out_f32 = c->dH; e1.ld_f32 = D;
   RC(lin_dgrad(c, c->dA, s.hid, M, c->W(pb + 8), s.hid, D, e1));
   RC(layernorm_bwd(c->dH, a.x_mid, a.mean2, a.rstd2, c->P(pb + 6), M, D, c->dX, c->dX, c->gX, DropoutCfg(),
-                   c->Gp(pb + 6), c->Gp(pb + 7), c->Gp(pb + 5) /* proj bias */, 1, c->st));
+                   c->Gp(pb + 6), c->Gp(pb + 7), c->Gp(pb + 5) /* proj bias */, 1, c->st, c->dps(&s, l, 0), s.S));
   // proj
   RC(lin_wgrad(c, c->gX, D, a.ao, D, M, D, D, c->Gp(pb + 4), nullptr, acc));
   GemmEpilogue ep;
@@ -500,7 +513,8 @@ int vit_block_bwd(Ctx* c, VitStack& s, int l) {
   RC(lin_dgrad(c, c->dQKV, 3 * D, M, c->W(pb + 2), 3 * D, D, eq));
   // the bf16 gradient emitted here is the dY of the PREVIOUS block's fc2: its bias gradient is folded in
   RC(layernorm_bwd(c->dH, a.x_in, a.mean1, a.rstd1, c->P(pb + 0), M, D, c->dX, c->dX, c->gX, DropoutCfg(),
-                   c->Gp(pb + 0), c->Gp(pb + 1), l > 0 ? c->Gp(pb - VIT_BLOCK_PARAMS + 11) : nullptr, 1, c->st));
+                   c->Gp(pb + 0), c->Gp(pb + 1), l > 0 ? c->Gp(pb - VIT_BLOCK_PARAMS + 11) : nullptr, 1, c->st,
+                   c->dps(&s, l - 1, 1), s.S));
   return 0;
 }
 
@@ -807,6 +821,122 @@ int image_losses_fwd(Ctx* c) {
 }
 
 }  // namespace
+
+// =============================================================================================
+// fine-tune classification (FT/Classification/models_vit.py:60-98 with global_pool; train.py:438-465): the same
+// encoder blocks on the FULL 197-token sequence (no masking), DropPath on both branches, mean over the patch tokens
+// -> fc_norm -> head.  Re-uses the context (parameter table entries patch_embed / cls_token / blocks.*, flat gradient
+// buffer, bf16 shadows); pos_embed (learnable here), fc_norm, head come in through ClsIO.
+// =============================================================================================
+namespace {
+int zero_small_grads(Ctx* c);  // defined with the backward entry points below
+constexpr int CLS_S = 197, CLS_PAD = 16;  // logits are padded to 16 columns (GEMM operand pitch: 16 bytes)
+
+size_t plan_cls(Ctx* c, uint8_t* base, int B) {
+  Bump bp{base};
+  const int M = B * CLS_S, Mp = B * L196;
+  c->tgt = bp.take<float>((size_t)Mp * PDIM);
+  c->cls_ids = bp.take<int32_t>((size_t)Mp);
+  c->a_pe = bp.take<bf16>((size_t)Mp * PDIM + 8);
+  c->pe = bp.take<float>((size_t)Mp * E + 4);
+  const int enc_base = param_index("blocks.0.norm1.weight");
+  plan_vit(bp, c->enc, EL, E, EH, CLS_S, EHID, M, enc_base, B);
+  c->cls_pooled = bp.take<float>((size_t)B * E);
+  c->cls_mean = bp.take<float>(B); c->cls_rstd = bp.take<float>(B);
+  c->cls_feat = bp.take<bf16>((size_t)B * E);
+  c->cls_dlogits = bp.take<bf16>((size_t)B * CLS_PAD);
+  c->cls_dfeat = bp.take<float>((size_t)B * E);
+  c->cls_dpooled = bp.take<float>((size_t)B * E);
+  c->dX = bp.take<float>((size_t)M * E);
+  c->dH = bp.take<float>((size_t)M * E);
+  c->gX = bp.take<bf16>((size_t)M * E);
+  c->dA = bp.take<bf16>((size_t)M * EHID);
+  c->dAO = bp.take<bf16>((size_t)M * E);
+  c->dQKV = bp.take<bf16>((size_t)M * 3 * E);
+  c->colsum_ws = bp.take<float>(64);
+  c->dw_pe = bp.take<float>((size_t)768 * 768);
+  c->delta = bp.take<float>((size_t)B * EH * CLS_S);
+  return bp.off + 256;
+}
+}  // namespace
+
+size_t cls_workspace_bytes(int B) {
+  Ctx tmp;
+  return plan_cls(&tmp, nullptr, B);
+}
+int ctx_set_cls_workspace(Ctx* c, void* ws, size_t bytes, int B) {
+  ECAMP_REQUIRE(B > 0, "cls workspace: bad batch %d", B);
+  ECAMP_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "cls workspace: base must be 256-byte aligned");
+  const size_t need = plan_cls(c, nullptr, B);
+  ECAMP_REQUIRE(bytes >= need, "cls workspace: need %zu bytes, got %zu", need, bytes);
+  plan_cls(c, static_cast<uint8_t*>(ws), B);
+  c->sh = Shape();
+  c->sh.B = B; c->sh.T = 1; c->sh.keep = L196; c->sh.has_big = 0; c->sh.ce_rows = 1;
+  c->planned = false;  // the pre-training plan (if any) no longer matches this workspace
+  c->cls_planned = true;
+  c->cls_B = B;
+  return 0;
+}
+
+int ctx_cls_forward(Ctx* c, const ClsIO& io, cudaStream_t st) {
+  ECAMP_REQUIRE(c->bound && c->cls_planned, "cls forward: context needs bind() and set_cls_workspace() first");
+  ECAMP_REQUIRE(io.image && io.pos_embed && io.fc_norm_w && io.fc_norm_b && io.head_w16 && io.head_b && io.logits,
+                "cls forward: null argument");
+  const int B = c->cls_B, M = B * CLS_S, Mp = B * L196;
+  c->st = st;
+  c->dp = io.dp_scale;
+  RC(patchify224(io.image, B, c->tgt, st));
+  RC(iota_mod_i32(c->cls_ids, (size_t)Mp, L196, st));
+  RC(gather_patches(c->tgt, c->cls_ids, B, L196, L196, PDIM, c->a_pe, st));
+  GemmEpilogue e;
+  e.bias = c->P(1); e.out_f32 = c->pe; e.ld_f32 = E;
+  RC(lin_fwd(c, c->a_pe, PDIM, Mp, c->W(0), E, PDIM, e));
+  RC(assemble_encoder_input(c->pe, c->P(2), io.pos_embed, c->cls_ids, B, L196, E, c->enc.a[0].x_in, st));
+  for (int l = 0; l < EL; ++l) RC(vit_block_fwd(c, c->enc, l, l + 1 < EL ? c->enc.a[l + 1].x_in : c->enc.x_out));
+  RC(mean_pool_tokens(c->enc.x_out, B, CLS_S, E, c->cls_pooled, st));
+  RC(layernorm_fwd(c->cls_pooled, io.fc_norm_w, io.fc_norm_b, 1e-6f, B, E, c->cls_feat, nullptr, c->cls_mean, c->cls_rstd, st));
+  GemmEpilogue eh;
+  eh.bias = io.head_b; eh.out_f32 = io.logits; eh.ld_f32 = CLS_PAD;
+  RC(gemm_bf16(c->cls_feat, E, 0, io.head_w16, E, 0, B, CLS_PAD, E, eh, 0, st));
+  (void)M;
+  return 0;
+}
+
+int ctx_cls_backward(Ctx* c, const ClsIO& io, int accumulate, cudaStream_t st) {
+  ECAMP_REQUIRE(c->bound && c->cls_planned, "cls backward: no forward has been run");
+  ECAMP_REQUIRE(io.d_logits && io.g_pos_embed && io.g_fc_norm_w && io.g_fc_norm_b && io.g_head_w && io.g_head_b,
+                "cls backward: null argument");
+  const int B = c->cls_B, M = B * CLS_S, Mp = B * L196;
+  c->st = st; c->acc = accumulate; c->dp = io.dp_scale;
+  if (!accumulate) RC(zero_small_grads(c));
+  // head: logits = feat W^T + b
+  RC(cast_f32_to_bf16(io.d_logits, c->cls_dlogits, (size_t)B * CLS_PAD, st));
+  GemmEpilogue ew;
+  ew.out_f32 = io.g_head_w; ew.ld_f32 = E;
+  if (accumulate) { ew.residual = io.g_head_w; ew.ld_res = E; }
+  RC(gemm_bf16(c->cls_dlogits, CLS_PAD, 1, c->cls_feat, E, 1, CLS_PAD, E, B, ew, 0, st));
+  RC(strided_rowsum(io.d_logits, B, CLS_PAD, CLS_PAD, io.g_head_b, accumulate, st));
+  GemmEpilogue ed;
+  ed.out_f32 = c->cls_dfeat; ed.ld_f32 = E;
+  RC(gemm_bf16(c->cls_dlogits, CLS_PAD, 0, io.head_w16, E, 1, B, E, CLS_PAD, ed, 0, st));
+  // fc_norm
+  RC(layernorm_bwd(c->cls_dfeat, c->cls_pooled, c->cls_mean, c->cls_rstd, io.fc_norm_w, B, E, nullptr, c->cls_dpooled, nullptr,
+                   DropoutCfg(), io.g_fc_norm_w, io.g_fc_norm_b, nullptr, accumulate, st));
+  // mean over the 196 patch tokens; the bf16 copy is the dY of the last block's fc2 (its DropPath scale, its bias gradient)
+  RC(mean_pool_tokens_bwd(c->cls_dpooled, B, CLS_S, E, c->dX, c->gX, c->dps(&c->enc, EL - 1, 1), st));
+  RC(colsum_bf16(c->gX, E, M, E, c->Gp(c->enc.pbase + (EL - 1) * VIT_BLOCK_PARAMS + 11), 1, c->colsum_ws, st));
+  for (int l = EL - 1; l >= 0; --l) RC(vit_block_bwd(c, c->enc, l));
+  // x0 = [cls + pos[0]; patch_embed + pos[1:]]: pos_embed is learnable here
+  RC(strided_rowsum(c->dX, B, (size_t)CLS_S * E, CLS_S * E, io.g_pos_embed, accumulate, st));
+  bf16* d_pe = c->dAO;  // [Mp, 768]
+  RC(assemble_encoder_input_bwd(c->dX, B, L196, E, d_pe, c->Gp(2), accumulate, st));
+  GemmEpilogue e;
+  e.out_f32 = c->dw_pe; e.ld_f32 = PDIM;
+  RC(gemm_bf16(d_pe, E, 1, c->a_pe, PDIM, 1, E, PDIM, Mp, e, 0, st));
+  RC(permute_pe_weight_grad(c->dw_pe, c->Gp(0), accumulate, st));
+  RC(colsum_bf16(d_pe, E, Mp, E, c->Gp(1), 1, c->colsum_ws, st));
+  return 0;
+}
 
 // =============================================================================================
 // forward / backward entry points

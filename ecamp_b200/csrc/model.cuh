@@ -63,4 +63,24 @@ int ctx_backward(Ctx*, const float* g3, int accumulate, int stage, cudaStream_t)
 int ctx_adamw(Ctx*, float lr, float b1, float b2, float eps, float wd, int step, float grad_scale, cudaStream_t);
 const void* ctx_debug_ptr(Ctx*, const char* name);
 
+// ---- fine-tune classification (FT/Classification/models_vit.py, global_pool = True) on the same context ----------
+struct ClsIO {
+  const float* image = nullptr;      // [B, 3, 224, 224]
+  const float* pos_embed = nullptr;  // [197, 768] (learnable in the fine-tune model)
+  const float *fc_norm_w = nullptr, *fc_norm_b = nullptr;
+  const bf16* head_w16 = nullptr;    // [16, 768]: the head weight padded to 16 rows (rows >= num_classes are zero)
+  const float* head_b = nullptr;     // [16]
+  const float* dp_scale = nullptr;   // DropPath: [12][2][B] mask / keep_prob per (block, branch, sample), or null
+  float* logits = nullptr;           // out [B, 16] fp32
+  // backward
+  const float* d_logits = nullptr;   // [B, 16] fp32 (columns >= num_classes zero)
+  float *g_pos_embed = nullptr, *g_fc_norm_w = nullptr, *g_fc_norm_b = nullptr, *g_head_w = nullptr /* [16, 768] */,
+        *g_head_b = nullptr /* [16] */;
+};
+size_t cls_workspace_bytes(int B);
+int ctx_set_cls_workspace(Ctx*, void* ws, size_t bytes, int B);
+int ctx_cls_forward(Ctx*, const ClsIO&, cudaStream_t);
+// encoder-parameter gradients go to the flat gradient buffer (same offsets as in pre-training), the rest to ClsIO
+int ctx_cls_backward(Ctx*, const ClsIO&, int accumulate, cudaStream_t);
+
 }  // namespace ecamp

@@ -204,6 +204,32 @@ ECAMP_API int ecamp_adamw_step(ecamp_ctx* ctx, float lr, float beta1, float beta
 /* named intermediate buffers for the parity tests ("latent", "pred", "tgt", ...), NULL if unknown */
 ECAMP_API const void* ecamp_debug_buffer(ecamp_ctx* ctx, const char* name);
 
+/* ---- fine-tune classification (ECAMP/Fine-tuning/Classification/models_vit.py:60-98 with global_pool, train.py:438-465) ----
+ * The same context (ecamp_ctx_create / ecamp_ctx_bind): the encoder parameters are the table entries patch_embed.*,
+ * cls_token and blocks.* (the remaining entries of the pre-training table may point at any scratch buffer of at
+ * least their size); their gradients land in the flat gradient buffer at the same offsets.  pos_embed (learnable
+ * here), fc_norm and the head come in through ecamp_cls_io; the head is padded to 16 outputs. */
+typedef struct ecamp_cls_io {
+  const float* image;        /* [B, 3, 224, 224]                                                   */
+  const float* pos_embed;    /* [197, 768]                                                         */
+  const float* fc_norm_w;    /* [768]                                                              */
+  const float* fc_norm_b;    /* [768]                                                              */
+  const void* head_w16;      /* bf16 [16, 768], rows >= num_classes zero                           */
+  const float* head_b;       /* [16]                                                               */
+  const float* dp_scale;     /* DropPath mask / keep_prob, [12][2][B], or NULL (eval / rate 0)     */
+  float* logits;             /* out [B, 16]                                                        */
+  const float* d_logits;     /* backward: [B, 16], columns >= num_classes zero                     */
+  float* g_pos_embed;        /* backward outputs: [197*768], [768], [768], [16*768], [16]          */
+  float* g_fc_norm_w;
+  float* g_fc_norm_b;
+  float* g_head_w;
+  float* g_head_b;
+} ecamp_cls_io;
+ECAMP_API int64_t ecamp_cls_workspace_bytes(int32_t B);
+ECAMP_API int ecamp_cls_set_workspace(ecamp_ctx* ctx, void* ws, int64_t bytes, int32_t B);
+ECAMP_API int ecamp_cls_forward(ecamp_ctx* ctx, const ecamp_cls_io* io, void* stream);
+ECAMP_API int ecamp_cls_backward(ecamp_ctx* ctx, const ecamp_cls_io* io, int32_t accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

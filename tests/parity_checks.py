@@ -467,6 +467,63 @@ def check_step():
 
 
 @guard
+def check_finetune_cls():
+    """BASELINE config 5: fine-tune classification (FT/Classification/models_vit.py, train.py:438-465): logits, BCE loss and
+    every parameter gradient of the native full-sequence ViT against the fp32 oracle, eval mode and training mode with
+    the SAME injected DropPath draw; state_dict keys = timm's; encoder keys load from a pre-training checkpoint."""
+    from ecamp_b200.models_vit import vit_base_patch16
+    from oracle.vit_cls_oracle import VitClsOracle
+    torch.manual_seed(0)
+    orc = VitClsOracle(num_classes=14, drop_path_rate=0.1).to(dev)
+    orc.load_state_dict({k: v.to(dev) for k, v in seeded_state_dict(orc, 3).items()})
+    m = vit_base_patch16(num_classes=14, drop_path_rate=0.1, global_pool=True).to(dev)
+    missing = m.load_state_dict(orc.state_dict(), strict=True)
+    B = 3
+    x = torch.randn(B, 3, 224, 224, device=dev)
+    y = (torch.rand(B, 14, device=dev) < 0.3).float()
+    loss_fct = torch.nn.BCEWithLogitsLoss()
+    for tag, dp in (("eval", None), ("droppath", orc.draw_drop_path(B, dev))):
+        if dp is not None:
+            dp[5, 0, 1] = 0.0; dp[9, 1, 0] = 0.0          # make sure both branches see a dropped sample
+            m.train(); orc.train()
+        else:
+            m.eval(); orc.eval()
+        for p in orc.parameters():
+            p.grad = None
+        lo = orc(x, dp); loss_o = loss_fct(lo, y); loss_o.backward()
+        m.zero_grad(set_to_none=True)
+        lm = m(x, dp); loss_m = loss_fct(lm, y); loss_m.backward()
+        torch.cuda.synchronize()
+        e_logits = rel(lm.detach(), lo.detach()); e_loss = abs(loss_m.item() - loss_o.item()) / abs(loss_o.item())
+        errs, _, total = grad_errors(orc, m)
+        g32 = {k: p.grad.clone() for k, p in orc.named_parameters()}
+        for p in orc.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):       # yardstick: the reference's own mixed-precision path
+            loss_fct(orc(x, dp).float(), y).backward()
+        yard = {k: ((p.grad.double() - g32[k].double()).norm() / g32[k].double().norm().clamp_min(1e-5)).item()
+                for k, p in orc.named_parameters()}
+        bad = {k: (e, yard[k]) for k, e in errs.items() if not e <= max(3e-2, 3.0 * yard[k])}
+        worst = sorted(((e, yard[k], k) for k, e in errs.items()), reverse=True)[:5]
+        report(f"finetune_cls_{tag}", e_logits < 2e-2 and e_loss < 5e-3 and not bad and total < 2e-2, logits=e_logits, loss=e_loss,
+               all_grads_rel=total, violations=list(bad.items())[:6], worst=worst, n_grads=len(errs))
+    # gradient accumulation (p.grad views stay attached) and eval without autograd
+    m.eval(); orc.eval()
+    m.zero_grad(set_to_none=True)
+    loss_fct(m(x), y).backward(); g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    loss_fct(m(x), y).backward()
+    e_acc = max(rel(p.grad, 2 * g1[k]) for k, p in m.named_parameters())
+    with torch.no_grad():
+        e_ng = rel(m(x), orc(x))
+    # a pre-training checkpoint loads by key name (train.py:131-143: strict=False, only head / fc_norm missing)
+    pre = ecamp().state_dict()
+    res = vit_base_patch16(num_classes=14).load_state_dict(pre, strict=False)
+    ok_keys = sorted(res.missing_keys) == ["fc_norm.bias", "fc_norm.weight", "head.bias", "head.weight"]
+    report("finetune_cls_misc", e_acc < 5e-3 and e_ng < 2e-2 and ok_keys, accumulation=e_acc, no_grad_logits=e_ng,
+           missing_keys_from_pretrain_ckpt=res.missing_keys)
+
+
+@guard
 def check_adamw():
     orc, m = build_pair(1)
     m.eval()
