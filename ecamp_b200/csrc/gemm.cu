@@ -67,7 +67,16 @@ struct EpiArgs {
   int split_k;  // > 1: the contraction is split over `split_k` work units per tile, partials added with fp32 atomics
   int kb_per;   // k-blocks per split
   int dbg;      // development: 1 = the epilogue only drains TMEM (no transpose / math / stores)
+  int n_fast;   // tile order: 1 = consecutive work units walk the N tiles of one row block (A is the big operand:
+                // its tile is fetched from DRAM once and served from L2 to the other column tiles), 0 = walk M
+  int n_tiles;
 };
+
+// work unit -> (row block, column block)
+ECAMP_DEVINL void decode_tile(const EpiArgs& ea, int tile, int m_tiles, int& m_blk, int& n_blk) {
+  if (ea.n_fast) { n_blk = tile % ea.n_tiles; m_blk = tile / ea.n_tiles; }
+  else { m_blk = tile % m_tiles; n_blk = tile / m_tiles; }
+}
 
 // ---------------------------------------------------------------------------------------------
 // epilogue.  The accumulator arrives from TMEM with one ROW per thread (tcgen05.ld 32x32b); writing global memory in
@@ -386,17 +395,20 @@ ECAMP_DEVINL void epilogue_loop(const EpiArgs& ea, uint32_t tmem_base, int q, in
   uint32_t acc_phase = 0;
   if (unit0 < num_units) {  // the first tile's operand: nobody prefetched it one tile ahead
     const int tile = unit0 % num_tiles;
-    epi_prefetch_l2<COLS, MODE>(ea.ep, (tile % m_tiles) * m_stride + m_off + q * 32, (tile / m_tiles) * BN + slice * COLS,
-                                M, N, lane);
+    int mb, nb;
+    decode_tile(ea, tile, m_tiles, mb, nb);
+    epi_prefetch_l2<COLS, MODE>(ea.ep, mb * m_stride + m_off + q * 32, nb * BN + slice * COLS, M, N, lane);
   }
   for (int unit = unit0; unit < num_units; unit += unit_step) {
     const int tile = unit % num_tiles;
-    const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+    int m_blk, n_blk;
+    decode_tile(ea, tile, m_tiles, m_blk, n_blk);
     int next_m0 = -1, next_ncol0 = 0;
     if (unit + unit_step < num_units) {
-      const int nt = (unit + unit_step) % num_tiles;
-      next_m0 = (nt % m_tiles) * m_stride + m_off + q * 32;
-      next_ncol0 = (nt / m_tiles) * BN + slice * COLS;
+      int mb, nb;
+      decode_tile(ea, (unit + unit_step) % num_tiles, m_tiles, mb, nb);
+      next_m0 = mb * m_stride + m_off + q * 32;
+      next_ncol0 = nb * BN + slice * COLS;
     }
     epilogue_warp<COLS, MODE>(ea, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slice * COLS),
                               m_blk * m_stride + m_off + q * 32, n_blk * BN + slice * COLS, M, N, stage, lane,
@@ -491,7 +503,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         const int tile = unit % num_tiles, ks = unit / num_tiles;
-        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        int m_blk, n_blk;
+        decode_tile(ea, tile, m_tiles, m_blk, n_blk);
         const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_kb, kb0 + ea.kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -653,7 +666,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       uint32_t phase = 0;
       for (int unit = pair; unit < num_units; unit += num_pairs) {
         const int tile = unit % num_tiles, ks = unit / num_tiles;
-        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        int m_blk, n_blk;
+        decode_tile(ea, tile, m_tiles, m_blk, n_blk);
         const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_kb, kb0 + ea.kb_per);
         const int m0 = m_blk * 2 * BM + (int)rank * BM;
         const int n0 = n_blk * BN + (int)rank * HB;
@@ -969,6 +983,13 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
   if (g_force_generic_epilogue) ea.mode = EM_GENERIC;
   static const int dbg = getenv("ECAMP_GEMM_DBG") ? atoi(getenv("ECAMP_GEMM_DBG")) : 0;
   ea.dbg = dbg;
+  // Tile order.  The operand that is larger than L2 can hold next to the output stream should be fetched from DRAM
+  // once: walking the column tiles of one row block first keeps the A tile in L2 for its other column tiles
+  // (ncu on 32768 x 768 x 768 + fp32 residual, row-block order: 268 MB read for 150 MB of operands - A came in once
+  // per column tile).  Split-K units keep the row-block order.
+  static const int order = getenv("ECAMP_GEMM_ORDER") ? atoi(getenv("ECAMP_GEMM_ORDER")) : -1;
+  ea.n_tiles = (N + bn - 1) / bn;
+  ea.n_fast = order >= 0 ? order : ((split_k == 1 && (long long)M > (long long)N) ? 1 : 0);
 
 #ifdef ECAMP_EPI_ONLY_MODE
   return launch<256, false, false>(ta, tb, M, N, K, ea, stream);
