@@ -116,7 +116,8 @@ int sr_loss_fwd(const float* pred, const float* big, const int64_t* column, cons
                 cudaStream_t st);
 int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, const int64_t* row, const float* w1,
                 const float* b1, const float* w2, const float* b2, int B, const float* g_res, float* d_u,
-                float* d_conv /*168: w1,b1,w2,b2*/, int accumulate, float* ws, cudaStream_t st);
+                float* d_conv /*168: w1,b1,w2,b2*/, int accumulate, float* ws, cudaStream_t st,
+                float* loss_tiles = nullptr /*B*196 scratch*/, float* loss_out = nullptr /*also emit the loss*/);
 size_t sr_ws_floats(int B);
 // d_pred[b, 0] = 0; d_pred[b, 1 + l, e] = g_mim * 2 * mask * (pred - tgt) / Nmim + bilinear^T(d_u) (if d_u)
 int pred_grad(const float* pred, const float* tgt, const float* mask, const float* d_u, const float* g_mim, int B,

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
                                                      const int64_t* __restrict__ column,
                                                      const int64_t* __restrict__ row, int B,
                                                      const float* __restrict__ g_res, float* __restrict__ d_u,
-                                                     float* __restrict__ ws) {
+                                                     float* __restrict__ ws, float* __restrict__ loss_tiles) {
   ECAMP_PDL_ENTRY();
   constexpr int OUT = 36, UW = 40, HW = 38, OW = 36, GW = 34;
   extern __shared__ float sm[];
@@ -226,13 +226,16 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
       for (int c = 0; c < 3; ++c) d_u[(((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox] = 0.f;
     }
     for (int i = threadIdx.x; i < 168; i += blockDim.x) ws_t[i] = 0.f;
+    if (loss_tiles && threadIdx.x == 0) loss_tiles[blockIdx.x] = 0.f;
     return;
   }
   const float* pred_b = pred + (size_t)b * 197 * PD;
   sr_forward_region<OUT>(pred_b, Y0 - 2, X0 - 2, sU, sH);
   const float gscale = 2.0f * (*g_res) / ((float)B * 3.f * BIG * BIG);
 
-  // d_out (pre-ReLU) on the 36x36 region with origin (Y0-2, X0-2)
+  // d_out (pre-ReLU) on the 36x36 region with origin (Y0-2, X0-2); the squared error of the OWNED in-window pixels
+  // is the tile's share of the loss (training steps skip sr_fwd_kernel and take the loss from here)
+  float lsum = 0.f;
   for (int t = threadIdx.x; t < OW * (OW / 4); t += blockDim.x) {
     const int oy = t / (OW / 4), ox0 = (t % (OW / 4)) * 4;
     const int Y = Y0 - 2 + oy;
@@ -245,7 +248,11 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float d = 0.f;
-        if (in_win && o[c][q] > 0.f) d = gscale * (o[c][q] - big[(((size_t)b * 3 + c) * BIG + Y) * BIG + X]);
+        if (in_win) {
+          const float e = fmaxf(o[c][q], 0.f) - big[(((size_t)b * 3 + c) * BIG + Y) * BIG + X];
+          if (o[c][q] > 0.f) d = gscale * e;
+          if (oy >= 2 && oy < 34 && ox0 + q >= 2 && ox0 + q < 34) lsum += e * e;
+        }
         sDO[c * OW * OW + oy * OW + ox0 + q] = d;
       }
     }
@@ -358,6 +365,10 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
       ws_t[(which == 0 ? 84 : 0) + threadIdx.x] = s;
     }
     __syncthreads();
+  }
+  if (loss_tiles) {
+    lsum = block_sum(lsum, &redw[0][0]);
+    if (threadIdx.x == 0) loss_tiles[blockIdx.x] = lsum;
   }
 }
 
@@ -560,7 +571,7 @@ int sr_loss_fwd(const float* pred, const float* big, const int64_t* column, cons
 
 int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, const int64_t* row, const float* w1,
                 const float* b1, const float* w2, const float* b2, int B, const float* g_res, float* d_u,
-                float* d_conv, int accumulate, float* ws, cudaStream_t st) {
+                float* d_conv, int accumulate, float* ws, cudaStream_t st, float* loss_tiles, float* loss_out) {
   static bool attr = false;
   if (!attr) {
     ECAMP_CUDA_OK(cudaFuncSetAttribute(sr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -569,10 +580,12 @@ int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, cons
   }
   if (int rc = upload_sr_weights(w1, b1, w2, b2, st)) return rc;
   ECAMP_CUDA_OK(launch_pdl(sr_bwd_kernel, B * GRID * GRID, 256, SR_BWD_SMEM_FLOATS * sizeof(float), st, pred, big, column, row, B, g_res,
-                                                                                   d_u, ws));
+                                                                                   d_u, ws, loss_tiles));
   LAUNCH_OK();
   ECAMP_CUDA_OK(launch_pdl(sr_wgrad_finalize_kernel, 168, 256, 0, st, ws, B * GRID * GRID, d_conv, accumulate));
   LAUNCH_OK();
+  if (loss_tiles && loss_out)
+    return sum_to_scalar(loss_tiles, (size_t)B * GRID * GRID, 1.0f / ((float)B * 3.f * BIG * BIG), loss_out, st);
   return 0;
 }
 

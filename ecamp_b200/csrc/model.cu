@@ -810,7 +810,9 @@ int image_decoder_fwd(Ctx* c) {
 int image_losses_fwd(Ctx* c) {
   const int B = c->sh.B;
   RC(mim_loss_fwd(c->pred, 197, c->tgt, c->maskf, B, L196, PDIM, c->losses + 0, c->loss_ws, c->st));
-  if (c->sh.has_big) {
+  if (c->sh.has_big && (c->flags & 2)) {
+    // fused training step: sr_bwd_kernel recomputes the head anyway and emits the loss (stage 8)
+  } else if (c->sh.has_big) {
     const int ps = param_index("super_res.conv1.weight");
     RC(sr_loss_fwd(c->pred, c->batch.image, c->batch.column, c->batch.row, c->P(ps), c->P(ps + 1), c->P(ps + 2),
                    c->P(ps + 3), B, c->losses + 1, c->loss_ws, c->st));
@@ -1049,7 +1051,8 @@ int run_stage(Ctx* c, int stage) {
     const int ps = param_index("super_res.conv1.weight");
     if (c->sh.has_big)
       RC(sr_loss_bwd(c->pred, c->batch.image, c->batch.column, c->batch.row, c->P(ps), c->P(ps + 1), c->P(ps + 2),
-                     c->P(ps + 3), B, c->g3 + 1, c->d_u, c->Gp(ps), acc, c->loss_ws, c->st));
+                     c->P(ps + 3), B, c->g3 + 1, c->d_u, c->Gp(ps), acc, c->loss_ws, c->st,
+                     (c->flags & 2) ? c->loss_ws + sr_ws_floats(B) : nullptr, (c->flags & 2) ? c->losses + 1 : nullptr));
     else if (!acc) ECAMP_CUDA_OK(cudaMemsetAsync(c->Gp(ps), 0, 168 * sizeof(float), c->st));
     RC(pred_grad(c->pred, c->tgt, c->maskf, c->sh.has_big ? c->d_u : nullptr, c->g3 + 0, B, c->gX, c->st));
     RC(lin_wgrad(c, c->gX, PDIM, c->dn, DD, Md, PDIM, DD, c->Gp(pn + 2), c->Gp(pn + 3), acc));

@@ -448,6 +448,18 @@ class ECAMP(nn.Module):
                 stage_callback(s, lo.value, hi.value)
         return handle["losses"]
 
+    _OLD_FUSION_KEY = "bert_encoder.model.bert.cross_attn_layer"
+    _FUSION_KEY = "bert_encoder.model.bert.context_fusion_layer"
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        """Accepts the released checkpoints' spelling `cross_attn_layer` for `context_fusion_layer`, the rename the
+        reference applies by hand at Visualization/main_visualization.py:88-93; otherwise nn.Module.load_state_dict."""
+        if any(k.startswith(self._OLD_FUSION_KEY) for k in state_dict):
+            state_dict = type(state_dict)((k.replace(self._OLD_FUSION_KEY, self._FUSION_KEY, 1)
+                                           if k.startswith(self._OLD_FUSION_KEY) else k, v)
+                                          for k, v in state_dict.items())
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
     def flat_grads(self):
         return self._rt["G"] if self._rt else None
 

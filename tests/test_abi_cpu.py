@@ -92,3 +92,26 @@ def test_module_layout_and_no_cpu_fallback(built_lib):
     with pytest.raises(ValueError):
         from ecamp_b200.model_ecamp import ECAMP
         ECAMP(embed_dim=384)
+
+
+def test_released_checkpoint_key_spelling(built_lib):
+    """Released checkpoints spell the fusion layer `cross_attn_layer`; the reference renames the keys by hand at
+    Visualization/main_visualization.py:88-93.  The drop-in's load_state_dict accepts both spellings, strict."""
+    from ecamp_b200.model_ecamp import ecamp
+    torch.manual_seed(1)
+    src = ecamp()
+    old = {k.replace("bert.context_fusion_layer", "bert.cross_attn_layer"): v.clone() for k, v in src.state_dict().items()}
+    assert sum("cross_attn_layer" in k for k in old) == 28
+    torch.manual_seed(2)
+    dst = ecamp()
+    missing, unexpected = dst.load_state_dict(old, strict=True)
+    assert not missing and not unexpected
+    a, b = src.state_dict(), dst.state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    # a {'model', 'optimizer', 'epoch', 'scaler', 'args'} checkpoint (util/misc.py:295-338) round-trips by key
+    import io
+    buf = io.BytesIO()
+    torch.save({"model": src.state_dict(), "epoch": 3}, buf)
+    buf.seek(0)
+    ck = torch.load(buf, map_location="cpu")
+    assert ck["epoch"] == 3 and not dst.load_state_dict(ck["model"]).missing_keys
