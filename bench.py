@@ -306,22 +306,30 @@ def main():
     del resident
     copy_stream = torch.cuda.Stream()
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    pinned_out = torch.empty(3, dtype=torch.float32).pin_memory()
     for i in range(2):
         dp.step(to_device(host[i % 2], dev))
     barrier()
-    nxt = to_device(host[0], dev, copy_stream)
+    pinned_out = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+    read_ev = [torch.cuda.Event() for _ in range(2)]
+    host_losses = []
+    nxt = to_device(host[0], dev, copy_stream)                         # pipeline fill (a loader's first prefetch)
     s.record()
     for i in range(args.steps):
         torch.cuda.current_stream().wait_stream(copy_stream)
         cur_batch = nxt
         for v in cur_batch.values():
             v.record_stream(torch.cuda.current_stream())
-        if i + 1 < args.steps:
-            nxt = to_device(host[(i + 1) % 2], dev, copy_stream)      # prefetch the next step's inputs
+        nxt = to_device(host[(i + 1) % 2], dev, copy_stream)          # prefetch the next step's inputs: exactly one
+                                                                       # H2D copy of a full batch per timed step
         losses = dp.step(cur_batch)
-        pinned_out.copy_(losses, non_blocking=True)
-        torch.cuda.current_stream().synchronize()                      # the step's result is read on the host
+        pinned_out[i % 2].copy_(losses, non_blocking=True)
+        read_ev[i % 2].record()
+        if i > 0:                                                      # the host reads step i-1's result while step i runs
+            read_ev[(i - 1) % 2].synchronize()
+            host_losses.append(pinned_out[(i - 1) % 2].tolist())
+    read_ev[(args.steps - 1) % 2].synchronize()
+    host_losses.append(pinned_out[(args.steps - 1) % 2].tolist())
+    assert len(host_losses) == args.steps
     e.record()
     barrier()
     ms_e2e = max_over_ranks(s.elapsed_time(e))
@@ -336,7 +344,10 @@ def main():
                    config=dict(workload=workload_name(args), global_batch=world * args.batch, per_gpu_batch=args.batch,
                                seq_len=args.seq, image_px="448 -> 224", mask_ratio=0.75, parallelism=f"dp{world}",
                                optimizer="fused AdamW lr 1.5e-4 betas (0.9,0.95) wd 0.05", weights="random init (reference initialize_weights)",
-                               l2="per-step working set (~16 GB of activations) is far larger than the 126 MB L2; two input batches alternate"),
+                               l2="per-step working set (~16 GB of activations) is far larger than the 126 MB L2; two input batches alternate",
+                               e2e_pipeline="per timed step: one H2D copy of a full pinned batch on a copy stream (prefetching the "
+                                            "next step's inputs while this step runs) and one D2H read of the 3 losses, which the "
+                                            "host consumes one step late so that it never stalls the launch queue"),
                    clocks=clocks, gpu_launches=int(launches),
                    e2e=dict(value=round(e2e_value, 2), unit="pairs/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=12,
                             ms_per_step=round(ms_e2e / args.steps, 3)),

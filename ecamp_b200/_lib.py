@@ -63,6 +63,10 @@ class Attn(ctypes.Structure):
                 ("cs_q", ctypes.c_void_p), ("cs_k", ctypes.c_void_p), ("cs_v", ctypes.c_void_p)]
 
 
+class SgdTensor(ctypes.Structure):
+    _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("buf", ctypes.c_void_p), ("numel", ctypes.c_int64)]
+
+
 # every symbol include/ecamp_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "ecamp_abi_version", "ecamp_last_error", "ecamp_launch_count", "ecamp_gemm_bf16", "ecamp_gemm_set_cta_pair", "ecamp_random_masking", "ecamp_resize_patchify",
@@ -74,6 +78,7 @@ SYMBOLS = [
     "ecamp_workspace_bytes", "ecamp_ctx_set_workspace", "ecamp_refresh_shadows", "ecamp_forward",
     "ecamp_backward_stage_count", "ecamp_backward_stage_range", "ecamp_backward", "ecamp_adamw_step",
     "ecamp_debug_buffer", "ecamp_cls_workspace_bytes", "ecamp_cls_set_workspace", "ecamp_cls_forward", "ecamp_cls_backward",
+    "ecamp_sgd_table_bytes", "ecamp_sgd_chunk_bytes", "ecamp_sgd_build_tables", "ecamp_grad_sumsq", "ecamp_sgd_momentum_step",
 ]
 
 _lib = None
@@ -92,7 +97,7 @@ def lib():
         _lib.ecamp_param_name.restype = ctypes.c_char_p
         for f in ("ecamp_param_numel", "ecamp_param_grad_offset", "ecamp_grad_floats", "ecamp_shadow_bytes",
                   "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_workspace_bytes", "ecamp_launch_count",
-                  "ecamp_cls_workspace_bytes"):
+                  "ecamp_cls_workspace_bytes", "ecamp_sgd_table_bytes", "ecamp_sgd_chunk_bytes"):
             getattr(_lib, f).restype = ctypes.c_int64
         for f in ("ecamp_layernorm_ws_floats", "ecamp_sr_ws_floats"):
             getattr(_lib, f).restype = ctypes.c_size_t

@@ -221,4 +221,28 @@ int ecamp_cls_backward(ecamp_ctx* ctx, const ecamp_cls_io* io, int32_t accumulat
   return ctx_cls_backward(ctx->impl, to_cls(io), accumulate, S(stream));
 }
 
+// ---- fused SGD-momentum + grad-norm clip ----------------------------------------------------------------------
+static_assert(sizeof(ecamp_sgd_tensor) == sizeof(SgdTensor), "ecamp_sgd_tensor layout");
+int64_t ecamp_sgd_table_bytes(int32_t n) { return (int64_t)sgd_table_bytes(n); }
+int64_t ecamp_sgd_chunk_bytes(const int64_t* numel, int32_t n) {
+  if (!numel || n <= 0) return 0;
+  return (int64_t)sgd_chunk_bytes(reinterpret_cast<const long long*>(numel), n);
+}
+int ecamp_sgd_build_tables(const ecamp_sgd_tensor* host, int32_t n, void* dev_table, void* dev_chunks, int64_t* n_chunks) {
+  long long c = 0;
+  const int rc = sgd_build_tables(reinterpret_cast<const SgdTensor*>(host), n, dev_table, dev_chunks, &c);
+  if (rc) return rc;
+  *n_chunks = c;
+  return 0;
+}
+int ecamp_grad_sumsq(const void* dev_table, const void* dev_chunks, int64_t n_chunks, float* sumsq, void* stream) {
+  return grad_sumsq(dev_table, dev_chunks, n_chunks, sumsq, S(stream));
+}
+int ecamp_sgd_momentum_step(const void* dev_table, const void* dev_chunks, int64_t n_chunks, float lr, float momentum,
+                            float weight_decay, int32_t first_step, float max_grad_norm, const float* sumsq,
+                            int32_t write_clipped_grads, void* stream) {
+  return sgd_momentum_step(dev_table, dev_chunks, n_chunks, lr, momentum, weight_decay, first_step, max_grad_norm, sumsq,
+                           write_clipped_grads, S(stream));
+}
+
 }  // extern "C"

@@ -147,4 +147,18 @@ int refresh_shadows(const void* dev_table, const void* dev_chunks, long long n_c
 size_t adamw_table_bytes(int n);
 size_t adamw_chunk_bytes(const AdamTensor* host, int n);
 
+// ---- sgd.cu: fused SGD-momentum + global grad-norm clip (fine-tune trainer) ---------------------
+struct SgdTensor {  // mirrors ecamp_sgd_tensor
+  float* p;
+  float* g;
+  float* buf;
+  long long numel;
+};
+size_t sgd_table_bytes(int n);
+size_t sgd_chunk_bytes(const long long* numel, int n);
+int sgd_build_tables(const SgdTensor* host, int n, void* dev_table, void* dev_chunks, long long* n_chunks);
+int grad_sumsq(const void* dev_table, const void* dev_chunks, long long n_chunks, float* sumsq, cudaStream_t st);
+int sgd_momentum_step(const void* dev_table, const void* dev_chunks, long long n_chunks, float lr, float momentum,
+                      float wd, int first, float max_norm, const float* sumsq, int write_grads, cudaStream_t st);
+
 }  // namespace ecamp

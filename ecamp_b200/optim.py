@@ -99,3 +99,97 @@ class FusedAdamW:
         if len(steps) > 1:
             raise RuntimeError("FusedAdamW keeps one step counter; the checkpoint has several")
         self.step_count = steps.pop() if steps else 0
+
+
+class FusedSGD(torch.optim.Optimizer):
+    """SGD with momentum + global gradient-norm clipping in two native launches (csrc/sgd.cu), no host sync.
+
+    Mirrors the fine-tune trainer's optimizer (ECAMP/Fine-tuning/Classification/train.py:377-380:
+    `torch.optim.SGD(model.parameters(), lr, momentum=0.9, weight_decay=wd)`) and folds in the
+    `torch.nn.utils.clip_grad_norm_(model.parameters(), args.max_grad_norm)` the trainer calls right before
+    `optimizer.step()` (train.py:459-463): pass `max_grad_norm` here and drop that call (or keep it: clipping twice
+    is idempotent).  It is a torch.optim.Optimizer, so the reference's WarmupCosineSchedule / LambdaLR
+    (train.py:388-392) drive `param_groups[i]["lr"]` unchanged and `state_dict()` has torch.optim.SGD's layout
+    (`momentum_buffer` per parameter).  Dampening and Nesterov are not supported (the reference uses neither).
+    Parameters must be contiguous fp32 CUDA tensors; there is no CPU path."""
+
+    def __init__(self, params, lr, momentum=0.9, weight_decay=0.0, max_grad_norm=0.0, write_clipped_grads=False):
+        if lr < 0 or momentum < 0 or weight_decay < 0:
+            raise ValueError("FusedSGD: lr, momentum and weight_decay must be non-negative")
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        self.max_grad_norm = float(max_grad_norm or 0.0)
+        self.write_clipped_grads = bool(write_clipped_grads)
+        self._tables = {}
+        self._sumsq = None
+
+    def _table(self, gi, group):
+        ps = [p for p in group["params"] if p.grad is not None]
+        for p in ps:
+            if p.device.type != "cuda" or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                raise RuntimeError("FusedSGD: parameters and gradients must be contiguous fp32 CUDA tensors (no CPU path)")
+            st = self.state[p]
+            if "momentum_buffer" not in st or st["momentum_buffer"] is None:
+                st["momentum_buffer"] = torch.zeros_like(p)
+                st["_fresh"] = True
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["momentum_buffer"].data_ptr()) for p in ps)
+        t = self._tables.get(gi)
+        if t is None or t["key"] != key:
+            lib = L.lib()
+            n = len(ps)
+            host = (L.SgdTensor * max(n, 1))()
+            numel = (ctypes.c_int64 * max(n, 1))()
+            for i, p in enumerate(ps):
+                host[i].p, host[i].g = p.data_ptr(), p.grad.data_ptr()
+                host[i].buf, host[i].numel = self.state[p]["momentum_buffer"].data_ptr(), p.numel()
+                numel[i] = p.numel()
+            dev = ps[0].device if ps else torch.device("cuda")
+            t = dict(key=key, n=n, chunks=ctypes.c_int64(0), params=ps)
+            if n:
+                t["tab"] = torch.empty(lib.ecamp_sgd_table_bytes(n), dtype=torch.uint8, device=dev)
+                t["chk"] = torch.empty(lib.ecamp_sgd_chunk_bytes(numel, n), dtype=torch.uint8, device=dev)
+                L.check(lib.ecamp_sgd_build_tables(host, n, L.ptr(t["tab"]), L.ptr(t["chk"]), ctypes.byref(t["chunks"])),
+                        "ecamp_sgd_build_tables")
+            self._tables[gi] = t
+        return t
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = L.lib()
+        tabs = [(g, self._table(gi, g)) for gi, g in enumerate(self.param_groups)]
+        tabs = [(g, t) for g, t in tabs if t["n"]]
+        if not tabs:
+            return loss
+        dev = tabs[0][1]["params"][0].device
+        clip = self.max_grad_norm > 0
+        if clip:
+            if self._sumsq is None or self._sumsq.device != dev:
+                self._sumsq = torch.zeros(len(self.param_groups) + 1, dtype=torch.float32, device=dev)
+            parts = self._sumsq[1:1 + len(tabs)]
+            for i, (g, t) in enumerate(tabs):      # one norm over ALL groups, as clip_grad_norm_(model.parameters())
+                L.check(lib.ecamp_grad_sumsq(L.ptr(t["tab"]), L.ptr(t["chk"]), t["chunks"], L.ptr(parts[i:i + 1]), L.cur_stream()),
+                        "ecamp_grad_sumsq")
+            total = self._sumsq[0:1]
+            torch.sum(parts, dim=0, keepdim=True, out=total) if len(tabs) > 1 else total.copy_(parts[0:1])
+        for g, t in tabs:
+            fresh = [bool(self.state[p].pop("_fresh", False)) for p in t["params"]]
+            if any(fresh) and not all(fresh):
+                raise RuntimeError("FusedSGD: a parameter group mixes first-step and later-step tensors")
+            L.check(lib.ecamp_sgd_momentum_step(L.ptr(t["tab"]), L.ptr(t["chk"]), t["chunks"], ctypes.c_float(g["lr"]),
+                                                ctypes.c_float(g["momentum"]), ctypes.c_float(g["weight_decay"]),
+                                                ctypes.c_int32(1 if all(fresh) else 0), ctypes.c_float(self.max_grad_norm),
+                                                L.ptr(self._sumsq[0:1]) if clip else ctypes.c_void_p(0),
+                                                ctypes.c_int32(1 if self.write_clipped_grads else 0), L.cur_stream()),
+                    "ecamp_sgd_momentum_step")
+            for p in t["params"]:   # updated in place by the kernel: bump ._version so modules re-derive their bf16 copies
+                torch.autograd.graph.increment_version(p)
+        return loss
+
+    def grad_norm(self):
+        """The global gradient norm of the last clipped step (device scalar), as clip_grad_norm_ returns it."""
+        if self._sumsq is None:
+            raise RuntimeError("FusedSGD.grad_norm(): no clipped step yet")
+        return self._sumsq[0].sqrt()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ECAMP_ABI_VERSION 2
+#define ECAMP_ABI_VERSION 3
 #if defined(__GNUC__)
 #define ECAMP_API __attribute__((visibility("default")))
 #else
@@ -229,6 +229,30 @@ ECAMP_API int64_t ecamp_cls_workspace_bytes(int32_t B);
 ECAMP_API int ecamp_cls_set_workspace(ecamp_ctx* ctx, void* ws, int64_t bytes, int32_t B);
 ECAMP_API int ecamp_cls_forward(ecamp_ctx* ctx, const ecamp_cls_io* io, void* stream);
 ECAMP_API int ecamp_cls_backward(ecamp_ctx* ctx, const ecamp_cls_io* io, int32_t accumulate, void* stream);
+
+/* ---- fused SGD-momentum + global gradient-norm clip (fine-tune trainer) ----
+ * Replaces `torch.nn.utils.clip_grad_norm_(model.parameters(), args.max_grad_norm)` followed by
+ * `torch.optim.SGD(model.parameters(), lr, momentum=0.9, weight_decay=wd).step()`
+ * (ECAMP/Fine-tuning/Classification/train.py:377-380,459-463).  The caller owns two device buffers of
+ * ecamp_sgd_table_bytes(n) / ecamp_sgd_chunk_bytes(numel, n) bytes; ecamp_sgd_build_tables fills them
+ * (synchronous, HOST array in).  Per step: ecamp_grad_sumsq writes sum g^2 over all tensors to *sumsq (device),
+ * ecamp_sgd_momentum_step applies  coef = min(1, max_norm / (sqrt(*sumsq) + 1e-6))  (max_norm <= 0: no clip),
+ * d = coef * g + wd * p, buf = first_step ? d : momentum * buf + d, p -= lr * buf;  the clipped gradients are
+ * written back only if write_clipped_grads != 0.  No host synchronisation. */
+typedef struct ecamp_sgd_tensor {
+  float* p;      /* parameter            */
+  float* g;      /* gradient             */
+  float* buf;    /* momentum buffer      */
+  int64_t numel;
+} ecamp_sgd_tensor;
+ECAMP_API int64_t ecamp_sgd_table_bytes(int32_t n);
+ECAMP_API int64_t ecamp_sgd_chunk_bytes(const int64_t* numel /* host */, int32_t n);
+ECAMP_API int ecamp_sgd_build_tables(const ecamp_sgd_tensor* host, int32_t n, void* dev_table, void* dev_chunks,
+                                     int64_t* n_chunks /* host out */);
+ECAMP_API int ecamp_grad_sumsq(const void* dev_table, const void* dev_chunks, int64_t n_chunks, float* sumsq, void* stream);
+ECAMP_API int ecamp_sgd_momentum_step(const void* dev_table, const void* dev_chunks, int64_t n_chunks, float lr,
+                                      float momentum, float weight_decay, int32_t first_step, float max_grad_norm,
+                                      const float* sumsq, int32_t write_clipped_grads, void* stream);
 
 #ifdef __cplusplus
 }

@@ -557,7 +557,45 @@ def check_adamw():
            loss_after=[x.item() for x in l_m], loss_after_ref=[x.item() for x in l_r])
 
 
-ALL_CHECKS = (check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
+@guard
+def check_sgd():
+    """FusedSGD (csrc/sgd.cu) vs torch.nn.utils.clip_grad_norm_ + torch.optim.SGD on the same tensors
+    (Fine-tuning/Classification/train.py:377-380,459-463): ragged sizes (unaligned tails, a 1-element tensor), two
+    parameter groups, three steps (first-step buffer initialisation, momentum), clipping active and inactive.
+    Tolerance: 2e-7 relative to the largest parameter magnitude per tensor (same fp32 operations; torch's foreach kernels
+    may contract differently), clip coefficient within 1e-6 relative."""
+    from ecamp_b200.optim import FusedSGD
+    torch.manual_seed(3)
+    shapes = [(768, 768), (3072,), (1,), (197, 768), (14, 768), (5, 3, 7), (4099,)]
+    for max_norm, gscale in ((1.0, 3.0), (1.0, 1e-3), (0.0, 1.0)):
+        ours = [torch.nn.Parameter(torch.randn(*sh, device=dev)) for sh in shapes]
+        ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+        o1 = FusedSGD([dict(params=ours[:4]), dict(params=ours[4:], lr=0.3)], lr=0.03, momentum=0.9, weight_decay=1e-4,
+                      max_grad_norm=max_norm)
+        o2 = torch.optim.SGD([dict(params=ref[:4]), dict(params=ref[4:], lr=0.3)], lr=0.03, momentum=0.9, weight_decay=1e-4)
+        worst, norm_err = 0.0, 0.0
+        for step in range(3):
+            for a, b_ in zip(ours, ref):
+                g = torch.randn_like(a) * gscale
+                a.grad = g.clone(); b_.grad = g.clone()
+            if max_norm > 0:
+                tn = torch.nn.utils.clip_grad_norm_(ref, max_norm)
+            o2.step(); o1.step()
+            if max_norm > 0:
+                norm_err = max(norm_err, abs(o1.grad_norm().item() - tn.item()) / tn.item())
+            for a, b_ in zip(ours, ref):
+                worst = max(worst, ((a.detach() - b_.detach()).abs().max() / b_.detach().abs().max().clamp_min(1e-6)).item())
+        bufs_ok = all(torch.allclose(o1.state[a]["momentum_buffer"], o2.state[b_]["momentum_buffer"], rtol=1e-5, atol=1e-6)
+                      for a, b_ in zip(ours, ref))
+        versions_bumped = all(a._version > 0 for a in ours)
+        report(f"sgd_clip{max_norm}_g{gscale}", worst < 2e-6 and norm_err < 1e-5 and bufs_ok and versions_bumped,
+               max_rel_param_diff=worst, grad_norm_rel_err=norm_err, bufs_ok=bufs_ok)
+    sd = o1.state_dict()
+    report("sgd_state_dict_layout", set(sd) == {"state", "param_groups"} and "momentum_buffer" in sd["state"][0]
+           and sd["param_groups"][1]["lr"] == 0.3)
+
+
+ALL_CHECKS = (check_sgd, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
 
 
 def run_check(fn):
