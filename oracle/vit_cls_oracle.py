@@ -4,9 +4,10 @@ Plain-torch restatement of ECAMP/Fine-tuning/Classification/models_vit.py:60-128
 drop_path_rate=0.1, global_pool=True)`, constructed at train.py:124-128): timm 0.4.12 VisionTransformer with the
 overridden forward_features (:78-98): patch_embed -> prepend cls -> + pos_embed (learnable) -> 12 Blocks with DropPath
 -> mean over the PATCH tokens -> fc_norm -> head; loss = BCEWithLogitsLoss (train.py:422-423,443).
-timm is not installed here and the reference class needs it as a base class, so this row is pinned only through the
-timm Block restatement that oracle/make_golden.py already checks against the reference's pre-training sources
-(same Block / Attention / Mlp / PatchEmbed classes): parity of the head (mean-pool, fc_norm, Linear) is UNPINNED.
+Pinned by oracle/make_cls_golden.py: the reference's models_vit.py is imported UNMODIFIED there (its timm 0.4.12 base class
+restated, since timm is neither installed nor vendored) and its logits, BCE loss and every parameter gradient equal this
+oracle's in eval mode and with injected DropPath draws (fixtures: tests/golden/cls_cases.json, re-checked on CPU by
+tests/test_oracle_cpu.py).
 DropPath follows timm.models.layers.drop_path: per-sample mask floor(keep + U[0,1)) / keep, rates linspace(0, rate, depth);
 the masks can be injected so that the CUDA path and the oracle see the same draw.
 """
@@ -50,3 +51,16 @@ class VitClsOracle(nn.Module):
                 x = x + drop_path_scales[l, 1].view(B, 1, 1) * blk.mlp(blk.norm2(x))
         x = x[:, 1:, :].mean(dim=1)          # global pool without cls token (models_vit.py:92)
         return self.head(self.fc_norm(x))
+
+
+def seeded_cls_state(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in sorted(model.state_dict().items()):   # sorted: independent of the registration order of the class
+        if k.endswith("norm1.weight") or k.endswith("norm2.weight") or k == "fc_norm.weight":
+            sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        elif v.dim() == 1:
+            sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+        else:
+            sd[k] = 0.03 * torch.randn(v.shape, generator=g)
+    return sd
