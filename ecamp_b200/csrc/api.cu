@@ -105,6 +105,11 @@ int ecamp_attention_bwd(const ecamp_attn* a, void* stream) {
   return attention_bwd(to_args(a), S(stream));
 }
 
+int ecamp_attention_probs(const ecamp_attn* a, float* probs, void* stream) {
+  ECAMP_REQUIRE(a && a->q && a->k && a->lse && probs, "ecamp_attention_probs: null argument");
+  return attention_probs(to_args(a), probs, S(stream));
+}
+
 int ecamp_mim_loss(const float* pred, const float* tgt, const float* mask, int32_t B, float* loss, float* ws,
                    void* stream) {
   return mim_loss_fwd(pred, 197, tgt, mask, B, 196, 768, loss, ws, S(stream));
@@ -193,6 +198,10 @@ int ecamp_adamw_step(ecamp_ctx* ctx, float lr, float beta1, float beta2, float e
                      float grad_scale, void* stream) {
   ECAMP_REQUIRE(ctx, "ecamp_adamw_step: null context");
   return ctx_adamw(ctx->impl, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
+}
+int ecamp_cross_attention_probs(ecamp_ctx* ctx, float* probs, void* stream) {
+  ECAMP_REQUIRE(ctx && probs, "ecamp_cross_attention_probs: null argument");
+  return ctx_cross_attention_probs(ctx->impl, probs, S(stream));
 }
 const void* ecamp_debug_buffer(ecamp_ctx* ctx, const char* name) {
   return (ctx && name) ? ctx_debug_ptr(ctx->impl, name) : nullptr;

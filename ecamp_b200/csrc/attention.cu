@@ -736,6 +736,75 @@ static int g_attn_tc = [] {
 }();
 void set_attention_tc(int on) { g_attn_tc = on; }
 
+// =============================================================================================
+// attention probabilities (inference tool): probs[b, h, i, j] = exp(scale * q_i . k_j - lse[b, h, i]), masked keys 0.
+// Replaces `output_attentions=True` of the cross-attention in Visualization/module/context_fusion.py:45-57 (the
+// heat-map tool reads cross_self_outputs[1]); the training kernels never materialise the probabilities.
+// One CTA = 8 query rows of one (batch, head); the K tile of the head is staged once in shared memory.
+// =============================================================================================
+namespace {
+constexpr int kProbRows = 8;
+__global__ void __launch_bounds__(256) attn_probs_kernel(AttnArgs a, float* __restrict__ probs) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int D = a.D, LDK = D + 8;
+  bf16* sK = reinterpret_cast<bf16*>(smem_raw);                       // [Sk][D + 8]
+  float* sQ = reinterpret_cast<float*>(sK + (size_t)a.Sk * LDK);      // [8][D]
+  float* sL = sQ + kProbRows * D;                                     // [8] lse
+  const int tid = threadIdx.x, q0 = blockIdx.x * kProbRows, h = blockIdx.y, b = blockIdx.z;
+  const uint64_t bh = (uint64_t)b * a.H + h;
+  const int cpr = D / 8;
+  for (int idx = tid; idx < a.Sk * cpr; idx += blockDim.x) {
+    const int r = idx / cpr, c = idx % cpr;
+    *reinterpret_cast<uint4*>(sK + (size_t)r * LDK + c * 8) =
+        *reinterpret_cast<const uint4*>(a.k + ((size_t)b * a.Sk + r) * a.ldk + h * D + c * 8);
+  }
+  for (int idx = tid; idx < kProbRows * D; idx += blockDim.x) {
+    const int r = idx / D, d = idx % D;
+    sQ[idx] = q0 + r < a.Sq ? __bfloat162float(a.q[((size_t)b * a.Sq + q0 + r) * a.ldq + h * D + d]) : 0.f;
+  }
+  if (tid < kProbRows) sL[tid] = q0 + tid < a.Sq ? a.lse[bh * a.Sq + q0 + tid] : INFINITY;
+  __syncthreads();
+  for (int j = tid; j < a.Sk; j += blockDim.x) {
+    float acc[kProbRows];
+#pragma unroll
+    for (int r = 0; r < kProbRows; ++r) acc[r] = 0.f;
+    for (int c = 0; c < cpr; ++c) {
+      const uint4 kv = *reinterpret_cast<const uint4*>(sK + (size_t)j * LDK + c * 8);
+      const float2 k0 = unpack_bf16x2(kv.x), k1 = unpack_bf16x2(kv.y), k2 = unpack_bf16x2(kv.z), k3 = unpack_bf16x2(kv.w);
+#pragma unroll
+      for (int r = 0; r < kProbRows; ++r) {
+        const float4 qa = *reinterpret_cast<const float4*>(sQ + r * D + c * 8);
+        const float4 qb = *reinterpret_cast<const float4*>(sQ + r * D + c * 8 + 4);
+        acc[r] += k0.x * qa.x + k0.y * qa.y + k1.x * qa.z + k1.y * qa.w + k2.x * qb.x + k2.y * qb.y + k3.x * qb.z + k3.y * qb.w;
+      }
+    }
+    const bool ok = a.key_mask == nullptr || a.key_mask[(size_t)b * a.Sk + j] != 0;
+#pragma unroll
+    for (int r = 0; r < kProbRows; ++r) {
+      if (q0 + r < a.Sq) {
+        const float l = sL[r];
+        probs[(bh * a.Sq + q0 + r) * (uint64_t)a.Sk + j] = (ok && l != -INFINITY) ? __expf(acc[r] * a.scale - l) : 0.f;
+      }
+    }
+  }
+}
+}  // namespace
+
+int attention_probs(const AttnArgs& a, float* probs, cudaStream_t st) {
+  ECAMP_REQUIRE(a.q && a.k && a.lse && probs, "attention_probs: null pointer");
+  ECAMP_REQUIRE(a.B > 0 && a.H > 0 && a.Sq > 0 && a.Sk > 0 && a.D % 8 == 0 && a.D >= 8 && a.D <= 128,
+                "attention_probs: unsupported shape B=%d H=%d Sq=%d Sk=%d D=%d", a.B, a.H, a.Sq, a.Sk, a.D);
+  ECAMP_REQUIRE(a.ldk % 8 == 0 && (reinterpret_cast<uintptr_t>(a.k) & 15) == 0, "attention_probs: K must be 16-byte aligned");
+  const size_t sm = (size_t)a.Sk * (a.D + 8) * 2 + (size_t)kProbRows * a.D * 4 + kProbRows * 4;
+  ECAMP_REQUIRE(sm <= (size_t)kMaxDynSmem, "attention_probs: %d keys do not fit in shared memory", a.Sk);
+  ECAMP_CUDA_OK(cudaFuncSetAttribute(attn_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  dim3 grid((a.Sq + kProbRows - 1) / kProbRows, a.H, a.B);
+  attn_probs_kernel<<<grid, 256, sm, st>>>(a, probs);
+  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_LAUNCHED();
+  return 0;
+}
+
 int attention_fwd(const AttnArgs& a, cudaStream_t st) {
   if (int rc = check_args(a, false)) return rc;
   // measured (scripts/attn_time.py): ViT encoder heads (50 x 50, head_dim 64) 27 us on the mma.sync kernel, 39 us on tcgen05

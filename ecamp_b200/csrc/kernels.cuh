@@ -105,6 +105,8 @@ struct AttnArgs {
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t st);
 int attention_bwd(const AttnArgs& a, cudaStream_t st);
+// probs[B, H, Sq, Sk] fp32 = exp(scale * q . k - lse), masked keys 0 (needs the lse of a preceding attention_fwd)
+int attention_probs(const AttnArgs& a, float* probs, cudaStream_t st);
 
 // ---- losses.cu --------------------------------------------------------------------------------
 // mim = sum_{masked patches} (pred - tgt)^2 / (B*3*224*224)       (model_ecamp.py:288-297)

@@ -241,19 +241,24 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
     const int Y = Y0 - 2 + oy;
     float o[3][4];
     sr_out_strip<OUT>(sU, sH, oy, ox0, o);
+    // the strip starts at an even X and windows / image edges are even: each PAIR of pixels is inside or outside as a whole
+    const bool row_in = Y >= wy0 && Y < wy1;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int X = X0 - 2 + ox0 + q;
-      const bool in_win = Y >= wy0 && Y < wy1 && X >= wx0 && X < wx1;  // inside the window (hence inside the image)
+    for (int pr = 0; pr < 2; ++pr) {
+      const int X = X0 - 2 + ox0 + 2 * pr;
+      const bool in_win = row_in && X >= wx0 && X < wx1;  // inside the window (hence inside the image)
+      const bool owned = oy >= 2 && oy < 34 && ox0 + 2 * pr >= 2 && ox0 + 2 * pr < 34;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float d = 0.f;
+        float d0 = 0.f, d1 = 0.f;
         if (in_win) {
-          const float e = fmaxf(o[c][q], 0.f) - big[(((size_t)b * 3 + c) * BIG + Y) * BIG + X];
-          if (o[c][q] > 0.f) d = gscale * e;
-          if (oy >= 2 && oy < 34 && ox0 + q >= 2 && ox0 + q < 34) lsum += e * e;
+          const float2 tg = *reinterpret_cast<const float2*>(big + (((size_t)b * 3 + c) * BIG + Y) * BIG + X);
+          const float e0 = fmaxf(o[c][2 * pr], 0.f) - tg.x, e1 = fmaxf(o[c][2 * pr + 1], 0.f) - tg.y;
+          if (o[c][2 * pr] > 0.f) d0 = gscale * e0;
+          if (o[c][2 * pr + 1] > 0.f) d1 = gscale * e1;
+          if (owned) lsum += e0 * e0 + e1 * e1;
         }
-        sDO[c * OW * OW + oy * OW + ox0 + q] = d;
+        *reinterpret_cast<float2*>(sDO + c * OW * OW + oy * OW + ox0 + 2 * pr) = make_float2(d0, d1);
       }
     }
   }

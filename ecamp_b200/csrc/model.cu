@@ -965,6 +965,18 @@ int ctx_forward(Ctx* c, const Batch& b, int flags, float drop_p, unsigned long l
   return 0;
 }
 
+// Visualization/module/model_ecamp.py:308-319 + context_fusion.py:45-57: the heat-map tool returns the probabilities of the
+// fusion layer's cross-attention.  They are re-derived from the q / k projections and the log-sum-exp that the forward
+// pass left in the workspace (no dropout: the tool runs in eval mode).
+int ctx_cross_attention_probs(Ctx* c, float* probs, cudaStream_t st) {
+  ECAMP_REQUIRE(c->bound && c->planned && c->losses, "cross_attention_probs: run ecamp_forward first");
+  AttnArgs at;
+  at.q = c->f_qc; at.ldq = 768; at.k = c->f_kv; at.v = c->f_kv + 768; at.ldk = at.ldv = 1536;
+  at.lse = c->f_lse_c;
+  at.B = c->sh.B; at.H = BH; at.Sq = c->sh.T; at.Sk = c->sh.keep; at.D = 128; at.scale = 1.0f / sqrtf(128.f);
+  return attention_probs(at, probs, st);
+}
+
 // stages: 0 LM head | 1..6 BERT layers 5..0 | 7 fusion+embeddings+bert_mlp | 8 losses+decoder head+SR |
 //         9..12 decoder blocks 3..0 | 13 decoder_embed+mask_token | 14 final norm | 15..26 encoder blocks 11..0 | 27 patch embed
 int backward_stage_count() { return 28; }

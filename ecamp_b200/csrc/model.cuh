@@ -56,6 +56,8 @@ int ctx_refresh_shadows(Ctx*, cudaStream_t);
 // flags: 1 = training (saves activations), 2 = defer the MLM loss to backward (fused head)
 int ctx_forward(Ctx*, const Batch&, int flags, float drop_p, unsigned long long seed, float* losses3, float* mask_out,
                 int64_t* ids_restore_out, int64_t* ids_keep_out, cudaStream_t);
+// after ctx_forward: probs[B, 6, T, keep] fp32 of the fusion layer's text -> image cross-attention (columns in ids_keep order)
+int ctx_cross_attention_probs(Ctx*, float* probs, cudaStream_t);
 int backward_stage_count();
 int backward_stage_range(int stage, long long* g_begin, long long* g_end);
 // g3: device pointer to the three upstream gradients (mim, res, mlm).  stage = -1 runs every stage.

@@ -460,6 +460,30 @@ class ECAMP(nn.Module):
                                           for k, v in state_dict.items())
         return super().load_state_dict(state_dict, strict=strict, assign=assign)
 
+    @torch.no_grad()
+    def cross_attention_map(self, imgs, text_ids, attention_mask, type_ids=None, mask_ratio=0.0, noise=None,
+                            restore_order=False):
+        """Probabilities of the fusion layer's text -> image cross-attention, `[B, 6, T, keep]` fp32: what the reference's
+        heat-map model returns (Visualization/module/model_ecamp.py:308-319 -> context_fusion.py:45-57,
+        `cross_self_outputs[1]`; used at main_visualization.py:153-154 as `attention[0, :, 4]`).  `imgs` is 224 px.
+        As in the reference the image tokens - hence the columns - are in `ids_keep` order (random_masking shuffles even
+        at mask_ratio = 0); `restore_order=True` scatters them back to raster order (only at mask_ratio = 0).  Call
+        `model.eval()` first, as the tool does: the probabilities are re-derived without dropout."""
+        if self.training:
+            raise RuntimeError("cross_attention_map: call model.eval() first (main_visualization.py:151)")
+        zeros = torch.zeros_like(text_ids)
+        t, B, T, keep = self._prepare(imgs, text_ids, zeros, attention_mask, type_ids, None, None, None, noise, mask_ratio, False)
+        handle = self._launch_forward(t, B, T, keep, False, defer_mlm=True)   # the vocabulary head is not needed
+        probs = torch.empty(B, 6, T, keep, dtype=torch.float32, device=handle["losses"].device)
+        L.check(L.lib().ecamp_cross_attention_probs(handle["rt"]["ctx"], L.ptr(probs), L.cur_stream()),
+                "ecamp_cross_attention_probs")
+        if restore_order:
+            if keep != 196:
+                raise ValueError("restore_order needs mask_ratio = 0 (all 196 patches kept)")
+            idx = self.last["ids_restore"][:, None, None, :].expand(B, 6, T, 196)
+            probs = torch.gather(probs, 3, idx)
+        return probs
+
     def flat_grads(self):
         return self._rt["G"] if self._rt else None
 
@@ -481,6 +505,19 @@ class ECAMP(nn.Module):
                 L.lib().ecamp_ctx_destroy(self._rt["ctx"])
         except Exception:
             pass
+
+
+class ECAMPVis(ECAMP):
+    """Drop-in for the heat-map tool's model (Visualization/module/model_ecamp.py): same parameters and state_dict,
+    `forward(imgs, text_ids, attention_mask, type_ids, mask_ratio=0)` returns the cross-attention probabilities."""
+
+    def forward(self, imgs, text_ids, attention_mask, type_ids, mask_ratio=0):
+        return self.cross_attention_map(imgs, text_ids, attention_mask, type_ids, mask_ratio=mask_ratio)
+
+
+def ecamp_vis(**kwargs):
+    """`Visualization/module/model_ecamp.py:322-327` (`ecamp(**kwargs)` there)."""
+    return ECAMPVis(**kwargs)
 
 
 def ecamp(**kwargs):

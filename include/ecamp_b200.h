@@ -126,6 +126,10 @@ typedef struct ecamp_attn {
 ECAMP_API void ecamp_attention_set_tcgen05(int32_t on);
 ECAMP_API int ecamp_attention_fwd(const ecamp_attn* a, void* stream);
 ECAMP_API int ecamp_attention_bwd(const ecamp_attn* a, void* stream);
+/* probs [B, H, Sq, Sk] fp32 = exp(scale * q . k - lse), 0 at masked keys; needs q, k, lse (of a preceding
+ * ecamp_attention_fwd), the shape and scale.  Replaces `output_attentions=True` of the cross-attention in
+ * Visualization/module/context_fusion.py:45-57 (inference tool; the training kernels never materialise P). */
+ECAMP_API int ecamp_attention_probs(const ecamp_attn* a, float* probs, void* stream);
 
 /* losses.  pred is [B, 197, 768] fp32 (row 0 of each sample = cls, ignored), tgt [B, 196, 768]. */
 ECAMP_API int ecamp_mim_loss(const float* pred, const float* tgt, const float* mask, int32_t B, float* loss,
@@ -201,6 +205,9 @@ ECAMP_API int ecamp_backward_stage_range(int32_t stage, int64_t* begin, int64_t*
 ECAMP_API int ecamp_backward(ecamp_ctx* ctx, const float* g3, int32_t accumulate, int32_t stage, void* stream);
 ECAMP_API int ecamp_adamw_step(ecamp_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
                                int32_t step, float grad_scale, void* stream);
+/* after ecamp_forward: probs [B, 6, T, keep] fp32 of the fusion layer's text -> image cross-attention, columns in
+ * ids_keep order — what Visualization/module/model_ecamp.py:308-319 returns at mask_ratio = 0 */
+ECAMP_API int ecamp_cross_attention_probs(ecamp_ctx* ctx, float* probs, void* stream);
 /* named intermediate buffers for the parity tests ("latent", "pred", "tgt", ...), NULL if unknown */
 ECAMP_API const void* ecamp_debug_buffer(ecamp_ctx* ctx, const char* name);
 

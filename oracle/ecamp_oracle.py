@@ -489,6 +489,22 @@ class EcampOracle(nn.Module):
         gap = latent[:, 1:, :].mean(dim=1).unsqueeze(1)
         return self.bert_encoder(latent[:, 1:, :], gap, ids, labels, attention_mask, type_ids, weights)
 
+    def cross_attention_map(self, imgs, text_ids, attention_mask, type_ids, mask_ratio=0.0, noise=None):
+        """Visualization/module/model_ecamp.py:272-278,308-319 + Visualization/module/context_fusion.py:26-57: image encoder
+        at mask_ratio (0 by default), bert_mlp, GAP token, embeddings, the fusion layer's self-attention, then the
+        probabilities `[B, 6, T, keep]` of its cross-attention (columns in ids_keep order, as in the reference)."""
+        latent, mask, ids_restore, ids_keep = self.image_encoder(imgs, mask_ratio, noise)
+        latent = self.bert_mlp(latent)
+        gap = latent[:, 1:, :].mean(dim=1).unsqueeze(1)
+        bert = self.bert_encoder.model.bert
+        lat = latent[:, 1:, :]
+        ext_text = (1.0 - attention_mask[:, None, None, :].to(lat.dtype)) * torch.finfo(lat.dtype).min
+        ext_img = torch.zeros(lat.shape[0], 1, 1, lat.shape[1], dtype=lat.dtype, device=lat.device)
+        emb = bert.embeddings(text_ids, type_ids)
+        _, probs = bert.context_fusion_layer(emb, lat, gap, ext_text, ext_img, return_probs=True)
+        self.last = dict(mask=mask, ids_restore=ids_restore, ids_keep=ids_keep, latent=latent)
+        return probs
+
     def forward(self, batch, input_ids=None, attention_mask=None, labels=None, mask_ratio=0.75, *, type_ids=None,
                 weights=None, big_imgs=None, column=None, row=None, noise=None):
         """Dict form = model_ecamp.py:303-325; positional form = SURVEY §8(b)(ii)."""

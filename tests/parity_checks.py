@@ -558,6 +558,65 @@ def check_adamw():
 
 
 @guard
+def check_attention_map():
+    """Cross-attention probabilities for the heat-map tool (Visualization/module/context_fusion.py:45-57).
+    (1) operator: ecamp_attention_probs after ecamp_attention_fwd vs softmax(q k^T / sqrt(d) + mask) in fp32 on the same
+    bf16 q / k: rows sum to 1, relative L2 < 2e-3 (exp of bf16-exact scores; only the exp approximation differs).
+    (2) model: ECAMPVis.forward == oracle.cross_attention_map at mask_ratio 0 and 0.75 (same weights / noise): ids_keep
+    bit-exact, probabilities within 5e-2 relative L2 (bf16 activations through 12 encoder blocks vs the fp32 oracle)."""
+    for (name, B, H, Sq, Sk, D, masked) in [("cross", 2, 6, 128, 196, 128, False), ("cross49", 3, 6, 37, 49, 128, False),
+                                            ("self_masked", 2, 6, 64, 64, 128, True), ("d32", 2, 16, 197, 197, 32, False)]:
+        q = torch.randn(B, Sq, H * D, device=dev).to(torch.bfloat16)
+        k = torch.randn(B, Sk, H * D, device=dev).to(torch.bfloat16)
+        v = torch.randn(B, Sk, H * D, device=dev).to(torch.bfloat16)
+        km = None
+        if masked:
+            lens = torch.randint(Sk // 3, Sk + 1, (B,), device=dev)
+            km = (torch.arange(Sk, device=dev)[None, :] < lens[:, None]).long()
+        o = torch.empty(B, Sq, H * D, dtype=torch.bfloat16, device=dev)
+        lse = torch.empty(B, H, Sq, device=dev)
+        a = L.Attn()
+        a.q, a.k, a.v, a.o, a.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr()
+        a.ldq = a.ldk = a.ldv = a.ldo = H * D
+        a.key_mask = km.data_ptr() if km is not None else None
+        a.B, a.H, a.Sq, a.Sk, a.D = B, H, Sq, Sk, D
+        a.scale = 1.0 / math.sqrt(D)
+        L.check(lib.ecamp_attention_fwd(ctypes.byref(a), L.cur_stream()), "attn_fwd")
+        probs = torch.full((B, H, Sq, Sk), -1.0, device=dev)
+        L.check(lib.ecamp_attention_probs(ctypes.byref(a), L.ptr(probs), L.cur_stream()), "attn_probs")
+        qr = q.float().view(B, Sq, H, D).transpose(1, 2)
+        kr = k.float().view(B, Sk, H, D).transpose(1, 2)
+        sc = (qr @ kr.transpose(-1, -2)) * a.scale
+        if km is not None:
+            sc = sc + (1.0 - km[:, None, None, :].float()) * torch.finfo(torch.float32).min
+        ref = sc.softmax(-1)
+        rows = (probs.sum(-1) - 1).abs().max().item()
+        masked_zero = True if km is None else bool((probs * (1 - km[:, None, None, :].float())).abs().max().item() == 0.0)
+        report(f"attention_probs_{name}", rel(probs, ref) < 2e-3 and rows < 2e-3 and masked_zero, rel=rel(probs, ref), row_sum_err=rows)
+    from ecamp_b200.model_ecamp import ecamp_vis
+    orc, m = build_pair(0)
+    vis = ecamp_vis().to(dev).eval()
+    vis.load_state_dict(m.state_dict())
+    orc.eval()
+    b = synthetic_batch(2, T=32, big=False, seed=7, device=dev)
+    for mr in (0.0, 0.75):
+        with torch.no_grad():
+            po = orc.cross_attention_map(b["image"], b["ids"], b["attention_mask"], b["type_ids"], mask_ratio=mr, noise=b["noise"])
+        pm = vis.cross_attention_map(b["image"], b["ids"], b["attention_mask"], b["type_ids"], mask_ratio=mr, noise=b["noise"])
+        same_ids = torch.equal(vis.last["ids_keep"], orc.last["ids_keep"])
+        e = rel(pm, po)
+        report(f"cross_attention_map_mask{mr}", same_ids and tuple(pm.shape) == tuple(po.shape) and e < 5e-2 and
+               (pm.sum(-1) - 1).abs().max().item() < 2e-3, rel=e, shape=list(pm.shape))
+    # the tool's call signature and the raster-order option
+    torch.manual_seed(5)
+    p1 = vis(b["image"], b["ids"], b["attention_mask"], b["type_ids"])
+    torch.manual_seed(5)
+    p2 = vis.cross_attention_map(b["image"], b["ids"], b["attention_mask"], b["type_ids"], restore_order=True)
+    back = torch.gather(p2, 3, vis.last["ids_keep"][:, None, None, :].expand_as(p2))
+    report("cross_attention_map_signature", tuple(p1.shape) == (2, 6, 32, 196) and torch.equal(back, p1))
+
+
+@guard
 def check_sgd():
     """FusedSGD (csrc/sgd.cu) vs torch.nn.utils.clip_grad_norm_ + torch.optim.SGD on the same tensors
     (Fine-tuning/Classification/train.py:377-380,459-463): ragged sizes (unaligned tails, a 1-element tensor), two
@@ -595,7 +654,7 @@ def check_sgd():
            and sd["param_groups"][1]["lr"] == 0.3)
 
 
-ALL_CHECKS = (check_sgd, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
+ALL_CHECKS = (check_sgd, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
 
 
 def run_check(fn):
