@@ -165,19 +165,29 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
   const uint64_t bh = (uint64_t)b * a.H + h;
   const int row_g = q0 + warp * 16 + g;  // this thread's rows: row_g and row_g + 8
 
-  for (int kb = 0; kb < kend; kb += 64) {
+  // One 64-key block.  FULL: all 64 keys exist and are attendable - no per-group tests, no mask bias, and the first
+  // k-step starts from the zero register (the tests and the accumulator clears were ~25 % of the executed instructions).
+  auto key_block = [&](const int kb, auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
     float s[8][4];
+    if (!FULL) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    }
 #pragma unroll
     for (int kt = 0; kt < D / 16; ++kt) {
 #pragma unroll
       for (int jp = 0; jp < 4; ++jp) {
-        if (kb + jp * 16 < kend) {
+        if (FULL || kb + jp * 16 < kend) {
           uint32_t bf[4];
           load_b_frag_nk<LDS>(bf, sK, kb + jp * 16, kt * 16, lane);
-          mma_bf16_16816(s[2 * jp], qf[kt], bf[0], bf[1]);
-          mma_bf16_16816(s[2 * jp + 1], qf[kt], bf[2], bf[3]);
+          if (FULL && kt == 0) {
+            mma_bf16_16816_z(s[2 * jp], qf[kt], bf[0], bf[1]);
+            mma_bf16_16816_z(s[2 * jp + 1], qf[kt], bf[2], bf[3]);
+          } else {
+            mma_bf16_16816(s[2 * jp], qf[kt], bf[0], bf[1]);
+            mma_bf16_16816(s[2 * jp + 1], qf[kt], bf[2], bf[3]);
+          }
         }
       }
     }
@@ -186,8 +196,8 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
       const int c0 = kb + jp * 16;
-      if (c0 < kend) {
-        if (c0 + 16 > kfull) {
+      if (FULL || c0 < kend) {
+        if (!FULL && c0 + 16 > kfull) {
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
     }
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
-      if (kb + jp * 16 < kend) {
+      if (FULL || kb + jp * 16 < kend) {
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int j = 2 * jp + jj;
@@ -238,7 +248,7 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
     // O += P V
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      if (kb + kk * 16 < kend) {
+      if (FULL || kb + kk * 16 < kend) {
         uint32_t pa[4];
         pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
         pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
@@ -253,6 +263,12 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
         }
       }
     }
+  };
+  {
+    const int kfast = min(kend, kfull) & ~63;  // keys [0, kfast): whole blocks without a masked or padded key
+    int kb = 0;
+    for (; kb < kfast; kb += 64) key_block(kb, std::true_type{});
+    for (; kb < kend; kb += 64) key_block(kb, std::false_type{});
   }
 
 #pragma unroll
@@ -360,12 +376,17 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
   float dsum[2] = {0.f, 0.f};
 #pragma unroll 1
   for (int pass = TR ? 1 : 0; pass < 2; ++pass) {
-  for (int cb = 0; cb < cend; cb += CB) {
+  // One block of CB columns.  FULL: every column exists (and, for the dQ pass, is attendable): no per-group tests, no
+  // mask bias, first k-step from the zero register.
+  auto col_block = [&](const int cb, auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
     float s[NT][4], dp[NT][4];
+    if (!FULL) {
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+      for (int j = 0; j < NT; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+      }
     }
 #pragma unroll
     for (int kt = 0; kt < D / 16; ++kt) {
@@ -374,21 +395,31 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
       load_a_frag<LDS>(a2, sR2, warp * 16, kt * 16, lane);
 #pragma unroll
       for (int jp = 0; jp < NT / 2; ++jp) {
-        if (cb + jp * 16 < cend) {
+        if (FULL || cb + jp * 16 < cend) {
           uint32_t bf[4];
           load_b_frag_nk<LDS>(bf, sC1, cb + jp * 16, kt * 16, lane);
-          mma_bf16_16816(s[2 * jp], a1, bf[0], bf[1]);
-          mma_bf16_16816(s[2 * jp + 1], a1, bf[2], bf[3]);
+          if (FULL && kt == 0) {
+            mma_bf16_16816_z(s[2 * jp], a1, bf[0], bf[1]);
+            mma_bf16_16816_z(s[2 * jp + 1], a1, bf[2], bf[3]);
+          } else {
+            mma_bf16_16816(s[2 * jp], a1, bf[0], bf[1]);
+            mma_bf16_16816(s[2 * jp + 1], a1, bf[2], bf[3]);
+          }
           load_b_frag_nk<LDS>(bf, sC2, cb + jp * 16, kt * 16, lane);
-          mma_bf16_16816(dp[2 * jp], a2, bf[0], bf[1]);
-          mma_bf16_16816(dp[2 * jp + 1], a2, bf[2], bf[3]);
+          if (FULL && kt == 0) {
+            mma_bf16_16816_z(dp[2 * jp], a2, bf[0], bf[1]);
+            mma_bf16_16816_z(dp[2 * jp + 1], a2, bf[2], bf[3]);
+          } else {
+            mma_bf16_16816(dp[2 * jp], a2, bf[0], bf[1]);
+            mma_bf16_16816(dp[2 * jp + 1], a2, bf[2], bf[3]);
+          }
         }
       }
     }
 #pragma unroll
     for (int jp = 0; jp < NT / 2; ++jp) {
       const int c0 = cb + jp * 16;
-      if (c0 < cend) {
+      if (FULL || c0 < cend) {
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int j = 2 * jp + jj;
@@ -396,7 +427,7 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
           float ce[2], cd[2];                     // per-column exponent offset / delta
           if (!TR) {
             ce[0] = ce[1] = 0.f;
-            if (c0 + 16 > cfull) { ce[0] = sColA[colb]; ce[1] = sColA[colb + 1]; }
+            if (!FULL && c0 + 16 > cfull) { ce[0] = sColA[colb]; ce[1] = sColA[colb + 1]; }
             cd[0] = cd[1] = 0.f;
           } else {
             const float2 la = *reinterpret_cast<const float2*>(sColA + colb);
@@ -427,11 +458,11 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
         }
       }
     }
-    if (pass == 0) continue;
+    if (pass == 0) return;
     // out1 += dS . C1 ; (TR) out2 += Pdrop . C2
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
-      if (cb + kk * 16 < cend) {
+      if (FULL || cb + kk * 16 < cend) {
         uint32_t da[4], pa[4];
         da[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
         da[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
@@ -457,7 +488,13 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
         }
       }
     }
-  }  // column blocks
+  };
+  {
+    const int cfast = (TR ? cend : min(cend, cfull)) & ~(CB - 1);  // whole blocks that need no test at all
+    int cb = 0;
+    for (; cb < cfast; cb += CB) col_block(cb, std::true_type{});
+    for (; cb < cend; cb += CB) col_block(cb, std::false_type{});
+  }
     if (pass == 0) {
 #pragma unroll
       for (int r = 0; r < 2; ++r) {

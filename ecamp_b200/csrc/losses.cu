@@ -92,6 +92,7 @@ template <int OUT>
 ECAMP_DEVINL void sr_forward_region(const float* __restrict__ pred_b, int Y0, int X0, float* sU, float* sH) {
   const SrWeights& w = c_sr;
   constexpr int UW = OUT + 4, HW = OUT + 2;
+#pragma unroll 2  // two positions' 24 gathers in flight (the loop was exposed to the latency of its global loads)
   for (int i = threadIdx.x; i < UW * UW; i += blockDim.x) {
     const int uy = i / UW, ux = i % UW;
     const int Y = Y0 - 2 + uy, X = X0 - 2 + ux;
@@ -239,21 +240,31 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
   for (int t = threadIdx.x; t < OW * (OW / 4); t += blockDim.x) {
     const int oy = t / (OW / 4), ox0 = (t % (OW / 4)) * 4;
     const int Y = Y0 - 2 + oy;
-    float o[3][4];
-    sr_out_strip<OUT>(sU, sH, oy, ox0, o);
-    // the strip starts at an even X and windows / image edges are even: each PAIR of pixels is inside or outside as a whole
+    // the strip starts at an even X and windows / image edges are even: each PAIR of pixels is inside or outside as a whole.
+    // The targets are fetched BEFORE the convolution of the strip so that their latency hides behind its 324 FMAs (ncu:
+    // a quarter of the kernel's stall samples sat on these loads when they were issued at the point of use).
     const bool row_in = Y >= wy0 && Y < wy1;
+    bool in_win[2];
+    float2 tg[2][3];
 #pragma unroll
     for (int pr = 0; pr < 2; ++pr) {
       const int X = X0 - 2 + ox0 + 2 * pr;
-      const bool in_win = row_in && X >= wx0 && X < wx1;  // inside the window (hence inside the image)
+      in_win[pr] = row_in && X >= wx0 && X < wx1;  // inside the window (hence inside the image)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        tg[pr][c] = in_win[pr] ? __ldg(reinterpret_cast<const float2*>(big + (((size_t)b * 3 + c) * BIG + Y) * BIG + X))
+                               : make_float2(0.f, 0.f);
+    }
+    float o[3][4];
+    sr_out_strip<OUT>(sU, sH, oy, ox0, o);
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
       const bool owned = oy >= 2 && oy < 34 && ox0 + 2 * pr >= 2 && ox0 + 2 * pr < 34;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float d0 = 0.f, d1 = 0.f;
-        if (in_win) {
-          const float2 tg = *reinterpret_cast<const float2*>(big + (((size_t)b * 3 + c) * BIG + Y) * BIG + X);
-          const float e0 = fmaxf(o[c][2 * pr], 0.f) - tg.x, e1 = fmaxf(o[c][2 * pr + 1], 0.f) - tg.y;
+        if (in_win[pr]) {
+          const float e0 = fmaxf(o[c][2 * pr], 0.f) - tg[pr][c].x, e1 = fmaxf(o[c][2 * pr + 1], 0.f) - tg[pr][c].y;
           if (o[c][2 * pr] > 0.f) d0 = gscale * e0;
           if (o[c][2 * pr + 1] > 0.f) d1 = gscale * e1;
           if (owned) lsum += e0 * e0 + e1 * e1;

@@ -517,7 +517,8 @@ class ECAMPVis(ECAMP):
 
 def ecamp_vis(**kwargs):
     """`Visualization/module/model_ecamp.py:322-327` (`ecamp(**kwargs)` there)."""
-    return ECAMPVis(**kwargs)
+    return ECAMPVis(patch_size=16, in_chans=3, embed_dim=768, depth=12, num_heads=12, decoder_embed_dim=512,
+                    decoder_depth=4, decoder_num_heads=16, mlp_ratio=4, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
 
 
 def ecamp(**kwargs):
