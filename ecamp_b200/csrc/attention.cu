@@ -62,6 +62,22 @@ ECAMP_DEVINL void load_b_frag_kn(uint32_t (&r)[4], const bf16* tile, int k0, int
   ldsm_x4_t(r, smem_u32(p));
 }
 
+// Lane-dependent part of the three fragment addresses, computed ONCE per kernel: a fragment load inside the unrolled
+// loops is then `base + block_offset + constant` (one integer add; the per-call index arithmetic was ~15 % of the
+// executed instructions of the head_dim-32 kernels).
+template <int LDS>
+ECAMP_DEVINL uint32_t frag_base_a(const bf16* tile, int row0, int lane) {  // + k0 * 2
+  return smem_u32(tile + (size_t)(row0 + (lane & 15)) * LDS + ((lane >> 4) << 3));
+}
+template <int LDS>
+ECAMP_DEVINL uint32_t frag_base_nk(const bf16* tile, int lane) {  // + (n0 * LDS + k0) * 2
+  return smem_u32(tile + (size_t)((lane & 7) + ((lane >> 4) << 3)) * LDS + (((lane >> 3) & 1) << 3));
+}
+template <int LDS>
+ECAMP_DEVINL uint32_t frag_base_kn(const bf16* tile, int lane) {  // + (k0 * LDS + n0) * 2
+  return smem_u32(tile + (size_t)(lane & 15) * LDS + ((lane >> 4) << 3));
+}
+
 // cooperative asynchronous copy of `rows` rows (zero-filled from `valid` on) of width D from global (row pitch ld)
 // to shared memory: every 16-byte chunk is one cp.async, so all of a thread's loads are in flight at once
 // (a plain load/store loop kept one load in flight per thread and dominated the kernels: long-scoreboard stalls).
@@ -152,6 +168,7 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
   uint32_t qf[D / 16][4];
 #pragma unroll
   for (int kt = 0; kt < D / 16; ++kt) load_a_frag<LDS>(qf[kt], sQ, warp * 16, kt * 16, lane);
+  const uint32_t kbase = frag_base_nk<LDS>(sK, lane), vbase = frag_base_kn<LDS>(sV, lane);
 
   float o[D / 8][4];
 #pragma unroll
@@ -165,12 +182,13 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
   const uint64_t bh = (uint64_t)b * a.H + h;
   const int row_g = q0 + warp * 16 + g;  // this thread's rows: row_g and row_g + 8
 
-  // One 64-key block.  FULL: all 64 keys exist and are attendable - no per-group tests, no mask bias, and the first
-  // k-step starts from the zero register (the tests and the accumulator clears were ~25 % of the executed instructions).
-  auto key_block = [&](const int kb, auto full_tag) {
-    constexpr bool FULL = decltype(full_tag)::value;
+  // One 64-key block.  ALL: all four 16-key groups lie below kend - no per-group tests, first k-step from the zero
+  // register; NOBIAS: every key of the block is attendable - no mask bias either (the tests and the accumulator clears
+  // were ~25 % of the executed instructions).
+  auto key_block = [&](const int kb, auto all_tag, auto nobias_tag) {
+    constexpr bool ALL = decltype(all_tag)::value, NOBIAS = decltype(nobias_tag)::value;
     float s[8][4];
-    if (!FULL) {
+    if (!ALL) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
     }
@@ -178,10 +196,10 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
     for (int kt = 0; kt < D / 16; ++kt) {
 #pragma unroll
       for (int jp = 0; jp < 4; ++jp) {
-        if (FULL || kb + jp * 16 < kend) {
+        if (ALL || kb + jp * 16 < kend) {
           uint32_t bf[4];
-          load_b_frag_nk<LDS>(bf, sK, kb + jp * 16, kt * 16, lane);
-          if (FULL && kt == 0) {
+          ldsm_x4(bf, kbase + (uint32_t)(kb * LDS * 2) + (uint32_t)((jp * 16 * LDS + kt * 16) * 2));
+          if (ALL && kt == 0) {
             mma_bf16_16816_z(s[2 * jp], qf[kt], bf[0], bf[1]);
             mma_bf16_16816_z(s[2 * jp + 1], qf[kt], bf[2], bf[3]);
           } else {
@@ -196,8 +214,8 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
       const int c0 = kb + jp * 16;
-      if (FULL || c0 < kend) {
-        if (!FULL && c0 + 16 > kfull) {
+      if (ALL || c0 < kend) {
+        if (!NOBIAS && c0 + 16 > kfull) {
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
@@ -227,7 +245,7 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
     }
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
-      if (FULL || kb + jp * 16 < kend) {
+      if (ALL || kb + jp * 16 < kend) {
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int j = 2 * jp + jj;
@@ -248,7 +266,7 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
     // O += P V
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      if (FULL || kb + kk * 16 < kend) {
+      if (ALL || kb + kk * 16 < kend) {
         uint32_t pa[4];
         pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
         pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
@@ -257,7 +275,7 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
         for (int dp = 0; dp < D / 16; ++dp) {
           uint32_t vf[4];
-          load_b_frag_kn<LDS>(vf, sV, kb + kk * 16, dp * 16, lane);
+          ldsm_x4_t(vf, vbase + (uint32_t)(kb * LDS * 2) + (uint32_t)((kk * 16 * LDS + dp * 16) * 2));
           mma_bf16_16816(o[2 * dp], pa, vf[0], vf[1]);
           mma_bf16_16816(o[2 * dp + 1], pa, vf[2], vf[3]);
         }
@@ -265,10 +283,12 @@ __global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(AttnArgs a) {
     }
   };
   {
-    const int kfast = min(kend, kfull) & ~63;  // keys [0, kfast): whole blocks without a masked or padded key
+    const int kall = kend & ~63;               // keys [0, kall): whole blocks
+    const int kfast = min(kall, kfull & ~63);  // keys [0, kfast): whole blocks without a masked or padded key
     int kb = 0;
-    for (; kb < kfast; kb += 64) key_block(kb, std::true_type{});
-    for (; kb < kend; kb += 64) key_block(kb, std::false_type{});
+    for (; kb < kfast; kb += 64) key_block(kb, std::true_type{}, std::true_type{});
+    for (; kb < kall; kb += 64) key_block(kb, std::true_type{}, std::false_type{});
+    for (; kb < kend; kb += 64) key_block(kb, std::false_type{}, std::false_type{});
   }
 
 #pragma unroll
@@ -376,12 +396,15 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
   float dsum[2] = {0.f, 0.f};
 #pragma unroll 1
   for (int pass = TR ? 1 : 0; pass < 2; ++pass) {
-  // One block of CB columns.  FULL: every column exists (and, for the dQ pass, is attendable): no per-group tests, no
-  // mask bias, first k-step from the zero register.
-  auto col_block = [&](const int cb, auto full_tag) {
-    constexpr bool FULL = decltype(full_tag)::value;
+  const uint32_t r1base = frag_base_a<LDS>(sR1, warp * 16, lane), r2base = frag_base_a<LDS>(sR2, warp * 16, lane);
+  const uint32_t c1nk = frag_base_nk<LDS>(sC1, lane), c2nk = frag_base_nk<LDS>(sC2, lane);
+  const uint32_t c1kn = frag_base_kn<LDS>(sC1, lane), c2kn = frag_base_kn<LDS>(sC2, lane);
+  // One block of CB columns.  ALL: every 16-column group lies below cend - no per-group tests, first k-step from the
+  // zero register; NOBIAS (dQ pass): every key of the block is attendable - no mask bias either.
+  auto col_block = [&](const int cb, auto all_tag, auto nobias_tag) {
+    constexpr bool ALL = decltype(all_tag)::value, NOBIAS = decltype(nobias_tag)::value;
     float s[NT][4], dp[NT][4];
-    if (!FULL) {
+    if (!ALL) {
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
@@ -391,22 +414,22 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
 #pragma unroll
     for (int kt = 0; kt < D / 16; ++kt) {
       uint32_t a1[4], a2[4];
-      load_a_frag<LDS>(a1, sR1, warp * 16, kt * 16, lane);
-      load_a_frag<LDS>(a2, sR2, warp * 16, kt * 16, lane);
+      ldsm_x4(a1, r1base + (uint32_t)(kt * 16 * 2));
+      ldsm_x4(a2, r2base + (uint32_t)(kt * 16 * 2));
 #pragma unroll
       for (int jp = 0; jp < NT / 2; ++jp) {
-        if (FULL || cb + jp * 16 < cend) {
+        if (ALL || cb + jp * 16 < cend) {
           uint32_t bf[4];
-          load_b_frag_nk<LDS>(bf, sC1, cb + jp * 16, kt * 16, lane);
-          if (FULL && kt == 0) {
+          ldsm_x4(bf, c1nk + (uint32_t)(cb * LDS * 2) + (uint32_t)((jp * 16 * LDS + kt * 16) * 2));
+          if (ALL && kt == 0) {
             mma_bf16_16816_z(s[2 * jp], a1, bf[0], bf[1]);
             mma_bf16_16816_z(s[2 * jp + 1], a1, bf[2], bf[3]);
           } else {
             mma_bf16_16816(s[2 * jp], a1, bf[0], bf[1]);
             mma_bf16_16816(s[2 * jp + 1], a1, bf[2], bf[3]);
           }
-          load_b_frag_nk<LDS>(bf, sC2, cb + jp * 16, kt * 16, lane);
-          if (FULL && kt == 0) {
+          ldsm_x4(bf, c2nk + (uint32_t)(cb * LDS * 2) + (uint32_t)((jp * 16 * LDS + kt * 16) * 2));
+          if (ALL && kt == 0) {
             mma_bf16_16816_z(dp[2 * jp], a2, bf[0], bf[1]);
             mma_bf16_16816_z(dp[2 * jp + 1], a2, bf[2], bf[3]);
           } else {
@@ -419,7 +442,7 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
 #pragma unroll
     for (int jp = 0; jp < NT / 2; ++jp) {
       const int c0 = cb + jp * 16;
-      if (FULL || c0 < cend) {
+      if (ALL || c0 < cend) {
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int j = 2 * jp + jj;
@@ -427,7 +450,7 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
           float ce[2], cd[2];                     // per-column exponent offset / delta
           if (!TR) {
             ce[0] = ce[1] = 0.f;
-            if (!FULL && c0 + 16 > cfull) { ce[0] = sColA[colb]; ce[1] = sColA[colb + 1]; }
+            if (!NOBIAS && c0 + 16 > cfull) { ce[0] = sColA[colb]; ce[1] = sColA[colb + 1]; }
             cd[0] = cd[1] = 0.f;
           } else {
             const float2 la = *reinterpret_cast<const float2*>(sColA + colb);
@@ -462,7 +485,7 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
     // out1 += dS . C1 ; (TR) out2 += Pdrop . C2
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
-      if (FULL || cb + kk * 16 < cend) {
+      if (ALL || cb + kk * 16 < cend) {
         uint32_t da[4], pa[4];
         da[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
         da[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
@@ -477,11 +500,11 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
 #pragma unroll
         for (int dd = 0; dd < D / 16; ++dd) {
           uint32_t cf[4];
-          load_b_frag_kn<LDS>(cf, sC1, cb + kk * 16, dd * 16, lane);
+          ldsm_x4_t(cf, c1kn + (uint32_t)(cb * LDS * 2) + (uint32_t)((kk * 16 * LDS + dd * 16) * 2));
           mma_bf16_16816(acc1[2 * dd], da, cf[0], cf[1]);
           mma_bf16_16816(acc1[2 * dd + 1], da, cf[2], cf[3]);
           if (TR) {
-            load_b_frag_kn<LDS>(cf, sC2, cb + kk * 16, dd * 16, lane);
+            ldsm_x4_t(cf, c2kn + (uint32_t)(cb * LDS * 2) + (uint32_t)((kk * 16 * LDS + dd * 16) * 2));
             mma_bf16_16816(acc2[2 * dd], pa, cf[0], cf[1]);
             mma_bf16_16816(acc2[2 * dd + 1], pa, cf[2], cf[3]);
           }
@@ -490,10 +513,12 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
     }
   };
   {
-    const int cfast = (TR ? cend : min(cend, cfull)) & ~(CB - 1);  // whole blocks that need no test at all
+    const int call = cend & ~(CB - 1);                          // whole blocks
+    const int cfast = TR ? call : min(call, cfull & ~(CB - 1));  // whole blocks that need no test at all
     int cb = 0;
-    for (; cb < cfast; cb += CB) col_block(cb, std::true_type{});
-    for (; cb < cend; cb += CB) col_block(cb, std::false_type{});
+    for (; cb < cfast; cb += CB) col_block(cb, std::true_type{}, std::true_type{});
+    for (; cb < call; cb += CB) col_block(cb, std::true_type{}, std::false_type{});
+    for (; cb < cend; cb += CB) col_block(cb, std::false_type{}, std::false_type{});
   }
     if (pass == 0) {
 #pragma unroll
@@ -708,6 +733,9 @@ int launch_fwd(const AttnArgs& a, cudaStream_t st) {
   static const int big = getenv("ECAMP_ATTN_BIG") ? atoi(getenv("ECAMP_ATTN_BIG")) : 0;  // measured slower (1 CTA / SM)
   if (big && D == 32 && a.Sq > 64 && a.Sq <= kBigNW * 16 && fwd_smem(D, a.Sk, kBigNW * 16) <= (size_t)kMaxDynSmem)
     return launch_fwd_nw<32, kBigNW>(a, st);
+  // 7 warps: two CTAs cover the 197 decoder queries (13 of 14 warps busy, K / V staged twice per head instead of 4 times)
+  static const int nw7 = getenv("ECAMP_ATTN_NW7") ? atoi(getenv("ECAMP_ATTN_NW7")) : 0;
+  if (nw7 && D == 32 && a.Sq > 112 && a.Sq <= 224) return launch_fwd_nw<32, 7>(a, st);
   return launch_fwd_nw<D, 4>(a, st);
 }
 template <int D>

@@ -19,5 +19,10 @@ elif kind == "gelu":
               bias=torch.randn(N, device=dev), flags=L.GEMM_GELU)
 elif kind == "res":
     kw = dict(out_f32=torch.empty(M, N, device=dev), residual=torch.randn(M, N, device=dev), bias=torch.randn(N, device=dev))
+elif kind == "dgelu":   # fc2 dgrad: x gelu'(pre-activation) -> bf16, + column sums (fc1 bias gradient)
+    kw = dict(out_bf16=torch.empty(M, N, device=dev, dtype=torch.bfloat16), aux_in=torch.randn(M, N, device=dev).to(torch.bfloat16),
+              colsum_out=torch.zeros(N, device=dev), flags=L.GEMM_DGELU)
+elif kind == "f32":
+    kw = dict(out_f32=torch.empty(M, N, device=dev))
 L.gemm(a, b, M=M, N=N, K=K, tile_n=256, **kw)
 torch.cuda.synchronize()
