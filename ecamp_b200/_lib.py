@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libecamp_b200.so")
+# ECAMP_B200_LIB: load another build of the SAME library (A/B measurements of kernel variants); never a fallback
+LIB_PATH = os.environ.get("ECAMP_B200_LIB") or os.path.join(_HERE, "lib", "libecamp_b200.so")
 
 GEMM_GELU, GEMM_DGELU, GEMM_DROPOUT = 1, 2, 4
 

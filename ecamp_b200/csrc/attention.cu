@@ -733,9 +733,7 @@ int launch_fwd(const AttnArgs& a, cudaStream_t st) {
   static const int big = getenv("ECAMP_ATTN_BIG") ? atoi(getenv("ECAMP_ATTN_BIG")) : 0;  // measured slower (1 CTA / SM)
   if (big && D == 32 && a.Sq > 64 && a.Sq <= kBigNW * 16 && fwd_smem(D, a.Sk, kBigNW * 16) <= (size_t)kMaxDynSmem)
     return launch_fwd_nw<32, kBigNW>(a, st);
-  // 7 warps: two CTAs cover the 197 decoder queries (13 of 14 warps busy, K / V staged twice per head instead of 4 times)
-  static const int nw7 = getenv("ECAMP_ATTN_NW7") ? atoi(getenv("ECAMP_ATTN_NW7")) : 0;
-  if (nw7 && D == 32 && a.Sq > 112 && a.Sq <= 224) return launch_fwd_nw<32, 7>(a, st);
+  // (7 warps = two CTAs per 197-query decoder head, K / V staged twice instead of 4 times: measured slower, 171 vs 143 us)
   return launch_fwd_nw<D, 4>(a, st);
 }
 template <int D>

@@ -102,14 +102,24 @@ ECAMP_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trap (CUDA error), never as a hung GPU.
+// A waiting warp backs off with nanosleep and reads the clock only every 256 polls: the tight poll loop (try_wait +
+// clock64 + compare + branch) of the producer / MMA warps was ~10 % of all executed instructions of an epilogue-bound
+// GEMM (ncu source view) and competed for issue slots with the two epilogue warps of the same scheduler.
 ECAMP_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("ecamp_b200: mbarrier wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x,
-             parity);
-      __trap();
+#ifndef ECAMP_MBAR_SPIN  // (A/B switch for measurements: -DECAMP_MBAR_SPIN polls without backing off)
+    __nanosleep(40);
+#endif
+    if ((++polls & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+        printf("ecamp_b200: mbarrier wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }

@@ -318,9 +318,11 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
   // the 84 per-thread sums are reduced across the warp with a halving butterfly (31 shuffles per 32 values instead
   // of 5 per value) and across the 8 warps through shared memory.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int soy = threadIdx.x >> 3, sox0 = (threadIdx.x & 7) * 4;
-#pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
+  // warps 0-3 take conv2, warps 4-7 conv1 (warp-uniform); every thread covers TWO strips (rows soy and soy + 16) before
+  // the warp reduction, so a warp runs one butterfly per 2 x 324 products instead of one per 324
+  const int which = warp >> 2;
+  const int soy = (threadIdx.x & 127) >> 3, sox0 = (threadIdx.x & 7) * 4;
+  {
     float acc[96];
 #pragma unroll
     for (int k = 0; k < 96; ++k) acc[k] = 0.f;
@@ -330,29 +332,37 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
     const int gW = which == 0 ? OW : GW, goff = which == 0 ? 2 : 1;
     const float* isrc = which == 0 ? sH : sU;
     const int iW = which == 0 ? HW : UW, ioff = which == 0 ? 2 : 3;
-    float g[3][4];
+    float g[2][3][4];  // the thread's two strips: rows soy and soy + 16
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+#pragma unroll
+      for (int co = 0; co < 3; ++co)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[half][co][q] = gsrc[co * gW * gW + (soy + 16 * half + goff) * gW + sox0 + goff + q];
 #pragma unroll
     for (int co = 0; co < 3; ++co)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) g[co][q] = gsrc[co * gW * gW + (soy + goff) * gW + sox0 + goff + q];
-#pragma unroll
-    for (int co = 0; co < 3; ++co) acc[81 + co] = (g[co][0] + g[co][1]) + (g[co][2] + g[co][3]);
+      acc[81 + co] = ((g[0][co][0] + g[0][co][1]) + (g[0][co][2] + g[0][co][3])) +
+                     ((g[1][co][0] + g[1][co][1]) + (g[1][co][2] + g[1][co][3]));
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const float* r = isrc + ci * iW * iW + (soy + ioff + ky) * iW + sox0 + ioff;
-        float v[6];
+        float v[2][6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) v[j] = r[j];
+        for (int j = 0; j < 6; ++j) { v[0][j] = r[j]; v[1][j] = r[16 * iW + j]; }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
           for (int co = 0; co < 3; ++co) {
-            float s = g[co][0] * v[kx];
-            s = fmaf(g[co][1], v[kx + 1], s);
-            s = fmaf(g[co][2], v[kx + 2], s);
-            s = fmaf(g[co][3], v[kx + 3], s);
+            float s = g[0][co][0] * v[0][kx];
+            s = fmaf(g[0][co][1], v[0][kx + 1], s);
+            s = fmaf(g[0][co][2], v[0][kx + 2], s);
+            s = fmaf(g[0][co][3], v[0][kx + 3], s);
+            s = fmaf(g[1][co][0], v[1][kx], s);
+            s = fmaf(g[1][co][1], v[1][kx + 1], s);
+            s = fmaf(g[1][co][2], v[1][kx + 2], s);
+            s = fmaf(g[1][co][3], v[1][kx + 3], s);
             acc[(co * 3 + ci) * 9 + ky * 3 + kx] = s;
           }
       }
@@ -373,12 +383,13 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
       if (grp * 32 + lane < 84) redw[warp][grp * 32 + lane] = acc[grp * 32];
     }
     __syncthreads();
-    if (threadIdx.x < 84) {
+    if (threadIdx.x < 168) {
+      const int cv = threadIdx.x / 84, idx = threadIdx.x % 84;
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += redw[w][threadIdx.x];
+      for (int w = 0; w < 4; ++w) s += redw[cv * 4 + w][idx];
       // ws layout per tile: [w1 81 | b1 3 | w2 81 | b2 3]
-      ws_t[(which == 0 ? 84 : 0) + threadIdx.x] = s;
+      ws_t[(cv == 0 ? 84 : 0) + idx] = s;
     }
     __syncthreads();
   }
