@@ -256,14 +256,17 @@ def main():
     from ecamp_b200.model_ecamp import ecamp
     from ecamp_b200.optim import FusedAdamW
     from ecamp_b200.parallel import DataParallelStep
-    from ecamp_b200.synthetic import make_batch
+    from ecamp_b200.synthetic import bind_host_to_gpu, make_batch
 
     torch.manual_seed(0)                      # identical random-init replicas on every rank
     model = ecamp(norm_pix_loss=True).to(dev).train()
     opt = FusedAdamW(model, lr=1.5e-4, betas=(0.9, 0.95), weight_decay=0.05)
     dp = DataParallelStep(model, opt, bucket_mb=64)
     torch.manual_seed(1234 + rank)            # per-rank masking noise / dropout (main_pretrain.py:189)
+    affinity = os.sched_getaffinity(0)
+    numa_cpus = bind_host_to_gpu(local)        # first-touch the pinned staging buffers on the GPU's own NUMA node ...
     host = [make_batch(args.batch, T=args.seq, big=True, seed=1234 + 17 * rank + i, pin=True) for i in range(2)]
+    os.sched_setaffinity(0, affinity)          # ... then give the process its CPUs back (the CPU baseline uses them all)
     for hb in host:
         hb.pop("noise")                       # the module draws torch.rand(N, L) itself, like the reference
     resident = [to_device(hb, dev) for hb in host]
@@ -347,7 +350,9 @@ def main():
                                l2="per-step working set (~16 GB of activations) is far larger than the 126 MB L2; two input batches alternate",
                                e2e_pipeline="per timed step: one H2D copy of a full pinned batch on a copy stream (prefetching the "
                                             "next step's inputs while this step runs) and one D2H read of the 3 losses, which the "
-                                            "host consumes one step late so that it never stalls the launch queue"),
+                                            "host consumes one step late so that it never stalls the launch queue",
+                               host_buffers=("pinned, first-touched on the GPU's NUMA node (%d CPUs)" % len(numa_cpus)) if numa_cpus
+                               else "pinned (NUMA topology unknown or single node)"),
                    clocks=clocks, gpu_launches=int(launches),
                    e2e=dict(value=round(e2e_value, 2), unit="pairs/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=12,
                             ms_per_step=round(ms_e2e / args.steps, 3)),

@@ -1,8 +1,34 @@
 """Synthetic pre-training batches with the shapes / value ranges of the reference's collate output
 (ECAMP/Pre-training/module/pretrain_datasets.py:202-239; recipe in SURVEY.md §8d).  Used by bench.py and smoke()."""
+import os
+
 import torch
 
 VOCAB = 30000
+
+
+def bind_host_to_gpu(device_index=0):
+    """Restrict this process to the CPUs of the NUMA node the GPU hangs off (sysfs `local_cpulist` of its PCI function),
+    so that pinned staging buffers allocated afterwards are first-touched on that node: a 617 MB batch copied from the
+    remote socket can take longer than the whole step.  Returns the CPU list used, or None if the topology is unknown
+    (single node, container without sysfs, ...) - then nothing is changed."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        text = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        cpus = []
+        for part in text.split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus += list(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in cpus if c in allowed)
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
 
 
 def make_batch(B, T=128, big=True, seed=1234, pin=False):
