@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # ECAMP_B200_LIB: load another build of the SAME library (A/B measurements of kernel variants); never a fallback
 LIB_PATH = os.environ.get("ECAMP_B200_LIB") or os.path.join(_HERE, "lib", "libecamp_b200.so")
 
-GEMM_GELU, GEMM_DGELU, GEMM_DROPOUT = 1, 2, 4
+GEMM_GELU, GEMM_DGELU, GEMM_DROPOUT, GEMM_AUX_GRAD = 1, 2, 4, 8
 
 
 class Epilogue(ctypes.Structure):

@@ -342,6 +342,22 @@ ECAMP_DEVINL float gelu_erf_grad(float x) {
   return fmaf(x * d, fmaf(-s, s, s), s);
 }
 
+// GELU and its derivative from one evaluation of Phi (the forward epilogue can store the derivative for backward:
+// 6 more FMA-pipe instructions there instead of the 16 of gelu_erf_grad per element in the dGELU epilogue)
+ECAMP_DEVINL void gelu_erf_both(float x, float& y, float& g) {
+  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
+  const float t = xc * xc;
+  float p = fmaf(ECAMP_PHI_K7, t, ECAMP_PHI_K5);
+  p = fmaf(p, t, ECAMP_PHI_K3);
+  p = fmaf(p, t, ECAMP_PHI_K1);
+  const float s = rcp_approx(1.0f + ex2_approx(xc * p));
+  float d = fmaf(-1.9163357e-4f, t, -1.9445258e-3f);
+  d = fmaf(d, t, 0.21927995f);
+  d = fmaf(d, t, 1.5956405f);
+  y = x * s;
+  g = fmaf(x * d, fmaf(-s, s, s), s);
+}
+
 // Philox4x32-10: counter-based, so forward and backward regenerate identical dropout masks from
 // (seed, stream offset, element index) regardless of how the work is tiled.
 struct Philox {

@@ -94,11 +94,15 @@ enum EpiMode : int {
   EM_BF16,          // (+bias) -> bf16
   EM_GELU,          // +bias -> bf16 pre-activation to aux_out -> GELU -> bf16
   EM_DGELU,         // * GELU'(aux_in) -> bf16
+  EM_GELU_G,        // EM_GELU, but aux_out receives bf16(GELU'(pre-activation)) (GEMM_AUX_GRAD)
+  EM_DGELU_G,       // * aux_in (the stored GELU') -> bf16 (GEMM_AUX_GRAD)
   EM_F32,           // (+bias) -> fp32
   EM_F32_RES,       // (+bias) + fp32 residual -> fp32
   EM_F32_RES_DROP,  // (+bias) -> dropout -> + fp32 residual -> fp32
   EM_ATOMIC,        // split-K partial: fp32 vector reduction into out_f32
 };
+__host__ __device__ constexpr bool is_gelu(int m) { return m == EM_GELU || m == EM_GELU_G; }
+__host__ __device__ constexpr bool is_dgelu(int m) { return m == EM_DGELU || m == EM_DGELU_G; }
 
 // scalar fall-back for one element (unaligned operands or a column tail that is not a multiple of 4)
 ECAMP_DEVINL void epi_scalar(const EpiArgs& ea, float v, int row, int col, int N) {
@@ -107,10 +111,15 @@ ECAMP_DEVINL void epi_scalar(const EpiArgs& ea, float v, int row, int col, int N
   if (ep.bias) v += __ldg(ep.bias + col);
   if (ep.flags & GEMM_GELU) {
     v = bf2f(f2bf(v));
-    if (ep.aux_out) ep.aux_out[(size_t)row * ep.ld_aux + col] = f2bf(v);
-    v = gelu_erf(v);
+    float gr = v;
+    if (ep.flags & GEMM_AUX_GRAD) gelu_erf_both(v, v, gr);
+    else v = gelu_erf(v);
+    if (ep.aux_out) ep.aux_out[(size_t)row * ep.ld_aux + col] = f2bf(gr);
   }
-  if (ep.flags & GEMM_DGELU) v *= gelu_erf_grad(bf2f(ep.aux_in[(size_t)row * ep.ld_aux + col]));
+  if (ep.flags & GEMM_DGELU) {
+    const float t = bf2f(ep.aux_in[(size_t)row * ep.ld_aux + col]);
+    v *= (ep.flags & GEMM_AUX_GRAD) ? t : gelu_erf_grad(t);
+  }
   if (ep.flags & GEMM_DROPOUT) {
     const Philox ph(ep.seed);
     const uint32_t w = philox_word(ph, (uint64_t)row * (uint64_t)N + (uint64_t)col, ep.stream);
@@ -160,14 +169,21 @@ ECAMP_DEVINL void epi_vec4_generic(const EpiArgs& ea, float4 v, int row, int col
   v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
   if (ep.flags & GEMM_GELU) {
     const uint2 u = pack4(v);
-    if (ep.aux_out) *reinterpret_cast<uint2*>(ep.aux_out + (size_t)row * ep.ld_aux + col) = u;
     const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-    v.x = gelu_erf(a.x); v.y = gelu_erf(a.y); v.z = gelu_erf(b.x); v.w = gelu_erf(b.y);
+    if (ep.flags & GEMM_AUX_GRAD) {
+      float4 gr;
+      gelu_erf_both(a.x, v.x, gr.x); gelu_erf_both(a.y, v.y, gr.y); gelu_erf_both(b.x, v.z, gr.z); gelu_erf_both(b.y, v.w, gr.w);
+      if (ep.aux_out) *reinterpret_cast<uint2*>(ep.aux_out + (size_t)row * ep.ld_aux + col) = pack4(gr);
+    } else {
+      if (ep.aux_out) *reinterpret_cast<uint2*>(ep.aux_out + (size_t)row * ep.ld_aux + col) = u;
+      v.x = gelu_erf(a.x); v.y = gelu_erf(a.y); v.z = gelu_erf(b.x); v.w = gelu_erf(b.y);
+    }
   }
   if (ep.flags & GEMM_DGELU) {
     const uint2 u = __ldg(reinterpret_cast<const uint2*>(ep.aux_in + (size_t)row * ep.ld_aux + col));
     const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-    v.x *= gelu_erf_grad(a.x); v.y *= gelu_erf_grad(a.y); v.z *= gelu_erf_grad(b.x); v.w *= gelu_erf_grad(b.y);
+    if (ep.flags & GEMM_AUX_GRAD) { v.x *= a.x; v.y *= a.y; v.z *= b.x; v.w *= b.y; }
+    else { v.x *= gelu_erf_grad(a.x); v.y *= gelu_erf_grad(a.y); v.z *= gelu_erf_grad(b.x); v.w *= gelu_erf_grad(b.y); }
   }
   if (ep.flags & GEMM_DROPOUT) v = dropout4(ep, v, row, col, N);
   if (ep.row_scale) {
@@ -193,13 +209,13 @@ ECAMP_DEVINL void epi_vec4_generic(const EpiArgs& ea, float4 v, int row, int col
 //  fetched two chunks ahead: that operand comes from HBM, one chunk of lead did not cover its latency)
 template <int MODE>
 ECAMP_DEVINL void epi_prefetch(const GemmEpilogue& ep, int row0, int col, int M, int N, uint4 (&p)[kSteps], bool hi = false) {
-  if (MODE != EM_F32_RES && MODE != EM_F32_RES_DROP && MODE != EM_DGELU) return;
+  if (MODE != EM_F32_RES && MODE != EM_F32_RES_DROP && !is_dgelu(MODE)) return;
   if (col >= N) return;
 #pragma unroll
   for (int i = 0; i < kSteps; ++i) {
     const int row = row0 + kRPS * i;
     if (row < M) {
-      if (MODE == EM_DGELU) {
+      if (is_dgelu(MODE)) {
         const uint2 u = __ldg(reinterpret_cast<const uint2*>(ep.aux_in + (size_t)row * ep.ld_aux + col));
         if (hi) { p[i].z = u.x; p[i].w = u.y; }
         else { p[i].x = u.x; p[i].y = u.y; }
@@ -226,15 +242,15 @@ ECAMP_DEVINL int epi_swz(int r) { return kCW == 32 ? (r & 7) : ((r >> 1) & 3); }
 // issued one tile ahead, so that the register prefetch of epi_prefetch (one chunk ahead) only ever pays L2 latency.
 template <int COLS, int MODE>
 ECAMP_DEVINL void epi_prefetch_l2(const GemmEpilogue& ep, int m0, int ncol0, int M, int N, int lane) {
-  if (MODE != EM_F32_RES && MODE != EM_F32_RES_DROP && MODE != EM_DGELU) return;
-  constexpr int ROW_BYTES = COLS * (MODE == EM_DGELU ? 2 : 4);
+  if (MODE != EM_F32_RES && MODE != EM_F32_RES_DROP && !is_dgelu(MODE)) return;
+  constexpr int ROW_BYTES = COLS * (is_dgelu(MODE) ? 2 : 4);
   constexpr int LINES = (ROW_BYTES + 127) / 128;  // 128-byte lines per row of the region
 #pragma unroll
   for (int j = 0; j < LINES; ++j) {
     const int row = m0 + lane;
-    const int col = ncol0 + j * (MODE == EM_DGELU ? 64 : 32);
+    const int col = ncol0 + j * (is_dgelu(MODE) ? 64 : 32);
     if (row < M && col < N && col < ncol0 + COLS) {
-      const void* p = MODE == EM_DGELU ? static_cast<const void*>(ep.aux_in + (size_t)row * ep.ld_aux + col)
+      const void* p = is_dgelu(MODE) ? static_cast<const void*>(ep.aux_in + (size_t)row * ep.ld_aux + col)
                                        : static_cast<const void*>(ep.residual + (size_t)row * ep.ld_res + col);
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
@@ -252,12 +268,12 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
   static_assert(COLS % kCW == 0, "column slice must be whole chunks");
   const GemmEpilogue& ep = ea.ep;
   const int sub = lane / kLPR, u = lane % kLPR;  // coalesced layout: step i -> row kRPS i + sub, 16-byte unit u
-  const bool vbias = MODE != EM_ATOMIC && MODE != EM_DGELU && ea.split_k == 1 && ep.bias && ea.vec_ok;
+  const bool vbias = MODE != EM_ATOMIC && !is_dgelu(MODE) && ea.split_k == 1 && ep.bias && ea.vec_ok;
   const int row0 = m0 + sub;
   const uint32_t stage_addr = smem_u32(stage);  // explicit shared-space accesses (a generic pointer compiled to LD.E / ST.E)
   uint4 pcur[kSteps], pnext[kSteps];
   epi_prefetch<MODE>(ep, row0, ncol0 + 4 * u, M, N, pcur);  // in flight while the accumulator is still being produced
-  if (MODE == EM_DGELU && NCH > 1) epi_prefetch<MODE>(ep, row0, ncol0 + kCW + 4 * u, M, N, pcur, true);
+  if (is_dgelu(MODE) && NCH > 1) epi_prefetch<MODE>(ep, row0, ncol0 + kCW + 4 * u, M, N, pcur, true);
   if (next_m0 >= 0) epi_prefetch_l2<COLS, MODE>(ep, next_m0, next_ncol0, M, N, lane);
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), bias_next = bias4;
   if (vbias && ncol0 + 4 * u + 4 <= N) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + ncol0 + 4 * u));
@@ -286,7 +302,7 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
     for (int j = 0; j < kLPR; ++j)
       sts128(stage_addr + (uint32_t)(lane * (kCW * 4) + ((j ^ epi_swz(lane)) << 4)), raw[4 * j], raw[4 * j + 1],
              raw[4 * j + 2], raw[4 * j + 3]);
-    if (MODE == EM_DGELU) {
+    if (is_dgelu(MODE)) {
       if (c + 2 < NCH) epi_prefetch<MODE>(ep, row0, col + 2 * kCW, M, N, pnext);  // two chunks ahead
     } else if (c + 1 < NCH) {
       epi_prefetch<MODE>(ep, row0, col + kCW, M, N, pnext);  // next chunk's operand in flight from here
@@ -321,16 +337,24 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
                            : "memory");
               continue;
             }
-            if (MODE != EM_DGELU) { x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w; }
-            if (MODE == EM_GELU) {
+            if (!is_dgelu(MODE)) { x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w; }
+            if (is_gelu(MODE)) {
               const uint2 pk = pack4(x);
-              *reinterpret_cast<uint2*>(ep.aux_out + (size_t)row * ep.ld_aux + col) = pk;
               const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y);
-              x.x = gelu_erf(a.x); x.y = gelu_erf(a.y); x.z = gelu_erf(b.x); x.w = gelu_erf(b.y);
+              if (MODE == EM_GELU_G) {  // backward only ever needs GELU'(pre-activation): store that instead
+                float4 gr;
+                gelu_erf_both(a.x, x.x, gr.x); gelu_erf_both(a.y, x.y, gr.y);
+                gelu_erf_both(b.x, x.z, gr.z); gelu_erf_both(b.y, x.w, gr.w);
+                *reinterpret_cast<uint2*>(ep.aux_out + (size_t)row * ep.ld_aux + col) = pack4(gr);
+              } else {
+                *reinterpret_cast<uint2*>(ep.aux_out + (size_t)row * ep.ld_aux + col) = pk;
+                x.x = gelu_erf(a.x); x.y = gelu_erf(a.y); x.z = gelu_erf(b.x); x.w = gelu_erf(b.y);
+              }
             }
-            if (MODE == EM_DGELU) {
+            if (is_dgelu(MODE)) {
               const float2 a = unpack_bf16x2(pcur[i].x), b = unpack_bf16x2(pcur[i].y);
-              x.x *= gelu_erf_grad(a.x); x.y *= gelu_erf_grad(a.y); x.z *= gelu_erf_grad(b.x); x.w *= gelu_erf_grad(b.y);
+              if (MODE == EM_DGELU_G) { x.x *= a.x; x.y *= a.y; x.z *= b.x; x.w *= b.y; }
+              else { x.x *= gelu_erf_grad(a.x); x.y *= gelu_erf_grad(a.y); x.z *= gelu_erf_grad(b.x); x.w *= gelu_erf_grad(b.y); }
             }
             if (MODE == EM_F32_RES_DROP) x = dropout4(ep, x, row, col, N);
             if (MODE == EM_F32_RES && ep.row_scale) {  // DropPath (fine-tune path only)
@@ -346,13 +370,13 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
             } else {
               const uint2 pk = pack4(x);
               *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ld_bf16 + col) = pk;
-              if (MODE == EM_DGELU) { csum.x += x.x; csum.y += x.y; csum.z += x.z; csum.w += x.w; }  // fp32, before rounding
+              if (is_dgelu(MODE)) { csum.x += x.x; csum.y += x.y; csum.z += x.z; csum.w += x.w; }  // fp32, before rounding
             }
           }
         }
       }
     }
-    if (MODE == EM_DGELU && ep.colsum_out) {
+    if (is_dgelu(MODE) && ep.colsum_out) {
       // lanes that differ only in `sub` hold the same four columns (different rows): fold them, then one vector
       // reduction per 4 columns and 32-row slab
 #pragma unroll
@@ -372,7 +396,7 @@ ECAMP_DEVINL void epilogue_warp(const EpiArgs& ea, uint32_t taddr, int m0, int n
 #pragma unroll
       for (int i = 0; i < kSteps; ++i) pcur[i] = pnext[i];
     }
-    if (MODE == EM_DGELU) {
+    if (is_dgelu(MODE)) {
 #pragma unroll
       for (int i = 0; i < kSteps; ++i) {
         pcur[i].x = pcur[i].z; pcur[i].y = pcur[i].w;    // chunk c + 1 becomes current
@@ -430,6 +454,8 @@ ECAMP_DEVINL void epilogue_dispatch(const EpiArgs& ea, uint32_t tmem_base, int q
     ECAMP_EPI_CASE(EM_BF16)
     ECAMP_EPI_CASE(EM_GELU)
     ECAMP_EPI_CASE(EM_DGELU)
+    ECAMP_EPI_CASE(EM_GELU_G)
+    ECAMP_EPI_CASE(EM_DGELU_G)
     ECAMP_EPI_CASE(EM_F32)
     ECAMP_EPI_CASE(EM_F32_RES)
     ECAMP_EPI_CASE(EM_F32_RES_DROP)
@@ -974,10 +1000,12 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
     else if (ep.flags == 0 && !ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_BF16;
     else if (ep.flags == GEMM_GELU && ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_GELU;
     else if (ep.flags == GEMM_DGELU && !ep.bias && !ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_DGELU;
+    else if (ep.flags == (GEMM_GELU | GEMM_AUX_GRAD) && ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_GELU_G;
+    else if (ep.flags == (GEMM_DGELU | GEMM_AUX_GRAD) && !ep.bias && !ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_DGELU_G;
     else if (ep.flags == 0 && !ep.aux_out && !ep.residual && only_f32) ea.mode = EM_F32;
     else if (ep.flags == 0 && !ep.aux_out && ep.residual && only_f32) ea.mode = EM_F32_RES;
     else if (ep.flags == GEMM_DROPOUT && !ep.aux_out && ep.residual && only_f32) ea.mode = EM_F32_RES_DROP;
-    if (ep.colsum_out && ea.mode != EM_DGELU) ea.mode = EM_GENERIC;  // only the dGELU mode folds the column sums in
+    if (ep.colsum_out && !is_dgelu(ea.mode)) ea.mode = EM_GENERIC;  // only the dGELU mode folds the column sums in
     if (ep.row_scale && ea.mode != EM_F32_RES) ea.mode = EM_GENERIC;
   }
   if (g_force_generic_epilogue) ea.mode = EM_GENERIC;

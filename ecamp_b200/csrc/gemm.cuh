@@ -8,6 +8,8 @@ enum GemmFlags : int {
   GEMM_GELU = 1,     // v = gelu(bf16(v)); the rounded pre-activation is stored to aux_out (bf16) if given
   GEMM_DGELU = 2,    // v *= gelu'(aux_in[m, n])   (aux_in = bf16 pre-activation saved by the forward)
   GEMM_DROPOUT = 4,  // v = keep(m, n) ? v / (1 - p) : 0   (Philox keyed by seed / stream / m * N + n)
+  GEMM_AUX_GRAD = 8,  // with GEMM_GELU: aux_out receives bf16(gelu'(pre-activation)) instead of the pre-activation;
+                      // with GEMM_DGELU: aux_in IS that stored derivative (v *= aux_in)
 };
 
 struct GemmEpilogue {

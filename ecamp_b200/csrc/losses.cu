@@ -440,6 +440,7 @@ __global__ void __launch_bounds__(256) pred_grad_kernel(const float* __restrict_
   if (d_u) {
     // stage the (34 x 34) x 3 neighbourhood of this patch of d_u (zero outside the image: those taps have weight 0)
     const int Y0 = 2 * hy * PATCH - 1, X0 = 2 * wx * PATCH - 1;
+#ifdef ECAMP_NEXT  // candidate (not yet verified on the GPU): row-wise staging
     // one warp per (channel, row) of the neighbourhood, lanes along x: no per-element index arithmetic, and a row is two
     // coalesced requests (32 + 2 floats)
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -456,6 +457,13 @@ __global__ void __launch_bounds__(256) pred_grad_kernel(const float* __restrict_
         dst[32 + lane] = (yin && X2 < BIG) ? src[X2] : 0.f;
       }
     }
+#else
+    for (int i = threadIdx.x; i < 3 * RW * RW; i += blockDim.x) {
+      const int c = i / (RW * RW), rem = i % (RW * RW), yy = rem / RW, xx = rem % RW;
+      const int Y = Y0 + yy, X = X0 + xx;
+      sdu[i] = (Y >= 0 && Y < BIG && X >= 0 && X < BIG) ? d_u[(((size_t)b * 3 + c) * BIG + Y) * BIG + X] : 0.f;
+    }
+#endif
     __syncthreads();
   }
   for (int e = threadIdx.x; e < PD; e += blockDim.x) {

@@ -413,6 +413,13 @@ const void* ctx_debug_ptr(Ctx* c, const char* name) {
 // building blocks
 // =============================================================================================
 namespace {
+// fc1 stores GELU'(pre-activation) for the backward pass instead of the pre-activation itself (the dGELU epilogue of the
+// fc2 dgrad is instruction-bound: 39 -> 23 instructions per element); -DECAMP_NEXT turns it on
+#ifdef ECAMP_NEXT  // candidate: becomes the default once the A/B on the GPU confirms it
+constexpr int kAuxGrad = GEMM_AUX_GRAD;
+#else
+constexpr int kAuxGrad = 0;
+#endif
 #define RC(expr)          \
   do {                    \
     int _rc = (expr);     \
@@ -469,7 +476,7 @@ int vit_block_fwd(Ctx* c, VitStack& s, int l, float* x_next) {
   RC(lin_fwd(c, a.ao, D, M, c->W(pb + 4), D, D, ep));
   RC(layernorm_fwd(a.x_mid, c->P(pb + 6), c->P(pb + 7), 1e-6f, M, D, a.ln2, nullptr, a.mean2, a.rstd2, c->st));
   GemmEpilogue e1;
-  e1.bias = c->P(pb + 9); e1.flags = GEMM_GELU; e1.aux_out = a.pre; e1.ld_aux = s.hid; e1.out_bf16 = a.act; e1.ld_bf16 = s.hid;
+  e1.bias = c->P(pb + 9); e1.flags = GEMM_GELU | kAuxGrad; e1.aux_out = a.pre; e1.ld_aux = s.hid; e1.out_bf16 = a.act; e1.ld_bf16 = s.hid;
   RC(lin_fwd(c, a.ln2, D, M, c->W(pb + 8), s.hid, D, e1));
   GemmEpilogue e2;
   e2.bias = c->P(pb + 11); e2.residual = a.x_mid; e2.ld_res = D; e2.out_f32 = x_next; e2.ld_f32 = D;
@@ -484,7 +491,7 @@ int vit_block_bwd(Ctx* c, VitStack& s, int l) {
   // fc2
   RC(lin_wgrad(c, c->gX, D, a.act, s.hid, M, D, s.hid, c->Gp(pb + 10), nullptr, acc));  // bias: by the producer of gX
   GemmEpilogue e2;
-  e2.flags = GEMM_DGELU; e2.aux_in = a.pre; e2.ld_aux = s.hid; e2.out_bf16 = c->dA; e2.ld_bf16 = s.hid;
+  e2.flags = GEMM_DGELU | kAuxGrad; e2.aux_in = a.pre; e2.ld_aux = s.hid; e2.out_bf16 = c->dA; e2.ld_bf16 = s.hid;
   e2.colsum_out = c->Gp(pb + 9);  // fc1 bias gradient = column sums of dA
   RC(lin_dgrad(c, c->gX, D, M, c->W(pb + 10), D, s.hid, e2));
   // fc1
@@ -562,7 +569,7 @@ int bert_attn_half_bwd(Ctx* c, BertAct& a, int pb, unsigned long long site) {
 int bert_ffn_half_fwd(Ctx* c, BertAct& a, int pi, const bf16* x, const float* x_f32, unsigned long long site) {
   const int Mt = c->sh.B * c->sh.T;
   GemmEpilogue e1;
-  e1.bias = c->P(pi + 1); e1.flags = GEMM_GELU; e1.aux_out = a.pre; e1.ld_aux = BHID; e1.out_bf16 = a.act; e1.ld_bf16 = BHID;
+  e1.bias = c->P(pi + 1); e1.flags = GEMM_GELU | kAuxGrad; e1.aux_out = a.pre; e1.ld_aux = BHID; e1.out_bf16 = a.act; e1.ld_bf16 = BHID;
   RC(lin_fwd(c, x, 768, Mt, c->W(pi), BHID, 768, e1));
   GemmEpilogue e2;
   e2.bias = c->P(pi + 3); e2.residual = x_f32; e2.ld_res = 768; e2.out_f32 = a.s2; e2.ld_f32 = 768;
@@ -578,7 +585,7 @@ int bert_ffn_half_bwd(Ctx* c, BertAct& a, int pi, const bf16* x, unsigned long l
                    c->Gp(pi + 4), c->Gp(pi + 5), c->Gp(pi + 3) /* output.dense bias */, 1, c->st));
   RC(lin_wgrad(c, c->gX, 768, a.act, BHID, Mt, 768, BHID, c->Gp(pi + 2), nullptr, acc));
   GemmEpilogue e2;
-  e2.flags = GEMM_DGELU; e2.aux_in = a.pre; e2.ld_aux = BHID; e2.out_bf16 = c->dA; e2.ld_bf16 = BHID;
+  e2.flags = GEMM_DGELU | kAuxGrad; e2.aux_in = a.pre; e2.ld_aux = BHID; e2.out_bf16 = c->dA; e2.ld_bf16 = BHID;
   e2.colsum_out = c->Gp(pi + 1);  // intermediate.dense bias gradient
   RC(lin_dgrad(c, c->gX, 768, Mt, c->W(pi + 2), 768, BHID, e2));
   RC(lin_wgrad(c, c->dA, BHID, x, 768, Mt, BHID, 768, c->Gp(pi), nullptr, acc));

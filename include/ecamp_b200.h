@@ -52,7 +52,9 @@ ECAMP_API int64_t ecamp_launch_count(void);
 enum {
   ECAMP_GEMM_GELU = 1,    /* v = gelu(bf16(v)), rounded pre-activation stored to aux_out          */
   ECAMP_GEMM_DGELU = 2,   /* v *= gelu'(aux_in[m, n])                                              */
-  ECAMP_GEMM_DROPOUT = 4  /* inverted dropout with a Philox mask keyed by (seed, site, m * N + n)  */
+  ECAMP_GEMM_DROPOUT = 4, /* inverted dropout with a Philox mask keyed by (seed, site, m * N + n)  */
+  ECAMP_GEMM_AUX_GRAD = 8 /* with GELU: aux_out = bf16(gelu'(pre-activation)); with DGELU: v *= aux_in (that
+                           * stored derivative) - what the step runtime uses for fc1 / fc2                  */
 };
 typedef struct ecamp_epilogue {
   const float* bias;     /* [N] or NULL                                   */

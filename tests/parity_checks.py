@@ -158,6 +158,13 @@ def check_gemm():
     cs = torch.full((N,), 3.0, device=dev)
     L.gemm(a, b, aux_in=pre, out_bf16=o16, flags=L.GEMM_DGELU, colsum_out=cs)
     e_dgelu = rel(o16.float(), lin * x.grad); e_cs = rel(cs - 3.0, (lin * x.grad).sum(0))
+    # GEMM_AUX_GRAD: the forward stores bf16(gelu'(pre-activation)), the dGELU epilogue multiplies by it (what the step uses)
+    gsto = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    L.gemm(a, b, bias=bias, aux_out=gsto, out_bf16=o16, flags=L.GEMM_GELU | L.GEMM_AUX_GRAD)
+    e_gelu_g = rel(o16.float(), F.gelu(pre_ref.float())); e_gsto = rel(gsto.float(), x.grad)
+    cs3 = torch.full((N,), 3.0, device=dev)
+    L.gemm(a, b, aux_in=gsto, out_bf16=o16, flags=L.GEMM_DGELU | L.GEMM_AUX_GRAD, colsum_out=cs3)
+    e_dgelu_g = rel(o16.float(), lin * gsto.float()); e_cs3 = rel(cs3 - 3.0, (lin * gsto.float()).sum(0))
     L.gemm(a, b, bias=bias, out_f32=o32)
     e_f32 = rel(o32, lin + bias)
     L.gemm(a, b, bias=bias, residual=res, out_f32=o32)
@@ -180,8 +187,8 @@ def check_gemm():
     e_gen = rel(o32, F.gelu(pre_ref.float()) + res); e_gcs = rel(cs2, o16.float().sum(0))
     report("gemm_epilogues", e_bf16 < 4e-3 and e_gelu < 6e-3 and e_pre < 4e-3 and e_dgelu < 6e-3 and e_cs < 2e-3 and e_f32 < 1e-5 and
            e_res < 1e-5 and abs(frac - 0.1) < 0.01 and e_drop < 1e-5 and same_mask and e_tile < 1e-6 and e_acc < 1e-5 and
-           e_gen < 2e-3 and e_gcs < 2e-3,
-           bf16=e_bf16, gelu=e_gelu, pre=e_pre, dgelu=e_dgelu, colsum=e_cs, f32=e_f32, residual=e_res, drop_frac=frac,
+           e_gen < 2e-3 and e_gcs < 2e-3 and e_gelu_g < 6e-3 and e_gsto < 4e-3 and e_dgelu_g < 4e-3 and e_cs3 < 2e-3,
+           gelu_auxgrad=e_gelu_g, stored_grad=e_gsto, dgelu_auxgrad=e_dgelu_g, colsum_auxgrad=e_cs3, bf16=e_bf16, gelu=e_gelu, pre=e_pre, dgelu=e_dgelu, colsum=e_cs, f32=e_f32, residual=e_res, drop_frac=frac,
            dropout=e_drop, dropout_mask_tiling_invariant=same_mask, dropout_tiling_rel=e_tile, accumulate=e_acc, generic=e_gen, generic_colsum=e_gcs)
 
 

@@ -55,3 +55,14 @@ def test_bucketed_allreduce_gloo_world2():
     edges = [n, 9000, 7001, 7000, 4242, 1000, 17, 0]
     ranges = [(lo, hi) for hi, lo in zip(edges, edges[1:])]
     mp.spawn(_worker, args=(2, port, n, ranges), nprocs=2, join=True)
+
+
+def test_numa_binding_is_a_noop_without_topology():
+    """bind_host_to_gpu must never fail or shrink the affinity to nothing when the GPU / sysfs topology is unavailable."""
+    import os
+    from ecamp_b200.synthetic import bind_host_to_gpu
+    before = os.sched_getaffinity(0)
+    r = bind_host_to_gpu(0)
+    after = os.sched_getaffinity(0)
+    assert (r is None and after == before) or (set(r) == after and after <= before and len(after) > 0)
+    os.sched_setaffinity(0, before)
