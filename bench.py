@@ -126,9 +126,9 @@ def gemm_roofline(B, T, peak_tflops):
         if kind in ("bf16", "gelu", "res", "res_drop", "f32"):
             kw["bias"] = torch.zeros(n, device=dev)
         if kind == "gelu":
-            kw["aux_out"] = torch.empty(rows, n, dtype=torch.bfloat16, device=dev); kw["flags"] = L.GEMM_GELU
+            kw["aux_out"] = torch.empty(rows, n, dtype=torch.bfloat16, device=dev); kw["flags"] = L.GEMM_GELU | L.GEMM_AUX_GRAD
         if kind == "dgelu":
-            kw["aux_in"] = torch.randn(rows, n, device=dev).to(torch.bfloat16); kw["flags"] = L.GEMM_DGELU
+            kw["aux_in"] = torch.randn(rows, n, device=dev).to(torch.bfloat16); kw["flags"] = L.GEMM_DGELU | L.GEMM_AUX_GRAD
             kw["colsum_out"] = torch.zeros(n, device=dev); kw.pop("bias", None)
         if kind in ("res", "res_drop"):
             kw["residual"] = torch.randn(rows, n, device=dev)
@@ -238,6 +238,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="pairs per GPU (BASELINE config 2: 256)")
     ap.add_argument("--seq", type=int, default=128)
+    ap.add_argument("--e2e-input", default="f32", choices=["f32", "u8"],
+                    help="host image format of the e2e arm: f32 = the reference collate's normalised [B,3,448,448] tensor "
+                         "(617 MB per step); u8 = the loader's 8-bit grayscale crop [B,448,448], normalised on the GPU")
     ap.add_argument("--no-extras", action="store_true", help="skip the roofline micro-timing and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -307,6 +310,12 @@ def main():
 
     # ---- arm 2: end to end through the public API, pinned-host inputs copied every step, losses read every step ----
     del resident
+    if args.e2e_input == "u8":
+        os.sched_setaffinity(0, numa_cpus or affinity)
+        host = [make_batch(args.batch, T=args.seq, big=True, seed=1234 + 17 * rank + i, pin=True, u8=True) for i in range(2)]
+        os.sched_setaffinity(0, affinity)
+        for hb in host:
+            hb.pop("noise")
     copy_stream = torch.cuda.Stream()
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     for i in range(2):
@@ -348,6 +357,9 @@ def main():
                                seq_len=args.seq, image_px="448 -> 224", mask_ratio=0.75, parallelism=f"dp{world}",
                                optimizer="fused AdamW lr 1.5e-4 betas (0.9,0.95) wd 0.05", weights="random init (reference initialize_weights)",
                                l2="per-step working set (~16 GB of activations) is far larger than the 126 MB L2; two input batches alternate",
+                               e2e_input=("reference collate format: normalised fp32 [B,3,448,448]" if args.e2e_input == "f32" else
+                                          "loader's 8-bit grayscale crop [B,448,448]; Grayscale(3)+ToTensor+Normalize on the GPU "
+                                          "(bit-exact with the CPU transform)"),
                                e2e_pipeline="per timed step: one H2D copy of a full pinned batch on a copy stream (prefetching the "
                                             "next step's inputs while this step runs) and one D2H read of the 3 losses, which the "
                                             "host consumes one step late so that it never stalls the launch queue",

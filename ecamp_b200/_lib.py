@@ -80,7 +80,7 @@ SYMBOLS = [
     "ecamp_backward_stage_count", "ecamp_backward_stage_range", "ecamp_backward", "ecamp_adamw_step",
     "ecamp_debug_buffer", "ecamp_cls_workspace_bytes", "ecamp_cls_set_workspace", "ecamp_cls_forward", "ecamp_cls_backward",
     "ecamp_sgd_table_bytes", "ecamp_sgd_chunk_bytes", "ecamp_sgd_build_tables", "ecamp_grad_sumsq", "ecamp_sgd_momentum_step",
-    "ecamp_attention_probs", "ecamp_cross_attention_probs",
+    "ecamp_attention_probs", "ecamp_cross_attention_probs", "ecamp_image_u8_normalize",
 ]
 
 _lib = None

@@ -78,6 +78,10 @@ int ecamp_random_masking(const float* noise, int32_t B, int32_t L, int32_t len_k
   return random_masking(noise, B, L, len_keep, r32, r32 + (size_t)B * L, mask, ids_restore, ids_keep, S(stream));
 }
 
+int ecamp_image_u8_normalize(const uint8_t* gray, int64_t n_images, int64_t pixels_per_image, float mean, float std_,
+                             float* out, void* stream) {
+  return image_u8_normalize(gray, n_images, pixels_per_image, mean, std_, out, S(stream));
+}
 int ecamp_resize_patchify(const float* big, int32_t B, int32_t side_in, float* tgt, void* stream) {
   ECAMP_REQUIRE(big && tgt, "ecamp_resize_patchify: null argument");
   if (side_in == 224) return patchify224(big, B, tgt, S(stream));

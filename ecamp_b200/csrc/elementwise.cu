@@ -721,4 +721,56 @@ int permute_pe_weight_grad(const float* dw_pqc, float* grad_cpq, int accumulate,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tail of the image loader on the GPU: Grayscale(3) + ToTensor + Normalize of pretrain_datasets.py:47-52 applied to the
+// loader's 8-bit grayscale crop, so that a step ships 1 byte per pixel over PCIe instead of 12 (3 identical fp32
+// channels: 617 MB per 256-pair batch, which can take longer than the step itself).  Bit-exact with the CPU transform:
+// ToTensor is u8 -> fp32 divided by 255 (correctly rounded division), Normalize is (x - mean) / std in fp32 - the
+// same three IEEE operations, no FMA contraction, no approximate division.  HBM-bound: 1 B read + 12 B written / pixel.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) u8_gray_normalize_kernel(const uint8_t* __restrict__ in, long long pixels_per_image,
+                                                                long long n_images, float mean, float stdv,
+                                                                float* __restrict__ out) {
+  const long long groups_per_image = pixels_per_image / 16;  // 16 pixels per thread (host checks divisibility)
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= groups_per_image * n_images) return;
+  const long long img = gid / groups_per_image, grp = gid - img * groups_per_image;
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + img * pixels_per_image) + grp);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float f[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const float x = __fdiv_rn((float)((w[k] >> (8 * b)) & 0xffu), 255.0f);  // ToTensor
+      f[b] = __fdiv_rn(__fsub_rn(x, mean), stdv);                                // Normalize
+    }
+    v[k] = make_float4(f[0], f[1], f[2], f[3]);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float4* dst = reinterpret_cast<float4*>(out + (img * 3 + c) * pixels_per_image) + grp * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = v[k];
+  }
+}
+}  // namespace
+
+int image_u8_normalize(const uint8_t* gray, long long n_images, long long pixels_per_image, float mean, float stdv,
+                       float* out, cudaStream_t st) {
+  ECAMP_REQUIRE(gray && out, "image_u8_normalize: null pointer");
+  ECAMP_REQUIRE(n_images > 0 && pixels_per_image > 0 && pixels_per_image % 16 == 0,
+                "image_u8_normalize: pixels per image must be a positive multiple of 16 (got %lld)", pixels_per_image);
+  ECAMP_REQUIRE((reinterpret_cast<uintptr_t>(gray) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "image_u8_normalize: buffers must be 16-byte aligned");
+  ECAMP_REQUIRE(stdv != 0.f, "image_u8_normalize: std must not be zero");
+  const long long groups = n_images * (pixels_per_image / 16);
+  u8_gray_normalize_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(gray, pixels_per_image, n_images, mean, stdv, out);
+  ECAMP_CUDA_OK(cudaGetLastError());
+  ECAMP_LAUNCHED();
+  return 0;
+}
+
 }  // namespace ecamp

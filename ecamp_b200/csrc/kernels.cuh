@@ -108,6 +108,10 @@ int attention_bwd(const AttnArgs& a, cudaStream_t st);
 // probs[B, H, Sq, Sk] fp32 = exp(scale * q . k - lse), masked keys 0 (needs the lse of a preceding attention_fwd)
 int attention_probs(const AttnArgs& a, float* probs, cudaStream_t st);
 
+// Grayscale(3) + ToTensor + Normalize of the loader's 8-bit crop on the GPU: out[n, c, :] = (gray[n, :] / 255 - mean) / std
+int image_u8_normalize(const uint8_t* gray, long long n_images, long long pixels_per_image, float mean, float stdv, float* out,
+                       cudaStream_t st);
+
 // ---- losses.cu --------------------------------------------------------------------------------
 // mim = sum_{masked patches} (pred - tgt)^2 / (B*3*224*224)       (model_ecamp.py:288-297)
 int mim_loss_fwd(const float* pred, int ld_pred_rows, const float* tgt, const float* mask, int B, int L, int PD,

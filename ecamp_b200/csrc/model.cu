@@ -414,11 +414,11 @@ const void* ctx_debug_ptr(Ctx* c, const char* name) {
 // =============================================================================================
 namespace {
 // fc1 stores GELU'(pre-activation) for the backward pass instead of the pre-activation itself (the dGELU epilogue of the
-// fc2 dgrad is instruction-bound: 39 -> 23 instructions per element); -DECAMP_NEXT turns it on
-#ifdef ECAMP_NEXT  // candidate: becomes the default once the A/B on the GPU confirms it
-constexpr int kAuxGrad = GEMM_AUX_GRAD;
-#else
+// fc2 dgrad is instruction-bound: 39 -> 23 instructions per element); -DECAMP_NO_AUX_GRAD builds the old behaviour
+#ifdef ECAMP_NO_AUX_GRAD
 constexpr int kAuxGrad = 0;
+#else
+constexpr int kAuxGrad = GEMM_AUX_GRAD;  // same-box A/B: ~0.4 ms of the 42 ms step
 #endif
 #define RC(expr)          \
   do {                    \

@@ -205,6 +205,7 @@ class ECAMP(nn.Module):
         self.dropout = float(dropout)       # bert_config.py:71-72 (hidden and attention-prob dropout)
         self.initialize_weights()
         # runtime state (not part of the state_dict)
+        self.image_mean, self.image_std = 0.4721, 0.3037   # transforms.Normalize of pretrain_datasets.py:52 (uint8 inputs)
         self._rt = None
         self._n_bound = 0
         self._dropout_step = 0
@@ -331,11 +332,23 @@ class ECAMP(nn.Module):
         B, T = ids.shape
         keep = int(196 * (1 - mask_ratio))  # model_ecamp.py:175, python double arithmetic
         side = 448 if has_big else 224
+        f32, i64 = torch.float32, torch.int64
+        if image.dtype == torch.uint8:
+            # the loader's 8-bit grayscale crop, [B, side, side] or [B, 1, side, side]: Grayscale(3) + ToTensor + Normalize
+            # (pretrain_datasets.py:49-52) run on the GPU, bit-exact with the CPU transform - 1 byte per pixel over PCIe
+            if tuple(image.shape) not in ((B, side, side), (B, 1, side, side)):
+                raise ValueError(f"ecamp_b200: expected a uint8 image of shape {(B, side, side)} or {(B, 1, side, side)}, "
+                                 f"got {tuple(image.shape)}")
+            gray = self._dev(image, torch.uint8, device)
+            img = torch.empty(B, 3, side, side, dtype=f32, device=device)
+            L.check(L.lib().ecamp_image_u8_normalize(L.ptr(gray), ctypes.c_int64(B), ctypes.c_int64(side * side),
+                                                     ctypes.c_float(self.image_mean), ctypes.c_float(self.image_std),
+                                                     L.ptr(img), L.cur_stream()), "ecamp_image_u8_normalize")
+            image = img
         if tuple(image.shape) != (B, 3, side, side):
             raise ValueError(f"ecamp_b200: expected image of shape {(B, 3, side, side)}, got {tuple(image.shape)}")
         if not (0 < keep <= 196) or T > MAXPOS:
             raise ValueError(f"ecamp_b200: unsupported mask_ratio {mask_ratio} / sequence length {T}")
-        f32, i64 = torch.float32, torch.int64
         t = dict(image=self._dev(image, f32, device), ids=self._dev(ids, i64, device), labels=self._dev(labels, i64, device),
                  attention_mask=self._dev(attention_mask, i64, device))
         t["type_ids"] = self._dev(type_ids, i64, device) if type_ids is not None else torch.zeros_like(t["ids"])

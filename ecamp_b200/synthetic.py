@@ -31,10 +31,15 @@ def bind_host_to_gpu(device_index=0):
         return None
 
 
-def make_batch(B, T=128, big=True, seed=1234, pin=False):
+def make_batch(B, T=128, big=True, seed=1234, pin=False, u8=False):
+    """u8=True: `image` is the loader's 8-bit grayscale crop [B, side, side] (the module applies Grayscale(3) + ToTensor +
+    Normalize on the GPU); otherwise the normalised fp32 [B, 3, side, side] tensor the reference's collate produces."""
     g = torch.Generator().manual_seed(seed)
     side = 448 if big else 224
-    img = torch.randn(B, 1, side, side, generator=g).expand(B, 3, side, side).contiguous()  # Grayscale(3) + Normalize
+    if u8:
+        img = torch.randint(0, 256, (B, side, side), generator=g, dtype=torch.uint8)
+    else:
+        img = torch.randn(B, 1, side, side, generator=g).expand(B, 3, side, side).contiguous()  # Grayscale(3) + Normalize
     length = torch.randint(T // 4, T + 1, (B,), generator=g)
     pos = torch.arange(T).unsqueeze(0)
     attn = (pos < length.unsqueeze(1)).long()

@@ -89,6 +89,11 @@ ECAMP_API int ecamp_random_masking(const float* noise, int32_t B, int32_t L, int
 
 /* bicubic 448 -> 224 of torchvision Resize (module/model_ecamp.py:318), result in patch layout
  * tgt[b, l, (p*16+q)*3+c] == patchify(resized) with p = 16. */
+/* Tail of the image transform of module/pretrain_datasets.py:47-52 on the GPU: Grayscale(3) + ToTensor + Normalize of the
+ * loader's 8-bit grayscale crop, out[n, c, :] = (gray[n, :] / 255 - mean) / std for c = 0..2, bit-exact with the CPU
+ * transform.  A step then copies 1 byte per pixel to the device instead of 12.  pixels_per_image % 16 == 0. */
+ECAMP_API int ecamp_image_u8_normalize(const uint8_t* gray, int64_t n_images, int64_t pixels_per_image, float mean,
+                                       float std_, float* out /* [n_images, 3, pixels_per_image] */, void* stream);
 ECAMP_API int ecamp_resize_patchify(const float* big, int32_t B, int32_t side_in, float* tgt, void* stream);
 
 /* LayerNorm forward / backward (fp32 in, bf16 and/or fp32 out). */

@@ -565,6 +565,38 @@ def check_adamw():
 
 
 @guard
+def check_image_u8():
+    """GPU tail of the image transform (pretrain_datasets.py:49-52): Grayscale(3) + ToTensor + Normalize of the 8-bit crop.
+    Bit-exact against the CPU formula torchvision applies (u8 -> fp32 / 255, then (x - mean) / std in fp32), and the module
+    gives bit-identical losses for the uint8 batch and for the fp32 batch the CPU transform would have produced."""
+    torch.manual_seed(11)
+    gray = torch.randint(0, 256, (3, 448, 448), dtype=torch.uint8)
+    gray[0, 0, :256] = torch.arange(256, dtype=torch.uint8)          # every code value at least once
+    mean, std = torch.tensor(0.4721, dtype=torch.float32), torch.tensor(0.3037, dtype=torch.float32)
+    ref = gray.to(torch.float32).div(255).sub(mean).div(std)            # ToTensor + Normalize on the CPU
+    ref3 = ref[:, None].expand(3, 3, 448, 448).contiguous()
+    g = gray.to(dev)
+    out = torch.full((3, 3, 448, 448), float("nan"), device=dev)
+    L.check(lib.ecamp_image_u8_normalize(L.ptr(g), ctypes.c_int64(3), ctypes.c_int64(448 * 448), ctypes.c_float(0.4721),
+                                         ctypes.c_float(0.3037), L.ptr(out), L.cur_stream()), "image_u8_normalize")
+    report("image_u8_normalize_bit_exact", bool(torch.equal(out.cpu(), ref3)), max_abs=(out.cpu() - ref3).abs().max().item())
+    rc = lib.ecamp_image_u8_normalize(L.ptr(g), ctypes.c_int64(3), ctypes.c_int64(17), ctypes.c_float(0.4721), ctypes.c_float(0.3037),
+                                      L.ptr(out), L.cur_stream())
+    report("image_u8_normalize_rejects_ragged", rc < 0)
+    orc, m = build_pair(0)
+    m.eval()
+    b = synthetic_batch(2, T=32, seed=3, device=dev)
+    g2 = torch.randint(0, 256, (2, 448, 448), dtype=torch.uint8)
+    b32 = dict(b); b32["image"] = g2.to(torch.float32).div(255).sub(mean).div(std)[:, None].expand(2, 3, 448, 448).contiguous().to(dev)
+    b8 = dict(b); b8["image"] = g2            # stays on the CPU: the module moves it (1 byte per pixel)
+    with torch.no_grad():
+        l32 = torch.stack(list(m(b32))); l8 = torch.stack(list(m(b8)))
+        b8["image"] = g2[:, None].to(dev)
+        l8b = torch.stack(list(m(b8)))
+    report("image_u8_forward_identical", bool(torch.equal(l32, l8)) and bool(torch.equal(l32, l8b)), f32=l32.tolist(), u8=l8.tolist())
+
+
+@guard
 def check_attention_map():
     """Cross-attention probabilities for the heat-map tool (Visualization/module/context_fusion.py:45-57).
     (1) operator: ecamp_attention_probs after ecamp_attention_fwd vs softmax(q k^T / sqrt(d) + mask) in fp32 on the same
@@ -661,7 +693,7 @@ def check_sgd():
            and sd["param_groups"][1]["lr"] == 0.3)
 
 
-ALL_CHECKS = (check_sgd, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
+ALL_CHECKS = (check_sgd, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
 
 
 def run_check(fn):
