@@ -310,42 +310,56 @@ def main():
 
     # ---- arm 2: end to end through the public API, pinned-host inputs copied every step, losses read every step ----
     del resident
-    if args.e2e_input == "u8":
-        os.sched_setaffinity(0, numa_cpus or affinity)
-        host = [make_batch(args.batch, T=args.seq, big=True, seed=1234 + 17 * rank + i, pin=True, u8=True) for i in range(2)]
-        os.sched_setaffinity(0, affinity)
-        for hb in host:
-            hb.pop("noise")
     copy_stream = torch.cuda.Stream()
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    for i in range(2):
-        dp.step(to_device(host[i % 2], dev))
-    barrier()
-    pinned_out = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
-    read_ev = [torch.cuda.Event() for _ in range(2)]
-    host_losses = []
-    nxt = to_device(host[0], dev, copy_stream)                         # pipeline fill (a loader's first prefetch)
-    s.record()
-    for i in range(args.steps):
-        torch.cuda.current_stream().wait_stream(copy_stream)
-        cur_batch = nxt
-        for v in cur_batch.values():
-            v.record_stream(torch.cuda.current_stream())
-        nxt = to_device(host[(i + 1) % 2], dev, copy_stream)          # prefetch the next step's inputs: exactly one
+
+    def run_e2e(host):
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+        for i in range(2):
+            dp.step(to_device(host[i % 2], dev))
+        barrier()
+        pinned_out = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+        read_ev = [torch.cuda.Event() for _ in range(2)]
+        host_losses = []
+        nxt = to_device(host[0], dev, copy_stream)                     # pipeline fill (a loader's first prefetch)
+        s.record()
+        for i in range(args.steps):
+            torch.cuda.current_stream().wait_stream(copy_stream)
+            cur_batch = nxt
+            for v in cur_batch.values():
+                v.record_stream(torch.cuda.current_stream())
+            nxt = to_device(host[(i + 1) % 2], dev, copy_stream)      # prefetch the next step's inputs: exactly one
                                                                        # H2D copy of a full batch per timed step
-        losses = dp.step(cur_batch)
-        pinned_out[i % 2].copy_(losses, non_blocking=True)
-        read_ev[i % 2].record()
-        if i > 0:                                                      # the host reads step i-1's result while step i runs
-            read_ev[(i - 1) % 2].synchronize()
-            host_losses.append(pinned_out[(i - 1) % 2].tolist())
-    read_ev[(args.steps - 1) % 2].synchronize()
-    host_losses.append(pinned_out[(args.steps - 1) % 2].tolist())
-    assert len(host_losses) == args.steps
-    e.record()
-    barrier()
-    ms_e2e = max_over_ranks(s.elapsed_time(e))
-    e2e_value = world * args.batch * args.steps / (ms_e2e * 1e-3)
+            losses = dp.step(cur_batch)
+            pinned_out[i % 2].copy_(losses, non_blocking=True)
+            read_ev[i % 2].record()
+            if i > 0:                                                  # the host reads step i-1's result while step i runs
+                read_ev[(i - 1) % 2].synchronize()
+                host_losses.append(pinned_out[(i - 1) % 2].tolist())
+        read_ev[(args.steps - 1) % 2].synchronize()
+        host_losses.append(pinned_out[(args.steps - 1) % 2].tolist())
+        assert len(host_losses) == args.steps
+        e.record()
+        barrier()
+        ms_ = max_over_ranks(s.elapsed_time(e))
+        return dict(value=round(world * args.batch * args.steps / (ms_ * 1e-3), 2), unit="pairs/s", h2d_bytes_per_step=int(h2d),
+                    d2h_bytes_per_step=12, ms_per_step=round(ms_ / args.steps, 3))
+
+    def u8_batches():
+        os.sched_setaffinity(0, numa_cpus or affinity)
+        hb = [make_batch(args.batch, T=args.seq, big=True, seed=1234 + 17 * rank + i, pin=True, u8=True) for i in range(2)]
+        os.sched_setaffinity(0, affinity)
+        for b_ in hb:
+            b_.pop("noise")
+        return hb
+
+    # headline: the reference collate's format (normalised fp32 [B,3,448,448]) unless --e2e-input u8; the other format is
+    # measured right after it and reported next to it
+    e2e_main = run_e2e(host if args.e2e_input == "f32" else u8_batches())
+    e2e_other = run_e2e(u8_batches() if args.e2e_input == "f32" else host)
+    e2e_f32, e2e_u8 = (e2e_main, e2e_other) if args.e2e_input == "f32" else (e2e_other, e2e_main)
+    e2e_u8["input"] = ("loader's 8-bit grayscale crop [B,448,448]; Grayscale(3)+ToTensor+Normalize run on the GPU, bit-exact with the "
+                       "CPU transform (tests/parity_checks.py::check_image_u8)")
+    e2e_f32["input"] = "reference collate format: normalised fp32 [B,3,448,448]"
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -357,18 +371,15 @@ def main():
                                seq_len=args.seq, image_px="448 -> 224", mask_ratio=0.75, parallelism=f"dp{world}",
                                optimizer="fused AdamW lr 1.5e-4 betas (0.9,0.95) wd 0.05", weights="random init (reference initialize_weights)",
                                l2="per-step working set (~16 GB of activations) is far larger than the 126 MB L2; two input batches alternate",
-                               e2e_input=("reference collate format: normalised fp32 [B,3,448,448]" if args.e2e_input == "f32" else
-                                          "loader's 8-bit grayscale crop [B,448,448]; Grayscale(3)+ToTensor+Normalize on the GPU "
-                                          "(bit-exact with the CPU transform)"),
+                               e2e_input=e2e_main["input"],
                                e2e_pipeline="per timed step: one H2D copy of a full pinned batch on a copy stream (prefetching the "
                                             "next step's inputs while this step runs) and one D2H read of the 3 losses, which the "
                                             "host consumes one step late so that it never stalls the launch queue",
                                host_buffers=("pinned, first-touched on the GPU's NUMA node (%d CPUs)" % len(numa_cpus)) if numa_cpus
                                else "pinned (NUMA topology unknown or single node)"),
                    clocks=clocks, gpu_launches=int(launches),
-                   e2e=dict(value=round(e2e_value, 2), unit="pairs/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=12,
-                            ms_per_step=round(ms_e2e / args.steps, 3)),
-                   losses_last_step=last_losses)
+                   e2e={k: v for k, v in e2e_main.items() if k != "input"},
+                   e2e_u8_input=e2e_u8, e2e_f32_input=e2e_f32, losses_last_step=last_losses)
         if gf:
             tf = value / world * gf / 1e3
             out["step_tflops_per_gpu"] = round(tf, 1)
