@@ -386,7 +386,7 @@ def main():
             out["step_frac_of_bf16_peak"] = dict(burst=round(tf / pk["bf16_tflops"], 4), sustained=round(tf / pk["bf16_tflops_sustained"], 4),
                                                  peaks=pk_kind, gflop_per_pair=gf)
         if not args.no_extras:
-            del nxt, cur_batch
+            del host
             torch.cuda.empty_cache()
             try:
                 out["roofline"] = gemm_roofline(args.batch, args.seq, pk["bf16_tflops"])
