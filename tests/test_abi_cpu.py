@@ -115,3 +115,26 @@ def test_released_checkpoint_key_spelling(built_lib):
     buf.seek(0)
     ck = torch.load(buf, map_location="cpu")
     assert ck["epoch"] == 3 and not dst.load_state_dict(ck["model"]).missing_keys
+
+
+def test_host_side_helpers_without_gpu(built_lib):
+    """Host logic that must behave without a GPU: synthetic uint8 batches, FusedSGD argument checks and its refusal of
+    CPU tensors (no CPU path), the GEMM flag constants of the header."""
+    from ecamp_b200.synthetic import make_batch
+    from ecamp_b200.optim import FusedSGD
+    b = make_batch(2, T=16, big=True, seed=3, u8=True)
+    assert b["image"].dtype == torch.uint8 and tuple(b["image"].shape) == (2, 448, 448)
+    assert tuple(make_batch(2, T=16, big=False, seed=3)["image"].shape) == (2, 3, 224, 224)
+    p = torch.nn.Parameter(torch.zeros(4))
+    with pytest.raises(ValueError):
+        FusedSGD([p], lr=-1.0)
+    opt = FusedSGD([p], lr=0.1, momentum=0.9, max_grad_norm=1.0)
+    assert isinstance(opt, torch.optim.Optimizer) and opt.param_groups[0]["momentum"] == 0.9
+    opt.step()                                  # no gradients yet: nothing to do, nothing touched
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()
+    hdr = open(os.path.join(ROOT, "include", "ecamp_b200.h")).read()
+    for name, val in (("ECAMP_GEMM_GELU", built_lib.GEMM_GELU), ("ECAMP_GEMM_DGELU", built_lib.GEMM_DGELU),
+                      ("ECAMP_GEMM_DROPOUT", built_lib.GEMM_DROPOUT), ("ECAMP_GEMM_AUX_GRAD", built_lib.GEMM_AUX_GRAD)):
+        assert f"{name} = {val}" in hdr, name
