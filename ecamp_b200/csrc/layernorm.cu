@@ -3,6 +3,8 @@
 // (model_ecamp.py:66-69,80-84) and every HF BertSelfOutput / BertOutput / BertEmbeddings LayerNorm.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace ecamp {
 namespace {
 
@@ -178,7 +180,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 6) ln_bwd_kernel(const float* 
 
 int bwd_blocks(int M) {
   const int need = (M + kBwdWarps - 1) / kBwdWarps;
-  return need < kBwdBlocks ? need : kBwdBlocks;
+  static const int cap = getenv("ECAMP_LN_BWD_BLOCKS") ? atoi(getenv("ECAMP_LN_BWD_BLOCKS")) : kBwdBlocks;  // tuning knob
+  return need < cap ? need : cap;
 }
 
 template <int NV, bool COLSUM>
