@@ -8,7 +8,9 @@ per-GPU batch 256 synthetic pairs (448-px radiograph -> in-model bicubic 224 px 
     python bench.py --impl reference ...      # the reference's CPU path (oracle port), reported baseline
 
 Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = the same through the public
-module API with pinned-host inputs copied every step and the losses read back every step.
+module API with pinned-host inputs copied every step and the losses read back every step (the reference collate's fp32
+image batch by default; `e2e_u8_input` = the same with the loader's 8-bit crops normalised on the GPU, `e2e_f32_input`
+repeats the headline with its input format spelled out).
 """
 import argparse
 import json
