@@ -16,6 +16,7 @@ views still attached accumulates, otherwise it overwrites.  bert.pooler.* never 
 (its output is dead code in the reference: bert_modeling.py:144).
 """
 import ctypes
+import os
 import math
 from functools import partial
 
@@ -209,7 +210,7 @@ class ECAMP(nn.Module):
         self._rt = None
         self._n_bound = 0
         self._dropout_step = 0
-        self.ce_rows = 2048
+        self.ce_rows = int(os.environ.get("ECAMP_CE_ROWS", "2048"))   # rows per vocabulary-head chunk (tuning knob)
 
     # ---- model_ecamp.py:105-137 -------------------------------------------------------------------
     def initialize_weights(self):
