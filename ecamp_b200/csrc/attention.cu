@@ -401,8 +401,10 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
   const uint32_t c1kn = frag_base_kn<LDS>(sC1, lane), c2kn = frag_base_kn<LDS>(sC2, lane);
   // One block of CB columns.  ALL: every 16-column group lies below cend - no per-group tests, first k-step from the
   // zero register; NOBIAS (dQ pass): every key of the block is attendable - no mask bias either.
-  auto col_block = [&](const int cb, auto all_tag, auto nobias_tag) {
-    constexpr bool ALL = decltype(all_tag)::value, NOBIAS = decltype(nobias_tag)::value;
+  // FUSED (dQ problem with a single column block, e.g. the encoder's 50 keys): the delta step and the dS step share one
+  // evaluation of S, dP and the exponentials - they stay in registers across the row reduction.
+  auto col_block = [&](const int cb, auto all_tag, auto nobias_tag, auto fused_tag) {
+    constexpr bool ALL = decltype(all_tag)::value, NOBIAS = decltype(nobias_tag)::value, FUSED = decltype(fused_tag)::value;
     float s[NT][4], dp[NT][4];
     if (!ALL) {
 #pragma unroll
@@ -471,7 +473,11 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
               dpe = keep ? dpe * keep_scale : 0.f;
               pd = keep ? p * keep_scale : 0.f;
             }
-            if (!TR && pass == 0) {
+            if (FUSED) {
+              dsum[r] = fmaf(p, dpe, dsum[r]);
+              s[j][e] = p;
+              dp[j][e] = dpe;
+            } else if (!TR && pass == 0) {
               dsum[r] = fmaf(p, dpe, dsum[r]);
             } else {
               s[j][e] = (p * a.scale) * (dpe - (TR ? cd[cc] : row_b[r]));  // dS
@@ -481,7 +487,26 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
         }
       }
     }
-    if (pass == 0) return;
+    if (FUSED) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        row_b[r] = quad_sum(dsum[r]);
+        const int row = row_g + r * 8;
+        if (t4 == 0 && row < Sr) a.delta[bh * a.Sq + row] = row_b[r];
+      }
+#pragma unroll
+      for (int jp = 0; jp < NT / 2; ++jp) {
+        if (ALL || cb + jp * 16 < cend) {
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              s[2 * jp + jj][e] = (s[2 * jp + jj][e] * a.scale) * (dp[2 * jp + jj][e] - row_b[e >> 1]);  // dS
+        }
+      }
+    } else if (pass == 0) {
+      return;
+    }
     // out1 += dS . C1 ; (TR) out2 += Pdrop . C2
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
@@ -512,13 +537,21 @@ ECAMP_DEVINL bool attn_bwd_compute(const AttnArgs& a, const bf16* sR1, const bf1
       }
     }
   };
+  if constexpr (!TR) {
+    if (cend <= CB) {  // a single column block: one fused evaluation instead of two passes
+      if (cend == CB && cfull >= CB) col_block(0, std::true_type{}, std::true_type{}, std::true_type{});
+      else if (cend == CB) col_block(0, std::true_type{}, std::false_type{}, std::true_type{});
+      else col_block(0, std::false_type{}, std::false_type{}, std::true_type{});
+      break;
+    }
+  }
   {
     const int call = cend & ~(CB - 1);                          // whole blocks
     const int cfast = TR ? call : min(call, cfull & ~(CB - 1));  // whole blocks that need no test at all
     int cb = 0;
-    for (; cb < cfast; cb += CB) col_block(cb, std::true_type{}, std::true_type{});
-    for (; cb < call; cb += CB) col_block(cb, std::true_type{}, std::false_type{});
-    for (; cb < cend; cb += CB) col_block(cb, std::false_type{}, std::false_type{});
+    for (; cb < cfast; cb += CB) col_block(cb, std::true_type{}, std::true_type{}, std::false_type{});
+    for (; cb < call; cb += CB) col_block(cb, std::true_type{}, std::false_type{}, std::false_type{});
+    for (; cb < cend; cb += CB) col_block(cb, std::false_type{}, std::false_type{}, std::false_type{});
   }
     if (pass == 0) {
 #pragma unroll
