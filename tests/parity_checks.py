@@ -565,6 +565,33 @@ def check_adamw():
 
 
 @guard
+def check_full_size_batch_split():
+    """Size-independent property at BASELINE config 2's FULL size (B = 256, T = 128, 448-px input), where the oracle is too
+    slow to run: every operation of the step is per-sample and the three losses are means with fixed denominators
+    (SURVEY §8e), so the losses of the full batch equal the mean of the losses of its two halves, and the gradients the
+    mean of the halves' gradients - the identity data parallelism rests on.  Tolerances: losses 1e-5 relative (fp32 sums
+    in a different order); all gradients concatenated 5e-3 relative L2 (bf16 GEMMs, split-K chosen per problem size and
+    fp32 atomics: the same bound as fused_equals_autograd)."""
+    from ecamp_b200.synthetic import make_batch
+    torch.manual_seed(0)
+    m = ecamp().to(dev).eval()
+    b = {k: v.to(dev) for k, v in make_batch(256, T=128, big=True, seed=9).items()}
+    m.zero_grad(set_to_none=True)
+    l_full = m.forward_backward(b).clone()
+    g_full = m.flat_grads().clone()
+    l_sum = torch.zeros_like(l_full); g_sum = torch.zeros_like(g_full)
+    for i in range(2):
+        h = {k: v[128 * i:128 * (i + 1)].contiguous() for k, v in b.items()}
+        m.zero_grad(set_to_none=True)
+        l_sum += m.forward_backward(h)
+        g_sum += m.flat_grads()
+    torch.cuda.synchronize()
+    el, eg = rel(l_sum / 2, l_full), rel(g_sum / 2, g_full)
+    fin = bool(torch.isfinite(g_full).all()) and g_full.norm().item() > 0
+    report("full_size_batch_split", fin and el < 1e-5 and eg < 5e-3, losses_rel=el, grads_rel=eg, losses=l_full.tolist())
+
+
+@guard
 def check_image_u8():
     """GPU tail of the image transform (pretrain_datasets.py:49-52): Grayscale(3) + ToTensor + Normalize of the 8-bit crop.
     Bit-exact against the CPU formula torchvision applies (u8 -> fp32 / 255, then (x - mean) / std in fp32), and the module
@@ -693,7 +720,7 @@ def check_sgd():
            and sd["param_groups"][1]["lr"] == 0.3)
 
 
-ALL_CHECKS = (check_sgd, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
+ALL_CHECKS = (check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
 
 
 def run_check(fn):
