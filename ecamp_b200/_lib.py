@@ -81,6 +81,7 @@ SYMBOLS = [
     "ecamp_debug_buffer", "ecamp_cls_workspace_bytes", "ecamp_cls_set_workspace", "ecamp_cls_forward", "ecamp_cls_backward",
     "ecamp_sgd_table_bytes", "ecamp_sgd_chunk_bytes", "ecamp_sgd_build_tables", "ecamp_grad_sumsq", "ecamp_sgd_momentum_step",
     "ecamp_attention_probs", "ecamp_cross_attention_probs", "ecamp_image_u8_normalize",
+    "ecamp_text_mask_draw_count", "ecamp_text_context_mask", "ecamp_text_template_weights", "ecamp_text_mask_and_weights",
 ]
 
 _lib = None

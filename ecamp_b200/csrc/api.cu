@@ -234,6 +234,30 @@ int ecamp_cls_backward(ecamp_ctx* ctx, const ecamp_cls_io* io, int32_t accumulat
   return ctx_cls_backward(ctx->impl, to_cls(io), accumulate, S(stream));
 }
 
+// ---- host-side report masking (HOST pointers) ---------------------------------------------------------------------------
+int32_t ecamp_text_mask_draw_count(const int64_t* ids, int32_t T, const uint8_t* is_sub, const uint8_t* is_entity, int32_t vocab) {
+  if (!ids || !is_sub || !is_entity || T < 2) return -1;
+  return text_mask_draw_count(reinterpret_cast<const long long*>(ids), T, is_sub, is_entity, vocab);
+}
+int ecamp_text_context_mask(const int64_t* ids, int32_t T, const uint8_t* is_sub, const uint8_t* is_entity, int32_t vocab,
+                            const double* draws, int32_t n_draws, int64_t* masked, int32_t* mask_pos, int32_t* n_mask_pos) {
+  return text_context_mask(reinterpret_cast<const long long*>(ids), T, is_sub, is_entity, vocab, draws, n_draws,
+                           reinterpret_cast<long long*>(masked), mask_pos, n_mask_pos);
+}
+int ecamp_text_template_weights(const int64_t* ids, int32_t n_ids, const int32_t* mask_pos, int32_t n_mask_pos, int32_t max_len,
+                                float* weights) {
+  return text_template_weights(reinterpret_cast<const long long*>(ids), n_ids, mask_pos, n_mask_pos, max_len, weights);
+}
+
+int ecamp_text_mask_and_weights(const int64_t* ids, int32_t T, const uint8_t* is_sub, const uint8_t* is_entity, int32_t vocab,
+                                const double* draws, int32_t n_draws, int64_t* masked, float* weights, int32_t* mask_pos,
+                                int32_t* n_mask_pos) {
+  ECAMP_REQUIRE(weights, "ecamp_text_mask_and_weights: null weights");
+  int rc = ecamp_text_context_mask(ids, T, is_sub, is_entity, vocab, draws, n_draws, masked, mask_pos, n_mask_pos);
+  if (rc) return rc;
+  return ecamp_text_template_weights(ids, T, mask_pos, *n_mask_pos, T, weights);
+}
+
 // ---- fused SGD-momentum + grad-norm clip ----------------------------------------------------------------------
 static_assert(sizeof(ecamp_sgd_tensor) == sizeof(SgdTensor), "ecamp_sgd_tensor layout");
 int64_t ecamp_sgd_table_bytes(int32_t n) { return (int64_t)sgd_table_bytes(n); }

@@ -153,6 +153,12 @@ int refresh_shadows(const void* dev_table, const void* dev_chunks, long long n_c
 size_t adamw_table_bytes(int n);
 size_t adamw_chunk_bytes(const AdamTensor* host, int n);
 
+// ---- text_host.cu: host-side report masking / re-weighting (pretrain_datasets.py:60-110,141-184), no CUDA ----------
+int text_mask_draw_count(const long long* ids, int T, const uint8_t* is_sub, const uint8_t* is_entity, int vocab);
+int text_context_mask(const long long* ids, int T, const uint8_t* is_sub, const uint8_t* is_entity, int vocab,
+                      const double* draws, int n_draws, long long* masked, int* mask_pos, int* n_mask_pos);
+int text_template_weights(const long long* ids, int n_ids, const int* mask_pos, int n_mask_pos, int max_len, float* w);
+
 // ---- sgd.cu: fused SGD-momentum + global grad-norm clip (fine-tune trainer) ---------------------
 struct SgdTensor {  // mirrors ecamp_sgd_tensor
   float* p;

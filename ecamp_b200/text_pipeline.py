@@ -29,6 +29,9 @@ class VocabTables:
 
     def __init__(self, is_sub, is_entity):
         self.is_sub, self.is_entity = is_sub, is_entity
+        # byte tables for the native path (converted once, not per report)
+        self.sub_u8 = np.ascontiguousarray(is_sub, dtype=np.uint8)
+        self.entity_u8 = np.ascontiguousarray(is_entity, dtype=np.uint8)
 
     @classmethod
     def from_vocab(cls, vocab):
@@ -146,6 +149,47 @@ def template_weights(ids, mask_pos, max_len):
     return w
 
 
+# ---- native (C, no CUDA) versions of the two per-token loops: csrc/text_host.cu through the C ABI -----------------------
+def _native():
+    import ctypes
+    from . import _lib as L
+    return ctypes, L
+
+
+def context_mask_native(ids, tables, rng=_random):
+    """`context_mask` in native code.  The draws are taken from `rng` here - exactly as many as the reference consumes
+    (a function of the tokens alone) - and handed to the library, so the generator ends at the same position."""
+    ctypes, L = _native()
+    lib = L.lib()
+    a = np.ascontiguousarray(ids, dtype=np.int64)
+    T = int(a.shape[0])
+    sub, ent = tables.sub_u8, tables.entity_u8
+    vocab = int(min(sub.shape[0], ent.shape[0]))
+    pp = lambda x, t: x.ctypes.data_as(ctypes.POINTER(t))
+    n = lib.ecamp_text_mask_draw_count(pp(a, ctypes.c_int64), T, pp(sub, ctypes.c_uint8), pp(ent, ctypes.c_uint8), vocab)
+    if n < 0:
+        raise ValueError("context_mask_native: bad arguments")
+    draws = np.array([rng.random() for _ in range(n)], dtype=np.float64)
+    masked = np.empty(T, dtype=np.int64)
+    mask_pos = np.empty(max(T, 1), dtype=np.int32)
+    cnt = ctypes.c_int32(0)
+    L.check(lib.ecamp_text_context_mask(pp(a, ctypes.c_int64), T, pp(sub, ctypes.c_uint8), pp(ent, ctypes.c_uint8), vocab,
+                                        pp(draws, ctypes.c_double), n, pp(masked, ctypes.c_int64), pp(mask_pos, ctypes.c_int32),
+                                        ctypes.byref(cnt)), "ecamp_text_context_mask")
+    return masked.tolist(), mask_pos[:cnt.value].tolist()
+
+
+def template_weights_native(ids, mask_pos, max_len):
+    ctypes, L = _native()
+    a = np.ascontiguousarray(ids, dtype=np.int64)
+    mp = np.ascontiguousarray(mask_pos, dtype=np.int32)
+    w = np.empty(max_len, dtype=np.float32)
+    pp = lambda x, t: x.ctypes.data_as(ctypes.POINTER(t))
+    L.check(L.lib().ecamp_text_template_weights(pp(a, ctypes.c_int64), int(a.shape[0]), pp(mp, ctypes.c_int32), int(mp.shape[0]),
+                                                int(max_len), pp(w, ctypes.c_float)), "ecamp_text_template_weights")
+    return w
+
+
 class ReportTextPipeline:
     """tokenizer (the reference's mimic_wordpiece.json, loaded with `tokenizers`) + the three steps above."""
 
@@ -164,3 +208,50 @@ class ReportTextPipeline:
         return dict(labels=np.asarray(ids, dtype=np.int64), ids=np.asarray(masked, dtype=np.int64),
                     attention_mask=np.asarray(enc.attention_mask, dtype=np.int64), type_ids=np.asarray(enc.type_ids, dtype=np.int64),
                     weights=template_weights(ids, mask_pos, self.max_len), mask_pos=mask_pos)
+
+
+class NativeTextMasker:
+    """`context_mask` + `template_weights` of one padded report in ONE native call (table pointers and output buffers are
+    set up once; a report costs one ids conversion, the pre-drawn random numbers and two ctypes calls)."""
+
+    def __init__(self, tables, max_len):
+        ctypes, L = _native()
+        self._ct, self._L, self._lib = ctypes, L, L.lib()
+        self.tables, self.T = tables, int(max_len)
+        self._vocab = int(min(tables.sub_u8.shape[0], tables.entity_u8.shape[0]))
+        vp, i32 = ctypes.c_void_p, ctypes.c_int32
+        self._lib.ecamp_text_mask_draw_count.argtypes = [vp, i32, vp, vp, i32]
+        self._lib.ecamp_text_mask_and_weights.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, vp, vp, vp]
+        self._sub, self._ent = tables.sub_u8.ctypes.data, tables.entity_u8.ctypes.data
+        self._mask_pos = np.empty(self.T, dtype=np.int32)
+        self._cnt = ctypes.c_int32(0)
+        self._cnt_p = ctypes.addressof(self._cnt)
+
+    def __call__(self, ids, rng=_random):
+        a = np.ascontiguousarray(ids, dtype=np.int64)
+        if a.shape[0] != self.T:
+            raise ValueError(f"NativeTextMasker: expected {self.T} padded ids, got {a.shape[0]}")
+        n = self._lib.ecamp_text_mask_draw_count(a.ctypes.data, self.T, self._sub, self._ent, self._vocab)
+        if n < 0:
+            raise ValueError("NativeTextMasker: bad arguments")
+        draws = np.array([rng.random() for _ in range(n)], dtype=np.float64)
+        masked = np.empty(self.T, dtype=np.int64)
+        weights = np.empty(self.T, dtype=np.float32)
+        self._L.check(self._lib.ecamp_text_mask_and_weights(a.ctypes.data, self.T, self._sub, self._ent, self._vocab, draws.ctypes.data, n,
+                                                            masked.ctypes.data, weights.ctypes.data, self._mask_pos.ctypes.data,
+                                                            self._cnt_p), "ecamp_text_mask_and_weights")
+        return a, masked, weights, self._mask_pos[:self._cnt.value].tolist()
+
+
+class NativeReportTextPipeline(ReportTextPipeline):
+    """Same outputs, same `random` stream position; the masking and re-weighting loops run in the native library."""
+
+    def __init__(self, tokenizer_json, max_caption_length=256):
+        super().__init__(tokenizer_json, max_caption_length)
+        self.masker = NativeTextMasker(self.tables, max_caption_length)
+
+    def __call__(self, report, llm_output, rng=_random):
+        enc = self.tokenizer.encode(splice_report(report, llm_output, rng))
+        labels, masked, weights, mask_pos = self.masker(enc.ids, rng)
+        return dict(labels=labels, ids=masked, attention_mask=np.asarray(enc.attention_mask, dtype=np.int64),
+                    type_ids=np.asarray(enc.type_ids, dtype=np.int64), weights=weights, mask_pos=mask_pos)

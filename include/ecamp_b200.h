@@ -244,6 +244,24 @@ ECAMP_API int ecamp_cls_set_workspace(ecamp_ctx* ctx, void* ws, int64_t bytes, i
 ECAMP_API int ecamp_cls_forward(ecamp_ctx* ctx, const ecamp_cls_io* io, void* stream);
 ECAMP_API int ecamp_cls_backward(ecamp_ctx* ctx, const ecamp_cls_io* io, int32_t accumulate, void* stream);
 
+/* ---- host-side report masking and loss re-weighting (HOST pointers, no CUDA) ----
+ * Native form of `ContextBertDataset._context_mask` and of the template re-weighting in `__getitem__`
+ * (ECAMP/Pre-training/module/pretrain_datasets.py:60-110, 141-184): same decisions in the same order.  The random numbers are
+ * passed in pre-drawn: draw exactly ecamp_text_mask_draw_count(...) values with `random.random()` and Python's generator
+ * ends where the reference leaves it.  is_sub[v] / is_entity[v]: word piece v starts with "##" / is one of the 44 entity
+ * words (:17-22).  mask_pos must hold T entries.  Bit-exact against tests/golden/text_masking.json. */
+ECAMP_API int32_t ecamp_text_mask_draw_count(const int64_t* ids, int32_t T, const uint8_t* is_sub, const uint8_t* is_entity,
+                                             int32_t vocab);
+ECAMP_API int ecamp_text_context_mask(const int64_t* ids, int32_t T, const uint8_t* is_sub, const uint8_t* is_entity,
+                                      int32_t vocab, const double* draws, int32_t n_draws, int64_t* masked,
+                                      int32_t* mask_pos, int32_t* n_mask_pos);
+ECAMP_API int ecamp_text_template_weights(const int64_t* ids, int32_t n_ids, const int32_t* mask_pos, int32_t n_mask_pos,
+                                          int32_t max_len, float* weights);
+/* both steps of one padded report (T = max_caption_length) in one call: masked[T], weights[T], mask_pos[T] */
+ECAMP_API int ecamp_text_mask_and_weights(const int64_t* ids, int32_t T, const uint8_t* is_sub, const uint8_t* is_entity,
+                                          int32_t vocab, const double* draws, int32_t n_draws, int64_t* masked,
+                                          float* weights, int32_t* mask_pos, int32_t* n_mask_pos);
+
 /* ---- fused SGD-momentum + global gradient-norm clip (fine-tune trainer) ----
  * Replaces `torch.nn.utils.clip_grad_norm_(model.parameters(), args.max_grad_norm)` followed by
  * `torch.optim.SGD(model.parameters(), lr, momentum=0.9, weight_decay=wd).step()`
