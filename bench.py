@@ -174,6 +174,150 @@ def gemm_roofline(B, T, peak_tflops):
                 flops_per_step=tot_flops, gemm_ms_per_step=round(tot_ms, 3), launches_per_step=launches, shapes=per_shape)
 
 
+
+def _timed_steps(step, steps, warmup):
+    """CUDA-event timing of `steps` calls of step(i) after `warmup` untimed calls; returns ms per step."""
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(steps):
+        step(i)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / steps
+
+
+def _frac(pairs_per_s, gflop_per_unit, pk):
+    tf = pairs_per_s * gflop_per_unit / 1e3
+    return dict(tflops=round(tf, 1), frac_of_bf16_burst_peak=round(tf / pk["bf16_tflops"], 4),
+                frac_of_bf16_sustained_peak=round(tf / pk["bf16_tflops_sustained"], 4))
+
+
+def dropin_path(model, batches, B, T, pk, steps=10):
+    """The reference trainer's call sequence on the drop-in module (main_pretrain.py:139-153): model(batch) under
+    autocast -> loss.backward() (staged autograd nodes, ordinary .grad tensors) -> torch.optim.AdamW.step() -> zero_grad.
+    Device-resident inputs; the vocabulary head is evaluated in forward AND recomputed in backward on this path."""
+    decay = [p for n, p in model.named_parameters() if p.requires_grad and not (p.dim() == 1 or n.endswith(".bias"))]
+    no_decay = [p for n, p in model.named_parameters() if p.requires_grad and (p.dim() == 1 or n.endswith(".bias"))]
+    opt = torch.optim.AdamW([dict(params=no_decay, weight_decay=0.0), dict(params=decay, weight_decay=0.05)], lr=1.5e-4, betas=(0.9, 0.95))
+    model.zero_grad(set_to_none=True)
+
+    def step(i):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            mim, res, mlm = model(batches[i % 2])
+            (mim + res + mlm).backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    ms = _timed_steps(step, steps, 3)
+    v = B / (ms * 1e-3)
+    del opt
+    model.zero_grad(set_to_none=True)
+    return dict(value=round(v, 1), unit="pairs/s", ms_per_step=round(ms, 3), steps=steps,
+                what="model(batch) + loss.backward() + torch.optim.AdamW.step() through the reference API", **_frac(v, GFLOP_PER_PAIR_STEP[T], pk))
+
+
+def gpu_eager_baseline(batches, B, T, pk, steps=5):
+    """The reference's own PyTorch path ON THIS GPU: the oracle restatement (plain torch modules,
+    cuBLAS / torch kernels) under bf16 autocast + torch.optim.AdamW, same batch size and inputs.  A reported baseline."""
+    from oracle.ecamp_oracle import ecamp_oracle
+    torch.manual_seed(0)
+    dev = batches[0]["image"].device
+    m = ecamp_oracle(dropout=0.1).to(dev).train()
+    decay = [p for n, p in m.named_parameters() if p.requires_grad and not (p.dim() == 1 or n.endswith(".bias"))]
+    no_decay = [p for n, p in m.named_parameters() if p.requires_grad and (p.dim() == 1 or n.endswith(".bias"))]
+    opt = torch.optim.AdamW([dict(params=no_decay, weight_decay=0.0), dict(params=decay, weight_decay=0.05)], lr=1.5e-4, betas=(0.9, 0.95))
+
+    def step(i):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            mim, res, mlm = m(batches[i % 2])
+            loss = mim + res + mlm
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    ms = _timed_steps(step, steps, 2)
+    v = B / (ms * 1e-3)
+    del m, opt
+    torch.cuda.empty_cache()
+    return dict(value=round(v, 1), unit="pairs/s", ms_per_step=round(ms, 3), steps=steps, kind="port",
+                what="oracle (plain torch modules) under bf16 autocast + torch.optim.AdamW on the same B200, same batch", **_frac(v, GFLOP_PER_PAIR_STEP[T], pk))
+
+
+def config4_quick(dp, model, B, pk, steps=10):
+    """BASELINE config 4's per-GPU shape: 448-px input, 256-token reports (the reference default), SR branch."""
+    from ecamp_b200.synthetic import make_batch
+    dev = next(model.parameters()).device
+    bs = [{k: v.to(dev) for k, v in make_batch(B, T=256, big=True, seed=4000 + i).items()} for i in range(2)]
+    for b_ in bs:
+        b_.pop("noise")
+    ms = _timed_steps(lambda i: dp.step(bs[i % 2]), steps, 3)
+    v = B / (ms * 1e-3)
+    return dict(value=round(v, 1), unit="pairs/s", ms_per_step=round(ms, 3), steps=steps, per_gpu_batch=B, seq_len=256,
+                what="config 4 shape on one GPU: fwd + bwd + fused AdamW, T = 256", **_frac(v, GFLOP_PER_PAIR_STEP[256], pk))
+
+
+def config5_quick(pk, B=512, steps=10):
+    """BASELINE config 5: fine-tune ViT-B/16, 14 classes, batch 512, 224 px: fwd + BCE + bwd + clip + SGD-momentum."""
+    from ecamp_b200.models_vit import vit_base_patch16
+    from ecamp_b200.optim import FusedSGD
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(0)
+    m = vit_base_patch16(num_classes=14, drop_path_rate=0.1, global_pool=True).to(dev).train()
+    xs = [torch.randn(B, 3, 224, 224, device=dev) for _ in range(2)]
+    ys = [(torch.rand(B, 14, device=dev) < 0.3).float() for _ in range(2)]
+    loss_fct = torch.nn.BCEWithLogitsLoss()
+    opt = FusedSGD(m.parameters(), lr=3e-3, momentum=0.9, weight_decay=0.0, max_grad_norm=1.0)
+
+    def step(i):
+        m.zero_grad(set_to_none=True)
+        loss_fct(m(xs[i % 2]), ys[i % 2]).backward()
+        opt.step()
+
+    ms = _timed_steps(step, steps, 3)
+    v = B / (ms * 1e-3)
+    del m, opt, xs
+    torch.cuda.empty_cache()
+    return dict(value=round(v, 1), unit="images/s", ms_per_step=round(ms, 3), steps=steps, batch=B,
+                what="config 5: ViT-B/16 14-class fine-tune step through ecamp_b200.models_vit + FusedSGD", **_frac(v, 105.38, pk))
+
+
+def multi_rank_checks(model, opt, dp, world, rank, dev, seq):
+    """N > 1, after the timed loops: (1) replicas bit-identical (parameters + Adam moments vs rank 0); (2) gradient of
+    the data-parallel step on per-rank slices of one batch == gradient of the whole batch on one GPU."""
+    import torch.distributed as dist
+    from ecamp_b200.synthetic import make_batch
+    rt = model._rt
+    vec = torch.cat([torch.cat([p.detach().flatten() for p in rt["params"]]), rt["M1"], rt["M2"]])
+    ref = vec.clone()
+    dist.broadcast(ref, src=0)
+    d = (ref - vec).abs().max().reshape(1)
+    dist.all_reduce(d, op=dist.ReduceOp.MAX)
+    out = dict(replicas_identical=bool(d.item() == 0.0), max_abs_replica_diff=float(d.item()))
+    del vec, ref
+    per = 8
+    full = {k: v.to(dev) for k, v in make_batch(per * world, T=seq, big=True, seed=777).items()}
+    mine = {k: v[per * rank:per * (rank + 1)].contiguous() for k, v in full.items()}
+    model.eval()
+    for g in opt.param_groups:
+        g["lr"] = 0.0
+    model.zero_grad(set_to_none=True)
+    dp.step(mine)                      # bucketed all-reduce overlapped with the staged backward; lr = 0: no update
+    g_dp = model.flat_grads() / world
+    g_dp = g_dp.clone()
+    model.zero_grad(set_to_none=True)
+    model.forward_backward(full)       # every rank: the whole batch on its own GPU, no communication
+    g_full = model.flat_grads()
+    r = ((g_dp.double() - g_full.double()).norm() / g_full.double().norm()).reshape(1).float()
+    dist.all_reduce(r, op=dist.ReduceOp.MAX)
+    out["dp_grad_rel"] = float(r.item())
+    out["dp_grad_what"] = f"{per} pairs per rank through DataParallelStep vs the same {per * world} pairs on one GPU, rel-L2 over all gradients, max over ranks"
+    model.train()
+    return out
+
+
 def cpu_baseline(T):
     """The reference's CPU path (oracle port) on config 1: batch 8, fp32, forward + three losses."""
     from oracle.ecamp_oracle import ecamp_oracle, synthetic_batch
@@ -235,7 +379,7 @@ def workload_name(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=80, help="timed steps (default: >= 3 s of timed region at ~40 ms per step)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="pairs per GPU (BASELINE config 2: 256)")
@@ -363,6 +507,12 @@ def main():
                        "CPU transform (tests/parity_checks.py::check_image_u8)")
     e2e_f32["input"] = "reference collate format: normalised fp32 [B,3,448,448]"
 
+    mr = None
+    if world > 1 and not args.no_extras:
+        try:
+            mr = multi_rank_checks(model, opt, dp, world, rank, dev, args.seq)
+        except Exception as ex:  # noqa
+            mr = dict(error=str(ex)[:300])
     if rank == 0:
         pk, pk_kind = peaks()
         gf = GFLOP_PER_PAIR_STEP.get(args.seq)
@@ -387,6 +537,21 @@ def main():
             out["step_tflops_per_gpu"] = round(tf, 1)
             out["step_frac_of_bf16_peak"] = dict(burst=round(tf / pk["bf16_tflops"], 4), sustained=round(tf / pk["bf16_tflops_sustained"], 4),
                                                  peaks=pk_kind, gflop_per_pair=gf)
+        if mr is not None:
+            out["multi_rank_checks"] = mr
+        if not args.no_extras and world == 1 and args.seq in GFLOP_PER_PAIR_STEP:
+            # outside the timed headline: the reference-API path, the eager-torch baseline on this GPU, configs 4 and 5
+            res2 = [to_device(hb, dev) for hb in host]
+            for name, fn in (("dropin_path", lambda: dropin_path(model, res2, args.batch, args.seq, pk)),
+                             ("gpu_eager_baseline", lambda: gpu_eager_baseline(res2, args.batch, args.seq, pk)),
+                             ("config4", lambda: config4_quick(dp, model, args.batch, pk)),
+                             ("config5", lambda: config5_quick(pk))):
+                try:
+                    out[name] = fn()
+                except Exception as ex:  # noqa
+                    out[name] = dict(error=str(ex)[:300])
+                torch.cuda.empty_cache()
+            del res2
         if not args.no_extras:
             del host
             torch.cuda.empty_cache()

@@ -9,11 +9,13 @@ Every FLOP of forward and backward is executed by libecamp_b200.so (hand-written
 through the C ABI in include/ecamp_b200.h; there is no CPU / PyTorch fallback — without the library
 or without a CUDA device `forward` raises.
 
-Gradient contract: backward writes parameter gradients into ONE flat fp32 buffer and exposes them as
-`p.grad` views (so GradScaler.unscale_, clip_grad_norm_, torch.optim.AdamW, checkpointing all work
-unchanged).  `zero_grad(set_to_none=True)` or `False` are both honoured: a backward that finds the
-views still attached accumulates, otherwise it overwrites.  bert.pooler.* never receives a gradient
-(its output is dead code in the reference: bert_modeling.py:144).
+Gradient contract.  Autograd path (`loss.backward()`, what the reference trainer and DistributedDataParallel use):
+the native backward runs as a chain of per-stage autograd nodes; each stage returns the slices of ONE flat fp32
+gradient buffer it has just finished as the gradients of its parameters, so `.grad` are ordinary tensors filled by
+AccumulateGrad stage by stage (gradient accumulation, GradScaler.unscale_, clip_grad_norm_, torch.optim.AdamW, DDP
+hooks all work unchanged).  Fused path (`forward_backward`, used by ecamp_b200.parallel / FusedAdamW): `.grad` are
+views of the flat buffer; a backward that finds the views still attached accumulates, otherwise it overwrites.
+bert.pooler.* never receives a gradient (its output is dead code in the reference: bert_modeling.py:144).
 """
 import ctypes
 import os
@@ -152,20 +154,44 @@ def _bert_masked_lm():
 
 
 # --------------------------------------------------------------------------------------------------
-class _Step(torch.autograd.Function):
-    """Autograd node of the whole step.  Parameter gradients are written straight into the flat gradient
-    buffer (exposed as p.grad views), so no gradient tensors are returned to autograd."""
+class _StageNode(torch.autograd.Function):
+    """ONE backward stage of the native schedule as an autograd node (ecamp_backward_stage_range: LM head, BERT layers
+    5..0, fusion + embeddings, decoder head, decoder blocks, ..., encoder blocks 11..0, patch embed).  The nodes are
+    chained through a dummy token in REVERSE stage order, so autograd runs stage 0 first; every node returns the slices of
+    the flat gradient buffer that its stage has just made final as the gradients of its parameters.  AccumulateGrad
+    (and with it the hooks of a stock DistributedDataParallel wrapper, main_pretrain.py:249) therefore fires stage by
+    stage while later stages still run: gradient accumulation, GradScaler.unscale_, clip_grad_norm_, torch.optim.AdamW
+    and DDP's bucketed all-reduce all see ordinary `.grad` tensors (hard part 2)."""
 
     @staticmethod
-    def forward(ctx, model, handle, *params):
-        ctx.model = model
+    def forward(ctx, model, handle, stage, token, *params):
+        ctx.model, ctx.handle, ctx.stage = model, handle, stage
+        return torch.empty((), dtype=torch.float32, device=token.device)   # value never read: ordering only
+
+    @staticmethod
+    def backward(ctx, gtoken):
+        views = ctx.model._backward_stage(ctx.handle, ctx.stage)
+        need = ctx.needs_input_grad[4:]
+        return (None, None, None, gtoken) + tuple(v if n else None for v, n in zip(views, need))
+
+
+class _LossNode(torch.autograd.Function):
+    """Head of the chain: hands out the three losses; its backward records the upstream gradients (3 floats)."""
+
+    @staticmethod
+    def forward(ctx, handle, token):
         ctx.handle = handle
         return handle["losses"].clone()
 
     @staticmethod
     def backward(ctx, g):
-        ctx.model._backward(ctx.handle, g)
-        return (None, None) + (None,) * ctx.model._n_bound
+        h = ctx.handle
+        if h.get("consumed"):
+            raise RuntimeError("ecamp_b200: backward() called twice on the same forward (retain_graph is not supported)")
+        h["consumed"] = True
+        h["g"] = g.detach().to(torch.float32).contiguous()
+        h["acc"] = 0   # the flat buffer is overwritten; accumulation over micro-steps happens in AccumulateGrad
+        return None, torch.empty((), dtype=torch.float32, device=g.device)
 
 
 class ECAMP(nn.Module):
@@ -208,7 +234,6 @@ class ECAMP(nn.Module):
         # runtime state (not part of the state_dict)
         self.image_mean, self.image_std = 0.4721, 0.3037   # transforms.Normalize of pretrain_datasets.py:52 (uint8 inputs)
         self._rt = None
-        self._n_bound = 0
         self._dropout_step = 0
         self.ce_rows = int(os.environ.get("ECAMP_CE_ROWS", "2048"))   # rows per vocabulary-head chunk (tuning knob)
 
@@ -275,8 +300,15 @@ class ECAMP(nn.Module):
             for k, nel in zip(rt["names"], rt["numel"]):
                 if named[k].numel() != nel:
                     raise RuntimeError(f"ecamp_b200: parameter {k} has {named[k].numel()} elements, expected {nel}")
+            ranges = []
+            lo, hi = ctypes.c_int64(), ctypes.c_int64()
+            for st in range(lib.ecamp_backward_stage_count()):
+                L.check(lib.ecamp_backward_stage_range(st, ctypes.byref(lo), ctypes.byref(hi)), "ecamp_backward_stage_range")
+                ranges.append((lo.value, hi.value))
+            rt["stage_params"] = [[i for i, o in enumerate(rt["goff"]) if a <= o < b] for a, b in ranges]
+            assert sorted(i for sp in rt["stage_params"] for i in sp) == list(range(n))
+            rt["gen"] = 0
             self._rt = rt
-            self._n_bound = n
         params = [named[k] for k in rt["names"]]
         rt["params"] = params
         for p in params + [self.pos_embed, self.decoder_pos_embed]:
@@ -385,16 +417,55 @@ class ECAMP(nn.Module):
                                   ctypes.c_float(self.dropout if self.training else 0.0), ctypes.c_uint64(seed),
                                   L.ptr(losses), L.ptr(mask), L.ptr(ids_restore), L.ptr(ids_keep), L.cur_stream()),
                 "ecamp_forward")
-        handle = dict(losses=losses, tensors=t, rt=rt, shape=rt["shape"], train=train)
+        rt["gen"] += 1   # the activations of this forward now own the (single) workspace
+        handle = dict(losses=losses, tensors=t, rt=rt, shape=rt["shape"], train=train, gen=rt["gen"])
         self.last = dict(mask=mask, ids_restore=ids_restore, ids_keep=ids_keep)
         return handle
+
+    @staticmethod
+    def _check_handle(handle):
+        rt = handle["rt"]
+        if rt["shape"] != handle["shape"] or rt["gen"] != handle["gen"]:
+            raise RuntimeError("ecamp_b200: another forward() of this module ran between this forward() and its backward(); "
+                               "the saved activations live in one shared workspace and have been overwritten")
+
+    def _backward_stage(self, handle, stage):
+        """Autograd path: run native backward stage `stage` into the flat buffer (overwriting) and return the gradient
+        views of the parameters that the stage finishes."""
+        lib = L.lib()
+        rt = handle["rt"]
+        self._check_handle(handle)
+        L.check(lib.ecamp_backward(rt["ctx"], L.ptr(handle["g"]), ctypes.c_int32(0), ctypes.c_int32(stage), L.cur_stream()),
+                "ecamp_backward")
+        return [rt["grad_views"][i] for i in rt["stage_params"][stage]]
+
+    def _sync_flat_grads(self, rt):
+        """Make the flat gradient buffer agree with the `.grad` tensors (autograd / DDP / GradScaler leave ordinary
+        tensors there, the fused path leaves views of the buffer): called by the fused optimizer before it reads it."""
+        src, dst, zero = [], [], []
+        for p, v in zip(rt["params"], rt["grad_views"]):
+            if p.grad is None:
+                zero.append(v)
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad); dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        if zero and len(zero) != len(rt["params"]):
+            torch._foreach_zero_(zero)
+        return len(zero) != len(rt["params"])
+
+    def _autograd_losses(self, handle):
+        rt = handle["rt"]
+        token = torch.empty((), dtype=torch.float32, device=handle["losses"].device)
+        for st in reversed(range(len(rt["stage_params"]))):
+            token = _StageNode.apply(self, handle, st, token, *[rt["params"][i] for i in rt["stage_params"][st]])
+        return _LossNode.apply(handle, token)
 
     def _backward(self, handle, g, stage=-1):
         """Run the native backward for upstream gradients g (3 floats); attaches p.grad views."""
         lib = L.lib()
         rt = handle["rt"]
-        if rt["shape"] != handle["shape"]:
-            raise RuntimeError("ecamp_b200: backward() after another forward() of a different shape is not supported")
+        self._check_handle(handle)
         params, views = rt["params"], rt["grad_views"]
         if stage <= 0:
             attached = [p.grad is v for p, v in zip(params, views)]
@@ -433,7 +504,7 @@ class ECAMP(nn.Module):
                                       mask_ratio, has_big)
         handle = self._launch_forward(t, B, T, keep, has_big, defer_mlm=False)
         if torch.is_grad_enabled() and any(p.requires_grad for p in handle["rt"]["params"]):
-            losses = _Step.apply(self, handle, *handle["rt"]["params"])
+            losses = self._autograd_losses(handle)
         else:
             losses = handle["losses"]
         return losses[0], losses[1], losses[2]

@@ -29,8 +29,10 @@ class _ClsStep(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        ctx.model._backward(ctx.handle, g)
-        return (None, None) + (None,) * ctx.model._n_params
+        # ordinary autograd semantics: the native backward overwrites the flat buffer, its views are returned as the
+        # parameter gradients and AccumulateGrad (hence DDP hooks, gradient accumulation, clip_grad_norm_) does the rest
+        views = ctx.model._backward(ctx.handle, g)
+        return (None, None) + tuple(v if n else None for v, n in zip(views, ctx.needs_input_grad[2:]))
 
 
 class VisionTransformer(nn.Module):
@@ -58,7 +60,6 @@ class VisionTransformer(nn.Module):
                 if m.bias is not None:
                     nn.init.zeros_(m.bias)
         self._rt = None
-        self._n_params = len(list(self.parameters()))
 
     # ---- native runtime ---------------------------------------------------------------------------------------
     def _runtime(self, device):
@@ -66,7 +67,7 @@ class VisionTransformer(nn.Module):
         rt = self._rt
         named = dict(self.named_parameters())
         if rt is None:
-            rt = dict(ctx=ctypes.c_void_p(), ws=None, B=None, ptrs=None, versions=None)
+            rt = dict(ctx=ctypes.c_void_p(), ws=None, B=None, ptrs=None, versions=None, gen=0)
             L.check(lib.ecamp_ctx_create(ctypes.byref(rt["ctx"])), "ecamp_ctx_create")
             n = lib.ecamp_param_count()
             rt["names"] = [lib.ecamp_param_name(i).decode() for i in range(n)]
@@ -154,7 +155,8 @@ class VisionTransformer(nn.Module):
             dp = dp.to(device=device, dtype=torch.float32).contiguous()
             if tuple(dp.shape) != (self.depth, 2, B):
                 raise ValueError("drop_path_scales must be [depth, 2, B]")
-        handle = dict(x=x, dp=dp, logits=torch.empty(B, PAD, dtype=torch.float32, device=device), rt=rt, B=B)
+        rt["gen"] += 1
+        handle = dict(x=x, dp=dp, logits=torch.empty(B, PAD, dtype=torch.float32, device=device), rt=rt, B=B, gen=rt["gen"])
         L.check(lib.ecamp_cls_forward(rt["ctx"], ctypes.byref(self._io(rt, handle)), L.cur_stream()), "ecamp_cls_forward")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             out = _ClsStep.apply(self, handle, *self.parameters())
@@ -165,23 +167,14 @@ class VisionTransformer(nn.Module):
     def _backward(self, handle, g):
         lib = L.lib()
         rt = handle["rt"]
-        if rt["B"] != handle["B"]:
-            raise RuntimeError("ecamp_b200: backward() after a forward() of a different batch size is not supported")
-        named = dict(self.named_parameters())
+        if rt["B"] != handle["B"] or rt["gen"] != handle["gen"]:
+            raise RuntimeError("ecamp_b200: another forward() of this module ran between this forward() and its backward(); "
+                               "the saved activations live in one shared workspace and have been overwritten")
         views = rt["views"]
-        attached = [named[k].grad is v for k, v in views.items()]
-        if not all(attached):
-            for (k, v), a in zip(views.items(), attached):
-                if not a and named[k].grad is not None:
-                    raise RuntimeError("ecamp_b200: a parameter has a foreign .grad tensor; call zero_grad(set_to_none=True) first")
-                if not a and any(attached):
-                    v.zero_()
-        acc = 1 if any(attached) else 0
         handle["d_logits"] = g.detach().to(torch.float32).contiguous()
-        L.check(lib.ecamp_cls_backward(rt["ctx"], ctypes.byref(self._io(rt, handle)), ctypes.c_int32(acc), L.cur_stream()),
+        L.check(lib.ecamp_cls_backward(rt["ctx"], ctypes.byref(self._io(rt, handle)), ctypes.c_int32(0), L.cur_stream()),
                 "ecamp_cls_backward")
-        for k, v in views.items():
-            named[k].grad = v
+        return [views[k] for k, _ in self.named_parameters()]
 
     def __del__(self):
         try:

@@ -36,15 +36,20 @@ class FusedAdamW:
                     p.grad.zero_()
 
     def _rt(self):
-        rt = self.model._rt
-        if rt is None or rt.get("G") is None:
-            raise RuntimeError("FusedAdamW.step() before any backward of the ECAMP module")
-        return rt
+        """The module's native runtime (flat gradient / Adam-state buffers).  Bound eagerly, so the optimizer state can be
+        restored before the first forward - where the reference's misc.load_model does it (util/misc.py:331-335)."""
+        p0 = self.param_groups[0]["params"][0]
+        if p0.device.type != "cuda":
+            raise RuntimeError("FusedAdamW: move the ECAMP module to the GPU first (there is no CPU path)")
+        return self.model._runtime(p0.device)
 
     @torch.no_grad()
     def step(self, grad_scale=1.0):
         rt = self._rt()
-        lrs = {g["lr"] * g.get("lr_scale", 1.0) for g in self.param_groups}
+        if not self.model._sync_flat_grads(rt):   # .grad tensors left by autograd / DDP / GradScaler -> flat buffer
+            return                                # no parameter has a gradient: torch.optim.AdamW would skip them all
+        # util/lr_sched.py:9-21 has already folded "lr_scale" into param_group["lr"]: use it as is
+        lrs = {g["lr"] for g in self.param_groups}
         if len(lrs) != 1:
             raise RuntimeError("FusedAdamW applies one learning rate to both groups (as the reference schedule does)")
         g1 = self.param_groups[1]
@@ -129,8 +134,7 @@ class FusedSGD(torch.optim.Optimizer):
                 raise RuntimeError("FusedSGD: parameters and gradients must be contiguous fp32 CUDA tensors (no CPU path)")
             st = self.state[p]
             if "momentum_buffer" not in st or st["momentum_buffer"] is None:
-                st["momentum_buffer"] = torch.zeros_like(p)
-                st["_fresh"] = True
+                st["momentum_buffer"] = torch.zeros_like(p)   # momentum * 0 + g == torch's first-step buf = g
         key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["momentum_buffer"].data_ptr()) for p in ps)
         t = self._tables.get(gi)
         if t is None or t["key"] != key:
@@ -175,12 +179,9 @@ class FusedSGD(torch.optim.Optimizer):
             total = self._sumsq[0:1]
             torch.sum(parts, dim=0, keepdim=True, out=total) if len(tabs) > 1 else total.copy_(parts[0:1])
         for g, t in tabs:
-            fresh = [bool(self.state[p].pop("_fresh", False)) for p in t["params"]]
-            if any(fresh) and not all(fresh):
-                raise RuntimeError("FusedSGD: a parameter group mixes first-step and later-step tensors")
             L.check(lib.ecamp_sgd_momentum_step(L.ptr(t["tab"]), L.ptr(t["chk"]), t["chunks"], ctypes.c_float(g["lr"]),
                                                 ctypes.c_float(g["momentum"]), ctypes.c_float(g["weight_decay"]),
-                                                ctypes.c_int32(1 if all(fresh) else 0), ctypes.c_float(self.max_grad_norm),
+                                                ctypes.c_int32(0), ctypes.c_float(self.max_grad_norm),
                                                 L.ptr(self._sumsq[0:1]) if clip else ctypes.c_void_p(0),
                                                 ctypes.c_int32(1 if self.write_clipped_grads else 0), L.cur_stream()),
                     "ecamp_sgd_momentum_step")
