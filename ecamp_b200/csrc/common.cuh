@@ -358,6 +358,12 @@ ECAMP_DEVINL void gelu_erf_both(float x, float& y, float& g) {
   g = fmaf(x * d, fmaf(-s, s, s), s);
 }
 
+// exact (erf) GELU and derivative for the fp32-accurate mode: x Phi(x), Phi(x) + x phi(x)
+ECAMP_DEVINL float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+ECAMP_DEVINL float gelu_exact_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+
 // Philox4x32-10: counter-based, so forward and backward regenerate identical dropout masks from
 // (seed, stream offset, element index) regardless of how the work is tiled.
 struct Philox {
@@ -443,5 +449,38 @@ ECAMP_DEVINL float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// activation element type.  Production: AT = bf16 (GEMM / attention operands, 16-bit like the reference's autocast).
+// fp32-accurate parity mode: AT = float - the SAME kernels instantiated with fp32 activations; the GEMMs then run on the
+// same tcgen05 kernel with error-compensated bf16 x 3 split operands (gemm.cu, gemm_hp).  The helpers below move 1 / 4 / 8
+// consecutive elements between memory and fp32 registers for either type.
+// ---------------------------------------------------------------------------------------------
+ECAMP_DEVINL float act_ld(const bf16* p) { return bf2f(*p); }
+ECAMP_DEVINL float act_ld(const float* p) { return *p; }
+ECAMP_DEVINL void act_st(bf16* p, float v) { *p = f2bf(v); }
+ECAMP_DEVINL void act_st(float* p, float v) { *p = v; }
+ECAMP_DEVINL float4 ld4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+ECAMP_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+ECAMP_DEVINL void st4(bf16* p, const float4& v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+ECAMP_DEVINL void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+// what the consumer of a stored activation reads back: the bf16-rounded value in production, the value itself in fp32
+ECAMP_DEVINL float4 act_round4(const bf16*, const float4& v) {
+  const float2 lo = unpack_bf16x2(pack_bf16x2(v.x, v.y)), hi = unpack_bf16x2(pack_bf16x2(v.z, v.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+ECAMP_DEVINL float4 act_round4(const float*, const float4& v) { return v; }
+template <typename AT> struct is_hp { static constexpr bool value = false; };
+template <> struct is_hp<float> { static constexpr bool value = true; };
 
 }  // namespace ecamp

@@ -81,16 +81,14 @@ __global__ void __launch_bounds__(224) patchify224_kernel(const float* __restric
 }
 
 // one block per output row, D/4 threads
+template <typename AT>
 __global__ void gather_patches_kernel(const float* __restrict__ tgt, const int32_t* __restrict__ ids_keep, int L,
-                                      int keep, int PD, bf16* __restrict__ out) {
+                                      int keep, int PD, AT* __restrict__ out) {
   ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / keep;
   const int src_l = ids_keep[r];
   const float4 v = reinterpret_cast<const float4*>(tgt + ((size_t)b * L + src_l) * PD)[threadIdx.x];
-  uint2 u;
-  u.x = pack_bf16x2(v.x, v.y);
-  u.y = pack_bf16x2(v.z, v.w);
-  reinterpret_cast<uint2*>(out + (size_t)r * PD)[threadIdx.x] = u;
+  st4(out + (size_t)r * PD + 4 * threadIdx.x, v);
 }
 
 __global__ void assemble_enc_kernel(const float* __restrict__ pe, const float* __restrict__ cls,
@@ -110,14 +108,12 @@ __global__ void assemble_enc_kernel(const float* __restrict__ pe, const float* _
   reinterpret_cast<float4*>(x0 + (size_t)r * D)[c4] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
 }
 
-__global__ void assemble_enc_bwd_kernel(const float* __restrict__ dx0, int keep, int D, bf16* __restrict__ d_pe) {
+template <typename AT>
+__global__ void assemble_enc_bwd_kernel(const float* __restrict__ dx0, int keep, int D, AT* __restrict__ d_pe) {
   ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / keep, j = r % keep;
   const float4 v = reinterpret_cast<const float4*>(dx0 + ((size_t)b * (keep + 1) + 1 + j) * D)[threadIdx.x];
-  uint2 u;
-  u.x = pack_bf16x2(v.x, v.y);
-  u.y = pack_bf16x2(v.z, v.w);
-  reinterpret_cast<uint2*>(d_pe + (size_t)r * D)[threadIdx.x] = u;
+  st4(d_pe + (size_t)r * D + 4 * threadIdx.x, v);
 }
 
 // out[d] (+)= sum_b x[b * stride + d]
@@ -131,7 +127,8 @@ __global__ void strided_rowsum_kernel(const float* __restrict__ x, int B, size_t
   out[d] = accumulate ? out[d] + s : s;
 }
 
-__global__ void assemble_dec_kernel(const bf16* __restrict__ e, const float* __restrict__ mask_token,
+template <typename AT>
+__global__ void assemble_dec_kernel(const AT* __restrict__ e, const float* __restrict__ mask_token,
                                     const float* __restrict__ dpos, const int32_t* __restrict__ ids_restore, int L,
                                     int keep, int D, float* __restrict__ xd) {
   ECAMP_PDL_ENTRY();
@@ -146,9 +143,7 @@ __global__ void assemble_dec_kernel(const bf16* __restrict__ e, const float* __r
     if (rr < keep) src = 1 + rr;
   }
   if (src >= 0) {
-    const uint2 u = reinterpret_cast<const uint2*>(e + ((size_t)b * (keep + 1) + src) * D)[c4];
-    const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
-    a = make_float4(lo.x, lo.y, hi.x, hi.y);
+    a = ld4(e + ((size_t)b * (keep + 1) + src) * D + 4 * c4);
   } else {
     // torch.cat of the half-precision decoder_embed output with the fp32 mask token promotes to fp32
     // (model_ecamp.py:245-246): the mask token is NOT rounded
@@ -158,8 +153,9 @@ __global__ void assemble_dec_kernel(const bf16* __restrict__ e, const float* __r
   reinterpret_cast<float4*>(xd + (size_t)r * D)[c4] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
 }
 
+template <typename AT>
 __global__ void assemble_dec_bwd_kernel(const float* __restrict__ dxd, const int32_t* __restrict__ ids_restore, int L,
-                                        int keep, int D, bf16* __restrict__ d_e) {
+                                        int keep, int D, AT* __restrict__ d_e) {
   ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / (L + 1), t = r % (L + 1);
   int dst = -1;
@@ -171,10 +167,7 @@ __global__ void assemble_dec_bwd_kernel(const float* __restrict__ dxd, const int
   }
   if (dst < 0) return;
   const float4 v = reinterpret_cast<const float4*>(dxd + (size_t)r * D)[threadIdx.x];
-  uint2 u;
-  u.x = pack_bf16x2(v.x, v.y);
-  u.y = pack_bf16x2(v.z, v.w);
-  reinterpret_cast<uint2*>(d_e + ((size_t)b * (keep + 1) + dst) * D)[threadIdx.x] = u;
+  st4(d_e + ((size_t)b * (keep + 1) + dst) * D + 4 * threadIdx.x, v);
 }
 
 // ws[b, d] = sum over masked positions l of dxd[b, 1 + l, d]
@@ -193,94 +186,83 @@ __global__ void mask_token_grad_kernel(const float* __restrict__ dxd, const int3
   reinterpret_cast<float4*>(ws + (size_t)b * D)[c4] = acc;
 }
 
-__global__ void split_latent_gap_kernel(const bf16* __restrict__ lat2, int keep, int D, bf16* __restrict__ img_tok,
-                                        bf16* __restrict__ gap) {
+template <typename AT>
+__global__ void split_latent_gap_kernel(const AT* __restrict__ lat2, int keep, int D, AT* __restrict__ img_tok,
+                                        AT* __restrict__ gap) {
   ECAMP_PDL_ENTRY();
   const int b = blockIdx.x, c4 = threadIdx.x;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int j = 0; j < keep; ++j) {
-    const uint2 u = reinterpret_cast<const uint2*>(lat2 + ((size_t)b * (keep + 1) + 1 + j) * D)[c4];
-    reinterpret_cast<uint2*>(img_tok + ((size_t)b * keep + j) * D)[c4] = u;
-    const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
-    acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
+    const float4 v = ld4(lat2 + ((size_t)b * (keep + 1) + 1 + j) * D + 4 * c4);
+    st4(img_tok + ((size_t)b * keep + j) * D + 4 * c4, v);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   const float inv = 1.0f / keep;
-  uint2 o;
-  o.x = pack_bf16x2(acc.x * inv, acc.y * inv);
-  o.y = pack_bf16x2(acc.z * inv, acc.w * inv);
-  reinterpret_cast<uint2*>(gap + (size_t)b * D)[c4] = o;
+  st4(gap + (size_t)b * D + 4 * c4, make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv));
 }
 
-__global__ void split_latent_gap_bwd_kernel(const bf16* __restrict__ d_img_tok, const bf16* __restrict__ d_gap,
-                                            int keep, int D, bf16* __restrict__ d_lat2) {
+template <typename AT>
+__global__ void split_latent_gap_bwd_kernel(const AT* __restrict__ d_img_tok, const AT* __restrict__ d_gap,
+                                            int keep, int D, AT* __restrict__ d_lat2) {
   ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / (keep + 1), s = r % (keep + 1);
   const int c4 = threadIdx.x;
-  uint2 o = make_uint2(0u, 0u);
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s > 0) {
-    const uint2 u = reinterpret_cast<const uint2*>(d_img_tok + ((size_t)b * keep + s - 1) * D)[c4];
-    const uint2 g = reinterpret_cast<const uint2*>(d_gap + (size_t)b * D)[c4];
+    const float4 u = ld4(d_img_tok + ((size_t)b * keep + s - 1) * D + 4 * c4);
+    const float4 g = ld4(d_gap + (size_t)b * D + 4 * c4);
     const float inv = 1.0f / keep;
-    const float2 ul = unpack_bf16x2(u.x), uh = unpack_bf16x2(u.y), gl = unpack_bf16x2(g.x), gh = unpack_bf16x2(g.y);
-    o.x = pack_bf16x2(ul.x + gl.x * inv, ul.y + gl.y * inv);
-    o.y = pack_bf16x2(uh.x + gh.x * inv, uh.y + gh.y * inv);
+    o = make_float4(u.x + g.x * inv, u.y + g.y * inv, u.z + g.z * inv, u.w + g.w * inv);
   }
-  reinterpret_cast<uint2*>(d_lat2 + (size_t)r * D)[c4] = o;
+  st4(d_lat2 + (size_t)r * D + 4 * c4, o);
 }
 
-__global__ void add_batch_rowvec_kernel(bf16* __restrict__ y, const bf16* __restrict__ vec, int T, int D) {
+template <typename AT>
+__global__ void add_batch_rowvec_kernel(AT* __restrict__ y, const AT* __restrict__ vec, int T, int D) {
   ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / T, c4 = threadIdx.x;
-  uint2 u = reinterpret_cast<uint2*>(y + (size_t)r * D)[c4];
-  const uint2 g = reinterpret_cast<const uint2*>(vec + (size_t)b * D)[c4];
-  const float2 ul = unpack_bf16x2(u.x), uh = unpack_bf16x2(u.y), gl = unpack_bf16x2(g.x), gh = unpack_bf16x2(g.y);
-  u.x = pack_bf16x2(ul.x + gl.x, ul.y + gl.y);
-  u.y = pack_bf16x2(uh.x + gh.x, uh.y + gh.y);
-  reinterpret_cast<uint2*>(y + (size_t)r * D)[c4] = u;
+  const float4 u = ld4(y + (size_t)r * D + 4 * c4), g = ld4(vec + (size_t)b * D + 4 * c4);
+  st4(y + (size_t)r * D + 4 * c4, make_float4(u.x + g.x, u.y + g.y, u.z + g.z, u.w + g.w));
 }
 
-__global__ void add_batch_rowvec_oop_kernel(const bf16* __restrict__ x, const bf16* __restrict__ vec, int T, int D,
-                                            bf16* __restrict__ y) {
+template <typename AT>
+__global__ void add_batch_rowvec_oop_kernel(const AT* __restrict__ x, const AT* __restrict__ vec, int T, int D,
+                                            AT* __restrict__ y) {
   ECAMP_PDL_ENTRY();
   const int r = blockIdx.x, b = r / T, c4 = threadIdx.x;
-  uint2 u = reinterpret_cast<const uint2*>(x + (size_t)r * D)[c4];
-  const uint2 g = reinterpret_cast<const uint2*>(vec + (size_t)b * D)[c4];
-  const float2 ul = unpack_bf16x2(u.x), uh = unpack_bf16x2(u.y), gl = unpack_bf16x2(g.x), gh = unpack_bf16x2(g.y);
-  u.x = pack_bf16x2(ul.x + gl.x, ul.y + gl.y);
-  u.y = pack_bf16x2(uh.x + gh.x, uh.y + gh.y);
-  reinterpret_cast<uint2*>(y + (size_t)r * D)[c4] = u;
+  const float4 u = ld4(x + (size_t)r * D + 4 * c4), g = ld4(vec + (size_t)b * D + 4 * c4);
+  st4(y + (size_t)r * D + 4 * c4, make_float4(u.x + g.x, u.y + g.y, u.z + g.z, u.w + g.w));
 }
 
-__global__ void gelu_bwd_bf16_kernel(const float* __restrict__ d, const bf16* __restrict__ pre, bf16* __restrict__ out,
+template <typename AT>
+__global__ void gelu_bwd_bf16_kernel(const float* __restrict__ d, const AT* __restrict__ pre, AT* __restrict__ out,
                                      size_t n) {
   ECAMP_PDL_ENTRY();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = f2bf(d[i] * gelu_erf_grad(bf2f(pre[i])));
+  if (i < n) act_st(out + i, d[i] * (is_hp<AT>::value ? gelu_exact_grad(act_ld(pre + i)) : gelu_erf_grad(act_ld(pre + i))));
 }
 
-__global__ void batch_colsum_kernel(const bf16* __restrict__ x, int T, int D, bf16* __restrict__ out) {
+template <typename AT>
+__global__ void batch_colsum_kernel(const AT* __restrict__ x, int T, int D, AT* __restrict__ out) {
   ECAMP_PDL_ENTRY();
   const int b = blockIdx.x, c4 = threadIdx.x;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = 0; t < T; ++t) {
-    const uint2 u = reinterpret_cast<const uint2*>(x + ((size_t)b * T + t) * D)[c4];
-    const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
-    acc.x += lo.x; acc.y += lo.y; acc.z += hi.x; acc.w += hi.y;
+    const float4 v = ld4(x + ((size_t)b * T + t) * D + 4 * c4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  uint2 o;
-  o.x = pack_bf16x2(acc.x, acc.y);
-  o.y = pack_bf16x2(acc.z, acc.w);
-  reinterpret_cast<uint2*>(out + (size_t)b * D)[c4] = o;
+  st4(out + (size_t)b * D + 4 * c4, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
 // HF BertEmbeddings.forward (called at bert_modeling.py:113-119): (word[id] + type[tt]) + pos[t] -> LN -> dropout
 // ---------------------------------------------------------------------------------------------
+template <typename AT>
 __global__ void __launch_bounds__(256) bert_emb_fwd_kernel(
     const int64_t* __restrict__ ids, const int64_t* __restrict__ type_ids, const float* __restrict__ word,
     const float* __restrict__ type, const float* __restrict__ pos, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, int M, int T, DropoutCfg drop, float* __restrict__ pre,
-    float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ out_bf16,
+    float* __restrict__ mean_out, float* __restrict__ rstd_out, AT* __restrict__ out_bf16,
     float* __restrict__ out_f32) {
   ECAMP_PDL_ENTRY();
   constexpr int NV = 6, D = 768;
@@ -335,10 +317,7 @@ __global__ void __launch_bounds__(256) bert_emb_fwd_kernel(
       y.w = rnd.w >= thr ? y.w * ks : 0.f;
     }
     if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)row * D)[c4] = y;
-    uint2 u;
-    u.x = pack_bf16x2(y.x, y.y);
-    u.y = pack_bf16x2(y.z, y.w);
-    reinterpret_cast<uint2*>(out_bf16 + (size_t)row * D)[c4] = u;
+    st4(out_bf16 + (size_t)row * D + 4 * c4, y);
   }
 }
 
@@ -434,7 +413,20 @@ __global__ void emb_type_finalize_kernel(const float* __restrict__ type_ws, int 
 // ---------------------------------------------------------------------------------------------
 // out[n] = sum_m x[m, n]: CTA = 256 columns x one row chunk; each lane owns 8 consecutive columns (128-bit loads),
 // the 8 warps stride over the rows of the chunk; per-chunk partials are reduced by a second tiny kernel.
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int ld, int M, int N,
+ECAMP_DEVINL void ld8(const bf16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+ECAMP_DEVINL void ld8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename AT>
+__global__ void __launch_bounds__(256) colsum_kernel(const AT* __restrict__ x, int ld, int M, int N,
                                                      float* __restrict__ out) {
   ECAMP_PDL_ENTRY();
   __shared__ float red[8][256];
@@ -446,28 +438,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (col < N) {  // N % 8 == 0 checked on the host
-    const bf16* base = x + col;
+    const AT* base = x + col;
     int r = r0 + warp;
-    for (; r + 24 < r1; r += 32) {  // four independent 128-bit loads in flight per lane
-      uint4 u[4];
+    for (; r + 24 < r1; r += 32) {  // four independent (128-bit) loads in flight per lane
+      float f[4][8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) u[i] = *reinterpret_cast<const uint4*>(base + (size_t)(r + 8 * i) * ld);
+      for (int i = 0; i < 4; ++i) ld8(base + (size_t)(r + 8 * i) * ld, f[i]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float2 f;
-        f = unpack_bf16x2(u[i].x); acc[0] += f.x; acc[1] += f.y;
-        f = unpack_bf16x2(u[i].y); acc[2] += f.x; acc[3] += f.y;
-        f = unpack_bf16x2(u[i].z); acc[4] += f.x; acc[5] += f.y;
-        f = unpack_bf16x2(u[i].w); acc[6] += f.x; acc[7] += f.y;
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[i][k];
     }
     for (; r < r1; r += 8) {
-      const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t)r * ld);
-      float2 f;
-      f = unpack_bf16x2(u.x); acc[0] += f.x; acc[1] += f.y;
-      f = unpack_bf16x2(u.y); acc[2] += f.x; acc[3] += f.y;
-      f = unpack_bf16x2(u.z); acc[4] += f.x; acc[5] += f.y;
-      f = unpack_bf16x2(u.w); acc[6] += f.x; acc[7] += f.y;
+      float f[8];
+      ld8(base + (size_t)r * ld, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += f[k];
     }
   }
 #pragma unroll
@@ -562,10 +548,11 @@ int patchify224(const float* imgs, int B, float* tgt, cudaStream_t st) {
   LAUNCH_OK();
   return 0;
 }
-int gather_patches(const float* tgt, const int32_t* ids_keep, int B, int L, int keep, int PD, bf16* out,
+template <typename AT>
+int gather_patches(const float* tgt, const int32_t* ids_keep, int B, int L, int keep, int PD, AT* out,
                    cudaStream_t st) {
   if (B * keep <= 0) return 0;
-  ECAMP_CUDA_OK(launch_pdl(gather_patches_kernel, B * keep, PD / 4, 0, st, tgt, ids_keep, L, keep, PD, out));
+  ECAMP_CUDA_OK(launch_pdl(gather_patches_kernel<AT>, B * keep, PD / 4, 0, st, tgt, ids_keep, L, keep, PD, out));
   LAUNCH_OK();
   return 0;
 }
@@ -575,25 +562,28 @@ int assemble_encoder_input(const float* pe, const float* cls, const float* pos, 
   LAUNCH_OK();
   return 0;
 }
-int assemble_encoder_input_bwd(const float* dx0, int B, int keep, int D, bf16* d_pe, float* d_cls, int accumulate,
+template <typename AT>
+int assemble_encoder_input_bwd(const float* dx0, int B, int keep, int D, AT* d_pe, float* d_cls, int accumulate,
                                cudaStream_t st) {
   if (keep > 0) {
-    ECAMP_CUDA_OK(launch_pdl(assemble_enc_bwd_kernel, B * keep, D / 4, 0, st, dx0, keep, D, d_pe));
+    ECAMP_CUDA_OK(launch_pdl(assemble_enc_bwd_kernel<AT>, B * keep, D / 4, 0, st, dx0, keep, D, d_pe));
     LAUNCH_OK();
   }
   ECAMP_CUDA_OK(launch_pdl(strided_rowsum_kernel, (D + 127) / 128, 128, 0, st, dx0, B, (size_t)(keep + 1) * D, D, d_cls, accumulate));
   LAUNCH_OK();
   return 0;
 }
-int assemble_decoder_input(const bf16* e, const float* mask_token, const float* dpos, const int32_t* ids_restore,
+template <typename AT>
+int assemble_decoder_input(const AT* e, const float* mask_token, const float* dpos, const int32_t* ids_restore,
                            int B, int L, int keep, int D, float* xd, cudaStream_t st) {
-  ECAMP_CUDA_OK(launch_pdl(assemble_dec_kernel, B * (L + 1), D / 4, 0, st, e, mask_token, dpos, ids_restore, L, keep, D, xd));
+  ECAMP_CUDA_OK(launch_pdl(assemble_dec_kernel<AT>, B * (L + 1), D / 4, 0, st, e, mask_token, dpos, ids_restore, L, keep, D, xd));
   LAUNCH_OK();
   return 0;
 }
-int assemble_decoder_input_bwd(const float* dxd, const int32_t* ids_restore, int B, int L, int keep, int D, bf16* d_e,
+template <typename AT>
+int assemble_decoder_input_bwd(const float* dxd, const int32_t* ids_restore, int B, int L, int keep, int D, AT* d_e,
                                float* d_mask_token, int accumulate, float* ws, cudaStream_t st) {
-  ECAMP_CUDA_OK(launch_pdl(assemble_dec_bwd_kernel, B * (L + 1), D / 4, 0, st, dxd, ids_restore, L, keep, D, d_e));
+  ECAMP_CUDA_OK(launch_pdl(assemble_dec_bwd_kernel<AT>, B * (L + 1), D / 4, 0, st, dxd, ids_restore, L, keep, D, d_e));
   LAUNCH_OK();
   ECAMP_CUDA_OK(launch_pdl(mask_token_grad_kernel, B, D / 4, 0, st, dxd, ids_restore, L, keep, D, ws));
   LAUNCH_OK();
@@ -601,45 +591,52 @@ int assemble_decoder_input_bwd(const float* dxd, const int32_t* ids_restore, int
   LAUNCH_OK();
   return 0;
 }
-int split_latent_gap(const bf16* lat2, int B, int keep, int D, bf16* img_tok, bf16* gap, cudaStream_t st) {
-  ECAMP_CUDA_OK(launch_pdl(split_latent_gap_kernel, B, D / 4, 0, st, lat2, keep, D, img_tok, gap));
+template <typename AT>
+int split_latent_gap(const AT* lat2, int B, int keep, int D, AT* img_tok, AT* gap, cudaStream_t st) {
+  ECAMP_CUDA_OK(launch_pdl(split_latent_gap_kernel<AT>, B, D / 4, 0, st, lat2, keep, D, img_tok, gap));
   LAUNCH_OK();
   return 0;
 }
-int split_latent_gap_bwd(const bf16* d_img_tok, const bf16* d_gap, int B, int keep, int D, bf16* d_lat2,
+template <typename AT>
+int split_latent_gap_bwd(const AT* d_img_tok, const AT* d_gap, int B, int keep, int D, AT* d_lat2,
                          cudaStream_t st) {
-  ECAMP_CUDA_OK(launch_pdl(split_latent_gap_bwd_kernel, B * (keep + 1), D / 4, 0, st, d_img_tok, d_gap, keep, D, d_lat2));
+  ECAMP_CUDA_OK(launch_pdl(split_latent_gap_bwd_kernel<AT>, B * (keep + 1), D / 4, 0, st, d_img_tok, d_gap, keep, D, d_lat2));
   LAUNCH_OK();
   return 0;
 }
-int add_batch_rowvec(bf16* y, const bf16* vec, int B, int T, int D, cudaStream_t st) {
-  ECAMP_CUDA_OK(launch_pdl(add_batch_rowvec_kernel, B * T, D / 4, 0, st, y, vec, T, D));
+template <typename AT>
+int add_batch_rowvec(AT* y, const AT* vec, int B, int T, int D, cudaStream_t st) {
+  ECAMP_CUDA_OK(launch_pdl(add_batch_rowvec_kernel<AT>, B * T, D / 4, 0, st, y, vec, T, D));
   LAUNCH_OK();
   return 0;
 }
-int add_batch_rowvec_oop(const bf16* x, const bf16* vec, int B, int T, int D, bf16* y, cudaStream_t st) {
-  ECAMP_CUDA_OK(launch_pdl(add_batch_rowvec_oop_kernel, B * T, D / 4, 0, st, x, vec, T, D, y));
+template <typename AT>
+int add_batch_rowvec_oop(const AT* x, const AT* vec, int B, int T, int D, AT* y, cudaStream_t st) {
+  ECAMP_CUDA_OK(launch_pdl(add_batch_rowvec_oop_kernel<AT>, B * T, D / 4, 0, st, x, vec, T, D, y));
   LAUNCH_OK();
   return 0;
 }
-int gelu_bwd_bf16(const float* d, const bf16* pre, bf16* out, size_t n, cudaStream_t st) {
+template <typename AT>
+int gelu_bwd_bf16(const float* d, const AT* pre, AT* out, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
-  ECAMP_CUDA_OK(launch_pdl(gelu_bwd_bf16_kernel, (unsigned)((n + 255) / 256), 256, 0, st, d, pre, out, n));
+  ECAMP_CUDA_OK(launch_pdl(gelu_bwd_bf16_kernel<AT>, (unsigned)((n + 255) / 256), 256, 0, st, d, pre, out, n));
   LAUNCH_OK();
   return 0;
 }
-int batch_colsum(const bf16* x, int B, int T, int D, bf16* out, cudaStream_t st) {
-  ECAMP_CUDA_OK(launch_pdl(batch_colsum_kernel, B, D / 4, 0, st, x, T, D, out));
+template <typename AT>
+int batch_colsum(const AT* x, int B, int T, int D, AT* out, cudaStream_t st) {
+  ECAMP_CUDA_OK(launch_pdl(batch_colsum_kernel<AT>, B, D / 4, 0, st, x, T, D, out));
   LAUNCH_OK();
   return 0;
 }
+template <typename AT>
 int bert_embeddings_fwd(const int64_t* ids, const int64_t* type_ids, const float* word, const float* type,
                         const float* pos, const float* gamma, const float* beta, float eps, int B, int T, int D,
-                        DropoutCfg drop, float* pre, float* mean, float* rstd, bf16* out_bf16, float* out_f32,
+                        DropoutCfg drop, float* pre, float* mean, float* rstd, AT* out_bf16, float* out_f32,
                         cudaStream_t st) {
   ECAMP_REQUIRE(D == 768, "bert embeddings: hidden size must be 768");
   const int M = B * T;
-  ECAMP_CUDA_OK(launch_pdl(bert_emb_fwd_kernel, (M + 7) / 8, 256, 0, st, ids, type_ids, word, type, pos, gamma, beta, eps, M, T, drop, pre,
+  ECAMP_CUDA_OK(launch_pdl(bert_emb_fwd_kernel<AT>, (M + 7) / 8, 256, 0, st, ids, type_ids, word, type, pos, gamma, beta, eps, M, T, drop, pre,
                                                    mean, rstd, out_bf16, out_f32));
   LAUNCH_OK();
   return 0;
@@ -668,7 +665,8 @@ int bert_embeddings_bwd(const float* d_pre, const int64_t* ids, const int64_t* t
   return 0;
 }
 size_t colsum_ws_floats(int) { return 64; }  // the column sums are added with atomics: no partials workspace any more
-int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate, float* /*ws*/, cudaStream_t st) {
+template <typename AT>
+int colsum_bf16(const AT* x, int ld, int M, int N, float* out, int accumulate, float* /*ws*/, cudaStream_t st) {
   ECAMP_REQUIRE(ld % 8 == 0 && N % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
                 "colsum: pitch and width must be multiples of 8 elements, base 16-byte aligned");
   int chunks = (M + 127) / 128;  // 128 rows per CTA: ~600-1500 CTAs for the shapes of the step
@@ -676,7 +674,7 @@ int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate,
   if (chunks < 1) chunks = 1;
   if (!accumulate) ECAMP_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
   dim3 grid((N + 255) / 256, chunks);
-  ECAMP_CUDA_OK(launch_pdl(colsum_kernel, grid, 256, 0, st, x, ld, M, N, out));
+  ECAMP_CUDA_OK(launch_pdl(colsum_kernel<AT>, grid, 256, 0, st, x, ld, M, N, out));
   LAUNCH_OK();
   return 0;
 }
@@ -720,6 +718,29 @@ int permute_pe_weight_grad(const float* dw_pqc, float* grad_cpq, int accumulate,
   LAUNCH_OK();
   return 0;
 }
+
+
+// ---- explicit instantiations: AT = bf16 (production) and float (fp32-accurate parity mode) ---------------------------
+#define ECAMP_INST_ELEMENTWISE(AT)                                                                                        \
+  template int gather_patches<AT>(const float*, const int32_t*, int, int, int, int, AT*, cudaStream_t);                   \
+  template int assemble_encoder_input_bwd<AT>(const float*, int, int, int, AT*, float*, int, cudaStream_t);               \
+  template int assemble_decoder_input<AT>(const AT*, const float*, const float*, const int32_t*, int, int, int, int,      \
+                                          float*, cudaStream_t);                                                          \
+  template int assemble_decoder_input_bwd<AT>(const float*, const int32_t*, int, int, int, int, AT*, float*, int, float*, \
+                                              cudaStream_t);                                                              \
+  template int split_latent_gap<AT>(const AT*, int, int, int, AT*, AT*, cudaStream_t);                                    \
+  template int split_latent_gap_bwd<AT>(const AT*, const AT*, int, int, int, AT*, cudaStream_t);                          \
+  template int add_batch_rowvec<AT>(AT*, const AT*, int, int, int, cudaStream_t);                                         \
+  template int add_batch_rowvec_oop<AT>(const AT*, const AT*, int, int, int, AT*, cudaStream_t);                          \
+  template int gelu_bwd_bf16<AT>(const float*, const AT*, AT*, size_t, cudaStream_t);                                     \
+  template int batch_colsum<AT>(const AT*, int, int, int, AT*, cudaStream_t);                                             \
+  template int bert_embeddings_fwd<AT>(const int64_t*, const int64_t*, const float*, const float*, const float*,          \
+                                       const float*, const float*, float, int, int, int, DropoutCfg, float*, float*,      \
+                                       float*, AT*, float*, cudaStream_t);                                                \
+  template int colsum_bf16<AT>(const AT*, int, int, int, float*, int, float*, cudaStream_t);
+ECAMP_INST_ELEMENTWISE(bf16)
+ECAMP_INST_ELEMENTWISE(float)
+#undef ECAMP_INST_ELEMENTWISE
 
 // ---------------------------------------------------------------------------------------------
 // Tail of the image loader on the GPU: Grayscale(3) + ToTensor + Normalize of pretrain_datasets.py:47-52 applied to the

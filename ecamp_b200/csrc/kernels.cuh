@@ -31,32 +31,41 @@ int random_masking(const float* noise, int B, int L, int len_keep, int32_t* ids_
 int resize_bicubic_patchify(const float* big, int B, int Hin, float* tgt, cudaStream_t st);
 int patchify224(const float* imgs, int B, float* tgt, cudaStream_t st);
 // A_pe[b*keep + j, :] = bf16(tgt[b, ids_keep[b, j], :])
-int gather_patches(const float* tgt, const int32_t* ids_keep, int B, int L, int keep, int PD, bf16* out,
+template <typename AT>
+int gather_patches(const float* tgt, const int32_t* ids_keep, int B, int L, int keep, int PD, AT* out,
                    cudaStream_t st);
 // x0[b, 0] = cls + pos[0]; x0[b, 1 + j] = pe[b*keep + j] + pos[1 + ids_keep[b, j]]      (model_ecamp.py:222-230)
 int assemble_encoder_input(const float* pe, const float* cls, const float* pos, const int32_t* ids_keep, int B,
                            int keep, int D, float* x0, cudaStream_t st);
 // backward of the above: d_pe (bf16, GEMM operand) and d_cls (sum over batch of row 0)
-int assemble_encoder_input_bwd(const float* dx0, int B, int keep, int D, bf16* d_pe, float* d_cls, int accumulate,
+template <typename AT>
+int assemble_encoder_input_bwd(const float* dx0, int B, int keep, int D, AT* d_pe, float* d_cls, int accumulate,
                                cudaStream_t st);
 // xd[b, 0] = e[b, 0] + dpos[0]; xd[b, 1 + l] = (r = ids_restore[b, l]) < keep ? e[b, 1 + r] : mask_token, + dpos[1 + l]
-int assemble_decoder_input(const bf16* e, const float* mask_token, const float* dpos, const int32_t* ids_restore,
+template <typename AT>
+int assemble_decoder_input(const AT* e, const float* mask_token, const float* dpos, const int32_t* ids_restore,
                            int B, int L, int keep, int D, float* xd, cudaStream_t st);
-int assemble_decoder_input_bwd(const float* dxd, const int32_t* ids_restore, int B, int L, int keep, int D, bf16* d_e,
+template <typename AT>
+int assemble_decoder_input_bwd(const float* dxd, const int32_t* ids_restore, int B, int L, int keep, int D, AT* d_e,
                                float* d_mask_token, int accumulate, float* ws, cudaStream_t st);
 // img_tok[b*keep + j] = lat2[b, 1 + j]; gap[b] = mean_j lat2[b, 1 + j]                  (model_ecamp.py:269-271)
-int split_latent_gap(const bf16* lat2, int B, int keep, int D, bf16* img_tok, bf16* gap, cudaStream_t st);
+template <typename AT>
+int split_latent_gap(const AT* lat2, int B, int keep, int D, AT* img_tok, AT* gap, cudaStream_t st);
 // d_lat2[b, 0] = 0; d_lat2[b, 1 + j] = d_img_tok[b*keep + j] + d_gap[b] / keep
-int split_latent_gap_bwd(const bf16* d_img_tok, const bf16* d_gap, int B, int keep, int D, bf16* d_lat2,
+template <typename AT>
+int split_latent_gap_bwd(const AT* d_img_tok, const AT* d_gap, int B, int keep, int D, AT* d_lat2,
                          cudaStream_t st);
 // y[b*T + t, :] += vec[b, :]   (context_fusion.py:54-55)
-int add_batch_rowvec(bf16* y, const bf16* vec, int B, int T, int D, cudaStream_t st);
+template <typename AT>
+int add_batch_rowvec(AT* y, const AT* vec, int B, int T, int D, cudaStream_t st);
 // out[b, :] = sum_t x[b*T + t, :]  (bf16 in, bf16 out, fp32 accumulate)
-int batch_colsum(const bf16* x, int B, int T, int D, bf16* out, cudaStream_t st);
+template <typename AT>
+int batch_colsum(const AT* x, int B, int T, int D, AT* out, cudaStream_t st);
 // BertEmbeddings: e = word[id] + type[tt] + pos[t] -> pre (fp32, saved); LN(1e-12) -> dropout -> bf16 + fp32
+template <typename AT>
 int bert_embeddings_fwd(const int64_t* ids, const int64_t* type_ids, const float* word, const float* type,
                         const float* pos, const float* gamma, const float* beta, float eps, int B, int T, int D,
-                        DropoutCfg drop, float* pre, float* mean, float* rstd, bf16* out_bf16, float* out_f32,
+                        DropoutCfg drop, float* pre, float* mean, float* rstd, AT* out_bf16, float* out_f32,
                         cudaStream_t st);
 // in-place inverted-dropout backward on an fp32 gradient (n % 4 == 0)
 int dropout_bwd_f32(float* g, size_t n, DropoutCfg drop, cudaStream_t st);
@@ -64,7 +73,8 @@ int dropout_bwd_f32(float* g, size_t n, DropoutCfg drop, cudaStream_t st);
 int bert_embeddings_bwd(const float* d_pre, const int64_t* ids, const int64_t* type_ids, int B, int T, int D,
                         float* d_word, float* d_type, float* d_pos, int accumulate, float* ws, cudaStream_t st);
 // bias gradient: out[n] (+)= sum_m x[m, n]
-int colsum_bf16(const bf16* x, int ld, int M, int N, float* out, int accumulate, float* ws, cudaStream_t st);
+template <typename AT>
+int colsum_bf16(const AT* x, int ld, int M, int N, float* out, int accumulate, float* ws, cudaStream_t st);
 size_t colsum_ws_floats(int N);
 // y = dropout(x) elementwise on bf16 (used for the dropout behind LayerNorm-less sites), in place allowed
 int scale_f32(float* x, const float* scale_dev, size_t n, cudaStream_t st);
@@ -78,9 +88,11 @@ int strided_rowsum(const float* x, int B, size_t stride, int D, float* out, int 
 // patch-embed weight: canonical [768, (c, p, q)] <-> GEMM K-order [768, (p, q, c)]
 int permute_pe_weight_grad(const float* dw_pqc, float* grad_cpq, int accumulate, cudaStream_t st);
 // out = bf16(d * gelu'(pre))   (LM-head transform: dense -> GELU -> LayerNorm, bert_modeling.py:208)
-int gelu_bwd_bf16(const float* d, const bf16* pre, bf16* out, size_t n, cudaStream_t st);
+template <typename AT>
+int gelu_bwd_bf16(const float* d, const AT* pre, AT* out, size_t n, cudaStream_t st);
 // y = x + vec[b] broadcast over the T rows of each batch element (out of place)
-int add_batch_rowvec_oop(const bf16* x, const bf16* vec, int B, int T, int D, bf16* y, cudaStream_t st);
+template <typename AT>
+int add_batch_rowvec_oop(const AT* x, const AT* vec, int B, int T, int D, AT* y, cudaStream_t st);
 
 // ---- attention.cu -----------------------------------------------------------------------------
 struct AttnArgs {

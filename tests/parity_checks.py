@@ -63,10 +63,12 @@ def guard(fn):
 PROJ_TOL, COS_TOL = 2e-3, 2e-4
 
 
-def grad_systematic(orc, m, min_numel=512, min_norm=1e-7):
-    """Per-tensor projection coefficient and cosine of the module's gradients on the oracle's.  Returns the violations
-    {name: (proj, cos)} and the worst |proj - 1| / (1 - cos) seen.  Tensors that are analytically zero (key biases), tiny
-    (< min_numel elements: the statistic is itself noisy) or numerically zero in the oracle are skipped."""
+def grad_systematic(orc, m, yard=None, min_numel=512, min_norm=1e-7):
+    """Per-tensor projection coefficient and cosine of the module's gradients on the oracle's.  `yard` (optional): the same
+    two statistics of the reference's own bf16-autocast path against its fp32 path, {name: (|proj - 1|, 1 - cos)}; a tensor
+    violates when |proj - 1| > max(PROJ_TOL, 3 x yardstick) or 1 - cos > max(COS_TOL, 3 x yardstick).  Returns the
+    violations {name: (proj, cos)} and the worst |proj - 1| / (1 - cos) seen.  Tensors that are analytically zero (key
+    biases), tiny (< min_numel elements: the statistic is itself noisy) or numerically zero in the oracle are skipped."""
     gm = dict(m.named_parameters())
     bad, worst_p, worst_c = {}, 0.0, 0.0
     for k, p in orc.named_parameters():
@@ -79,9 +81,25 @@ def grad_systematic(orc, m, min_numel=512, min_norm=1e-7):
         proj = (a * r).sum().item() / rr
         cos = (a * r).sum().item() / max(math.sqrt(rr) * a.norm().item(), 1e-300)
         worst_p, worst_c = max(worst_p, abs(proj - 1)), max(worst_c, 1 - cos)
-        if abs(proj - 1) > PROJ_TOL or 1 - cos > COS_TOL:
+        yp, yc = yard.get(k, (0.0, 0.0)) if yard else (0.0, 0.0)
+        if abs(proj - 1) > max(PROJ_TOL, 3 * yp) or 1 - cos > max(COS_TOL, 3 * yc):
             bad[k] = (proj, cos)
     return bad, worst_p, worst_c
+
+
+def systematic_yardstick(g_ref, g_test):
+    """{name: (|proj - 1|, 1 - cos)} of g_test on g_ref (dicts of tensors)."""
+    out = {}
+    for k, r in g_ref.items():
+        if k not in g_test:
+            continue
+        a, r = g_test[k].double().flatten(), r.double().flatten()
+        rr = (r * r).sum().item()
+        if rr <= 0:
+            continue
+        dot = (a * r).sum().item()
+        out[k] = (abs(dot / rr - 1), 1 - dot / max(math.sqrt(rr) * a.norm().item(), 1e-300))
+    return out
 
 
 def grad_errors(orc, m, floor=1e-5):
@@ -463,9 +481,12 @@ def check_step():
         med = statistics.median(errs.values())
         worst = sorted(((e, yard.get(k, 0.0), k) for k, e in errs.items()), reverse=True)[:8]
         gm = dict(m.named_parameters())
-        sys_bad, sys_p, sys_c = grad_systematic(orc_g32_view(orc, g32), m)
+        ysys = systematic_yardstick(g32, {k: p.grad for k, p in orc.named_parameters() if p.grad is not None})
+        sys_bad, sys_p, sys_c = grad_systematic(orc_g32_view(orc, g32), m, ysys)
         report(f"step_systematic_B{B}_T{T}", not sys_bad, worst_proj_dev=sys_p, worst_one_minus_cos=sys_c,
-               violations=sorted(((abs(v[0] - 1), v[1], k) for k, v in sys_bad.items()), reverse=True)[:8])
+               yardstick_worst_proj_dev=max(v[0] for k, v in ysys.items() if not k.endswith("key.bias")),
+               yardstick_worst_one_minus_cos=max(v[1] for k, v in ysys.items() if not k.endswith("key.bias")),
+               violations=sorted(((abs(v[0] - 1), v[1], ysys.get(k), k) for k, v in sys_bad.items()), reverse=True)[:8])
         report(f"step_backward_B{B}_T{T}", not bad and total < 1.5e-2 and kb < 1e-4, median=med, all_grads_rel=total,
                yardstick_median=statistics.median(yard.values()), key_bias_grad_norm_max=kb, violations=list(bad.items())[:8],
                worst=worst, pooler_none=gm["bert_encoder.model.bert.pooler.dense.weight"].grad is None,
@@ -801,11 +822,20 @@ def check_step_full_size():
         errs, kb, total = grad_errors(orc, m)
         med = statistics.median(errs.values())
         worst = sorted(((e, k) for k, e in errs.items()), reverse=True)[:6]
-        sys_bad, sys_p, sys_c = grad_systematic(orc, m)
+        g32 = {k: p.grad.clone() for k, p in orc.named_parameters() if p.grad is not None}
+        for p in orc.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):     # yardstick: the reference's own mixed-precision path
+            la = orc(b)
+            (la[0] + la[1] + la[2]).backward()
+        ysys = systematic_yardstick(g32, {k: p.grad for k, p in orc.named_parameters() if p.grad is not None})
+        sys_bad, sys_p, sys_c = grad_systematic(orc_g32_view(orc, g32), m, ysys)
         report(f"full_size_oracle_B{B}_T{T}", ids_ok and max(le) < 1e-3 and total < 1.5e-2 and worst[0][0] < max(3e-2, 3 * med) and not sys_bad,
                ids_ok=ids_ok, loss_rel=le, all_grads_rel=total, median=med, worst=worst, worst_proj_dev=sys_p,
-               worst_one_minus_cos=sys_c, systematic_violations=sorted(((abs(v[0] - 1), v[1], k) for k, v in sys_bad.items()), reverse=True)[:6])
-        del lo, lm
+               worst_one_minus_cos=sys_c, yardstick_worst_proj_dev=max(v[0] for k, v in ysys.items() if not k.endswith("key.bias")),
+               yardstick_worst_one_minus_cos=max(v[1] for k, v in ysys.items() if not k.endswith("key.bias")),
+               systematic_violations=sorted(((abs(v[0] - 1), v[1], ysys.get(k), k) for k, v in sys_bad.items()), reverse=True)[:6])
+        del lo, lm, la, g32
         for p in orc.parameters():
             p.grad = None
         torch.cuda.empty_cache()
@@ -1016,11 +1046,13 @@ def check_optimizer_resume():
     same_hyper = opt2.param_groups[1]["lr"] == 1.5e-4 and tuple(opt2.param_groups[1]["betas"]) == (0.9, 0.95) and \
         opt2.param_groups[1]["weight_decay"] == 0.05 and opt2.param_groups[0]["weight_decay"] == 0.0 and opt2.step_count == 2
     same_state = torch.equal(m2._rt["M1"], m._rt["M1"]) and torch.equal(m2._rt["M2"], m._rt["M2"])
-    m.forward_backward(bs[2]); opt.step(); opt.zero_grad()
-    m2.forward_backward(bs[2]); opt2.step(); opt2.zero_grad()
+    # one more step on both with IDENTICAL gradients (two backward runs differ by fp32-atomics noise, which Adam's
+    # normalisation turns into sign flips on noise-level tensors such as the key biases): parameters must stay bit-equal
+    m.forward_backward(bs[2]); m2.forward_backward(bs[2])
+    m2.flat_grads().copy_(m.flat_grads())
+    opt.step(); opt.zero_grad(); opt2.step(); opt2.zero_grad()
     torch.cuda.synchronize()
-    e_p = max(((a.detach() - b_.detach()).abs().max() / b_.detach().abs().max().clamp_min(1e-6)).item()
-              for a, b_ in zip(m2.parameters(), m.parameters()))
+    e_p = max((a.detach() - b_.detach()).abs().max().item() for a, b_ in zip(m2.parameters(), m.parameters()))
     # torch.optim.AdamW accepts the dictionary, and FusedAdamW accepts torch's
     ref = ecamp().to(dev)
     topt = torch.optim.AdamW(_add_weight_decay(ref, 0.05), lr=1.0, betas=(0.9, 0.95))
@@ -1037,12 +1069,12 @@ def check_optimizer_resume():
     for p, off, n in zip(m._rt["params"], m._rt["goff"], m._rt["numel"]):
         st = ck["optimizer"]["state"][idx[id(p)]]
         ok_back = ok_back and torch.equal(m1_back[off:off + n].cpu(), st["exp_avg"].reshape(-1))
-    report("optimizer_resume", same_hyper and same_state and e_p < 2e-5 and torch_ok and ok_back and ck["epoch"] == 7,
-           same_hyper=same_hyper, same_state=same_state, max_rel_param_diff_after_step=e_p, torch_state_entries=n_state,
+    report("optimizer_resume", same_hyper and same_state and e_p == 0.0 and torch_ok and ok_back and ck["epoch"] == 7,
+           same_hyper=same_hyper, same_state=same_state, max_abs_param_diff_after_step=e_p, torch_state_entries=n_state,
            restored_through_torch_layout=ok_back)
 
 
-ALL_CHECKS = (check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
+ALL_CHECKS = (check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
 
 
 def run_check(fn):
