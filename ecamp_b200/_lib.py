@@ -70,13 +70,13 @@ class SgdTensor(ctypes.Structure):
 
 # every symbol include/ecamp_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "ecamp_abi_version", "ecamp_last_error", "ecamp_launch_count", "ecamp_gemm_bf16", "ecamp_gemm_set_cta_pair", "ecamp_random_masking", "ecamp_resize_patchify",
+    "ecamp_abi_version", "ecamp_last_error", "ecamp_launch_count", "ecamp_gemm_bf16", "ecamp_gemm_fp32", "ecamp_gemm_fp32_ws_bytes", "ecamp_gemm_set_cta_pair", "ecamp_random_masking", "ecamp_resize_patchify",
     "ecamp_layernorm_fwd", "ecamp_layernorm_bwd", "ecamp_layernorm_ws_floats", "ecamp_attention_set_tcgen05", "ecamp_attention_fwd",
     "ecamp_attention_bwd", "ecamp_mim_loss", "ecamp_sr_loss_fwd", "ecamp_sr_loss_bwd", "ecamp_sr_ws_floats",
     "ecamp_pred_grad", "ecamp_ce_rows", "ecamp_param_count", "ecamp_param_name", "ecamp_param_numel",
     "ecamp_param_decay", "ecamp_param_grad_offset", "ecamp_grad_floats", "ecamp_shadow_bytes",
     "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_ctx_create", "ecamp_ctx_destroy", "ecamp_ctx_bind",
-    "ecamp_workspace_bytes", "ecamp_ctx_set_workspace", "ecamp_refresh_shadows", "ecamp_forward",
+    "ecamp_workspace_bytes", "ecamp_ctx_set_precision", "ecamp_ctx_workspace_bytes", "ecamp_ctx_set_workspace", "ecamp_refresh_shadows", "ecamp_forward",
     "ecamp_backward_stage_count", "ecamp_backward_stage_range", "ecamp_backward", "ecamp_adamw_step",
     "ecamp_debug_buffer", "ecamp_cls_workspace_bytes", "ecamp_cls_set_workspace", "ecamp_cls_forward", "ecamp_cls_backward",
     "ecamp_sgd_table_bytes", "ecamp_sgd_chunk_bytes", "ecamp_sgd_build_tables", "ecamp_grad_sumsq", "ecamp_sgd_momentum_step",
@@ -99,7 +99,7 @@ def lib():
         _lib.ecamp_abi_version.restype = ctypes.c_int
         _lib.ecamp_param_name.restype = ctypes.c_char_p
         for f in ("ecamp_param_numel", "ecamp_param_grad_offset", "ecamp_grad_floats", "ecamp_shadow_bytes",
-                  "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_workspace_bytes", "ecamp_launch_count",
+                  "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_workspace_bytes", "ecamp_ctx_workspace_bytes", "ecamp_launch_count", "ecamp_gemm_fp32_ws_bytes",
                   "ecamp_cls_workspace_bytes", "ecamp_sgd_table_bytes", "ecamp_sgd_chunk_bytes"):
             getattr(_lib, f).restype = ctypes.c_int64
         for f in ("ecamp_layernorm_ws_floats", "ecamp_sr_ws_floats"):
@@ -151,3 +151,31 @@ def gemm(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, bias=None, aux
                                ctypes.c_int32(N), ctypes.c_int32(K), ctypes.byref(ep), ctypes.c_int32(tile_n),
                                cur_stream())
     check(rc, "ecamp_gemm_bf16")
+
+
+def gemm_fp32(a, b, *, a_mn=False, b_mn=False, bias=None, aux_in=None, aux_out=None, residual=None, out_f32=None, out_act=None,
+              flags=0, drop_p=0.0, seed=0, site=0, colsum_out=None):
+    """fp32-accurate GEMM (bf16 x 3 split operands on the tcgen05 kernel).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N])."""
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.stride(-1) == 1 and b.stride(-1) == 1
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N = b.shape[1] if b_mn else b.shape[0]
+    ep = Epilogue()
+    ep.bias = bias.data_ptr() if bias is not None else None
+    ep.aux_in = aux_in.data_ptr() if aux_in is not None else None
+    ep.aux_out = aux_out.data_ptr() if aux_out is not None else None
+    aux = aux_in if aux_in is not None else aux_out
+    ep.ld_aux = aux.stride(0) if aux is not None else 0
+    ep.residual = residual.data_ptr() if residual is not None else None
+    ep.ld_res = residual.stride(0) if residual is not None else 0
+    ep.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+    ep.ld_f32 = out_f32.stride(0) if out_f32 is not None else 0
+    ep.out_bf16 = out_act.data_ptr() if out_act is not None else None
+    ep.ld_bf16 = out_act.stride(0) if out_act is not None else 0
+    ep.flags, ep.drop_p, ep.seed, ep.site = flags, drop_p, seed, site
+    ep.colsum_out = colsum_out.data_ptr() if colsum_out is not None else None
+    need = lib().ecamp_gemm_fp32_ws_bytes(M, N, K)
+    ws = torch.empty(need, dtype=torch.uint8, device=a.device)
+    rc = lib().ecamp_gemm_fp32(ptr(a), ctypes.c_int32(a.stride(0)), ctypes.c_int32(int(a_mn)), ptr(b), ctypes.c_int32(b.stride(0)),
+                               ctypes.c_int32(int(b_mn)), ctypes.c_int32(M), ctypes.c_int32(N), ctypes.c_int32(K), ctypes.byref(ep),
+                               ptr(ws), ctypes.c_int64(need), cur_stream())
+    check(rc, "ecamp_gemm_fp32")

@@ -22,6 +22,19 @@ struct Chunk {
 
 ECAMP_DEVINL void store_shadow(const AdamTensor& t, long long i, float4 p, bool vec) {
   if (t.shadow32) *reinterpret_cast<float4*>(t.shadow32 + i) = p;
+  if (t.shadow_f) {  // fp32-accurate mode: the same copies (incl. the patch-embed K-order) in fp32
+    if (t.shadow_kind == 0) {
+      *reinterpret_cast<float4*>(t.shadow_f + i) = p;
+    } else {
+      const float vals[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long e = i + k;
+        const int n = (int)(e / 768), kk = (int)(e % 768), c = kk / 256, pq = kk % 256;
+        t.shadow_f[(size_t)n * 768 + pq * 3 + c] = vals[k];
+      }
+    }
+  }
   if (!t.shadow) return;
   if (t.shadow_kind == 0) {
     if (vec) {
@@ -55,7 +68,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict
   const bool aligned = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
                          reinterpret_cast<uintptr_t>(t.m) | reinterpret_cast<uintptr_t>(t.v)) & 15) == 0 &&
                        (t.shadow == nullptr || (reinterpret_cast<uintptr_t>(t.shadow) & 7) == 0) &&
-                       (t.shadow32 == nullptr || (reinterpret_cast<uintptr_t>(t.shadow32) & 15) == 0);
+                       (t.shadow32 == nullptr || (reinterpret_cast<uintptr_t>(t.shadow32) & 15) == 0) &&
+                       (t.shadow_f == nullptr || (reinterpret_cast<uintptr_t>(t.shadow_f) & 15) == 0);
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const long long i = ch.start + ((long long)it * 256 + threadIdx.x) * 4;
@@ -94,6 +108,14 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict
           t.v[e] = v;
         }
         if (t.shadow32) t.shadow32[e] = p;
+        if (t.shadow_f) {
+          if (t.shadow_kind == 0) {
+            t.shadow_f[e] = p;
+          } else {
+            const int n = (int)(e / 768), kk = (int)(e % 768), c = kk / 256, pq = kk % 256;
+            t.shadow_f[(size_t)n * 768 + pq * 3 + c] = p;
+          }
+        }
         if (t.shadow) {
           if (t.shadow_kind == 0) {
             t.shadow[e] = f2bf(p);

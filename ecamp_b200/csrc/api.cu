@@ -71,6 +71,29 @@ int ecamp_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int
                    S(stream));
 }
 
+int64_t ecamp_gemm_fp32_ws_bytes(int32_t M, int32_t N, int32_t K) { return (int64_t)gemm_hp_ws_bytes(M, N, K); }
+int ecamp_gemm_fp32(const float* A, int32_t lda, int32_t a_mn, const float* B, int32_t ldb, int32_t b_mn, int32_t M,
+                    int32_t N, int32_t K, const ecamp_epilogue* ep, void* ws, int64_t ws_bytes, void* stream) {
+  ECAMP_REQUIRE(A && B && ep && ws, "ecamp_gemm_fp32: null argument");
+  GemmEpilogueT<float> e;
+  e.bias = ep->bias;
+  e.aux_in = static_cast<const float*>(ep->aux_in);
+  e.aux_out = static_cast<float*>(ep->aux_out);
+  e.ld_aux = ep->ld_aux;
+  e.residual = ep->residual;
+  e.ld_res = ep->ld_res;
+  e.out_f32 = ep->out_f32;
+  e.ld_f32 = ep->ld_f32;
+  e.out_bf16 = static_cast<float*>(ep->out_bf16);
+  e.ld_bf16 = ep->ld_bf16;
+  e.flags = ep->flags;
+  e.drop_p = ep->drop_p;
+  e.seed = ep->seed;
+  e.stream = ep->site;
+  e.colsum_out = ep->colsum_out;
+  return gemm_hp(A, lda, a_mn, B, ldb, b_mn, M, N, K, e, ws, (size_t)ws_bytes, S(stream));
+}
+
 int ecamp_random_masking(const float* noise, int32_t B, int32_t L, int32_t len_keep, int64_t* ids_restore,
                          int64_t* ids_keep, float* mask, void* scratch_i32, void* stream) {
   ECAMP_REQUIRE(noise && ids_restore && ids_keep && mask && scratch_i32, "ecamp_random_masking: null argument");
@@ -148,7 +171,7 @@ int64_t ecamp_param_numel(int32_t i) { return (i >= 0 && i < ecamp_param_count()
 int32_t ecamp_param_decay(int32_t i) { return (i >= 0 && i < ecamp_param_count()) ? param_specs()[i].decay : -1; }
 int64_t ecamp_param_grad_offset(int32_t i) { return (i >= 0 && i < ecamp_param_count()) ? param_specs()[i].g_off : -1; }
 int64_t ecamp_grad_floats(void) { return grad_total_floats(); }
-int64_t ecamp_shadow_bytes(void) { return ((shadow_bf16_elems() + 7) & ~7LL) * 2 + shadow_f32_elems() * 4 + 64; }
+int64_t ecamp_shadow_bytes(void) { return ((shadow_bf16_elems() + 7) & ~7LL) * 4 + shadow_f32_elems() * 4 + 64; }
 int64_t ecamp_adam_table_bytes(void) { return (int64_t)ctx_adam_table_bytes(); }
 int64_t ecamp_adam_chunk_bytes(void) { return (int64_t)ctx_adam_chunk_bytes(); }
 
@@ -169,7 +192,14 @@ int ecamp_ctx_bind(ecamp_ctx* ctx, float* const* params_host, int32_t n, float* 
   return ctx_bind(ctx->impl, params_host, n, grads, adam_m, adam_v, shadows, pos_embed, decoder_pos_embed, adam_table,
                   adam_chunks);
 }
-int64_t ecamp_workspace_bytes(const ecamp_shape* s) { return s ? (int64_t)workspace_bytes(to_shape(s)) : -1; }
+int64_t ecamp_workspace_bytes(const ecamp_shape* s) { return s ? (int64_t)workspace_bytes(to_shape(s), 0) : -1; }
+int ecamp_ctx_set_precision(ecamp_ctx* ctx, int32_t fp32_accurate) {
+  ECAMP_REQUIRE(ctx, "ecamp_ctx_set_precision: null context");
+  return ctx_set_precision(ctx->impl, fp32_accurate);
+}
+int64_t ecamp_ctx_workspace_bytes(ecamp_ctx* ctx, const ecamp_shape* s) {
+  return (ctx && s) ? (int64_t)workspace_bytes(to_shape(s), ctx_precision(ctx->impl)) : -1;
+}
 int ecamp_ctx_set_workspace(ecamp_ctx* ctx, void* ws, int64_t bytes, const ecamp_shape* s) {
   ECAMP_REQUIRE(ctx && ws && s, "ecamp_ctx_set_workspace: null argument");
   return ctx_set_workspace(ctx->impl, ws, (size_t)bytes, to_shape(s));

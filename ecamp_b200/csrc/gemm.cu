@@ -70,6 +70,13 @@ struct EpiArgs {
   int n_fast;   // tile order: 1 = consecutive work units walk the N tiles of one row block (A is the big operand:
                 // its tile is fetched from DRAM once and served from L2 to the other column tiles), 0 = walk M
   int n_tiles;
+  // fp32-accurate mode (gemm_hp): the contraction runs over `nterms` (A-plane, B-plane) pairs of bf16 x 3 split operands;
+  // k-blocks are numbered virtually, v = term * num_kb + kb, and split over work units like a plain split-K.  1 otherwise.
+  int nterms;
+  unsigned char term_a[6], term_b[6];
+};
+struct TmaSet {  // one tensor map per operand plane (production: plane 0 only)
+  CUtensorMap a[3], b[3];
 };
 
 // work unit -> (row block, column block)
@@ -472,8 +479,7 @@ ECAMP_DEVINL void epilogue_dispatch(const EpiArgs& ea, uint32_t tmem_base, int q
 // ---------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
-                    int N, int K, EpiArgs ea) {
+gemm_tcgen05_kernel(const __grid_constant__ TmaSet maps, int M, int N, int K, EpiArgs ea) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -493,11 +499,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
+  const int num_vkb = num_kb * ea.nterms;         // virtual k-blocks (= num_kb in production)
   const int num_units = num_tiles * ea.split_k;  // work unit = (tile, k-split); unit % num_tiles = tile
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b[0]);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -531,25 +538,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int tile = unit % num_tiles, ks = unit / num_tiles;
         int m_blk, n_blk;
         decode_tile(ea, tile, m_tiles, m_blk, n_blk);
-        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_kb, kb0 + ea.kb_per);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_vkb, kb0 + ea.kb_per);
+        for (int vkb = kb0; vkb < kb1; ++vkb) {
+          const int term = ea.nterms > 1 ? vkb / num_kb : 0, kb = vkb - term * num_kb;
+          const CUtensorMap* tma_a = &maps.a[ea.term_a[term]];
+          const CUtensorMap* tma_b = &maps.b[ea.term_b[term]];
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* a_dst = sA + stage * C::A_BYTES;
           uint8_t* b_dst = sB + stage * C::B_BYTES;
           if (!A_MN) {
-            tma_load_2d(a_dst, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d(a_dst, tma_a, &full_bar[stage], kb * BK, m_blk * BM);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(a_dst + j * (BK * 128), &tma_a, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
+              tma_load_2d(a_dst + j * (BK * 128), tma_a, &full_bar[stage], m_blk * BM + j * 64, kb * BK);
           }
           if (!B_MN) {
-            tma_load_2d(b_dst, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+            tma_load_2d(b_dst, tma_b, &full_bar[stage], kb * BK, n_blk * BN);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(b_dst + j * (BK * 128), &tma_b, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+              tma_load_2d(b_dst + j * (BK * 128), tma_b, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -565,7 +575,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       if (lane == 0) {
         const int ks = unit / num_tiles;
-        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_kb, kb0 + ea.kb_per);
+        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_vkb, kb0 + ea.kb_per);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -631,8 +641,7 @@ struct Cfg2 {
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
-                         int N, int K, EpiArgs ea) {
+gemm_tcgen05_2cta_kernel(const __grid_constant__ TmaSet maps, int M, int N, int K, EpiArgs ea) {
   using C = Cfg2<BN>;
   constexpr int STAGES = C::STAGES;
   constexpr int HB = BN / 2;  // B rows staged by each CTA
@@ -656,11 +665,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
+  const int num_vkb = num_kb * ea.nterms;  // virtual k-blocks (= num_kb in production)
   const int num_units = num_tiles * ea.split_k;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b[0]);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -694,27 +704,30 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         const int tile = unit % num_tiles, ks = unit / num_tiles;
         int m_blk, n_blk;
         decode_tile(ea, tile, m_tiles, m_blk, n_blk);
-        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_kb, kb0 + ea.kb_per);
+        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_vkb, kb0 + ea.kb_per);
         const int m0 = m_blk * 2 * BM + (int)rank * BM;
         const int n0 = n_blk * BN + (int)rank * HB;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int vkb = kb0; vkb < kb1; ++vkb) {
+          const int term = ea.nterms > 1 ? vkb / num_kb : 0, kb = vkb - term * num_kb;
+          const CUtensorMap* tma_a = &maps.a[ea.term_a[term]];
+          const CUtensorMap* tma_b = &maps.b[ea.term_b[term]];
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
           uint8_t* a_dst = sA + stage * C::A_BYTES;
           uint8_t* b_dst = sB + stage * C::B_BYTES;
           if (!A_MN) {
-            tma_load_2d_2sm(a_dst, &tma_a, &full_bar[stage], kb * BK, m0);
+            tma_load_2d_2sm(a_dst, tma_a, &full_bar[stage], kb * BK, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d_2sm(a_dst + j * (BK * 128), &tma_a, &full_bar[stage], m0 + j * 64, kb * BK);
+              tma_load_2d_2sm(a_dst + j * (BK * 128), tma_a, &full_bar[stage], m0 + j * 64, kb * BK);
           }
           if (!B_MN) {
-            tma_load_2d_2sm(b_dst, &tma_b, &full_bar[stage], kb * BK, n0);
+            tma_load_2d_2sm(b_dst, tma_b, &full_bar[stage], kb * BK, n0);
           } else {
 #pragma unroll
             for (int j = 0; j < HB / 64; ++j)
-              tma_load_2d_2sm(b_dst + j * (BK * 128), &tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
+              tma_load_2d_2sm(b_dst + j * (BK * 128), tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -730,7 +743,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       uint32_t acc_phase = 0;
       for (int unit = pair; unit < num_units; unit += num_pairs) {
         const int ks = unit / num_tiles;
-        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_kb, kb0 + ea.kb_per);
+        const int kb0 = ks * ea.kb_per, kb1 = ea.dbg == 2 ? kb0 + 1 : min(num_vkb, kb0 + ea.kb_per);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -875,7 +888,7 @@ void pick_config(int M, int N, int K, bool splittable, int force_bn, bool cta2, 
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
+int launch(const TmaSet& maps, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
   auto kfn = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -884,13 +897,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * ea.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  ECAMP_CUDA_OK(launch_pdl(kfn, grid, kThreads, Cfg<BN>::SMEM_BYTES, st, ta, tb, M, N, K, ea));
+  ECAMP_CUDA_OK(launch_pdl(kfn, grid, kThreads, Cfg<BN>::SMEM_BYTES, st, maps, M, N, K, ea));
   ECAMP_LAUNCHED();
   return 0;
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
+int launch2(const TmaSet& maps, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
   auto kfn = gemm_tcgen05_2cta_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -914,27 +927,25 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, c
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  ECAMP_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, ta, tb, M, N, K, ea));
+  ECAMP_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, maps, M, N, K, ea));
   ECAMP_LAUNCHED();
   return 0;
 }
 
 template <int BN>
-int launch_major2(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
-                  const EpiArgs& ea, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch2<BN, false, false>(ta, tb, M, N, K, ea, st);
-  if (!a_mn && b_mn) return launch2<BN, false, true>(ta, tb, M, N, K, ea, st);
-  if (a_mn && b_mn) return launch2<BN, true, true>(ta, tb, M, N, K, ea, st);
-  return launch2<BN, true, false>(ta, tb, M, N, K, ea, st);
+int launch_major2(int a_mn, int b_mn, const TmaSet& maps, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2<BN, false, false>(maps, M, N, K, ea, st);
+  if (!a_mn && b_mn) return launch2<BN, false, true>(maps, M, N, K, ea, st);
+  if (a_mn && b_mn) return launch2<BN, true, true>(maps, M, N, K, ea, st);
+  return launch2<BN, true, false>(maps, M, N, K, ea, st);
 }
 
 template <int BN>
-int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
-                 const EpiArgs& ea, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, M, N, K, ea, st);
-  if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, M, N, K, ea, st);
-  if (a_mn && b_mn) return launch<BN, true, true>(ta, tb, M, N, K, ea, st);
-  return launch<BN, true, false>(ta, tb, M, N, K, ea, st);
+int launch_major(int a_mn, int b_mn, const TmaSet& maps, int M, int N, int K, const EpiArgs& ea, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(maps, M, N, K, ea, st);
+  if (!a_mn && b_mn) return launch<BN, false, true>(maps, M, N, K, ea, st);
+  if (a_mn && b_mn) return launch<BN, true, true>(maps, M, N, K, ea, st);
+  return launch<BN, true, false>(maps, M, N, K, ea, st);
 }
 
 }  // namespace
@@ -944,8 +955,11 @@ int make_tmap_bf16(void* map, const bf16* ptr, unsigned long long inner, unsigne
   return make_tmap(static_cast<CUtensorMap*>(map), ptr, inner, outer, pitch_elems, box_outer);
 }
 
-int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
-              const GemmEpilogue& ep, int force_bn, cudaStream_t stream) {
+namespace {
+// The launch shared by the production GEMM (one plane per operand) and the fp32-accurate one (three bf16 planes per
+// operand, six plane pairs accumulated; `plane_a` / `plane_b` = elements between consecutive planes, 0 = production).
+int gemm_launch(const bf16* A, size_t plane_a, int lda, int a_mn, const bf16* B, size_t plane_b, int ldb, int b_mn, int M,
+                int N, int K, const GemmEpilogue& ep, int force_bn, bool hp, cudaStream_t stream) {
   ECAMP_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem %d x %d x %d", M, N, K);
   ECAMP_REQUIRE(ep.out_f32 || ep.out_bf16, "gemm: no output given");
   if (ep.flags & GEMM_DROPOUT)
@@ -961,25 +975,46 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
                           (ep.residual == nullptr || accumulate);
   int bn = 256, split_k = 1;
   const bool cta2 = g_cta_pair_mode == 2 || (g_cta_pair_mode == 0 && M > BM);
-  pick_config(M, N, K, splittable, force_bn, cta2, b_mn != 0, &bn, &split_k);
+  const int num_kb = (K + BK - 1) / BK;
+  const int nterms = hp ? 6 : 1;
+  if (!hp) {
+    pick_config(M, N, K, splittable, force_bn, cta2, b_mn != 0, &bn, &split_k);
+  } else {
+    // fp32-accurate mode: the tensor core accumulates with truncation, which shows as a bias that grows with the length
+    // of the accumulation (measured, scripts/tc_accum_probe.py: 7e-5 relative at 6 x 32768 all-positive products,
+    // 1e-6 when every <= 1024 products are summed outside in fp32).  So the 6 x K contraction is cut into units of at
+    // most 16 k-blocks whose partial sums are added with fp32 atomics (round to nearest) into a zeroed accumulator.
+    ECAMP_REQUIRE(splittable && !accumulate, "gemm_hp: the tensor-core pass takes a plain fp32 accumulator");
+    bn = force_bn ? force_bn : 256;
+    split_k = (nterms * num_kb + 15) / 16;
+  }
   ECAMP_REQUIRE(!(cta2 && b_mn && bn == 192), "gemm: tile N 192 is not available to the CTA-pair kernel with an MN-major B");
 
-  CUtensorMap ta, tb;
+  TmaSet maps;
   int rc;
   // K-major operand: inner = contraction, outer = rows, box [rows_tile, 64]
   // MN-major operand: inner = output index, outer = contraction, box [64 (k), 64]
-  rc = a_mn ? make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK)
-            : make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM);
-  if (rc) return rc;
-  rc = b_mn ? make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK)
-            : make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)(cta2 ? bn / 2 : bn));
-  if (rc) return rc;
+  for (int pl = 0; pl < (hp ? 3 : 1); ++pl) {
+    const bf16* Ap = A + pl * plane_a;
+    const bf16* Bp = B + pl * plane_b;
+    rc = a_mn ? make_tmap(&maps.a[pl], Ap, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK)
+              : make_tmap(&maps.a[pl], Ap, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM);
+    if (rc) return rc;
+    rc = b_mn ? make_tmap(&maps.b[pl], Bp, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK)
+              : make_tmap(&maps.b[pl], Bp, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)(cta2 ? bn / 2 : bn));
+    if (rc) return rc;
+  }
+  if (!hp) { maps.a[1] = maps.a[2] = maps.a[0]; maps.b[1] = maps.b[2] = maps.b[0]; }
 
   EpiArgs ea;
   ea.ep = ep;
   ea.split_k = split_k;
-  ea.kb_per = (((K + BK - 1) / BK) + split_k - 1) / split_k;
-  if (split_k > 1) {
+  ea.nterms = nterms;
+  // plane pairs of x = hi + mid + lo (8 mantissa bits each): everything down to 2^-24 relative
+  static const unsigned char TA[6] = {0, 0, 1, 1, 0, 2}, TB[6] = {0, 1, 0, 1, 2, 0};
+  for (int t = 0; t < 6; ++t) { ea.term_a[t] = hp ? TA[t] : 0; ea.term_b[t] = hp ? TB[t] : 0; }
+  ea.kb_per = hp ? 16 : (num_kb + split_k - 1) / split_k;
+  if (split_k > 1 || hp) {
     ea.ep.residual = nullptr;  // partial sums are added atomically on top of the running gradient / zeros
     if (!accumulate)
       ECAMP_CUDA_OK(cudaMemset2DAsync(ep.out_f32, (size_t)ep.ld_f32 * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M,
@@ -996,7 +1031,7 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
   ea.mode = EM_GENERIC;
   if (ea.vec_ok && N % 4 == 0) {
     const bool only_bf16 = ep.out_bf16 && !ep.out_f32, only_f32 = ep.out_f32 && !ep.out_bf16;
-    if (split_k > 1) ea.mode = EM_ATOMIC;
+    if (split_k > 1 || hp) ea.mode = EM_ATOMIC;
     else if (ep.flags == 0 && !ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_BF16;
     else if (ep.flags == GEMM_GELU && ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_GELU;
     else if (ep.flags == GEMM_DGELU && !ep.bias && !ep.aux_out && !ep.residual && only_bf16) ea.mode = EM_DGELU;
@@ -1009,6 +1044,7 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
     if (ep.row_scale && ea.mode != EM_F32_RES) ea.mode = EM_GENERIC;
   }
   if (g_force_generic_epilogue) ea.mode = EM_GENERIC;
+  // (hp with split_k == 1, i.e. K <= 170: one unit per tile, the generic / scalar paths store into the zeroed accumulator)
   static const int dbg = getenv("ECAMP_GEMM_DBG") ? atoi(getenv("ECAMP_GEMM_DBG")) : 0;
   ea.dbg = dbg;
   // Tile order.  The operand that is larger than L2 can hold next to the output stream should be fetched from DRAM
@@ -1020,16 +1056,112 @@ int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn
   ea.n_fast = order >= 0 ? order : ((split_k == 1 && (long long)M > (long long)N) ? 1 : 0);
 
 #ifdef ECAMP_EPI_ONLY_MODE
-  return launch<256, false, false>(ta, tb, M, N, K, ea, stream);
+  return launch<256, false, false>(maps, M, N, K, ea, stream);
 #endif
   if (cta2) {
-    if (bn == 256) return launch_major2<256>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
-    if (bn == 192) return launch_major2<192>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
-    return launch_major2<128>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
+    if (bn == 256) return launch_major2<256>(a_mn, b_mn, maps, M, N, K, ea, stream);
+    if (bn == 192) return launch_major2<192>(a_mn, b_mn, maps, M, N, K, ea, stream);
+    return launch_major2<128>(a_mn, b_mn, maps, M, N, K, ea, stream);
   }
-  if (bn == 256) return launch_major<256>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
-  if (bn == 192) return launch_major<192>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
-  return launch_major<128>(a_mn, b_mn, ta, tb, M, N, K, ea, stream);
+  if (bn == 256) return launch_major<256>(a_mn, b_mn, maps, M, N, K, ea, stream);
+  if (bn == 192) return launch_major<192>(a_mn, b_mn, maps, M, N, K, ea, stream);
+  return launch_major<128>(a_mn, b_mn, maps, M, N, K, ea, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32-accurate mode: operand split and fp32 epilogue
+// ---------------------------------------------------------------------------------------------
+// x (fp32 [R, C], pitch ld) -> three bf16 planes [3][R][Cp]: hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid);
+// hi + mid + lo reproduces x to 2^-24 relative (the subtractions are exact in fp32).  Columns C..Cp-1 are zero.
+__global__ void split3_kernel(const float* __restrict__ x, int R, int C, int ld, int Cp, bf16* __restrict__ planes) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)R * Cp) return;
+  const int r = (int)(i / Cp), c = (int)(i % Cp);
+  const float v = c < C ? x[(size_t)r * ld + c] : 0.f;
+  const bf16 h = f2bf(v);
+  const float r1 = v - bf2f(h);
+  const bf16 m = f2bf(r1);
+  const bf16 l = f2bf(r1 - bf2f(m));
+  const size_t plane = (size_t)R * Cp;
+  planes[i] = h; planes[plane + i] = m; planes[2 * plane + i] = l;
+}
+
+// The epilogue operators of the production kernel (epi_scalar above) on the fp32 accumulator, without any 16-bit rounding
+// and with the exact erf GELU: bias -> GELU (aux_out = pre-activation or GELU') -> x GELU'(aux_in) -> dropout -> row scale
+// -> + residual -> outputs (+ column sums of the emitted activation).
+__global__ void hp_epilogue_kernel(const float* __restrict__ acc, int ldacc, int M, int N, GemmEpilogueT<float> ep) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * N) return;
+  const int row = (int)(i / N), col = (int)(i % N);
+  float v = acc[(size_t)row * ldacc + col];
+  if (ep.bias) v += ep.bias[col];
+  if (ep.flags & GEMM_GELU) {
+    const float pre = v;
+    v = gelu_exact(pre);
+    if (ep.aux_out) ep.aux_out[(size_t)row * ep.ld_aux + col] = (ep.flags & GEMM_AUX_GRAD) ? gelu_exact_grad(pre) : pre;
+  }
+  if (ep.flags & GEMM_DGELU) {
+    const float t = ep.aux_in[(size_t)row * ep.ld_aux + col];
+    v *= (ep.flags & GEMM_AUX_GRAD) ? t : gelu_exact_grad(t);
+  }
+  if (ep.flags & GEMM_DROPOUT) {
+    const Philox ph(ep.seed);
+    const uint32_t w = philox_word(ph, (uint64_t)row * (uint64_t)N + (uint64_t)col, ep.stream);
+    v = (w >= dropout_threshold(ep.drop_p)) ? v * (1.0f / (1.0f - ep.drop_p)) : 0.f;
+  }
+  if (ep.row_scale) v *= ep.row_scale[row / ep.rows_per_scale];
+  if (ep.residual) v += ep.residual[(size_t)row * ep.ld_res + col];
+  if (ep.out_f32) ep.out_f32[(size_t)row * ep.ld_f32 + col] = v;
+  if (ep.out_bf16) ep.out_bf16[(size_t)row * ep.ld_bf16 + col] = v;
+  if (ep.colsum_out) atomicAdd(ep.colsum_out + col, v);
+}
+}  // namespace
+
+int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
+              const GemmEpilogue& ep, int force_bn, cudaStream_t stream) {
+  return gemm_launch(A, 0, lda, a_mn, B, 0, ldb, b_mn, M, N, K, ep, force_bn, false, stream);
+}
+
+size_t gemm_hp_ws_bytes(int M, int N, int K) {
+  auto pad8 = [](size_t c) { return (c + 7) & ~(size_t)7; };
+  // K-major operand [rows, K]; MN-major operand [K, rows]: either way rows * K elements up to the pitch padding
+  const size_t a = 3 * (pad8((size_t)K) * M > pad8((size_t)M) * K ? pad8((size_t)K) * M : pad8((size_t)M) * K) * sizeof(bf16);
+  const size_t b = 3 * (pad8((size_t)K) * N > pad8((size_t)N) * K ? pad8((size_t)K) * N : pad8((size_t)N) * K) * sizeof(bf16);
+  const size_t acc = (size_t)M * (((size_t)N + 3) & ~(size_t)3) * sizeof(float);
+  return ((a + 255) & ~(size_t)255) + ((b + 255) & ~(size_t)255) + acc + 1024;
+}
+
+int gemm_hp(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M, int N, int K,
+            const GemmEpilogueT<float>& ep, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  ECAMP_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_hp: empty problem %d x %d x %d", M, N, K);
+  ECAMP_REQUIRE(ws && ws_bytes >= gemm_hp_ws_bytes(M, N, K), "gemm_hp: workspace of %zu bytes needed, %zu given",
+                gemm_hp_ws_bytes(M, N, K), ws_bytes);
+  ECAMP_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "gemm_hp: workspace must be 256-byte aligned");
+  // stored shape of each operand: K-major [rows, K], MN-major [K, rows]
+  const int Ra = a_mn ? K : M, Ca = a_mn ? M : K, Rb = b_mn ? K : N, Cb = b_mn ? N : K;
+  const int Cpa = (Ca + 7) & ~7, Cpb = (Cb + 7) & ~7;
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  bf16* pa = reinterpret_cast<bf16*>(w);
+  w += (3 * (size_t)Ra * Cpa * sizeof(bf16) + 255) & ~(size_t)255;
+  bf16* pb = reinterpret_cast<bf16*>(w);
+  w += (3 * (size_t)Rb * Cpb * sizeof(bf16) + 255) & ~(size_t)255;
+  float* acc = reinterpret_cast<float*>(w);
+  const int ldacc = (N + 3) & ~3;
+  {
+    const size_t na = (size_t)Ra * Cpa, nb = (size_t)Rb * Cpb;
+    split3_kernel<<<(unsigned)((na + 255) / 256), 256, 0, stream>>>(A, Ra, Ca, lda, Cpa, pa);
+    ECAMP_LAUNCHED();
+    split3_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(B, Rb, Cb, ldb, Cpb, pb);
+    ECAMP_LAUNCHED();
+  }
+  GemmEpilogue raw;
+  raw.out_f32 = acc;
+  raw.ld_f32 = ldacc;
+  if (int rc = gemm_launch(pa, (size_t)Ra * Cpa, Cpa, a_mn, pb, (size_t)Rb * Cpb, Cpb, b_mn, M, N, K, raw, 0, true, stream)) return rc;
+  const size_t n = (size_t)M * N;
+  hp_epilogue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(acc, ldacc, M, N, ep);
+  ECAMP_LAUNCHED();
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -12,16 +12,18 @@ enum GemmFlags : int {
                       // with GEMM_DGELU: aux_in IS that stored derivative (v *= aux_in)
 };
 
-struct GemmEpilogue {
+// AT = activation element type: bf16 in production, float in the fp32-accurate parity mode (gemm_hp)
+template <typename AT>
+struct GemmEpilogueT {
   const float* bias = nullptr;      // [N], added first
-  const bf16* aux_in = nullptr;     // [M, ld_aux]
-  bf16* aux_out = nullptr;          // [M, ld_aux]
+  const AT* aux_in = nullptr;       // [M, ld_aux]
+  AT* aux_out = nullptr;            // [M, ld_aux]
   int ld_aux = 0;
   const float* residual = nullptr;  // [M, ld_res] fp32, added last (may alias out_f32: accumulate)
   int ld_res = 0;
   float* out_f32 = nullptr;
   int ld_f32 = 0;
-  bf16* out_bf16 = nullptr;
+  AT* out_bf16 = nullptr;           // activation-typed output
   int ld_bf16 = 0;
   float* colsum_out = nullptr;      // [N] fp32: += column sums of the emitted values (atomics; the bias gradient of the
                                     // Linear that consumes this output).  Only with out_bf16, not with split-K.
@@ -31,6 +33,7 @@ struct GemmEpilogue {
   float drop_p = 0.f;
   unsigned long long seed = 0, stream = 0;
 };
+typedef GemmEpilogueT<bf16> GemmEpilogue;
 
 // D[M, N] = A . B^T over the contraction dimension K, bf16 inputs, fp32 accumulation in TMEM.
 //   a_mn == 0: A is stored [M, K] row-major with pitch lda (K-major);  a_mn == 1: stored [K, M] with pitch lda.
@@ -40,6 +43,14 @@ struct GemmEpilogue {
 // wgrad    dW = dy^T x    : A = dy stored [rows, N'] (a_mn 1), B = x stored [rows, K'] (b_mn 1)
 int gemm_bf16(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
               const GemmEpilogue& ep, int force_bn, cudaStream_t stream);
+
+// fp32-accurate mode: the same product from fp32 operands.  Each operand is split into three bf16 planes (hi + mid + lo,
+// 24 mantissa bits), the six significant plane pairs are accumulated by the SAME tcgen05 kernel (fp32 in TMEM, units of
+// <= 1024 products summed outside with fp32 atomics), then the epilogue operators run in fp32 with the exact erf GELU.
+// `ws`: scratch of gemm_hp_ws_bytes(M, N, K) bytes, 256-byte aligned.
+size_t gemm_hp_ws_bytes(int M, int N, int K);
+int gemm_hp(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M, int N, int K,
+            const GemmEpilogueT<float>& ep, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // 2-D TMA descriptor (128-byte swizzle, box = [box_outer rows, 64 elements]) over a row-major bf16 matrix;
 // `map` points to a CUtensorMap (kept opaque here so that callers need not include <cuda.h>).

@@ -12,12 +12,14 @@ struct DropoutCfg {
 
 // ---- layernorm.cu -----------------------------------------------------------------------------
 // y = LN(x) * gamma + beta, fp32 statistics; D in {512, 768}.  Any of out_bf16 / out_f32 may be null.
-int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int D, bf16* out_bf16,
+template <typename AT>
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int D, AT* out_bf16,
                   float* out_f32, float* mean, float* rstd, cudaStream_t st);
 // dx = addend + LNbwd(dy); dx_bf16 = dropout_bwd(dx) (optional, mask of the forward's dense-output dropout);
 // dgamma/dbeta partials are reduced and ADDED to dgamma/dbeta when accumulate != 0, else stored.
+template <typename AT>
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
-                  int D, const float* addend, float* dx_f32, bf16* dx_bf16, DropoutCfg drop, float* dgamma,
+                  int D, const float* addend, float* dx_f32, AT* dx_bf16, DropoutCfg drop, float* dgamma,
                   float* dbeta, float* colsum_out, int accumulate, cudaStream_t st, const float* out_row_scale = nullptr,
                   int rows_per_scale = 1);
 size_t layernorm_bwd_ws_floats(int D);
@@ -95,10 +97,11 @@ template <typename AT>
 int add_batch_rowvec_oop(const AT* x, const AT* vec, int B, int T, int D, AT* y, cudaStream_t st);
 
 // ---- attention.cu -----------------------------------------------------------------------------
-struct AttnArgs {
-  const bf16 *q = nullptr, *k = nullptr, *v = nullptr;  // head h lives at columns [h*D, (h+1)*D) of each row
+template <typename AT>
+struct AttnArgsT {
+  const AT *q = nullptr, *k = nullptr, *v = nullptr;  // head h lives at columns [h*D, (h+1)*D) of each row
   int ldq = 0, ldk = 0, ldv = 0;
-  bf16* o = nullptr;
+  AT* o = nullptr;
   int ldo = 0;
   float* lse = nullptr;              // [B, H, Sq]
   const int64_t* key_mask = nullptr;  // [B, Sk], nonzero = attend (HF attention_mask); null = all valid
@@ -106,15 +109,22 @@ struct AttnArgs {
   float scale = 1.f;
   DropoutCfg drop;
   // backward only
-  const bf16* d_o = nullptr;
+  const AT* d_o = nullptr;
   int ld_do = 0;
   float* delta = nullptr;  // [B, H, Sq] scratch
-  bf16 *dq = nullptr, *dk = nullptr, *dv = nullptr;
+  AT *dq = nullptr, *dk = nullptr, *dv = nullptr;
   int lddq = 0, lddk = 0, lddv = 0;
   // optional [H * D] fp32 each: += column sums over all (batch, position) rows of dq / dk / dv (atomic adds) = the bias
   // gradients of the query / key / value projections, folded into the kernel that produces their operand
   float *cs_q = nullptr, *cs_k = nullptr, *cs_v = nullptr;
+  // fp32-accurate mode only: scratch of 2 * B * H * Sq * Sk floats (dS and the dropped probabilities between the two
+  // backward kernels)
+  float* hp_ws = nullptr;
 };
+typedef AttnArgsT<bf16> AttnArgs;
+// fp32-accurate mode (attention_hp.cu): the same attention on fp32 q / k / v with fp32 CUDA-core arithmetic
+int attention_fwd(const AttnArgsT<float>& a, cudaStream_t st);
+int attention_bwd(const AttnArgsT<float>& a, cudaStream_t st);
 int attention_fwd(const AttnArgs& a, cudaStream_t st);
 int attention_bwd(const AttnArgs& a, cudaStream_t st);
 // probs[B, H, Sq, Sk] fp32 = exp(scale * q . k - lse), masked keys 0 (needs the lse of a preceding attention_fwd)
@@ -138,12 +148,15 @@ int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, cons
                 float* loss_tiles = nullptr /*B*196 scratch*/, float* loss_out = nullptr /*also emit the loss*/);
 size_t sr_ws_floats(int B);
 // d_pred[b, 0] = 0; d_pred[b, 1 + l, e] = g_mim * 2 * mask * (pred - tgt) / Nmim + bilinear^T(d_u) (if d_u)
+template <typename AT>
 int pred_grad(const float* pred, const float* tgt, const float* mask, const float* d_u, const float* g_mim, int B,
-              bf16* d_pred, cudaStream_t st);
+              AT* d_pred, cudaStream_t st);
 // weighted cross-entropy over a chunk of rows, logits bf16 [rows, V] (ld = ldl); optionally overwrites the
 // logits with d_logits = (softmax - onehot) * w * g / total_rows           (bert_modeling.py:211-217)
 int ce_chunk(bf16* logits, int ldl, int rows, int V, const int64_t* labels, const float* weights, float* row_loss,
              const float* g_mlm, float inv_total, int write_grad, cudaStream_t st);
+int ce_chunk(float* logits, int ldl, int rows, int V, const int64_t* labels, const float* weights, float* row_loss,
+             const float* g_mlm, float inv_total, int write_grad, cudaStream_t st);  // fp32-accurate mode
 int sum_to_scalar(const float* x, size_t n, float scale, float* out, cudaStream_t st);
 
 // ---- adamw.cu ---------------------------------------------------------------------------------
@@ -153,6 +166,7 @@ struct AdamTensor {
   float* m;
   float* v;
   bf16* shadow;        // bf16 GEMM copy, may be null
+  float* shadow_f;     // fp32-accurate mode: the GEMM copy in fp32 (same layouts), may be null
   float* shadow32;     // fp32 copy (fused q|k|v bias vectors), may be null
   long long numel;
   int decay;           // 1 = apply weight decay

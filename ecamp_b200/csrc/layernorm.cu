@@ -12,10 +12,10 @@ constexpr int kRowsPerBlock = 8;
 constexpr int kBwdWarps = 4;     // rows in flight per backward CTA (one shared-memory slab of column sums per warp)
 constexpr int kBwdBlocks = 740;  // 148 SMs x 5 resident CTAs (slabs + gamma: 27-40 KB per CTA)
 
-template <int NV>
+template <int NV, typename AT>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float eps, int M,
-                                                     bf16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                                                     AT* __restrict__ out_bf16, float* __restrict__ out_f32,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   ECAMP_PDL_ENTRY();
   constexpr int D = NV * 128;
@@ -53,12 +53,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     y.z = (v[i].z - mean) * rstd * g.z + b.z;
     y.w = (v[i].w - mean) * rstd * g.w + b.w;
     if (out_f32) reinterpret_cast<float4*>(out_f32 + (size_t)row * D)[c4] = y;
-    if (out_bf16) {
-      uint2 u;
-      u.x = pack_bf16x2(y.x, y.y);
-      u.y = pack_bf16x2(y.z, y.w);
-      reinterpret_cast<uint2*>(out_bf16 + (size_t)row * D)[c4] = u;
-    }
+    if (out_bf16) st4(out_bf16 + (size_t)row * D + 4 * c4, y);
   }
 }
 
@@ -69,12 +64,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 // at 151 registers / one CTA per SM and 2.9 TB/s.  At the end the eight slabs are summed and added to global memory
 // with fp32 atomics (the destinations are zeroed at the start of the backward pass), which also removes the
 // separate finalize kernel.
-template <int NV, bool COLSUM>
+template <int NV, bool COLSUM, typename AT>
 __global__ void __launch_bounds__(kBwdWarps * 32, 6) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, int M,
                                                      const float* __restrict__ addend, float* __restrict__ dx_f32,
-                                                     bf16* __restrict__ dx_bf16, DropoutCfg drop,
+                                                     AT* __restrict__ dx_bf16, DropoutCfg drop,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      float* __restrict__ colsum_out,
                                                      const float* __restrict__ out_row_scale, int rows_per_scale) {
@@ -154,14 +149,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 6) ln_bwd_kernel(const float* 
           r.z = rnd.z >= thr ? r.z * keep_scale : 0.f;
           r.w = rnd.w >= thr ? r.w * keep_scale : 0.f;
         }
-        uint2 u;
-        u.x = pack_bf16x2(r.x, r.y);
-        u.y = pack_bf16x2(r.z, r.w);
-        reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * D)[c4] = u;
+        st4(dx_bf16 + (size_t)row * D + 4 * c4, r);
         if (COLSUM) {  // bias gradient of the Linear fed by dx_bf16: column sum of what that GEMM reads
-          const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+          const float4 rr = act_round4(dx_bf16, r);
           float4 cs = my_cs[c4];
-          cs.x += lo.x; cs.y += lo.y; cs.z += hi.x; cs.w += hi.y;
+          cs.x += rr.x; cs.y += rr.y; cs.z += rr.z; cs.w += rr.w;
           my_cs[c4] = cs;
         }
       }
@@ -184,13 +176,13 @@ int bwd_blocks(int M) {
   return need < cap ? need : cap;
 }
 
-template <int NV, bool COLSUM>
+template <int NV, bool COLSUM, typename AT>
 int launch_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
-                  const float* addend, float* dx_f32, bf16* dx_bf16, DropoutCfg drop, float* dgamma, float* dbeta,
+                  const float* addend, float* dx_f32, AT* dx_bf16, DropoutCfg drop, float* dgamma, float* dbeta,
                   float* colsum_out, cudaStream_t st, const float* out_row_scale, int rows_per_scale) {
   constexpr int D = NV * 128;
   constexpr size_t smem = (size_t)(D + kBwdWarps * (COLSUM ? 3 : 2) * D) * sizeof(float);
-  auto kfn = ln_bwd_kernel<NV, COLSUM>;
+  auto kfn = ln_bwd_kernel<NV, COLSUM, AT>;
   static bool attr = false;
   if (!attr) {
     ECAMP_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -205,21 +197,23 @@ int launch_ln_bwd(const float* dy, const float* x, const float* mean, const floa
 
 size_t layernorm_bwd_ws_floats(int) { return 0; }  // kept for the C ABI: the backward no longer needs a workspace
 
-int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int D, bf16* out_bf16,
+template <typename AT>
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int M, int D, AT* out_bf16,
                   float* out_f32, float* mean, float* rstd, cudaStream_t st) {
   ECAMP_REQUIRE(D == 768 || D == 512, "layernorm: D must be 512 or 768 (got %d)", D);
   if (M <= 0) return 0;
   const int grid = (M + kRowsPerBlock - 1) / kRowsPerBlock;
   if (D == 768)
-    ECAMP_CUDA_OK(launch_pdl(ln_fwd_kernel<6>, grid, 256, 0, st, x, gamma, beta, eps, M, out_bf16, out_f32, mean, rstd));
+    ECAMP_CUDA_OK(launch_pdl(ln_fwd_kernel<6, AT>, grid, 256, 0, st, x, gamma, beta, eps, M, out_bf16, out_f32, mean, rstd));
   else
-    ECAMP_CUDA_OK(launch_pdl(ln_fwd_kernel<4>, grid, 256, 0, st, x, gamma, beta, eps, M, out_bf16, out_f32, mean, rstd));
+    ECAMP_CUDA_OK(launch_pdl(ln_fwd_kernel<4, AT>, grid, 256, 0, st, x, gamma, beta, eps, M, out_bf16, out_f32, mean, rstd));
   ECAMP_LAUNCHED();
   return 0;
 }
 
+template <typename AT>
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
-                  int D, const float* addend, float* dx_f32, bf16* dx_bf16, DropoutCfg drop, float* dgamma,
+                  int D, const float* addend, float* dx_f32, AT* dx_bf16, DropoutCfg drop, float* dgamma,
                   float* dbeta, float* colsum_out, int accumulate, cudaStream_t st, const float* out_row_scale,
                   int rows_per_scale) {
   ECAMP_REQUIRE(D == 768 || D == 512, "layernorm: D must be 512 or 768 (got %d)", D);
@@ -231,11 +225,21 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
     if (colsum_out) ECAMP_CUDA_OK(cudaMemsetAsync(colsum_out, 0, (size_t)D * sizeof(float), st));
   }
   if (D == 768) {
-    if (colsum_out) return launch_ln_bwd<6, true>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out, st, out_row_scale, rows_per_scale);
-    return launch_ln_bwd<6, false>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, nullptr, st, out_row_scale, rows_per_scale);
+    if (colsum_out) return launch_ln_bwd<6, true, AT>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out, st, out_row_scale, rows_per_scale);
+    return launch_ln_bwd<6, false, AT>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, nullptr, st, out_row_scale, rows_per_scale);
   }
-  if (colsum_out) return launch_ln_bwd<4, true>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out, st, out_row_scale, rows_per_scale);
-  return launch_ln_bwd<4, false>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, nullptr, st, out_row_scale, rows_per_scale);
+  if (colsum_out) return launch_ln_bwd<4, true, AT>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, colsum_out, st, out_row_scale, rows_per_scale);
+  return launch_ln_bwd<4, false, AT>(dy, x, mean, rstd, gamma, M, addend, dx_f32, dx_bf16, drop, dgamma, dbeta, nullptr, st, out_row_scale, rows_per_scale);
 }
+
+#define ECAMP_INST_LN(AT)                                                                                              \
+  template int layernorm_fwd<AT>(const float*, const float*, const float*, float, int, int, AT*, float*, float*, float*, \
+                                 cudaStream_t);                                                                          \
+  template int layernorm_bwd<AT>(const float*, const float*, const float*, const float*, const float*, int, int,         \
+                                 const float*, float*, AT*, DropoutCfg, float*, float*, float*, int, cudaStream_t,       \
+                                 const float*, int);
+ECAMP_INST_LN(bf16)
+ECAMP_INST_LN(float)
+#undef ECAMP_INST_LN
 
 }  // namespace ecamp

@@ -421,17 +421,18 @@ ECAMP_DEVINL void bilinear_t_weights(int y, float (&w)[4]) {
   if (y == 0) { w[0] = 0.f; w[1] = 1.0f; }
   if (y == IMG - 1) { w[2] = 1.0f; w[3] = 0.f; }
 }
+template <typename AT>
 __global__ void __launch_bounds__(256) pred_grad_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
                                                         const float* __restrict__ mask, const float* __restrict__ d_u,
                                                         const float* __restrict__ g_mim, int B,
-                                                        bf16* __restrict__ d_pred) {
+                                                        AT* __restrict__ d_pred) {
   ECAMP_PDL_ENTRY();
   constexpr int RW = 34;  // 16 source pixels x 2 + one halo pixel on each side, in the up-sampled grid
   __shared__ float sdu[3 * RW * RW];
   const int r = blockIdx.x, b = r / 197, t = r % 197;
-  bf16* out = d_pred + (size_t)r * PD;
+  AT* out = d_pred + (size_t)r * PD;
   if (t == 0) {
-    for (int e = threadIdx.x; e < PD; e += blockDim.x) out[e] = f2bf(0.f);
+    for (int e = threadIdx.x; e < PD; e += blockDim.x) act_st(out + e, 0.f);
     return;
   }
   const int l = t - 1, hy = l / GRID, wx = l % GRID;
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(256) pred_grad_kernel(const float* __restrict_
       }
       g += acc;
     }
-    out[e] = f2bf(g);
+    act_st(out + e, g);
   }
 }
 
@@ -558,6 +559,45 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(bf16* __restrict__ logits,
   }
 }
 
+// fp32-accurate mode: the same cross-entropy on fp32 logits (three passes over the row in global / L2: max, sum of
+// exponentials with expf / logf, gradient written over the logits)
+__global__ void __launch_bounds__(256) ce_rows_f32_kernel(float* __restrict__ logits, int ldl, int V,
+                                                          const int64_t* __restrict__ labels,
+                                                          const float* __restrict__ weights, float* __restrict__ row_loss,
+                                                          const float* __restrict__ g_mlm, float inv_total,
+                                                          int write_grad) {
+  ECAMP_PDL_ENTRY();
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  float* grow = logits + (size_t)r * ldl;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, grow[i]);
+  mx = warp_max(mx);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  const long long label = labels[r];
+  const bool valid = label >= 0 && label < V;
+  const float z_label = valid ? grow[label] : 0.f;
+  float se = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) se += expf(grow[i] - mx);
+  se = block_sum(se, red);
+  const float lse = mx + logf(se);
+  const float w = weights[r];
+  if (threadIdx.x == 0) row_loss[r] = valid ? (lse - z_label) * w : 0.f;
+  if (!write_grad) return;
+  __syncthreads();  // every thread has read the label logit before the row is overwritten
+  const float coef = valid ? w * (*g_mlm) * inv_total : 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    float g = expf(grow[i] - lse) * coef;
+    if (valid && i == (int)label) g -= coef;
+    grow[i] = g;
+  }
+}
+
 }  // namespace
 
 #define LAUNCH_OK() ECAMP_LAUNCHED()
@@ -617,9 +657,22 @@ int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, cons
   return 0;
 }
 
+template <typename AT>
 int pred_grad(const float* pred, const float* tgt, const float* mask, const float* d_u, const float* g_mim, int B,
-              bf16* d_pred, cudaStream_t st) {
-  ECAMP_CUDA_OK(launch_pdl(pred_grad_kernel, B * 197, 256, 0, st, pred, tgt, mask, d_u, g_mim, B, d_pred));
+              AT* d_pred, cudaStream_t st) {
+  ECAMP_CUDA_OK(launch_pdl(pred_grad_kernel<AT>, B * 197, 256, 0, st, pred, tgt, mask, d_u, g_mim, B, d_pred));
+  LAUNCH_OK();
+  return 0;
+}
+
+template int pred_grad<bf16>(const float*, const float*, const float*, const float*, const float*, int, bf16*, cudaStream_t);
+template int pred_grad<float>(const float*, const float*, const float*, const float*, const float*, int, float*, cudaStream_t);
+
+int ce_chunk(float* logits, int ldl, int rows, int V, const int64_t* labels, const float* weights, float* row_loss,
+             const float* g_mlm, float inv_total, int write_grad, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  ECAMP_CUDA_OK(launch_pdl(ce_rows_f32_kernel, rows, 256, 0, st, logits, ldl, V, labels, weights, row_loss, g_mlm, inv_total,
+                           write_grad));
   LAUNCH_OK();
   return 0;
 }

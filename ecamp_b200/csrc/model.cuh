@@ -50,7 +50,11 @@ int ctx_bind(Ctx*, float* const* params, int n, float* G, float* M1, float* M2, 
              const float* pos_embed, const float* dec_pos_embed, void* adam_table, void* adam_chunks);
 size_t ctx_adam_table_bytes();
 size_t ctx_adam_chunk_bytes();
-size_t workspace_bytes(const Shape&);
+size_t workspace_bytes(const Shape&, int hp);
+// 0 = production (bf16 GEMM / attention operands), 1 = fp32-accurate parity mode (fp32 activations, bf16 x 3 split-operand
+// GEMMs on the same tcgen05 kernel).  Changing it resets the context: bind() and set_workspace() must follow.
+int ctx_set_precision(Ctx*, int hp);
+int ctx_precision(Ctx*);
 int ctx_set_workspace(Ctx*, void* ws, size_t bytes, const Shape&);
 int ctx_refresh_shadows(Ctx*, cudaStream_t);
 // flags: 1 = training (saves activations), 2 = defer the MLM loss to backward (fused head)

@@ -234,6 +234,7 @@ class ECAMP(nn.Module):
         # runtime state (not part of the state_dict)
         self.image_mean, self.image_std = 0.4721, 0.3037   # transforms.Normalize of pretrain_datasets.py:52 (uint8 inputs)
         self._rt = None
+        self._precision = 0                 # 0 = production (bf16 operands), 1 = fp32-accurate parity mode (set_precision)
         self._dropout_step = 0
         self.ce_rows = int(os.environ.get("ECAMP_CE_ROWS", "2048"))   # rows per vocabulary-head chunk (tuning knob)
 
@@ -287,7 +288,7 @@ class ECAMP(nn.Module):
         rt = self._rt
         named = dict(self.named_parameters())
         if rt is None:
-            rt = dict(ctx=ctypes.c_void_p(), names=[], ws=None, shape=None, versions=None, ptrs=None)
+            rt = dict(ctx=ctypes.c_void_p(), names=[], ws=None, shape=None, versions=None, ptrs=None, precision=0)
             L.check(lib.ecamp_ctx_create(ctypes.byref(rt["ctx"])), "ecamp_ctx_create")
             n = lib.ecamp_param_count()
             for i in range(n):
@@ -315,6 +316,9 @@ class ECAMP(nn.Module):
             if p.device.type != "cuda" or p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("ecamp_b200: parameters must be contiguous fp32 CUDA tensors (call model.cuda())")
         ptrs = tuple(p.data_ptr() for p in params) + (self.pos_embed.data_ptr(), self.decoder_pos_embed.data_ptr())
+        if rt["precision"] != self._precision:   # buffers are laid out per precision: re-bind, re-plan the workspace
+            L.check(lib.ecamp_ctx_set_precision(rt["ctx"], ctypes.c_int32(self._precision)), "ecamp_ctx_set_precision")
+            rt["precision"], rt["ptrs"], rt["shape"], rt["ws"] = self._precision, None, None, None
         if rt["ptrs"] != ptrs:
             if rt.get("G") is None or rt["G"].device != device:
                 gf = lib.ecamp_grad_floats()
@@ -343,7 +347,7 @@ class ECAMP(nn.Module):
         if rt["shape"] != shape:
             lib = L.lib()
             s = L.Shape(*shape)
-            need = lib.ecamp_workspace_bytes(ctypes.byref(s))
+            need = lib.ecamp_ctx_workspace_bytes(rt["ctx"], ctypes.byref(s))
             if rt["ws"] is None or rt["ws"].numel() < need:
                 rt["ws"] = None
                 rt["ws"] = torch.empty(need, dtype=torch.uint8, device=device)
@@ -568,6 +572,16 @@ class ECAMP(nn.Module):
             idx = self.last["ids_restore"][:, None, None, :].expand(B, 6, T, 196)
             probs = torch.gather(probs, 3, idx)
         return probs
+
+    def set_precision(self, precision):
+        """"bf16" (default): production - GEMM / attention operands in bf16 with fp32 accumulation, the reference's
+        autocast.  "fp32": the fp32-accurate parity mode - the same native schedule with fp32 activations, every GEMM on
+        the same tcgen05 kernel with error-compensated bf16 x 3 split operands, attention in fp32; exists to pin the
+        algebra of the step against the fp32 oracle at 1e-5 and is roughly an order of magnitude slower."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self._precision = 1 if precision == "fp32" else 0
+        return self
 
     def flat_grads(self):
         return self._rt["G"] if self._rt else None

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ECAMP_ABI_VERSION 3
+#define ECAMP_ABI_VERSION 4
 #if defined(__GNUC__)
 #define ECAMP_API __attribute__((visibility("default")))
 #else
@@ -80,6 +80,15 @@ typedef struct ecamp_epilogue {
 ECAMP_API void ecamp_gemm_set_cta_pair(int32_t mode);
 ECAMP_API int ecamp_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int32_t ldb, int32_t b_mn,
                               int32_t M, int32_t N, int32_t K, const ecamp_epilogue* ep, int32_t tile_n, void* stream);
+
+/* The same product from fp32 operands in the fp32-accurate parity mode: each operand is split into three bf16 planes,
+ * the six significant plane pairs are accumulated by the same tcgen05 kernel, the epilogue runs in fp32 (exact erf GELU).
+ * In `ep`, aux_in / aux_out / out_bf16 point to FP32 arrays here.  `ws`: ecamp_gemm_fp32_ws_bytes(M, N, K) bytes, 256-byte
+ * aligned. */
+ECAMP_API int64_t ecamp_gemm_fp32_ws_bytes(int32_t M, int32_t N, int32_t K);
+ECAMP_API int ecamp_gemm_fp32(const float* A, int32_t lda, int32_t a_mn, const float* B, int32_t ldb, int32_t b_mn,
+                              int32_t M, int32_t N, int32_t K, const ecamp_epilogue* ep, void* ws, int64_t ws_bytes,
+                              void* stream);
 
 /* random_masking on caller-supplied noise (module/model_ecamp.py:168-193): stable ascending argsort.
  * ids_restore / ids_keep int64 as in the reference, mask fp32 {0,1} (1 = removed). */
@@ -168,7 +177,7 @@ ECAMP_API int64_t ecamp_param_numel(int32_t i);
 ECAMP_API int32_t ecamp_param_decay(int32_t i);        /* timm add_weight_decay group         */
 ECAMP_API int64_t ecamp_param_grad_offset(int32_t i);  /* floats into the flat grad buffer    */
 ECAMP_API int64_t ecamp_grad_floats(void);
-ECAMP_API int64_t ecamp_shadow_bytes(void);            /* bf16 GEMM copies + fused fp32 biases */
+ECAMP_API int64_t ecamp_shadow_bytes(void);            /* GEMM copies (sized for either precision) + fused fp32 biases */
 ECAMP_API int64_t ecamp_adam_table_bytes(void);
 ECAMP_API int64_t ecamp_adam_chunk_bytes(void);
 
@@ -183,7 +192,15 @@ ECAMP_API int ecamp_ctx_bind(ecamp_ctx* ctx, float* const* params_host, int32_t 
 typedef struct ecamp_shape {
   int32_t B, T, len_keep, has_big, ce_rows;
 } ecamp_shape;
-ECAMP_API int64_t ecamp_workspace_bytes(const ecamp_shape* s);
+ECAMP_API int64_t ecamp_workspace_bytes(const ecamp_shape* s);   /* production precision */
+/* Precision of the step: 0 = production (bf16 GEMM / attention operands with fp32 accumulation, the reference's autocast
+ * in bf16), 1 = fp32-accurate parity mode: the SAME schedule and kernels instantiated with fp32 activations, every GEMM on
+ * the same tcgen05 kernel with error-compensated bf16 x 3 split operands (gemm.cu: gemm_hp), attention in fp32.  It exists
+ * to pin the algebra of the step against the fp32 oracle at 1e-5 (north_star's fp32 tolerance); it is ~10 x slower.
+ * Changing the precision resets the context: ecamp_ctx_bind() and ecamp_ctx_set_workspace() must follow; the workspace
+ * size of the current precision comes from ecamp_ctx_workspace_bytes(). */
+ECAMP_API int ecamp_ctx_set_precision(ecamp_ctx* ctx, int32_t fp32_accurate);
+ECAMP_API int64_t ecamp_ctx_workspace_bytes(ecamp_ctx* ctx, const ecamp_shape* s);
 ECAMP_API int ecamp_ctx_set_workspace(ecamp_ctx* ctx, void* ws, int64_t bytes, const ecamp_shape* s);
 /* re-derive the bf16 / fused copies from the fp32 parameters (after load_state_dict, an external
  * optimizer step, ...). */
