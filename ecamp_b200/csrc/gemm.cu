@@ -49,6 +49,10 @@ constexpr int kSteps = 32 / kRPS;                  // steps per chunk (= kLPR)
 constexpr int kStageFloats = 32 * kCW;             // transpose tile of one warp
 
 
+constexpr int kBarBytes = 512;      // mbarriers + TMEM slot
+constexpr int kTmaSlots = 3;        // TMA epilogue: per epilogue warp a ring of 32 x 32 fp32 tiles (4 KB each)
+constexpr int kTmaSlotBytes = 4096;
+
 template <int BN>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -56,7 +60,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 128) ? 6 : 4;
   static constexpr int EPI_BYTES = kNumEpiWarps * kStageFloats * 4;  // one 32 x kCW fp32 transpose tile per epilogue warp
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + kBarBytes /*barriers*/ + 1024 /*alignment slack*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget of one CTA exceeded");
 };
 
@@ -74,10 +78,15 @@ struct EpiArgs {
   // k-blocks are numbered virtually, v = term * num_kb + kb, and split over work units like a plain split-K.  1 otherwise.
   int nterms;
   unsigned char term_a[6], term_b[6];
+  int stages;     // depth of the operand ring (what the shared memory left by the epilogue region holds)
+  int epi_bytes;  // shared memory of the epilogue region
+  int tma_epi;    // 1: fp32-output epilogue through TMA (residual tiles loaded, results stored by cp.async.bulk.tensor)
 };
-struct TmaSet {  // one tensor map per operand plane (production: plane 0 only)
+struct TmaSet {  // one tensor map per operand plane (production: plane 0 only) + the fp32 epilogue operands
   CUtensorMap a[3], b[3];
+  CUtensorMap res, out;  // tma_epi: fp32 [M, N] residual / output, box 32 x 32, 128-byte swizzle
 };
+
 
 // work unit -> (row block, column block)
 ECAMP_DEVINL void decode_tile(const EpiArgs& ea, int tile, int m_tiles, int& m_blk, int& n_blk) {
@@ -447,6 +456,144 @@ ECAMP_DEVINL void epilogue_loop(const EpiArgs& ea, uint32_t tmem_base, int q, in
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
 }
+// ---------------------------------------------------------------------------------------------
+// fp32-output epilogue through TMA (EM_F32 / EM_F32_RES / EM_F32_RES_DROP on the CTA-pair kernel).  tcgen05.ld hands every
+// thread one ROW of the accumulator; instead of transposing to a coalesced layout, each epilogue warp keeps a ring of three
+// 32 x 32 fp32 tiles in shared memory with the 128-byte swizzle of the tensor maps: the residual tile arrives by TMA (two
+// chunks ahead, across tile boundaries - nothing waits in registers), thread r combines its row with row r of the tile in
+// place (16-byte unit j of row r lives at j ^ (r & 7): conflict-free for row-per-thread access), and one lane sends the
+// tile to global memory with a TMA store.  No global loads / stores go through the LSU any more.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int MODE>
+ECAMP_DEVINL void epilogue_tma_loop(const EpiArgs& ea, const TmaSet& maps, uint32_t tmem_base, int q, int slice, int unit0,
+                                    int unit_step, int num_units, int num_tiles, int m_tiles, int m_stride, int m_off, int M,
+                                    int N, uint8_t* slots, uint64_t* res_bar, int lane, uint64_t* tmem_full,
+                                    uint64_t* tmem_empty, bool remote_empty) {
+  constexpr bool RES = MODE != EM_F32;
+  constexpr int COLS = BN / kSlices, NCH = COLS / 32;
+  static_assert(kCW == 32, "the TMA epilogue works on 32-column chunks");
+  const GemmEpilogue& ep = ea.ep;
+  const uint32_t slot_base = smem_u32(slots);
+  // chunk stream of this warp: (unit, c) for unit = unit0, unit0 + unit_step, ... and c = 0 .. NCH-1; chunks whose rows or
+  // columns lie completely outside the matrix are skipped by both cursors
+  auto coords = [&](int unit, int c, int& row0, int& col0) {
+    int mb, nb;
+    decode_tile(ea, unit % num_tiles, m_tiles, mb, nb);
+    row0 = mb * m_stride + m_off + q * 32;
+    col0 = nb * BN + slice * COLS + c * 32;
+    return row0 < M && col0 < N;
+  };
+  uint32_t n_issued = 0, n_done = 0;  // residual loads issued / chunks completed
+  int lu = unit0, lc = 0;            // load cursor
+  auto issue_next_load = [&]() {     // lane 0 only
+    while (lu < num_units) {
+      int r0, c0;
+      const bool act = coords(lu, lc, r0, c0);
+      if (++lc == NCH) { lc = 0; lu += unit_step; }
+      if (act) {
+        const uint32_t s = n_issued % kTmaSlots;
+        mbar_arrive_expect_tx(&res_bar[s], kTmaSlotBytes);
+        tma_load_2d(slots + s * kTmaSlotBytes, &maps.res, &res_bar[s], c0, r0);
+        ++n_issued;
+        return;
+      }
+    }
+  };
+  if (RES && lane == 0) { issue_next_load(); issue_next_load(); }
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  const Philox ph(ep.seed);
+  const uint32_t thr = dropout_threshold(ep.drop_p);
+  const float keep_scale = 1.0f / (1.0f - ep.drop_p);
+  for (int unit = unit0; unit < num_units; unit += unit_step) {
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slice * COLS);
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32(taddr + (uint32_t)(c * 32), raw);
+      int row0, col0;
+      const bool act = coords(unit, c, row0, col0);
+      tmem_ld_wait();
+      if (c == NCH - 1) {  // all of this warp's TMEM reads for the tile are done: hand the accumulator stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (remote_empty) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+      }
+      if (!act) continue;
+      const uint32_t s = n_done % kTmaSlots;
+      const uint32_t sa = slot_base + s * kTmaSlotBytes + (uint32_t)lane * 128u;
+      if (RES) {
+        mbar_wait(&res_bar[s], (n_done / kTmaSlots) & 1u);
+      } else {
+        // the slot was the source of the store two chunks ago: that store must have read it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+      }
+      const int row = row0 + lane;
+      float rs = 1.0f;
+      if (MODE == EM_F32_RES && ep.row_scale && row < M) rs = __ldg(ep.row_scale + row / ep.rows_per_scale);  // DropPath
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t a = sa + (uint32_t)((j ^ (lane & 7)) << 4);
+        float4 x = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+                               __uint_as_float(raw[4 * j + 3]));
+        const int col = col0 + 4 * j;
+        if (ep.bias && col < N) {  // N % 4 == 0 (host-checked): a 4-column group is inside or outside as a whole
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+          x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+        }
+        if (MODE == EM_F32_RES_DROP) {
+          const uint4 r = ph((((uint64_t)row * (uint64_t)N + (uint64_t)col)) >> 2, ep.stream);
+          x.x = (r.x >= thr) ? x.x * keep_scale : 0.f;
+          x.y = (r.y >= thr) ? x.y * keep_scale : 0.f;
+          x.z = (r.z >= thr) ? x.z * keep_scale : 0.f;
+          x.w = (r.w >= thr) ? x.w * keep_scale : 0.f;
+        }
+        if (RES) {
+          const float4 r4 = lds128(a);
+          x.x = fmaf(x.x, rs, r4.x); x.y = fmaf(x.y, rs, r4.y); x.z = fmaf(x.z, rs, r4.z); x.w = fmaf(x.w, rs, r4.w);
+        }
+        sts128(a, __float_as_uint(x.x), __float_as_uint(x.y), __float_as_uint(x.z), __float_as_uint(x.w));
+      }
+      fence_proxy_async_smem();  // generic-proxy writes of the tile -> visible to the TMA store
+      __syncwarp();
+      ++n_done;
+      if (lane == 0) {
+        tma_store_2d(&maps.out, slots + s * kTmaSlotBytes, col0, row0);
+        tma_store_commit();
+        if (RES) {
+          // the next load goes to the slot of the chunk BEFORE this one: its store must have read the tile
+          tma_store_wait_read<1>();
+          issue_next_load();
+        }
+      }
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
+  if (lane == 0) tma_store_wait_all();  // the stores read shared memory that dies with the CTA
+}
+
+template <int BN>
+ECAMP_DEVINL void epilogue_tma_dispatch(const EpiArgs& ea, const TmaSet& maps, uint32_t tmem_base, int q, int slice, int unit0,
+                                        int unit_step, int num_units, int num_tiles, int m_tiles, int m_stride, int m_off,
+                                        int M, int N, uint8_t* slots, uint64_t* res_bar, int lane, uint64_t* tmem_full,
+                                        uint64_t* tmem_empty, bool remote_empty) {
+  if (ea.mode == EM_F32)
+    epilogue_tma_loop<BN, EM_F32>(ea, maps, tmem_base, q, slice, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride, m_off,
+                                  M, N, slots, res_bar, lane, tmem_full, tmem_empty, remote_empty);
+  else if (ea.mode == EM_F32_RES)
+    epilogue_tma_loop<BN, EM_F32_RES>(ea, maps, tmem_base, q, slice, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride,
+                                      m_off, M, N, slots, res_bar, lane, tmem_full, tmem_empty, remote_empty);
+  else
+    epilogue_tma_loop<BN, EM_F32_RES_DROP>(ea, maps, tmem_base, q, slice, unit0, unit_step, num_units, num_tiles, m_tiles,
+                                           m_stride, m_off, M, N, slots, res_bar, lane, tmem_full, tmem_empty, remote_empty);
+}
+
 template <int BN>
 ECAMP_DEVINL void epilogue_dispatch(const EpiArgs& ea, uint32_t tmem_base, int q, int slice, int unit0, int unit_step,
                                     int num_units, int num_tiles, int m_tiles, int m_stride, int m_off, int M, int N,
@@ -481,13 +628,13 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ TmaSet maps, int M, int N, int K, EpiArgs ea) {
   using C = Cfg<BN>;
-  constexpr int STAGES = C::STAGES;
+  const int STAGES = ea.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * C::A_BYTES;
   float* s_epi = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::EPI_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + ea.epi_bytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -635,7 +782,11 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 128) ? 8 : 6;
   static constexpr int EPI_BYTES = kNumEpiWarps * kStageFloats * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + kBarBytes + 1024;
+  static constexpr int TMA_EPI_BYTES = kNumEpiWarps * kTmaSlots * kTmaSlotBytes;  // 96 KB
+  // operand ring of the TMA-epilogue variant: whatever fits next to the 96 KB of residual / output tiles
+  static constexpr int TMA_STAGES = (227 * 1024 - 1024 - kBarBytes - TMA_EPI_BYTES) / STAGE_BYTES;
+  static_assert(TMA_STAGES >= 3, "operand ring too shallow");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget of one CTA exceeded");
 };
 
@@ -643,18 +794,19 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ TmaSet maps, int M, int N, int K, EpiArgs ea) {
   using C = Cfg2<BN>;
-  constexpr int STAGES = C::STAGES;
+  const int STAGES = ea.stages;
   constexpr int HB = BN / 2;  // B rows staged by each CTA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * C::A_BYTES;
   float* s_epi = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + C::EPI_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + ea.epi_bytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // [kNumEpiWarps][kTmaSlots] (tma_epi)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -681,6 +833,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ TmaSet maps, int M, int N, int 
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * kNumEpiWarps);
     }
+    if (ea.tma_epi)
+      for (int i = 0; i < kNumEpiWarps * kTmaSlots; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -771,10 +925,17 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ TmaSet maps, int M, int N, int 
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int q = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
-    float* stage4k = s_epi + (warp - kEpiWarp0) * kStageFloats;
     // the leader's MMA warp owns the accumulator hand-back: both CTAs arrive on ITS barrier
-    epilogue_dispatch<BN>(ea, tmem_base, q, half, pair, num_pairs, num_units, num_tiles, m_tiles, 2 * BM, (int)rank * BM, M,
-                          N, stage4k, lane, tmem_full, tmem_empty, true);
+    if (ea.tma_epi) {
+      const int ew = warp - kEpiWarp0;
+      epilogue_tma_dispatch<BN>(ea, maps, tmem_base, q, half, pair, num_pairs, num_units, num_tiles, m_tiles, 2 * BM,
+                                (int)rank * BM, M, N, reinterpret_cast<uint8_t*>(s_epi) + ew * kTmaSlots * kTmaSlotBytes,
+                                res_bar + ew * kTmaSlots, lane, tmem_full, tmem_empty, true);
+    } else {
+      float* stage4k = s_epi + (warp - kEpiWarp0) * kStageFloats;
+      epilogue_dispatch<BN>(ea, tmem_base, q, half, pair, num_pairs, num_units, num_tiles, m_tiles, 2 * BM, (int)rank * BM, M,
+                            N, stage4k, lane, tmem_full, tmem_empty, true);
+    }
   }
 
   tc_fence_before();
@@ -826,6 +987,22 @@ int make_tmap(CUtensorMap* map, const bf16* ptr, uint64_t inner, uint64_t outer,
   return 0;
 }
 
+// fp32 matrix [outer, inner] row-major with a row pitch; box = 32 x 32 elements (128-byte rows), 128-byte swizzle
+int make_tmap_f32(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems) {
+  EncodeTiledFn fn = get_encode_fn();
+  ECAMP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ECAMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32) failed with %d (inner %llu outer %llu pitch %llu)", (int)r,
+                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems);
+  return 0;
+}
+
 // 0 = automatic (CTA pairs whenever the problem has more than one 128-row tile), 1 = single-CTA kernel only,
 // 2 = CTA-pair kernel always.  ECAMP_GEMM_CTA_PAIR overrides the default; ecamp_gemm_set_cta_pair() at run time.
 // Default 0: once the epilogue stopped being the bound (coalesced stores through the shared-memory transpose), the
@@ -833,6 +1010,11 @@ int make_tmap(CUtensorMap* map, const bf16* ptr, uint64_t inner, uint64_t outer,
 // of the step (profiles/r01c_gemm_tile_sweep.log: 8192^3 1411 vs 1289 TFLOP/s, BERT qkv 1222 vs 1020).
 int g_cta_pair_mode = [] {
   const char* e = getenv("ECAMP_GEMM_CTA_PAIR");
+  return e ? atoi(e) : 0;
+}();
+
+int g_tma_epilogue = [] {
+  const char* e = getenv("ECAMP_GEMM_TMA_EPI");
   return e ? atoi(e) : 0;
 }();
 
@@ -897,7 +1079,9 @@ int launch(const TmaSet& maps, int M, int N, int K, const EpiArgs& ea, cudaStrea
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * ea.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  ECAMP_CUDA_OK(launch_pdl(kfn, grid, kThreads, Cfg<BN>::SMEM_BYTES, st, maps, M, N, K, ea));
+  EpiArgs e2 = ea;
+  e2.stages = Cfg<BN>::STAGES; e2.epi_bytes = Cfg<BN>::EPI_BYTES; e2.tma_epi = 0;
+  ECAMP_CUDA_OK(launch_pdl(kfn, grid, kThreads, Cfg<BN>::SMEM_BYTES, st, maps, M, N, K, e2));
   ECAMP_LAUNCHED();
   return 0;
 }
@@ -907,16 +1091,20 @@ int launch2(const TmaSet& maps, int M, int N, int K, const EpiArgs& ea, cudaStre
   auto kfn = gemm_tcgen05_2cta_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
-    ECAMP_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM_BYTES));
+    ECAMP_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  EpiArgs e2 = ea;
+  e2.stages = ea.tma_epi ? Cfg2<BN>::TMA_STAGES : Cfg2<BN>::STAGES;
+  e2.epi_bytes = ea.tma_epi ? Cfg2<BN>::TMA_EPI_BYTES : Cfg2<BN>::EPI_BYTES;
+  const int smem_bytes = e2.stages * Cfg2<BN>::STAGE_BYTES + e2.epi_bytes + kBarBytes + 1024;
   const int units = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN) * ea.split_k;
   const int max_pairs = num_sms() / 2;
   const int pairs = units < max_pairs ? units : max_pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg2<BN>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -927,7 +1115,7 @@ int launch2(const TmaSet& maps, int M, int N, int K, const EpiArgs& ea, cudaStre
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  ECAMP_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, maps, M, N, K, ea));
+  ECAMP_CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, maps, M, N, K, e2));
   ECAMP_LAUNCHED();
   return 0;
 }
@@ -1044,6 +1232,24 @@ int gemm_launch(const bf16* A, size_t plane_a, int lda, int a_mn, const bf16* B,
     if (ep.row_scale && ea.mode != EM_F32_RES) ea.mode = EM_GENERIC;
   }
   if (g_force_generic_epilogue) ea.mode = EM_GENERIC;
+  // fp32 outputs of the CTA-pair kernel can leave through TMA (ecamp_gemm_set_tma_epilogue / ECAMP_GEMM_TMA_EPI=1).  OFF by
+  // default: measured on B200 (profiles/r02c_gemm_tma_epilogue_ab.md) the residual tiles' extra trips through shared
+  // memory (TMA write, row read, row write, TMA read - the transpose path makes two) and the operand ring shrinking from
+  // 6 to 4 stages cost more than the LSU traffic they remove on every shape but the dropout+residual ones.
+  ea.tma_epi = 0;
+  if (g_tma_epilogue && cta2 && kCW == 32 && (ea.mode == EM_F32 || ea.mode == EM_F32_RES || ea.mode == EM_F32_RES_DROP)) {
+    ea.tma_epi = 1;
+    rc = make_tmap_f32(&maps.out, ep.out_f32, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld_f32);
+    if (rc) return rc;
+    if (ea.mode != EM_F32) {
+      rc = make_tmap_f32(&maps.res, ep.residual, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld_res);
+      if (rc) return rc;
+    } else {
+      maps.res = maps.out;
+    }
+  } else {
+    maps.res = maps.a[0]; maps.out = maps.a[0];
+  }
   // (hp with split_k == 1, i.e. K <= 170: one unit per tile, the generic / scalar paths store into the zeroed accumulator)
   static const int dbg = getenv("ECAMP_GEMM_DBG") ? atoi(getenv("ECAMP_GEMM_DBG")) : 0;
   ea.dbg = dbg;
@@ -1173,6 +1379,7 @@ int pdl_enabled() {
   return on;
 }
 void set_cta_pair_mode(int mode) { g_cta_pair_mode = mode; }
+void set_tma_epilogue(int on) { g_tma_epilogue = on; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }

@@ -78,6 +78,9 @@ typedef struct ecamp_epilogue {
  * contiguous); = 1: stored [contraction, rows].  tile_n = 0 lets the library choose. */
 /* 0 = automatic, 1 = single-CTA tcgen05 kernel only, 2 = CTA-pair (cta_group::2) kernel always (testing knob) */
 ECAMP_API void ecamp_gemm_set_cta_pair(int32_t mode);
+/* 1 = fp32-output epilogues of the CTA-pair kernel go through TMA (residual tiles loaded and results stored with
+ * cp.async.bulk.tensor); 0 (default) = LSU epilogue through the per-warp transpose tile.  Same results either way. */
+ECAMP_API void ecamp_gemm_set_tma_epilogue(int32_t on);
 ECAMP_API int ecamp_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int32_t ldb, int32_t b_mn,
                               int32_t M, int32_t N, int32_t K, const ecamp_epilogue* ep, int32_t tile_n, void* stream);
 

@@ -189,6 +189,12 @@ def check_gemm():
         case("splitk_wgrad", 768, 768, 12800 + 37, True, True, 0, mode)
         case("vocab_tail", 700, 30000, 768, False, False, 0, mode)
     lib.ecamp_gemm_set_cta_pair(0)
+    for tma in (1, 0):   # fp32-output epilogues through TMA (cp.async.bulk.tensor load / store), then the default LSU route
+        lib.ecamp_gemm_set_tma_epilogue(tma)
+        _check_gemm_epilogues("tma" if tma else "lsu")
+
+
+def _check_gemm_epilogues(tag):
     # epilogues (each one is a specialised mode of the kernel; the last combination takes the generic path)
     M, N, K = 520, 768, 256
     a = torch.randn(M, K, device=dev).to(torch.bfloat16); b = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
@@ -232,7 +238,7 @@ def check_gemm():
     L.gemm(a, b, bias=bias, aux_out=pre, residual=res, out_f32=o32, out_bf16=o16, flags=L.GEMM_GELU, colsum_out=cs2)   # generic path
     torch.cuda.synchronize()
     e_gen = rel(o32, F.gelu(pre_ref.float()) + res); e_gcs = rel(cs2, o16.float().sum(0))
-    report("gemm_epilogues", e_bf16 < 4e-3 and e_gelu < 6e-3 and e_pre < 4e-3 and e_dgelu < 6e-3 and e_cs < 2e-3 and e_f32 < 1e-5 and
+    report(f"gemm_epilogues_{tag}", e_bf16 < 4e-3 and e_gelu < 6e-3 and e_pre < 4e-3 and e_dgelu < 6e-3 and e_cs < 2e-3 and e_f32 < 1e-5 and
            e_res < 1e-5 and abs(frac - 0.1) < 0.01 and e_drop < 1e-5 and same_mask and e_tile < 1e-6 and e_acc < 1e-5 and
            e_gen < 2e-3 and e_gcs < 2e-3 and e_gelu_g < 6e-3 and e_gsto < 4e-3 and e_dgelu_g < 4e-3 and e_cs3 < 2e-3,
            gelu_auxgrad=e_gelu_g, stored_grad=e_gsto, dgelu_auxgrad=e_dgelu_g, colsum_auxgrad=e_cs3, bf16=e_bf16, gelu=e_gelu, pre=e_pre, dgelu=e_dgelu, colsum=e_cs, f32=e_f32, residual=e_res, drop_frac=frac,
