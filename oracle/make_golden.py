@@ -4,13 +4,15 @@ Pins oracle/ecamp_oracle.py against outputs of the reference's own sources and w
 fixtures under tests/golden/ that tests/test_oracle.py (CPU) and tests/test_parity_gpu.py (GPU) check:
 
   * state_dict layout of the reference class                       -> state_dict_layout.json
-  * ViT half (random_masking, image_encoder, image_decoder, mask_2_pixel, unpatchify, super_res,
-    forward_loss) executed FROM THE REFERENCE SOURCE (module/model_ecamp.py, timm stubbed per
-    oracle/_ref_shims.py) with injected noise                      -> golden_cases.json
-  * BERT half executed by composing the installed Hugging Face modules that the reference class
-    itself instantiated (BertEmbeddings / BertAttention / BertLayer / BertLMPredictionHead ...) in the
-    order of module/context_fusion.py:21-67 and module/bert_modeling.py:113-217 (the reference's own
-    BertModel.forward override does not run on transformers 5.x)
+  * the WHOLE step executed FROM THE REFERENCE SOURCE: `ECAMP.forward(batch)` (module/model_ecamp.py:303-325) unmodified,
+    i.e. bicubic resize, random_masking, image_encoder, image_decoder, mask_2_pixel, unpatchify, super_res, forward_loss,
+    forward_report_decoder, MultiModalBertEncoder.forward (bert_encoder.py), MultimodalBertMaskedLM.forward and
+    MultimodalBertModel.forward (bert_modeling.py:15-228), ECAMPFusionLayer.forward (context_fusion.py:21-72), with
+    injected noise; losses and every parameter gradient                 -> golden_cases.json
+    (timm 0.4.12 PatchEmbed / Block are stubbed and the transformers-4.42.4 leaf entry points the reference calls -
+    BertSelfAttention / BertAttention / BertEncoder.forward signatures, get_extended_attention_mask, get_head_mask -
+    get their 4.42.4 calling convention back on transformers 5.x, both per oracle/_ref_shims.py; torchvision's Resize
+    keeps the pinned 0.14.1 default antialias=False)
   * tie-breaking of argsort on deliberately tied noise, from the reference's random_masking.
 
 Usage:  python oracle/make_golden.py          (re-generates tests/golden/*.json; asserts oracle == reference)
@@ -45,35 +47,6 @@ def with_noise(noise, fn):
         torch.rand = orig
 
 
-def hf_mlm(ref, latent, b):
-    """BERT half from the HF modules owned by the reference model, composed per the reference sources."""
-    from transformers.models.bert.modeling_bert import BertCrossAttention
-    mlmodel = ref.bert_encoder.model
-    bert = mlmodel.bert
-    fl = bert.context_fusion_layer
-    lat = ref.bert_mlp(latent)                                   # model_ecamp.py:268
-    gap = lat[:, 1:, :].mean(dim=1).unsqueeze(1)                 # :269-270
-    lat = lat[:, 1:, :]                                          # :271
-    am = b["attention_mask"]
-    ext = (1.0 - am[:, None, None, :].float()) * torch.finfo(torch.float32).min   # bert_modeling.py:92
-    emb = bert.embeddings(input_ids=b["ids"], token_type_ids=b["type_ids"])        # :113-119
-    att = fl.attention(emb, ext)[0]                              # context_fusion.py:32-39
-    cross = BertCrossAttention(bert.config)                      # HF cross-attention with the reference's q/k/v
-    cross.query, cross.key, cross.value = (fl.cross_self_attention.query, fl.cross_self_attention.key,
-                                           fl.cross_self_attention.value)   # share the reference's parameters
-    cross.eval()
-    c = cross(att, encoder_hidden_states=lat, attention_mask=None)[0]              # :45-53 (image mask is all zeros)
-    c = c + fl.gap_mlp(gap)                                      # :54-55
-    att2 = fl.out_layer(c, att)                                  # :56
-    h = fl.output(fl.intermediate(att2), att2)                   # :62-72
-    for layer in bert.encoder.layer:                             # bert_modeling.py:131-142
-        h = layer(h, ext)
-        h = h[0] if isinstance(h, tuple) else h
-    logits = mlmodel.cls.predictions.decoder(mlmodel.cls.predictions.transform(h))  # :208-209
-    ce = F.cross_entropy(logits.view(-1, 30000), b["labels"].view(-1), reduction="none")
-    return (ce * b["weights"].view(-1)).mean()                   # :211-217
-
-
 def main():
     torch.manual_seed(0)
     ref = ecamp(norm_pix_loss=True)
@@ -96,6 +69,7 @@ def main():
     ref.bert_encoder.model.cls.predictions.decoder.bias = ref.bert_encoder.model.cls.predictions.bias
     ref.eval()
     orc.eval()
+    _ref_shims.install_bert_adapters(ref)
 
     cases = []
     for (B, T, seed) in [(2, 32, 1), (3, 128, 2), (2, 256, 3)]:
@@ -105,16 +79,16 @@ def main():
         from torchvision.transforms.functional import InterpolationMode
         imgs = torchvision.transforms.Resize([224, 224], interpolation=InterpolationMode.BICUBIC, antialias=False)(big)
 
-        def ref_vit():
-            lat, mask, idr, idk = ref.image_encoder(imgs, 0.75)
-            pred = ref.image_decoder(lat, idr)
-            mim, res = ref.forward_loss(imgs, big, pred, mask, b["column"], b["row"])
-            return lat, mask, idr, idk, pred, mim, res
+        def ref_pieces():   # intermediates for the fixtures (the reference's forward does not return them)
+            with torch.no_grad():
+                lat, mask, idr, idk = ref.image_encoder(imgs, 0.75)
+                pred = ref.image_decoder(lat, idr)
+            return lat, mask, idr, idk, pred
 
         for p in ref.parameters():
             p.grad = None
-        lat, mask, idr, idk, pred, mim, res = with_noise(b["noise"], ref_vit)
-        mlm = hf_mlm(ref, lat, b)
+        lat, mask, idr, idk, pred = with_noise(b["noise"], ref_pieces)
+        mim, res, mlm = with_noise(b["noise"], lambda: ref(b))   # ECAMP.forward from the reference source, end to end
         (mim + res + mlm).backward()
         gref = {k: p.grad.clone() for k, p in ref.named_parameters() if p.grad is not None}
 
@@ -188,7 +162,7 @@ def main():
                 mask=mask_o.int().tolist(), contract="stable ascending argsort (lower index first on ties)",
                 len_keep={str(r): int(196 * (1 - r)) for r in (0.75, 0.9, 0.7, 0.5, 0.6)})
     json.dump(dict(cases=cases, ties=ties, tolerance=TOL,
-                   generator="oracle/make_golden.py against /root/reference sources + installed transformers "
+                   generator="oracle/make_golden.py: ECAMP.forward run from the /root/reference sources end to end; transformers "
                              + __import__("transformers").__version__),
               open(os.path.join(GOLD, "golden_cases.json"), "w"))
     print("wrote", GOLD)
