@@ -80,7 +80,8 @@ SYMBOLS = [
     "ecamp_backward_stage_count", "ecamp_backward_stage_range", "ecamp_backward", "ecamp_adamw_step",
     "ecamp_debug_buffer", "ecamp_cls_workspace_bytes", "ecamp_cls_set_workspace", "ecamp_cls_forward", "ecamp_cls_backward",
     "ecamp_sgd_table_bytes", "ecamp_sgd_chunk_bytes", "ecamp_sgd_build_tables", "ecamp_grad_sumsq", "ecamp_sgd_momentum_step",
-    "ecamp_attention_probs", "ecamp_cross_attention_probs", "ecamp_image_u8_normalize",
+    "ecamp_attention_probs", "ecamp_cross_attention_probs", "ecamp_image_u8_normalize", "ecamp_image_resample_kmax", "ecamp_image_resized_crop_ws_bytes", "ecamp_image_resized_crop",
+    "ecamp_image_resized_crop_host",
     "ecamp_text_mask_draw_count", "ecamp_text_context_mask", "ecamp_text_template_weights", "ecamp_text_mask_and_weights",
 ]
 
@@ -99,7 +100,7 @@ def lib():
         _lib.ecamp_abi_version.restype = ctypes.c_int
         _lib.ecamp_param_name.restype = ctypes.c_char_p
         for f in ("ecamp_param_numel", "ecamp_param_grad_offset", "ecamp_grad_floats", "ecamp_shadow_bytes",
-                  "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_workspace_bytes", "ecamp_ctx_workspace_bytes", "ecamp_launch_count", "ecamp_gemm_fp32_ws_bytes",
+                  "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_workspace_bytes", "ecamp_ctx_workspace_bytes", "ecamp_launch_count", "ecamp_gemm_fp32_ws_bytes", "ecamp_image_resized_crop_ws_bytes",
                   "ecamp_cls_workspace_bytes", "ecamp_sgd_table_bytes", "ecamp_sgd_chunk_bytes"):
             getattr(_lib, f).restype = ctypes.c_int64
         for f in ("ecamp_layernorm_ws_floats", "ecamp_sr_ws_floats"):

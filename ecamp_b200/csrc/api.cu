@@ -107,6 +107,18 @@ int ecamp_image_u8_normalize(const uint8_t* gray, int64_t n_images, int64_t pixe
                              float* out, void* stream) {
   return image_u8_normalize(gray, n_images, pixels_per_image, mean, std_, out, S(stream));
 }
+int32_t ecamp_image_resample_kmax(int32_t in_size, int32_t out) { return image_resample_kmax(in_size, out); }
+int64_t ecamp_image_resized_crop_ws_bytes(int32_t B, int32_t out, int32_t kmax, int64_t tmp_bytes) {
+  return (int64_t)image_resized_crop_ws_bytes(B, out, kmax, tmp_bytes);
+}
+int ecamp_image_resized_crop(const uint8_t* crops, const ecamp_crop_desc* desc_dev, int32_t B, int32_t hmax, int32_t out,
+                             int32_t kmax, void* ws, int64_t ws_bytes, int64_t tmp_bytes, uint8_t* dst, void* stream) {
+  static_assert(sizeof(ecamp_crop_desc) == 32, "ecamp_crop_desc layout");
+  return image_resized_crop(crops, desc_dev, B, hmax, out, kmax, ws, (size_t)ws_bytes, tmp_bytes, dst, S(stream));
+}
+int ecamp_image_resized_crop_host(const uint8_t* crop, int32_t h, int32_t w, int32_t flip, int32_t out, uint8_t* dst) {
+  return image_resized_crop_host(crop, h, w, flip, out, dst);
+}
 int ecamp_resize_patchify(const float* big, int32_t B, int32_t side_in, float* tgt, void* stream) {
   ECAMP_REQUIRE(big && tgt, "ecamp_resize_patchify: null argument");
   if (side_in == 224) return patchify224(big, B, tgt, S(stream));

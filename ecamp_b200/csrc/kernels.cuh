@@ -134,6 +134,13 @@ int attention_probs(const AttnArgs& a, float* probs, cudaStream_t st);
 int image_u8_normalize(const uint8_t* gray, long long n_images, long long pixels_per_image, float mean, float stdv, float* out,
                        cudaStream_t st);
 
+// ---- image_pipeline.cu: RandomResizedCrop (Pillow-exact antialiased bicubic) + horizontal flip of 8-bit frames ------------
+size_t image_resized_crop_ws_bytes(int B, int out, int kmax, long long tmp_bytes);
+int image_resample_kmax(int in_size, int out);
+int image_resized_crop(const uint8_t* crops, const void* desc_dev, int B, int hmax, int out, int kmax, void* ws, size_t ws_bytes,
+                       long long tmp_bytes, uint8_t* dst, cudaStream_t st);
+int image_resized_crop_host(const uint8_t* crop, int h, int w, int flip, int out, uint8_t* dst);  // host restatement (tests)
+
 // ---- losses.cu --------------------------------------------------------------------------------
 // mim = sum_{masked patches} (pred - tgt)^2 / (B*3*224*224)       (model_ecamp.py:288-297)
 int mim_loss_fwd(const float* pred, int ld_pred_rows, const float* tgt, const float* mask, int B, int L, int PD,

@@ -99,6 +99,28 @@ ECAMP_API int ecamp_random_masking(const float* noise, int32_t B, int32_t L, int
                                    int64_t* ids_keep, float* mask, void* scratch_i32 /* (B*L + B*len_keep) int32 */,
                                    void* stream);
 
+/* ---- image half of the loader (module/pretrain_datasets.py:47-52): RandomResizedCrop(448, scale 0.2-1, BICUBIC) +
+ * RandomHorizontalFlip of a decoded 8-bit grayscale frame.  The crop box and the flip are drawn on the host with torch's
+ * generator in torchvision's order (ecamp_b200/image_pipeline.py); the crop boxes of a batch are packed back to back in
+ * `crops`, image b being [h, w] row-major at desc[b].src_off.  The resampling is Pillow's (two passes with an 8-bit
+ * intermediate, antialiased bicubic a = -0.5, 22-bit fixed-point weights), so the bytes equal what the reference transform
+ * produces on the PIL image; out is [B, out, out] uint8 - ecamp_image_u8_normalize (or the uint8 input of the step) does
+ * Grayscale(3) + ToTensor + Normalize.  tmp_off: offsets into the intermediate image buffer ([h, out] bytes per image,
+ * `tmp_bytes` in total); kmax = max over the batch of ecamp_image_resample_kmax(max(h, w), out). */
+typedef struct ecamp_crop_desc {
+  int64_t src_off, tmp_off;
+  int32_t h, w, flip, pad;
+} ecamp_crop_desc;
+ECAMP_API int32_t ecamp_image_resample_kmax(int32_t in_size, int32_t out);
+ECAMP_API int64_t ecamp_image_resized_crop_ws_bytes(int32_t B, int32_t out, int32_t kmax, int64_t tmp_bytes);
+ECAMP_API int ecamp_image_resized_crop(const uint8_t* crops, const ecamp_crop_desc* desc_dev, int32_t B, int32_t hmax,
+                                       int32_t out, int32_t kmax, void* ws, int64_t ws_bytes, int64_t tmp_bytes,
+                                       uint8_t* dst, void* stream);
+/* the same arithmetic on the host for ONE crop box: test infrastructure (checked against Pillow without a GPU), never
+ * called by the product */
+ECAMP_API int ecamp_image_resized_crop_host(const uint8_t* crop, int32_t h, int32_t w, int32_t flip, int32_t out,
+                                            uint8_t* dst);
+
 /* bicubic 448 -> 224 of torchvision Resize (module/model_ecamp.py:318), result in patch layout
  * tgt[b, l, (p*16+q)*3+c] == patchify(resized) with p = 16. */
 /* Tail of the image transform of module/pretrain_datasets.py:47-52 on the GPU: Grayscale(3) + ToTensor + Normalize of the

@@ -1163,7 +1163,44 @@ def check_step_fp32():
            rel(m.flat_grads(), g1) < 1.5e-2, losses=l2.tolist(), grads_vs_fp32_mode=rel(m.flat_grads(), g1))
 
 
-ALL_CHECKS = (check_gemm_fp32, check_step_fp32, check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
+@guard
+def check_image_pipeline():
+    """Image half of the loader on the GPU: RandomResizedCrop(448, 0.2-1, BICUBIC) + RandomHorizontalFlip of
+    8-bit frames.  One ragged batch of all fixture cases (oracle/make_image_golden.py: the UNMODIFIED reference transform):
+    parameters drawn by GpuImageTransform from the seeded torch generator, crop boxes shipped packed, kernels' bytes equal
+    to the reference's (SHA-256 per image), the normalised fp32 tensor equal to the reference's `image` tensor (SHA-256),
+    and a step on the uint8 batch runs."""
+    import hashlib
+    from ecamp_b200.image_pipeline import GpuImageTransform
+    from tests.image_frames import make_frame
+    gold = json.load(open(os.path.join(os.path.dirname(GOLDEN), "image_pipeline.json")))["cases"]
+    t = GpuImageTransform(device=dev)
+    frames, params = [], []
+    for c in gold:
+        frames.append(torch.from_numpy(make_frame(c["H"], c["W"], c["frame_seed"])))
+        torch.manual_seed(c["torch_seed"])
+        params.append(t.draw_params(c["H"], c["W"]))
+    drawn_ok = all(p == (c["i"], c["j"], c["h"], c["w"], c["flip"]) for p, c in zip(params, gold))
+    out = t(frames, params)
+    f32 = t.normalize(out)
+    torch.cuda.synchronize()
+    o, f = out.cpu().numpy(), f32.cpu().numpy()
+    bad_u8 = [c["torch_seed"] for k, c in enumerate(gold) if hashlib.sha256(o[k].tobytes()).hexdigest() != c["sha256_u8"]]
+    bad_f32 = [c["torch_seed"] for k, c in enumerate(gold) if hashlib.sha256(f[k].tobytes()).hexdigest() != c["sha256_f32"]]
+    report("image_pipeline_bit_exact", drawn_ok and not bad_u8 and not bad_f32, n=len(gold), params_ok=drawn_ok, bad_u8=bad_u8[:5],
+           bad_f32=bad_f32[:5], upscaled=sum(1 for c in gold if c["h"] < 448 or c["w"] < 448))
+    # the transform feeds the step: uint8 batch in, same losses as the fp32 batch the reference collate would have built
+    torch.manual_seed(3)
+    m = ecamp().to(dev).eval()
+    b = synthetic_batch(2, T=32, seed=3, device=dev)
+    b8 = dict(b); b8["image"] = out[:2]
+    b32 = dict(b); b32["image"] = f32[:2]
+    with torch.no_grad():
+        l8 = torch.stack(list(m(b8))); l32 = torch.stack(list(m(b32)))
+    report("image_pipeline_feeds_step", bool(torch.equal(l8, l32)) and bool(torch.isfinite(l8).all()), losses=l8.tolist())
+
+
+ALL_CHECKS = (check_image_pipeline, check_gemm_fp32, check_step_fp32, check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
 
 
 def run_check(fn):
