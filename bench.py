@@ -195,6 +195,33 @@ def _frac(pairs_per_s, gflop_per_unit, pk):
                 frac_of_bf16_sustained_peak=round(tf / pk["bf16_tflops_sustained"], 4))
 
 
+def e2e_gpu_loader(dp, host, B, dev, steps=10, frame=512):
+    """End to end with the image half of the loader on the GPU (ecamp_b200.image_pipeline): per step the host draws the
+    RandomResizedCrop / flip parameters for B decoded 8-bit frames (torch generator, torchvision's order), packs the crop boxes
+    into pinned memory, ships them (H2D), the GPU resamples them to 448 x 448 with Pillow's arithmetic, and the step runs on
+    the uint8 batch; the losses are read back every step."""
+    from ecamp_b200.image_pipeline import GpuImageTransform
+    t = GpuImageTransform(device=dev)
+    g = torch.Generator().manual_seed(99)
+    frames = [torch.randint(0, 256, (frame, frame), generator=g, dtype=torch.uint8) for _ in range(B)]
+    text = [{k: v for k, v in hb.items() if k != "image"} for hb in host]
+    h2d = [0]
+
+    def step(i):
+        params = [t.draw_params(frame, frame) for _ in range(B)]
+        img = t(frames, params)
+        b = to_device(text[i % 2], dev)
+        b["image"] = img
+        h2d[0] = sum(p[2] * p[3] for p in params) + sum(v.numel() * v.element_size() for v in text[0].values())
+        return dp.step(b).tolist()
+
+    ms = _timed_steps(step, steps, 3)
+    return dict(value=round(B / (ms * 1e-3), 1), unit="pairs/s", ms_per_step=round(ms, 3), steps=steps, h2d_bytes_per_step=int(h2d[0]),
+                d2h_bytes_per_step=12, frame=f"{frame} x {frame} uint8",
+                what="decoded 8-bit frames on the host -> crop boxes H2D -> GPU RandomResizedCrop(448, bicubic) + flip -> step on the uint8 batch; "
+                     "parameter draw and packing run in this (single) Python thread inside the timed region")
+
+
 def dropin_path(model, batches, B, T, pk, steps=10):
     """The reference trainer's call sequence on the drop-in module (main_pretrain.py:139-153): model(batch) under
     autocast -> loss.backward() (staged autograd nodes, ordinary .grad tensors) -> torch.optim.AdamW.step() -> zero_grad.
@@ -384,6 +411,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="pairs per GPU (BASELINE config 2: 256)")
     ap.add_argument("--seq", type=int, default=128)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling (BASELINE config 3: 2048): the per-GPU batch becomes global / n_gpus and `scaling` "
+                         "is reported as strong; 0 = weak scaling with --batch pairs per GPU")
     ap.add_argument("--e2e-input", default="f32", choices=["f32", "u8"],
                     help="host image format of the e2e arm: f32 = the reference collate's normalised [B,3,448,448] tensor "
                          "(617 MB per step); u8 = the loader's 8-bit grayscale crop [B,448,448], normalised on the GPU")
@@ -395,6 +425,10 @@ def main():
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be a multiple of the number of GPUs")
+        args.batch = args.global_batch // world
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -507,6 +541,21 @@ def main():
                        "CPU transform (tests/parity_checks.py::check_image_u8)")
     e2e_f32["input"] = "reference collate format: normalised fp32 [B,3,448,448]"
 
+    tl = None
+    if world > 1:   # one recorded step: per-bucket all-reduce timeline (CUDA events), exposed communication per rank
+        try:
+            resident2 = to_device(host[0], dev)
+            dp.timeline = []
+            dp.step(resident2)
+            t = dp.bucket_timeline()
+            ex = torch.tensor([t["exposed_ms"]], device=dev)
+            dist.all_reduce(ex, op=dist.ReduceOp.MAX)
+            tl = dict(rank0=t, exposed_ms_max_over_ranks=round(float(ex.item()), 3), n_buckets=len(t["buckets"]),
+                      nccl=dict(NCCL_ALGO=os.environ.get("NCCL_ALGO"), NCCL_MAX_CTAS=os.environ.get("NCCL_MAX_CTAS"),
+                                NCCL_NVLS_ENABLE=os.environ.get("NCCL_NVLS_ENABLE")))
+            del resident2
+        except Exception as ex_:  # noqa
+            tl = dict(error=str(ex_)[:300])
     mr = None
     if world > 1 and not args.no_extras:
         try:
@@ -517,7 +566,8 @@ def main():
         pk, pk_kind = peaks()
         gf = GFLOP_PER_PAIR_STEP.get(args.seq)
         out = dict(metric="pretrain_pairs_per_sec", value=round(value, 2), unit="pairs/s", n_gpus=world, steps=args.steps,
-                   warmup=args.warmup, ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="weak",
+                   warmup=args.warmup, ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
+                   scaling="strong" if args.global_batch else "weak",
                    vs_baseline=None, dtype="bf16", data="synthetic",
                    config=dict(workload=workload_name(args), global_batch=world * args.batch, per_gpu_batch=args.batch,
                                seq_len=args.seq, image_px="448 -> 224", mask_ratio=0.75, parallelism=f"dp{world}",
@@ -539,10 +589,13 @@ def main():
                                                  peaks=pk_kind, gflop_per_pair=gf)
         if mr is not None:
             out["multi_rank_checks"] = mr
+        if tl is not None:
+            out["allreduce_timeline"] = tl
         if not args.no_extras and world == 1 and args.seq in GFLOP_PER_PAIR_STEP:
             # outside the timed headline: the reference-API path, the eager-torch baseline on this GPU, configs 4 and 5
             res2 = [to_device(hb, dev) for hb in host]
-            for name, fn in (("dropin_path", lambda: dropin_path(model, res2, args.batch, args.seq, pk)),
+            for name, fn in (("e2e_gpu_loader", lambda: e2e_gpu_loader(dp, host, args.batch, dev)),
+                             ("dropin_path", lambda: dropin_path(model, res2, args.batch, args.seq, pk)),
                              ("gpu_eager_baseline", lambda: gpu_eager_baseline(res2, args.batch, args.seq, pk)),
                              ("config4", lambda: config4_quick(dp, model, args.batch, pk)),
                              ("config5", lambda: config5_quick(pk))):

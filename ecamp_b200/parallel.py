@@ -25,9 +25,12 @@ def stage_ranges(lib):
     return out
 
 
-def plan_buckets(ranges, bucket_floats):
+def plan_buckets(ranges, bucket_floats, tail_floats=0):
     """Merge consecutive backward stages (whose ranges tile the buffer back to front) into buckets of at least
-    `bucket_floats`.  Returns [(last_stage, lo, hi)]: after `last_stage` has run, flat[lo:hi] is final."""
+    `bucket_floats`.  Returns [(last_stage, lo, hi)]: after `last_stage` has run, flat[lo:hi] is final.
+    `tail_floats` > 0 tapers the end of backward: once at most that many floats remain below the current position,
+    every stage becomes its own bucket - the all-reduce of the LAST bucket cannot overlap with anything, so it should be
+    the smallest possible slice (patch embedding: 2.4 MB) instead of a full-size bucket that has waited for it."""
     buckets, cur_hi, cur_lo = [], None, None
     for s, (lo, hi) in enumerate(ranges):
         if cur_hi is None:
@@ -35,7 +38,7 @@ def plan_buckets(ranges, bucket_floats):
         elif hi != cur_lo:
             raise ValueError("backward stage ranges must be contiguous and descending")
         cur_lo = lo
-        if cur_hi - cur_lo >= bucket_floats or s == len(ranges) - 1:
+        if cur_hi - cur_lo >= bucket_floats or s == len(ranges) - 1 or cur_hi <= tail_floats:
             buckets.append((s, cur_lo, cur_hi))
             cur_hi = None
     return buckets
@@ -52,12 +55,15 @@ def allreduce_flat(flat, buckets, group=None, after_stage=None):
 
 
 class DataParallelStep:
-    def __init__(self, model, optimizer, bucket_mb=64, group=None):
+    def __init__(self, model, optimizer, bucket_mb=64, group=None, tail_mb=96):
+        """bucket_mb: minimum bucket size; tail_mb: below this many MB from the front of the buffer (= the end of
+        backward: encoder blocks 2..0 and the patch embedding) every backward stage is reduced on its own."""
         from . import _lib as L
         self.model, self.optimizer, self.group = model, optimizer, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.buckets = plan_buckets(stage_ranges(L.lib()), int(bucket_mb * (1 << 20) // 4))
+        self.buckets = plan_buckets(stage_ranges(L.lib()), int(bucket_mb * (1 << 20) // 4), int(tail_mb * (1 << 20) // 4))
         self.comm = torch.cuda.Stream() if self.world > 1 else None
+        self.timeline = None   # set to [] to record per-bucket CUDA events of the next step (see bucket_timeline)
 
     def step(self, batch, loss_weights=(1.0, 1.0, 1.0), update=True):
         """forward + backward (+ overlapped gradient all-reduce) (+ fused AdamW).  Returns the 3 local losses."""
@@ -68,19 +74,49 @@ class DataParallelStep:
             self.comm.wait_stream(cur)
             ends = {b[0]: b for b in self.buckets}
 
+            rec = self.timeline is not None
+            if rec:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(cur)
+
             def on_stage(stage, lo, hi):
                 b = ends.get(stage)
                 if b is None or not update:
                     return
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=rec)
                 ev.record(cur)
                 self.comm.wait_event(ev)
                 with torch.cuda.stream(self.comm):
+                    if rec:
+                        st = torch.cuda.Event(enable_timing=True); st.record(self.comm)
                     dist.all_reduce(self.model.flat_grads()[b[1]:b[2]], op=dist.ReduceOp.SUM, group=self.group)
+                    if rec:
+                        en = torch.cuda.Event(enable_timing=True); en.record(self.comm)
+                        self.timeline.append((stage, b[1], b[2], ev, st, en))
 
             losses = self.model.forward_backward(batch, loss_weights, stage_callback=on_stage)
+            if rec:
+                bwd_end = torch.cuda.Event(enable_timing=True)
+                bwd_end.record(cur)
             cur.wait_stream(self.comm)
+            if rec:
+                joined = torch.cuda.Event(enable_timing=True)
+                joined.record(cur)
+                self._marks = (t0, bwd_end, joined)
         if update:
             self.optimizer.step(grad_scale=1.0 / self.world)
             self.optimizer.zero_grad(set_to_none=True)
         return losses
+
+    def bucket_timeline(self):
+        """After a step recorded with `self.timeline = []`: per bucket (stage, MB, ready_ms, start_ms, end_ms) on the
+        step's clock (0 = step start), plus when backward ended and when the compute stream had joined the last
+        all-reduce; exposed = joined - backward_end is the communication that did not overlap."""
+        torch.cuda.synchronize()
+        t0, bwd_end, joined = self._marks
+        rows = [dict(stage=s, mb=round((hi - lo) * 4 / 2 ** 20, 1), ready_ms=round(t0.elapsed_time(ev), 3),
+                     start_ms=round(t0.elapsed_time(st), 3), end_ms=round(t0.elapsed_time(en), 3)) for s, lo, hi, ev, st, en in self.timeline]
+        out = dict(buckets=rows, backward_end_ms=round(t0.elapsed_time(bwd_end), 3), joined_ms=round(t0.elapsed_time(joined), 3))
+        out["exposed_ms"] = round(out["joined_ms"] - out["backward_end_ms"], 3)
+        self.timeline = None
+        return out

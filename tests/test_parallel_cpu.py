@@ -21,6 +21,11 @@ def test_plan_buckets(built_lib):
         assert all(b[0] < nb[0] for b, nb in zip(buckets, buckets[1:]))       # in stage order
         assert all(hi - lo >= mb * (1 << 20) // 4 for _, lo, hi in buckets[:-1])
     assert len(plan_buckets(ranges, 1 << 40)) == 1
+    # tapered tail: below 96 MB from the front of the buffer every stage is its own bucket, the last one the patch embedding
+    taper = plan_buckets(ranges, 64 * (1 << 20) // 4, 96 * (1 << 20) // 4)
+    assert taper[0][2] == total and taper[-1][1] == 0 and all(b[1] == nb[2] for b, nb in zip(taper, taper[1:]))
+    assert (taper[-1][2] - taper[-1][1]) * 4 < 4 * (1 << 20)           # ~2.4 MB: what cannot overlap with anything
+    assert len(taper) >= len(plan_buckets(ranges, 64 * (1 << 20) // 4)) + 1
 
 
 def _worker(rank, world, port, n, ranges):
