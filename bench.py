@@ -414,9 +414,11 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling (BASELINE config 3: 2048): the per-GPU batch becomes global / n_gpus and `scaling` "
                          "is reported as strong; 0 = weak scaling with --batch pairs per GPU")
-    ap.add_argument("--e2e-input", default="f32", choices=["f32", "u8"],
-                    help="host image format of the e2e arm: f32 = the reference collate's normalised [B,3,448,448] tensor "
-                         "(617 MB per step); u8 = the loader's 8-bit grayscale crop [B,448,448], normalised on the GPU")
+    ap.add_argument("--e2e-input", default="u8", choices=["f32", "u8"],
+                    help="host image format of the headline e2e arm: u8 (default) = the loader's 8-bit grayscale crop [B,448,448] "
+                         "(INTEGRATION.md section 1, data loader: Grayscale(3) + ToTensor + Normalize run on the GPU, bit-identical "
+                         "batch, 52 MB per step); f32 = the reference collate's normalised [B,3,448,448] tensor (617 MB per step). "
+                         "The other format is always measured too and reported next to it")
     ap.add_argument("--no-extras", action="store_true", help="skip the roofline micro-timing and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -550,7 +552,18 @@ def main():
             t = dp.bucket_timeline()
             ex = torch.tensor([t["exposed_ms"]], device=dev)
             dist.all_reduce(ex, op=dist.ReduceOp.MAX)
-            tl = dict(rank0=t, exposed_ms_max_over_ranks=round(float(ex.item()), 3), n_buckets=len(t["buckets"]),
+            mine = torch.tensor([t["backward_end_ms"], t["joined_ms"], t["exposed_ms"]], device=dev)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            per_rank = [dict(rank=r, backward_end_ms=round(float(v[0]), 3), joined_ms=round(float(v[1]), 3), exposed_ms=round(float(v[2]), 3))
+                        for r, v in enumerate(allr)]
+            # the all-reduce of a bucket completes when the SLOWEST rank has delivered it: on the fast ranks "exposed" is time
+            # spent waiting for the straggler (GPU-to-GPU clock differences under the power cap), on the slowest rank it is
+            # the communication that really did not overlap
+            slowest = max(per_rank, key=lambda r: r["backward_end_ms"])
+            tl = dict(rank0=t, per_rank=per_rank, slowest_rank=slowest, backward_end_skew_ms=round(slowest["backward_end_ms"] -
+                      min(r["backward_end_ms"] for r in per_rank), 3),
+                      exposed_ms_max_over_ranks=round(float(ex.item()), 3), n_buckets=len(t["buckets"]),
                       nccl=dict(NCCL_ALGO=os.environ.get("NCCL_ALGO"), NCCL_MAX_CTAS=os.environ.get("NCCL_MAX_CTAS"),
                                 NCCL_NVLS_ENABLE=os.environ.get("NCCL_NVLS_ENABLE")))
             del resident2
