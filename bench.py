@@ -166,7 +166,7 @@ def gemm_roofline(B, T, peak_tflops):
     achieved = tot_flops / (tot_ms * 1e-3) / 1e12
     traffic = None
     try:  # DRAM bytes per GEMM launch from the committed ncu capture of one step (profiles/, see r01c_ncu_summary.md)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01h_ncu_gemm_traffic.json")))["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02g_ncu_gemm_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         pass
     return dict(bound="tensor", achieved=round(achieved, 1), peak=peak_tflops, unit="TFLOP/s", frac=round(achieved / peak_tflops, 4),

@@ -236,7 +236,7 @@ class ECAMP(nn.Module):
         self._rt = None
         self._precision = 0                 # 0 = production (bf16 operands), 1 = fp32-accurate parity mode (set_precision)
         self._dropout_step = 0
-        self.ce_rows = int(os.environ.get("ECAMP_CE_ROWS", "2048"))   # rows per vocabulary-head chunk (tuning knob)
+        self.ce_rows = int(os.environ.get("ECAMP_CE_ROWS", "4096"))   # rows per vocabulary-head chunk (tuning knob)
 
     # ---- model_ecamp.py:105-137 -------------------------------------------------------------------
     def initialize_weights(self):
