@@ -392,10 +392,28 @@ def run_reference(args):
     sample = f"{Bc} pairs per step (448-px input, T={args.seq}), fp32 forward + backward + AdamW, {torch.get_num_threads()} threads"
     print(json.dumps(dict(impl="reference", metric="pretrain_pairs_per_sec", value=round(v, 4), unit="pairs/s", n_gpus=args.gpus,
                           steps=args.steps, warmup=args.warmup, ms_per_step=round(1e3 * dt / args.steps, 2), higher_is_better=True,
-                          scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                          config=dict(workload=workload_name(args), seq_len=args.seq, sample_batch=Bc),
+                          scaling="strong" if args.global_batch else "weak", vs_baseline=None, dtype="f32", data="synthetic",
+                          config=workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
                           cpu_baseline=dict(value=round(v, 4), unit="pairs/s", cores=torch.get_num_threads(), kind="port", sample=sample),
                           e2e=dict(value=round(v, 4), unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))), flush=True)
+
+
+E2E_INPUT_TEXT = {
+    "u8": ("loader's 8-bit grayscale crop [B,448,448]; Grayscale(3)+ToTensor+Normalize run on the GPU, bit-exact with the "
+           "CPU transform (tests/parity_checks.py::check_image_u8)"),
+    "f32": "reference collate format: normalised fp32 [B,3,448,448]",
+}
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line: a function of the command line only, so that the reference arm prints the
+    SAME object (the driver compares the two arms' configs); run-specific notes go to `run_notes`."""
+    return dict(workload=workload_name(args), global_batch=world * args.batch, per_gpu_batch=args.batch,
+                seq_len=args.seq, image_px="448 -> 224", mask_ratio=0.75, parallelism=f"dp{world}",
+                optimizer="AdamW lr 1.5e-4 betas (0.9,0.95) wd 0.05 over timm add_weight_decay groups",
+                weights="random init (reference initialize_weights)",
+                l2="per-step working set (~16 GB of activations) is far larger than the 126 MB L2; two input batches alternate",
+                e2e_input=E2E_INPUT_TEXT[args.e2e_input])
 
 
 def workload_name(args):
@@ -422,15 +440,16 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the roofline micro-timing and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.global_batch:
+        w_ = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.global_batch % w_:
+            raise SystemExit("--global-batch must be a multiple of the number of GPUs")
+        args.batch = args.global_batch // w_
     if args.impl == "reference":
         return run_reference(args)
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.global_batch:
-        if args.global_batch % world:
-            raise SystemExit("--global-batch must be a multiple of the number of GPUs")
-        args.batch = args.global_batch // world
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -539,9 +558,8 @@ def main():
     e2e_main = run_e2e(host if args.e2e_input == "f32" else u8_batches())
     e2e_other = run_e2e(u8_batches() if args.e2e_input == "f32" else host)
     e2e_f32, e2e_u8 = (e2e_main, e2e_other) if args.e2e_input == "f32" else (e2e_other, e2e_main)
-    e2e_u8["input"] = ("loader's 8-bit grayscale crop [B,448,448]; Grayscale(3)+ToTensor+Normalize run on the GPU, bit-exact with the "
-                       "CPU transform (tests/parity_checks.py::check_image_u8)")
-    e2e_f32["input"] = "reference collate format: normalised fp32 [B,3,448,448]"
+    e2e_u8["input"] = E2E_INPUT_TEXT["u8"]
+    e2e_f32["input"] = E2E_INPUT_TEXT["f32"]
 
     tl = None
     if world > 1:   # one recorded step: per-bucket all-reduce timeline (CUDA events), exposed communication per rank
@@ -582,16 +600,13 @@ def main():
                    warmup=args.warmup, ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
                    scaling="strong" if args.global_batch else "weak",
                    vs_baseline=None, dtype="bf16", data="synthetic",
-                   config=dict(workload=workload_name(args), global_batch=world * args.batch, per_gpu_batch=args.batch,
-                               seq_len=args.seq, image_px="448 -> 224", mask_ratio=0.75, parallelism=f"dp{world}",
-                               optimizer="fused AdamW lr 1.5e-4 betas (0.9,0.95) wd 0.05", weights="random init (reference initialize_weights)",
-                               l2="per-step working set (~16 GB of activations) is far larger than the 126 MB L2; two input batches alternate",
-                               e2e_input=e2e_main["input"],
-                               e2e_pipeline="per timed step: one H2D copy of a full pinned batch on a copy stream (prefetching the "
-                                            "next step's inputs while this step runs) and one D2H read of the 3 losses, which the "
-                                            "host consumes one step late so that it never stalls the launch queue",
-                               host_buffers=("pinned, first-touched on the GPU's NUMA node (%d CPUs)" % len(numa_cpus)) if numa_cpus
-                               else "pinned (NUMA topology unknown or single node)"),
+                   config=workload_config(args, world),
+                   run_notes=dict(optimizer_impl="fused AdamW (ecamp_b200.optim.FusedAdamW)",
+                                  e2e_pipeline="per timed step: one H2D copy of a full pinned batch on a copy stream (prefetching the "
+                                               "next step's inputs while this step runs) and one D2H read of the 3 losses, which the "
+                                               "host consumes one step late so that it never stalls the launch queue",
+                                  host_buffers=("pinned, first-touched on the GPU's NUMA node (%d CPUs)" % len(numa_cpus)) if numa_cpus
+                                  else "pinned (NUMA topology unknown or single node)"),
                    clocks=clocks, gpu_launches=int(launches),
                    e2e={k: v for k, v in e2e_main.items() if k != "input"},
                    e2e_u8_input=e2e_u8, e2e_f32_input=e2e_f32, losses_last_step=last_losses)
