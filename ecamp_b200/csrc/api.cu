@@ -11,6 +11,7 @@ const char* last_error_cstr();
 long long launch_count();
 void set_cta_pair_mode(int mode);
 void set_tma_epilogue(int on);
+void set_direct_epilogue(int on);
 void set_attention_tc(int on);
 }
 using namespace ecamp;
@@ -48,6 +49,7 @@ const char* ecamp_last_error(void) { return ecamp::last_error_cstr(); }
 int64_t ecamp_launch_count(void) { return ecamp::launch_count(); }
 void ecamp_gemm_set_cta_pair(int32_t mode) { ecamp::set_cta_pair_mode(mode); }
 void ecamp_gemm_set_tma_epilogue(int32_t on) { ecamp::set_tma_epilogue(on); }
+void ecamp_gemm_set_direct_epilogue(int32_t on) { ecamp::set_direct_epilogue(on); }
 void ecamp_attention_set_tcgen05(int32_t on) { ecamp::set_attention_tc(on); }
 
 int ecamp_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int32_t ldb, int32_t b_mn, int32_t M,

@@ -81,6 +81,7 @@ struct EpiArgs {
   int stages;     // depth of the operand ring (what the shared memory left by the epilogue region holds)
   int epi_bytes;  // shared memory of the epilogue region
   int tma_epi;    // 1: fp32-output epilogue through TMA (residual tiles loaded, results stored by cp.async.bulk.tensor)
+  int direct_epi;  // 1: bf16-output epilogue straight from the TMEM row-per-thread layout with 256-bit stores (no transpose)
 };
 struct TmaSet {  // one tensor map per operand plane (production: plane 0 only) + the fp32 epilogue operands
   CUtensorMap a[3], b[3];
@@ -457,6 +458,164 @@ ECAMP_DEVINL void epilogue_loop(const EpiArgs& ea, uint32_t tmem_base, int q, in
   }
 }
 // ---------------------------------------------------------------------------------------------
+// bf16-output epilogue WITHOUT the shared-memory transpose (EM_BF16 / EM_GELU_G / EM_DGELU_G).  tcgen05.ld hands every
+// thread one row of the accumulator; 32 bf16 columns of a row are 64 contiguous bytes = two 256-bit stores (STG.256, new on
+// sm_100).  A warp store then touches 32 lines, but with one FULL 32-byte sector each, so L2 / DRAM see only whole sectors;
+// per 128 x 256 tile that is 64 store instructions (~4.2 k LSU cycles, under the 6.1 k cycles of the tile's MMAs at K = 768),
+// while the transpose tile cost 262 KB of shared-memory traffic per tile on top of the 768 KB of operand traffic - and
+// shared-memory bandwidth is what bounds these kernels.  dGELU reads its operand the same way (two 256-bit loads per row
+// and chunk, fetched one chunk ahead) and reduces the column sums with a halving butterfly across the warp.
+// ---------------------------------------------------------------------------------------------
+ECAMP_DEVINL void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+ECAMP_DEVINL void ldg256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+template <int BN, int MODE>
+ECAMP_DEVINL void epilogue_direct_loop(const EpiArgs& ea, uint32_t tmem_base, int q, int slice, int unit0, int unit_step,
+                                       int num_units, int num_tiles, int m_tiles, int m_stride, int m_off, int M, int N, int lane,
+                                       uint64_t* tmem_full, uint64_t* tmem_empty, bool remote_empty) {
+  constexpr int COLS = BN / kSlices, NCH = COLS / 32;
+  static_assert(kCW == 32, "the direct epilogue works on 32-column chunks");
+  const GemmEpilogue& ep = ea.ep;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int unit = unit0; unit < num_units; unit += unit_step) {
+    int m_blk, n_blk;
+    decode_tile(ea, unit % num_tiles, m_tiles, m_blk, n_blk);
+    const int row = m_blk * m_stride + m_off + q * 32 + lane;
+    const int ncol0 = n_blk * BN + slice * COLS;
+    const bool rvalid = row < M;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slice * COLS);
+    uint32_t aux_cur[16], aux_next[16];
+    if (MODE == EM_DGELU_G) {  // operand of the first chunk in flight while the accumulator is still being produced
+      if (rvalid && ncol0 + 32 <= N) {
+        const bf16* ap = ep.aux_in + (size_t)row * ep.ld_aux + ncol0;
+        ldg256(ap, reinterpret_cast<uint32_t(&)[8]>(aux_cur[0]));
+        ldg256(ap + 16, reinterpret_cast<uint32_t(&)[8]>(aux_cur[8]));
+      }
+    }
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32(taddr + (uint32_t)(c * 32), raw);
+      const int col0 = ncol0 + c * 32;
+      const bool full = col0 + 32 <= N;  // N % 8 == 0 (host-checked): a partial chunk is handled in 8-column pieces
+      if (MODE == EM_DGELU_G && c + 1 < NCH && rvalid && col0 + 64 <= N) {
+        const bf16* ap = ep.aux_in + (size_t)row * ep.ld_aux + col0 + 32;
+        ldg256(ap, reinterpret_cast<uint32_t(&)[8]>(aux_next[0]));
+        ldg256(ap + 16, reinterpret_cast<uint32_t(&)[8]>(aux_next[8]));
+      }
+      tmem_ld_wait();
+      if (c == NCH - 1) {  // all of this warp's TMEM reads for the tile are done: hand the accumulator stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (remote_empty) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
+      }
+      if (col0 >= N) continue;
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(raw[j]);
+      if (MODE != EM_DGELU_G && ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (col0 + 4 * j < N) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + 4 * j));
+            x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+          }
+        }
+      }
+      uint32_t out[16], aux[16];
+      if (MODE == EM_GELU_G) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 a = unpack_bf16x2(pack_bf16x2(x[2 * j], x[2 * j + 1]));  // GELU of the bf16-rounded pre-activation
+          float y0, y1, g0, g1;
+          gelu_erf_both(a.x, y0, g0);
+          gelu_erf_both(a.y, y1, g1);
+          out[j] = pack_bf16x2(y0, y1);
+          aux[j] = pack_bf16x2(g0, g1);
+        }
+      } else if (MODE == EM_DGELU_G) {
+        if (!full && rvalid) {  // partial chunk at the right edge: fetch the operand in 16-byte pieces
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col0 + 8 * j < N) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(ep.aux_in + (size_t)row * ep.ld_aux + col0 + 8 * j));
+              aux_cur[4 * j] = u.x; aux_cur[4 * j + 1] = u.y; aux_cur[4 * j + 2] = u.z; aux_cur[4 * j + 3] = u.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 a = unpack_bf16x2(aux_cur[j]);
+          x[2 * j] *= a.x;
+          x[2 * j + 1] *= a.y;
+          out[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) out[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+      }
+      if (rvalid) {
+        bf16* op = ep.out_bf16 + (size_t)row * ep.ld_bf16 + col0;
+        if (full) {
+          stg256(op, reinterpret_cast<uint32_t(&)[8]>(out[0]));
+          stg256(op + 16, reinterpret_cast<uint32_t(&)[8]>(out[8]));
+          if (MODE == EM_GELU_G) {
+            bf16* xp = ep.aux_out + (size_t)row * ep.ld_aux + col0;
+            stg256(xp, reinterpret_cast<uint32_t(&)[8]>(aux[0]));
+            stg256(xp + 16, reinterpret_cast<uint32_t(&)[8]>(aux[8]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col0 + 8 * j < N) {
+              *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+              if (MODE == EM_GELU_G)
+                *reinterpret_cast<uint4*>(ep.aux_out + (size_t)row * ep.ld_aux + col0 + 8 * j) =
+                    make_uint4(aux[4 * j], aux[4 * j + 1], aux[4 * j + 2], aux[4 * j + 3]);
+            }
+        }
+      }
+      if (MODE == EM_DGELU_G && ep.colsum_out) {
+        // column sums over the warp's 32 rows (fp32, before rounding): after the step with distance d a lane keeps the half of
+        // its values selected by (lane & d); in the end lane l holds the total of column l
+        if (!rvalid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = 0.f;
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+          const bool up = (lane & d) != 0;
+#pragma unroll
+          for (int i = 0; i < d; ++i) {
+            const float lo = x[i], hi = x[i + d];
+            const float send = up ? lo : hi, keep = up ? hi : lo;
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+          }
+        }
+        if (col0 + lane < N) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(ep.colsum_out + col0 + lane), "f"(x[0]) : "memory");
+      }
+      if (MODE == EM_DGELU_G) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) aux_cur[j] = aux_next[j];
+      }
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fp32-output epilogue through TMA (EM_F32 / EM_F32_RES / EM_F32_RES_DROP on the CTA-pair kernel).  tcgen05.ld hands every
 // thread one ROW of the accumulator; instead of transposing to a coalesced layout, each epilogue warp keeps a ring of three
 // 32 x 32 fp32 tiles in shared memory with the 128-byte swizzle of the tensor maps: the residual tile arrives by TMA (two
@@ -599,6 +758,18 @@ ECAMP_DEVINL void epilogue_dispatch(const EpiArgs& ea, uint32_t tmem_base, int q
                                     int num_units, int num_tiles, int m_tiles, int m_stride, int m_off, int M, int N,
                                     float* stage, int lane, uint64_t* tmem_full, uint64_t* tmem_empty,
                                     bool remote_empty) {
+  if (ea.direct_epi) {
+    if (ea.mode == EM_BF16)
+      epilogue_direct_loop<BN, EM_BF16>(ea, tmem_base, q, slice, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride, m_off, M, N,
+                                        lane, tmem_full, tmem_empty, remote_empty);
+    else if (ea.mode == EM_GELU_G)
+      epilogue_direct_loop<BN, EM_GELU_G>(ea, tmem_base, q, slice, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride, m_off, M,
+                                          N, lane, tmem_full, tmem_empty, remote_empty);
+    else
+      epilogue_direct_loop<BN, EM_DGELU_G>(ea, tmem_base, q, slice, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride, m_off, M,
+                                           N, lane, tmem_full, tmem_empty, remote_empty);
+    return;
+  }
 #define ECAMP_EPI_CASE(MODE_)                                                                                        \
   case MODE_:                                                                                                         \
     epilogue_loop<BN, MODE_>(ea, tmem_base, q, slice, unit0, unit_step, num_units, num_tiles, m_tiles, m_stride, m_off, \
@@ -1013,6 +1184,10 @@ int g_cta_pair_mode = [] {
   return e ? atoi(e) : 0;
 }();
 
+int g_direct_epilogue = [] {
+  const char* e = getenv("ECAMP_GEMM_DIRECT_EPI");
+  return e ? atoi(e) : 1;
+}();
 int g_tma_epilogue = [] {
   const char* e = getenv("ECAMP_GEMM_TMA_EPI");
   return e ? atoi(e) : 0;
@@ -1236,6 +1411,19 @@ int gemm_launch(const bf16* A, size_t plane_a, int lda, int a_mn, const bf16* B,
   // default: measured on B200 (profiles/r02c_gemm_tma_epilogue_ab.md) the residual tiles' extra trips through shared
   // memory (TMA write, row read, row write, TMA read - the transpose path makes two) and the operand ring shrinking from
   // 6 to 4 stages cost more than the LSU traffic they remove on every shape but the dropout+residual ones.
+  // bf16 outputs straight from the TMEM row-per-thread layout with 256-bit stores (ecamp_gemm_set_direct_epilogue /
+  // ECAMP_GEMM_DIRECT_EPI): needs 32-byte aligned rows
+  ea.direct_epi = 0;
+  // Measured (profiles/r02h_gemm_direct_epilogue_ab.md): the plain bf16 epilogue gains 2 - 5 % (vocabulary projection 1298 ->
+  // 1365 TFLOP/s), the GELU (two outputs: four 256-bit stores per row and chunk) and dGELU ones lose 15 - 25 % - their LSU
+  // wavefronts then outweigh the shared-memory traffic saved.  Mode 1 (default) = plain bf16 only, 2 = all three.
+  if (g_direct_epilogue && kCW == 32 && N % 8 == 0 &&
+      (ea.mode == EM_BF16 || (g_direct_epilogue >= 2 && (ea.mode == EM_GELU_G || ea.mode == EM_DGELU_G)))) {
+    auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+    bool ok = al32(ep.out_bf16) && ep.ld_bf16 % 16 == 0;
+    if (ea.mode != EM_BF16) ok = ok && ep.ld_aux % 16 == 0 && al32(ea.mode == EM_GELU_G ? (const void*)ep.aux_out : (const void*)ep.aux_in);
+    ea.direct_epi = ok ? 1 : 0;
+  }
   ea.tma_epi = 0;
   if (g_tma_epilogue && cta2 && kCW == 32 && (ea.mode == EM_F32 || ea.mode == EM_F32_RES || ea.mode == EM_F32_RES_DROP)) {
     ea.tma_epi = 1;
@@ -1380,6 +1568,7 @@ int pdl_enabled() {
 }
 void set_cta_pair_mode(int mode) { g_cta_pair_mode = mode; }
 void set_tma_epilogue(int on) { g_tma_epilogue = on; }
+void set_direct_epilogue(int on) { g_direct_epilogue = on; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }

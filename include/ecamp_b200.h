@@ -81,6 +81,10 @@ ECAMP_API void ecamp_gemm_set_cta_pair(int32_t mode);
 /* 1 = fp32-output epilogues of the CTA-pair kernel go through TMA (residual tiles loaded and results stored with
  * cp.async.bulk.tensor); 0 (default) = LSU epilogue through the per-warp transpose tile.  Same results either way. */
 ECAMP_API void ecamp_gemm_set_tma_epilogue(int32_t on);
+/* bf16-output epilogues written straight from the TMEM row-per-thread layout with 256-bit stores instead of through the
+ * per-warp shared-memory transpose tile: 0 = never, 1 (default) = the plain bias -> bf16 epilogue, 2 = also GELU + stored
+ * GELU' and x stored GELU' with column sums (measured slower).  Same results. */
+ECAMP_API void ecamp_gemm_set_direct_epilogue(int32_t on);
 ECAMP_API int ecamp_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int32_t ldb, int32_t b_mn,
                               int32_t M, int32_t N, int32_t K, const ecamp_epilogue* ep, int32_t tile_n, void* stream);
 

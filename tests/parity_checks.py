@@ -189,9 +189,21 @@ def check_gemm():
         case("splitk_wgrad", 768, 768, 12800 + 37, True, True, 0, mode)
         case("vocab_tail", 700, 30000, 768, False, False, 0, mode)
     lib.ecamp_gemm_set_cta_pair(0)
-    for tma in (1, 0):   # fp32-output epilogues through TMA (cp.async.bulk.tensor load / store), then the default LSU route
+    # epilogue routes: fp32 outputs through TMA (cp.async.bulk.tensor load / store) or the LSU transpose tile; bf16 outputs
+    # straight from the TMEM row layout with 256-bit stores or through the transpose tile.  Last = the defaults.
+    for tag, tma, direct in (("tma_transpose", 1, 0), ("lsu_direct_all", 0, 2), ("lsu_direct", 0, 1)):
         lib.ecamp_gemm_set_tma_epilogue(tma)
-        _check_gemm_epilogues("tma" if tma else "lsu")
+        lib.ecamp_gemm_set_direct_epilogue(direct)
+        _check_gemm_epilogues(tag)
+        # bf16 output with a partial 32-column chunk at the right edge (N = 30000) and a ragged row count
+        M, N, K = 130, 30000, 128
+        a = torch.randn(M, K, device=dev).to(torch.bfloat16); b = (torch.randn(N, K, device=dev) * 0.1).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        o16 = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev)
+        L.gemm(a, b, bias=bias, out_bf16=o16)
+        torch.cuda.synchronize()
+        e = rel(o16.float(), a.float() @ b.float().t() + bias)
+        report(f"gemm_bf16_vocab_tail_{tag}", e < 4e-3 and bool(torch.isfinite(o16.float()).all()), err=e)
 
 
 def _check_gemm_epilogues(tag):
