@@ -57,12 +57,13 @@ ECAMP_DEVINL void store_shadow(const AdamTensor& t, long long i, float4 p, bool 
 
 template <bool UPDATE>
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict__ table,
-                                                    const Chunk* __restrict__ chunks, float lr, float beta1,
-                                                    float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                                                    float grad_scale) {
+                                                    const Chunk* __restrict__ chunks, float lr_decay, float lr_nodecay,
+                                                    float beta1, float beta2, float eps, float wd, float bc1,
+                                                    float bc2_sqrt, float grad_scale) {
   ECAMP_PDL_ENTRY();
   const Chunk ch = chunks[blockIdx.x];
   const AdamTensor t = table[ch.tensor];
+  const float lr = t.decay ? lr_decay : lr_nodecay;  // timm add_weight_decay: two parameter groups, each with its own lr
   const float decay = t.decay ? 1.0f - lr * wd : 1.0f;
   const float step_size = lr / bc1;
   const bool aligned = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
@@ -148,14 +149,14 @@ int adamw_build_tables(const AdamTensor* host, int n, void* dev_table, void* dev
   return 0;
 }
 
-int adamw_step(const void* dev_table, const void* dev_chunks, long long n_chunks, float lr, float beta1, float beta2,
-               float eps, float wd, int step, float grad_scale, cudaStream_t st) {
+int adamw_step(const void* dev_table, const void* dev_chunks, long long n_chunks, float lr, float lr_nodecay, float beta1,
+               float beta2, float eps, float wd, int step, float grad_scale, cudaStream_t st) {
   ECAMP_REQUIRE(step >= 1, "adamw: step counts from 1");
   if (n_chunks <= 0) return 0;
   const float bc1 = 1.0f - (float)pow((double)beta1, (double)step);
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   ECAMP_CUDA_OK(launch_pdl(adamw_kernel<true>, (unsigned)n_chunks, 256, 0, st, static_cast<const AdamTensor*>(dev_table),
-                                                         static_cast<const Chunk*>(dev_chunks), lr, beta1, beta2,
+                                                         static_cast<const Chunk*>(dev_chunks), lr, lr_nodecay, beta1, beta2,
                                                          eps, wd, bc1, bc2_sqrt, grad_scale));
   ECAMP_LAUNCHED();
   return 0;
@@ -164,7 +165,7 @@ int adamw_step(const void* dev_table, const void* dev_chunks, long long n_chunks
 int refresh_shadows(const void* dev_table, const void* dev_chunks, long long n_chunks, cudaStream_t st) {
   if (n_chunks <= 0) return 0;
   ECAMP_CUDA_OK(launch_pdl(adamw_kernel<false>, (unsigned)n_chunks, 256, 0, st, static_cast<const AdamTensor*>(dev_table),
-                                                          static_cast<const Chunk*>(dev_chunks), 0.f, 0.f, 0.f, 0.f,
+                                                          static_cast<const Chunk*>(dev_chunks), 0.f, 0.f, 0.f, 0.f, 0.f,
                                                           0.f, 1.f, 1.f, 1.f));
   ECAMP_LAUNCHED();
   return 0;

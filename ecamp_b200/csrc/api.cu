@@ -247,7 +247,12 @@ int ecamp_backward(ecamp_ctx* ctx, const float* g3, int32_t accumulate, int32_t 
 int ecamp_adamw_step(ecamp_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                      float grad_scale, void* stream) {
   ECAMP_REQUIRE(ctx, "ecamp_adamw_step: null context");
-  return ctx_adamw(ctx->impl, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
+  return ctx_adamw(ctx->impl, lr, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
+}
+int ecamp_adamw_step_groups(ecamp_ctx* ctx, float lr_decay, float lr_no_decay, float beta1, float beta2, float eps,
+                            float weight_decay, int32_t step, float grad_scale, void* stream) {
+  ECAMP_REQUIRE(ctx, "ecamp_adamw_step_groups: null context");
+  return ctx_adamw(ctx->impl, lr_decay, lr_no_decay, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
 }
 int ecamp_cross_attention_probs(ecamp_ctx* ctx, float* probs, void* stream) {
   ECAMP_REQUIRE(ctx && probs, "ecamp_cross_attention_probs: null argument");

@@ -180,8 +180,9 @@ struct AdamTensor {
   int shadow_kind;     // 0 plain, 1 patch-embed (c,p,q)->(p,q,c)
 };
 int adamw_build_tables(const AdamTensor* host, int n, void* dev_table, void* dev_chunks, long long* n_chunks);
-int adamw_step(const void* dev_table, const void* dev_chunks, long long n_chunks, float lr, float beta1, float beta2,
-               float eps, float wd, int step, float grad_scale, cudaStream_t st);
+// lr: learning rate of the weight-decay group, lr_nodecay: of the no-decay group (timm add_weight_decay's two groups)
+int adamw_step(const void* dev_table, const void* dev_chunks, long long n_chunks, float lr, float lr_nodecay, float beta1,
+               float beta2, float eps, float wd, int step, float grad_scale, cudaStream_t st);
 int refresh_shadows(const void* dev_table, const void* dev_chunks, long long n_chunks, cudaStream_t st);
 size_t adamw_table_bytes(int n);
 size_t adamw_chunk_bytes(const AdamTensor* host, int n);

@@ -268,10 +268,10 @@ int t_refresh_shadows(CtxT<AT>* c, cudaStream_t st) {
   return refresh_shadows(c->adam_table, c->adam_chunks, c->adam_nchunks, st);
 }
 template <typename AT>
-int t_adamw(CtxT<AT>* c, float lr, float b1, float b2, float eps, float wd, int step, float grad_scale,
+int t_adamw(CtxT<AT>* c, float lr, float lr_nodecay, float b1, float b2, float eps, float wd, int step, float grad_scale,
               cudaStream_t st) {
   ECAMP_REQUIRE(c->bound && c->M1 && c->M2, "adamw: context not bound with optimizer state");
-  return adamw_step(c->adam_table, c->adam_chunks, c->adam_nchunks, lr, b1, b2, eps, wd, step, grad_scale, st);
+  return adamw_step(c->adam_table, c->adam_chunks, c->adam_nchunks, lr, lr_nodecay, b1, b2, eps, wd, step, grad_scale, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1248,9 +1248,10 @@ int ctx_cross_attention_probs(Ctx* c, float* probs, cudaStream_t st) {
 int ctx_backward(Ctx* c, const float* g3, int accumulate, int stage, cudaStream_t st) {
   return ECAMP_DISPATCH(t_backward(&c->lp, g3, accumulate, stage, st), t_backward(&c->hp32, g3, accumulate, stage, st));
 }
-int ctx_adamw(Ctx* c, float lr, float b1, float b2, float eps, float wd, int step, float grad_scale, cudaStream_t st) {
-  return ECAMP_DISPATCH(t_adamw(&c->lp, lr, b1, b2, eps, wd, step, grad_scale, st),
-                        t_adamw(&c->hp32, lr, b1, b2, eps, wd, step, grad_scale, st));
+int ctx_adamw(Ctx* c, float lr, float lr_nodecay, float b1, float b2, float eps, float wd, int step, float grad_scale,
+              cudaStream_t st) {
+  return ECAMP_DISPATCH(t_adamw(&c->lp, lr, lr_nodecay, b1, b2, eps, wd, step, grad_scale, st),
+                        t_adamw(&c->hp32, lr, lr_nodecay, b1, b2, eps, wd, step, grad_scale, st));
 }
 const void* ctx_debug_ptr(Ctx* c, const char* name) {
   return ECAMP_DISPATCH(t_debug_ptr(&c->lp, name), t_debug_ptr(&c->hp32, name));

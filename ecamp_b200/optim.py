@@ -48,16 +48,16 @@ class FusedAdamW:
         rt = self._rt()
         if not self.model._sync_flat_grads(rt):   # .grad tensors left by autograd / DDP / GradScaler -> flat buffer
             return                                # no parameter has a gradient: torch.optim.AdamW would skip them all
-        # util/lr_sched.py:9-21 has already folded "lr_scale" into param_group["lr"]: use it as is
-        lrs = {g["lr"] for g in self.param_groups}
-        if len(lrs) != 1:
-            raise RuntimeError("FusedAdamW applies one learning rate to both groups (as the reference schedule does)")
-        g1 = self.param_groups[1]
+        # util/lr_sched.py:9-21 has already folded "lr_scale" into param_group["lr"]: use it as is, one rate per group
+        g0, g1 = self.param_groups
+        if tuple(g0["betas"]) != tuple(g1["betas"]) or g0["eps"] != g1["eps"]:
+            raise RuntimeError("FusedAdamW: the two parameter groups must share betas and eps")
         self.step_count += 1
-        L.check(L.lib().ecamp_adamw_step(rt["ctx"], ctypes.c_float(lrs.pop()), ctypes.c_float(g1["betas"][0]),
-                                         ctypes.c_float(g1["betas"][1]), ctypes.c_float(g1["eps"]),
-                                         ctypes.c_float(g1["weight_decay"]), ctypes.c_int32(self.step_count),
-                                         ctypes.c_float(grad_scale), L.cur_stream()), "ecamp_adamw_step")
+        L.check(L.lib().ecamp_adamw_step_groups(rt["ctx"], ctypes.c_float(g1["lr"]), ctypes.c_float(g0["lr"]),
+                                                ctypes.c_float(g1["betas"][0]), ctypes.c_float(g1["betas"][1]),
+                                                ctypes.c_float(g1["eps"]), ctypes.c_float(g1["weight_decay"]),
+                                                ctypes.c_int32(self.step_count), ctypes.c_float(grad_scale), L.cur_stream()),
+                "ecamp_adamw_step_groups")
 
     # ---- torch.optim-compatible checkpoint layout -------------------------------------------------------
     def _index(self):

@@ -258,6 +258,9 @@ ECAMP_API int ecamp_backward_stage_range(int32_t stage, int64_t* begin, int64_t*
 ECAMP_API int ecamp_backward(ecamp_ctx* ctx, const float* g3, int32_t accumulate, int32_t stage, void* stream);
 ECAMP_API int ecamp_adamw_step(ecamp_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
                                int32_t step, float grad_scale, void* stream);
+/* the same with one learning rate per timm add_weight_decay group (PT/main_pretrain.py:253: [no-decay, decay]) */
+ECAMP_API int ecamp_adamw_step_groups(ecamp_ctx* ctx, float lr_decay, float lr_no_decay, float beta1, float beta2, float eps,
+                                      float weight_decay, int32_t step, float grad_scale, void* stream);
 /* after ecamp_forward: probs [B, 6, T, keep] fp32 of the fusion layer's text -> image cross-attention, columns in
  * ids_keep order — what Visualization/module/model_ecamp.py:308-319 returns at mask_ratio = 0 */
 ECAMP_API int ecamp_cross_attention_probs(ecamp_ctx* ctx, float* probs, void* stream);

@@ -1212,7 +1212,34 @@ def check_image_pipeline():
     report("image_pipeline_feeds_step", bool(torch.equal(l8, l32)) and bool(torch.isfinite(l8).all()), losses=l8.tolist())
 
 
-ALL_CHECKS = (check_image_pipeline, check_gemm_fp32, check_step_fp32, check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
+@guard
+def check_adamw_groups():
+    """FusedAdamW honours one learning rate per parameter group (the reference schedule writes param_group["lr"] per group,
+    util/lr_sched.py:9-21): two steps with lr 3e-4 on the no-decay group and 1e-4 on the decay group against torch.optim.AdamW
+    over the same add_weight_decay groups, same gradients.  Tolerance 1e-6 absolute (same fp32 update rule)."""
+    from ecamp_b200.optim import FusedAdamW
+    torch.manual_seed(2)
+    m = ecamp().to(dev).eval()
+    ref = ecamp().to(dev).eval()
+    ref.load_state_dict(m.state_dict())
+    b = synthetic_batch(2, T=32, seed=9, device=dev)
+    opt = FusedAdamW(m, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    opt.param_groups[0]["lr"] = 3e-4
+    topt = torch.optim.AdamW(_add_weight_decay(ref, 0.05), lr=1e-4, betas=(0.9, 0.95))
+    topt.param_groups[0]["lr"] = 3e-4
+    rn = dict(ref.named_parameters())
+    for it in range(2):
+        m.zero_grad(set_to_none=True)
+        m.forward_backward(b)
+        for k, p in m.named_parameters():
+            rn[k].grad = p.grad.clone() if p.grad is not None else None
+        opt.step(); topt.step()
+    torch.cuda.synchronize()
+    worst = max((p.detach() - rn[k].detach()).abs().max().item() for k, p in m.named_parameters())
+    report("adamw_param_group_lrs", worst < 1e-6, max_abs_param_diff=worst)
+
+
+ALL_CHECKS = (check_adamw_groups, check_image_pipeline, check_gemm_fp32, check_step_fp32, check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
 
 
 def run_check(fn):
