@@ -138,6 +138,7 @@ int ecamp_layernorm_bwd(const float* dy, const float* x, const float* mean, cons
                        dgamma, dbeta, colsum_out, accumulate, S(stream));
 }
 size_t ecamp_layernorm_ws_floats(void) { return layernorm_bwd_ws_floats(768); }
+void ecamp_layernorm_set_bwd_slab(int32_t on) { layernorm_set_bwd_slab(on); }
 
 int ecamp_attention_fwd(const ecamp_attn* a, void* stream) {
   ECAMP_REQUIRE(a && a->q && a->k && a->v && a->o, "ecamp_attention_fwd: null argument");

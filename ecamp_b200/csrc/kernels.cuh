@@ -23,6 +23,7 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
                   float* dbeta, float* colsum_out, int accumulate, cudaStream_t st, const float* out_row_scale = nullptr,
                   int rows_per_scale = 1);
 size_t layernorm_bwd_ws_floats(int D);
+void layernorm_set_bwd_slab(int on);  // 1: the round-1 slab kernel instead of the staged one (A/B measurements)
 
 // ---- elementwise.cu ---------------------------------------------------------------------------
 // model_ecamp.py:168-193 on given noise: stable ascending rank == ids_restore; ids_keep; mask (1 = removed).

@@ -145,6 +145,9 @@ ECAMP_API int ecamp_layernorm_bwd(const float* dy, const float* x, const float* 
                                   void* dx_bf16, float* dgamma, float* dbeta, float* colsum_out, int32_t accumulate,
                                   float* ws /* unused */, void* stream);
 ECAMP_API size_t ecamp_layernorm_ws_floats(void);
+/* Measurement switch: 1 selects the slab form of the backward kernel (740 CTAs, per-warp shared-memory column sums), 0 (default)
+ * the staged form (one CTA per SM, rows staged by cp.async.bulk, column sums in registers).  Same results up to fp32 summation order. */
+ECAMP_API void ecamp_layernorm_set_bwd_slab(int32_t on);
 
 /* fused attention (timm Attention; HF BertSelfAttention eager path incl. key-padding mask and
  * probability dropout; cross-attention of module/context_fusion.py:45-53). */

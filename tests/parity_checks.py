@@ -265,8 +265,10 @@ def _check_gemm_epilogues(tag):
 
 @guard
 def check_layernorm():
-    for D in (768, 512):
-        M = 1000
+    # M = 7001: ragged, ~6 rows per warp of the staged backward (its row rings wrap twice); M = 3: fewer rows than warps
+    for D, M, slab, with_add in [(768, 1000, 0, 1), (512, 1000, 0, 1), (768, 7001, 0, 1), (768, 7001, 0, 0), (512, 7001, 0, 1),
+                                 (512, 7001, 0, 0), (768, 3, 0, 1), (768, 7001, 1, 1), (512, 1000, 1, 0)]:
+        lib.ecamp_layernorm_set_bwd_slab(slab)
         x = torch.randn(M, D, device=dev) * 2 + 0.5
         g = torch.randn(D, device=dev); b = torch.randn(D, device=dev)
         ob = torch.empty(M, D, dtype=torch.bfloat16, device=dev); of = torch.empty(M, D, device=dev)
@@ -277,18 +279,21 @@ def check_layernorm():
         e1 = (of - ref).abs().max().item()
         dy = torch.randn(M, D, device=dev)
         ref.backward(dy)
-        add = torch.randn(M, D, device=dev)
+        add = torch.randn(M, D, device=dev) if with_add else None
         dx = torch.empty(M, D, device=dev); dxb = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
         dg = torch.full((D,), 7.0, device=dev); db = torch.full((D,), -3.0, device=dev)   # accumulate = 0 must overwrite
         cs = torch.full((D,), 5.0, device=dev)
-        L.check(lib.ecamp_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(g), M, D, L.ptr(add), L.ptr(dx), L.ptr(dxb), L.ptr(dg), L.ptr(db), L.ptr(cs), 0, None, L.cur_stream()), "lnb")
-        e2 = rel(dx - add, xr.grad); e3 = rel(dg, gr.grad); e4 = rel(db, br.grad)
+        L.check(lib.ecamp_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(g), M, D, L.ptr(add) if with_add else None, L.ptr(dx), L.ptr(dxb), L.ptr(dg), L.ptr(db), L.ptr(cs), 0, None, L.cur_stream()), "lnb")
+        e2 = rel(dx - add if with_add else dx, xr.grad); e3 = rel(dg, gr.grad); e4 = rel(db, br.grad)
         e5 = rel(cs, dxb.float().sum(0)); e6 = rel(dxb.float(), dx)
-        # accumulate = 1 adds on top of the running values
-        L.check(lib.ecamp_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(g), M, D, L.ptr(add), L.ptr(dx), L.ptr(dxb), L.ptr(dg), L.ptr(db), None, 1, None, L.cur_stream()), "lnb")
-        e7 = rel(dg, 2 * gr.grad)
-        report(f"layernorm_{D}", e1 < 1e-4 and e2 < 1e-4 and e3 < 1e-4 and e4 < 1e-4 and e5 < 1e-4 and e6 < 5e-3 and e7 < 1e-4,
-               fwd=e1, dx=e2, dgamma=e3, dbeta=e4, colsum=e5, bf16=e6, accumulate=e7)
+        # accumulate = 1 adds on top of the running values; no column sum, fp32 output only
+        dx2 = torch.empty(M, D, device=dev)
+        L.check(lib.ecamp_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(g), M, D, L.ptr(add) if with_add else None, L.ptr(dx2), None, L.ptr(dg), L.ptr(db), None, 1, None, L.cur_stream()), "lnb")
+        e7 = rel(dg, 2 * gr.grad); e8 = (dx2 - dx).abs().max().item()
+        report(f"layernorm_{D}_M{M}_{'slab' if slab else 'staged'}_{'addend' if with_add else 'plain'}",
+               e1 < 1e-4 and e2 < 1e-4 and e3 < 1e-4 and e4 < 1e-4 and e5 < 1e-4 and e6 < 5e-3 and e7 < 1e-4 and e8 == 0.0,
+               fwd=e1, dx=e2, dgamma=e3, dbeta=e4, colsum=e5, bf16=e6, accumulate=e7, dx_repeat=e8)
+    lib.ecamp_layernorm_set_bwd_slab(0)
 
 
 def attn_ref(q, k, v, key_mask, scale):
