@@ -179,6 +179,14 @@ int ecamp_ce_rows(void* logits_bf16, int32_t ld, int32_t rows, int32_t V, const 
                   write_grad, S(stream));
 }
 
+int ecamp_ce_rows_bias(void* logits_bf16, int32_t ld, int32_t rows, int32_t V, const int64_t* labels, const float* weights,
+                       float* row_loss, const float* g, float inv_total_rows, float* bias_grad, void* stream) {
+  return ce_chunk(static_cast<bf16*>(logits_bf16), ld, rows, V, labels, weights, row_loss, g, inv_total_rows, 1, S(stream),
+                  bias_grad);
+}
+void ecamp_ce_set_fused(int32_t on) { ce_set_fused(on); }
+void ecamp_sr_set_window_skip(int32_t on) { sr_set_window_skip(on); }
+
 // ---- runtime -----------------------------------------------------------------------------------
 int32_t ecamp_param_count(void) { return (int32_t)param_specs().size(); }
 const char* ecamp_param_name(int32_t i) {

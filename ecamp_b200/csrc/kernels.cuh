@@ -161,8 +161,11 @@ int pred_grad(const float* pred, const float* tgt, const float* mask, const floa
               AT* d_pred, cudaStream_t st);
 // weighted cross-entropy over a chunk of rows, logits bf16 [rows, V] (ld = ldl); optionally overwrites the
 // logits with d_logits = (softmax - onehot) * w * g / total_rows           (bert_modeling.py:211-217)
+void sr_set_window_skip(int on);  // measurement switch: 0 = SR backward computes every stage on whole tiles
+void ce_set_fused(int on);  // measurement switch: 0 = one CTA per row + separate column-sum pass
+// bias_grad (optional, [V], ADDED to): column sums of the gradient = gradient of the vocabulary bias, folded into the same pass
 int ce_chunk(bf16* logits, int ldl, int rows, int V, const int64_t* labels, const float* weights, float* row_loss,
-             const float* g_mlm, float inv_total, int write_grad, cudaStream_t st);
+             const float* g_mlm, float inv_total, int write_grad, cudaStream_t st, float* bias_grad = nullptr);
 int ce_chunk(float* logits, int ldl, int rows, int V, const int64_t* labels, const float* weights, float* row_loss,
              const float* g_mlm, float inv_total, int write_grad, cudaStream_t st);  // fp32-accurate mode
 int sum_to_scalar(const float* x, size_t n, float scale, float* out, cudaStream_t st);

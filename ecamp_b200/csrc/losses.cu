@@ -88,8 +88,12 @@ ECAMP_DEVINL void conv3_strip4(const float* in, int y0, int x0, const float* wt,
 // Forward of the SR head on an OUT x OUT output region whose top-left output pixel is (Y0, X0):
 //   sU: (OUT+4)^2 x 3 up-sampled input, origin (Y0-2, X0-2), zero outside the image (conv zero padding)
 //   sH: (OUT+2)^2 x 3 relu(conv1), origin (Y0-1, X0-1), zero outside the image
+// (ny0, ny1, nx0, nx1): the pixels whose OUTPUT the caller will use (the loss window); u is only needed within 2 pixels
+// and relu(conv1) within 1 pixel of them - everything else is written as zero without being computed, which is what
+// makes the tiles that merely border the window cheap.
 template <int OUT>
-ECAMP_DEVINL void sr_forward_region(const float* __restrict__ pred_b, int Y0, int X0, float* sU, float* sH) {
+ECAMP_DEVINL void sr_forward_region(const float* __restrict__ pred_b, int Y0, int X0, float* sU, float* sH,
+                                    int ny0 = -(1 << 20), int ny1 = 1 << 20, int nx0 = -(1 << 20), int nx1 = 1 << 20) {
   const SrWeights& w = c_sr;
   constexpr int UW = OUT + 4, HW = OUT + 2;
 #pragma unroll 2  // two positions' 24 gathers in flight (the loop was exposed to the latency of its global loads)
@@ -97,7 +101,7 @@ ECAMP_DEVINL void sr_forward_region(const float* __restrict__ pred_b, int Y0, in
     const int uy = i / UW, ux = i % UW;
     const int Y = Y0 - 2 + uy, X = X0 - 2 + ux;
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (Y >= 0 && Y < BIG && X >= 0 && X < BIG) {
+    if (Y >= 0 && Y < BIG && X >= 0 && X < BIG && Y >= ny0 - 2 && Y < ny1 + 2 && X >= nx0 - 2 && X < nx1 + 2) {
       int y0, y1, x0, x1;
       float ly, lx;
       bilinear_src(Y, y0, y1, ly);
@@ -123,13 +127,14 @@ ECAMP_DEVINL void sr_forward_region(const float* __restrict__ pred_b, int Y0, in
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[c][q] = w.b1[c];
-    conv3_strip4<UW, UW * UW, false>(sU, hy, hx0, w.w1, acc);
     const int Y = Y0 - 1 + hy;
+    const bool need = Y >= ny0 - 1 && Y < ny1 + 1 && X0 - 1 + hx0 + 3 >= nx0 - 1 && X0 - 1 + hx0 < nx1 + 1;
+    if (need) conv3_strip4<UW, UW * UW, false>(sU, hy, hx0, w.w1, acc);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int hx = hx0 + q, X = X0 - 1 + hx;
       if (hx < HW) {
-        const bool in_img = Y >= 0 && Y < BIG && X >= 0 && X < BIG;  // outside: conv2's zero padding
+        const bool in_img = need && Y >= 0 && Y < BIG && X >= 0 && X < BIG;  // outside: conv2's zero padding
 #pragma unroll
         for (int c = 0; c < 3; ++c) sH[c * HW * HW + hy * HW + hx] = in_img ? fmaxf(acc[c][q], 0.f) : 0.f;
       }
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
                                                      const int64_t* __restrict__ column,
                                                      const int64_t* __restrict__ row, int B,
                                                      const float* __restrict__ g_res, float* __restrict__ d_u,
-                                                     float* __restrict__ ws, float* __restrict__ loss_tiles) {
+                                                     float* __restrict__ ws, float* __restrict__ loss_tiles, int skip) {
   ECAMP_PDL_ENTRY();
   constexpr int OUT = 36, UW = 40, HW = 38, OW = 36, GW = 34;
   extern __shared__ float sm[];
@@ -231,7 +236,9 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
     return;
   }
   const float* pred_b = pred + (size_t)b * 197 * PD;
-  sr_forward_region<OUT>(pred_b, Y0 - 2, X0 - 2, sU, sH);
+  // work is limited to what the window can reach (skip == 0: the round-1 behaviour, every stage on the whole tile)
+  const int ky0 = skip ? wy0 : -(1 << 20), ky1 = skip ? wy1 : 1 << 20, kx0 = skip ? wx0 : -(1 << 20), kx1 = skip ? wx1 : 1 << 20;
+  sr_forward_region<OUT>(pred_b, Y0 - 2, X0 - 2, sU, sH, ky0, ky1, kx0, kx1);
   const float gscale = 2.0f * (*g_res) / ((float)B * 3.f * BIG * BIG);
 
   // d_out (pre-ReLU) on the 36x36 region with origin (Y0-2, X0-2); the squared error of the OWNED in-window pixels
@@ -254,6 +261,14 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
       for (int c = 0; c < 3; ++c)
         tg[pr][c] = in_win[pr] ? __ldg(reinterpret_cast<const float2*>(big + (((size_t)b * 3 + c) * BIG + Y) * BIG + X))
                                : make_float2(0.f, 0.f);
+    }
+    if (skip && !in_win[0] && !in_win[1]) {  // no pixel of the strip is in the window: d_out = 0, nothing to convolve
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        *reinterpret_cast<float2*>(sDO + c * OW * OW + oy * OW + ox0) = make_float2(0.f, 0.f);
+        *reinterpret_cast<float2*>(sDO + c * OW * OW + oy * OW + ox0 + 2) = make_float2(0.f, 0.f);
+      }
+      continue;
     }
     float o[3][4];
     sr_out_strip<OUT>(sU, sH, oy, ox0, o);
@@ -284,13 +299,15 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int q = 0; q < 4; ++q) d[c][q] = 0.f;
-    conv3_strip4<OW, OW * OW, true>(sDO, gy, gx0, sw.w2, d);
     const int Y = Y0 - 1 + gy;
+    // d_h1 is zero further than one pixel from the window (d_out is zero outside it)
+    const bool need = Y >= ky0 - 1 && Y < ky1 + 1 && X0 - 1 + gx0 + 3 >= kx0 - 1 && X0 - 1 + gx0 < kx1 + 1;
+    if (need) conv3_strip4<OW, OW * OW, true>(sDO, gy, gx0, sw.w2, d);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int gx = gx0 + q, X = X0 - 1 + gx;
       if (gx < GW) {
-        const bool in_img = Y >= 0 && Y < BIG && X >= 0 && X < BIG;
+        const bool in_img = need && Y >= 0 && Y < BIG && X >= 0 && X < BIG;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           sDH[c * GW * GW + gy * GW + gx] = (in_img && sH[c * HW * HW + (gy + 2) * HW + gx + 2] > 0.f) ? d[c][q] : 0.f;
@@ -307,7 +324,9 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
 #pragma unroll
       for (int q = 0; q < 4; ++q) d[c][q] = sDO[c * OW * OW + (oy + 2) * OW + ox0 + q + 2];
     // dH region coords of (Y - ky + 1, X - kx + 1) with (Y, X) = (Y0 + oy, X0 + ox): (oy + 2 - ky, ox + 2 - kx)
-    conv3_strip4<GW, GW * GW, true>(sDH, oy, ox0, sw.w1, d);
+    // (d_u is zero further than two pixels from the window: d_out and d_h1 are zero there)
+    if (Y0 + oy >= ky0 - 2 && Y0 + oy < ky1 + 2 && X0 + ox0 + 3 >= kx0 - 2 && X0 + ox0 < kx1 + 2)
+      conv3_strip4<GW, GW * GW, true>(sDH, oy, ox0, sw.w1, d);
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       *reinterpret_cast<float4*>(d_u + (((size_t)b * 3 + c) * BIG + Y0 + oy) * BIG + X0 + ox0) =
@@ -339,10 +358,19 @@ __global__ void __launch_bounds__(256, 3) sr_bwd_kernel(const float* __restrict_
       for (int co = 0; co < 3; ++co)
 #pragma unroll
         for (int q = 0; q < 4; ++q) g[half][co][q] = gsrc[co * gW * gW + (soy + 16 * half + goff) * gW + sox0 + goff + q];
+    bool nz = false;  // a tile that only borders the window has d_out = 0 on its own pixels and d_h1 != 0 on a 1-pixel band
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+#pragma unroll
+      for (int co = 0; co < 3; ++co)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nz = nz || g[half][co][q] != 0.f;
+    const bool warp_has_work = __any_sync(0xffffffffu, nz || !skip);
 #pragma unroll
     for (int co = 0; co < 3; ++co)
       acc[81 + co] = ((g[0][co][0] + g[0][co][1]) + (g[0][co][2] + g[0][co][3])) +
                      ((g[1][co][0] + g[1][co][1]) + (g[1][co][2] + g[1][co][3]));
+    if (warp_has_work)
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
@@ -563,6 +591,166 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(bf16* __restrict__ logits,
   }
 }
 
+// Persistent form with the bias gradient folded in (default for the training step).  One CTA per SM walks rows
+// r, r + grid, ...; the NEXT two rows are in flight as bulk asynchronous copies into a two-slot shared-memory ring while
+// the current one is reduced, so the loads no longer wait behind the three block-wide phases of a row.  Every thread
+// owns the same columns in every row (uint4 groups tid, tid + 512, ...), so the column sums of the gradient it writes
+// (= the gradient of cls.predictions.bias) stay in registers for the whole launch and leave as one vector atomic per
+// four columns and CTA: the separate column-sum pass re-read all V x rows gradients (245 MB per 4096-row chunk, 0.39 ms
+// per step).  The sums are taken over the fp32 values before they are rounded to bf16 for the GEMMs.
+int g_ce_fused = -1;  // 1 (default): persistent kernel with the bias gradient folded in; 0: one CTA per row + column-sum pass
+constexpr int kCeThreads = 512;
+constexpr int kCeGroups = 8;  // uint4 groups per thread: V <= 8 * 512 * 8 = 32768
+
+ECAMP_DEVINL void ce_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kCeThreads, 1)
+    ce_rows_fused_kernel(bf16* __restrict__ logits, int ldl, int V, int rows, const int64_t* __restrict__ labels,
+                         const float* __restrict__ weights, float* __restrict__ row_loss, const float* __restrict__ g_mlm,
+                         float inv_total, float* __restrict__ colsum) {
+  extern __shared__ __align__(128) uint8_t ce_smem[];
+  __shared__ __align__(8) uint64_t full[2];
+  __shared__ float red[32];
+  __shared__ float s_zlabel;
+  const int nv = V / 8;
+  const uint32_t row_bytes = (uint32_t)V * 2u;
+  const uint32_t slot_bytes = (row_bytes + 127u) & ~127u;
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+  ECAMP_PDL_ENTRY();
+  const int stride = gridDim.x;
+  auto issue = [&](int slot, int r) {  // thread 0 only
+    mbar_arrive_expect_tx(&full[slot], row_bytes);
+    ce_bulk_load(ce_smem + (size_t)slot * slot_bytes, logits + (size_t)r * ldl, row_bytes, &full[slot]);
+  };
+  if (threadIdx.x == 0) {
+    if ((int)blockIdx.x < rows) issue(0, blockIdx.x);
+    if ((int)blockIdx.x + stride < rows) issue(1, blockIdx.x + stride);
+  }
+  float cs[kCeGroups][8];
+#pragma unroll
+  for (int j = 0; j < kCeGroups; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cs[j][k] = 0.f;
+  const float gm = *g_mlm;
+  int it = 0;
+  for (int r = blockIdx.x; r < rows; r += stride, ++it) {
+    const int slot = it & 1;
+    mbar_wait(&full[slot], (uint32_t)(it >> 1) & 1u);
+    uint4* srow = reinterpret_cast<uint4*>(ce_smem + (size_t)slot * slot_bytes);
+    const long long label = labels[r];
+    const bool valid = label >= 0 && label < V;  // CrossEntropyLoss ignore_index (-100) -> no loss, no gradient
+    const int lgroup = valid ? (int)(label >> 3) : -1, lsub = (int)(label & 7);
+    const float w = weights[r];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kCeGroups; ++j) {
+      const int i = threadIdx.x + j * kCeThreads;
+      if (i < nv) {
+        const uint4 u = srow[i];
+        float2 f;
+        f = unpack_bf16x2(u.x); mx = fmaxf(mx, fmaxf(f.x, f.y));
+        f = unpack_bf16x2(u.y); mx = fmaxf(mx, fmaxf(f.x, f.y));
+        f = unpack_bf16x2(u.z); mx = fmaxf(mx, fmaxf(f.x, f.y));
+        f = unpack_bf16x2(u.w); mx = fmaxf(mx, fmaxf(f.x, f.y));
+      }
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int wi = 1; wi < kCeThreads / 32; ++wi) mx = fmaxf(mx, red[wi]);
+    __syncthreads();  // red is reused by the sum below
+    // e_j = exp(z_j - max), once: summed in fp32 and kept (bf16, over the staged logit) for the gradient pass
+    const float mx2 = mx * 1.4426950408889634f;
+    float se = 0.f;
+#pragma unroll
+    for (int j = 0; j < kCeGroups; ++j) {
+      const int i = threadIdx.x + j * kCeThreads;
+      if (i < nv) {
+        const uint4 u = srow[i];
+        float v[8];
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+        if (i == lgroup) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k == lsub) s_zlabel = v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k] = ex2_approx(fmaf(v[k], 1.4426950408889634f, -mx2));
+          se += v[k];
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        srow[i] = o;
+      }
+    }
+    se = block_sum(se, red);
+    if (threadIdx.x == 0) row_loss[r] = valid ? (mx + __logf(se) - s_zlabel) * w : 0.f;
+    const float coef = valid ? w * gm * inv_total : 0.f;
+    const float pscale = coef / se;  // softmax_j * coef = e_j * coef / sum
+    uint4* grow = reinterpret_cast<uint4*>(logits + (size_t)r * ldl);
+#pragma unroll
+    for (int j = 0; j < kCeGroups; ++j) {
+      const int i = threadIdx.x + j * kCeThreads;
+      if (i < nv) {
+        const uint4 u = srow[i];
+        float v[8];
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] = f.x * pscale; v[1] = f.y * pscale;
+        f = unpack_bf16x2(u.y); v[2] = f.x * pscale; v[3] = f.y * pscale;
+        f = unpack_bf16x2(u.z); v[4] = f.x * pscale; v[5] = f.y * pscale;
+        f = unpack_bf16x2(u.w); v[6] = f.x * pscale; v[7] = f.y * pscale;
+        if (i == lgroup) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k == lsub) v[k] -= coef;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cs[j][k] += v[k];
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        grow[i] = o;
+      }
+    }
+    __syncthreads();  // every thread is done with this slot (and with s_zlabel / red) before the slot is refilled
+    if (threadIdx.x == 0 && r + 2 * stride < rows) issue(slot, r + 2 * stride);
+  }
+  if (colsum) {
+    const bool vec = (reinterpret_cast<uintptr_t>(colsum) & 15) == 0;  // the flat gradient buffer packs tensors without padding
+#pragma unroll
+    for (int j = 0; j < kCeGroups; ++j) {
+      const int i = threadIdx.x + j * kCeThreads;
+      if (i < nv) {
+        if (vec) {
+          atomicAdd(reinterpret_cast<float4*>(colsum + 8 * (size_t)i), make_float4(cs[j][0], cs[j][1], cs[j][2], cs[j][3]));
+          atomicAdd(reinterpret_cast<float4*>(colsum + 8 * (size_t)i + 4), make_float4(cs[j][4], cs[j][5], cs[j][6], cs[j][7]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) atomicAdd(colsum + 8 * (size_t)i + k, cs[j][k]);
+        }
+      }
+    }
+  }
+}
+
 // fp32-accurate mode: the same cross-entropy on fp32 logits (three passes over the row in global / L2: max, sum of
 // exponentials with expf / logf, gradient written over the logits)
 __global__ void __launch_bounds__(256) ce_rows_f32_kernel(float* __restrict__ logits, int ldl, int V,
@@ -641,6 +829,9 @@ int sr_loss_fwd(const float* pred, const float* big, const int64_t* column, cons
   return sum_to_scalar(ws, (size_t)B * GRID * GRID, 1.0f / ((float)B * 3.f * BIG * BIG), loss_out, st);
 }
 
+int g_sr_window_skip = 1;  // measurement switch (ecamp_sr_set_window_skip): 0 = every stage on the whole tile
+void sr_set_window_skip(int on) { g_sr_window_skip = on ? 1 : 0; }
+
 int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, const int64_t* row, const float* w1,
                 const float* b1, const float* w2, const float* b2, int B, const float* g_res, float* d_u,
                 float* d_conv, int accumulate, float* ws, cudaStream_t st, float* loss_tiles, float* loss_out) {
@@ -652,7 +843,7 @@ int sr_loss_bwd(const float* pred, const float* big, const int64_t* column, cons
   }
   if (int rc = upload_sr_weights(w1, b1, w2, b2, st)) return rc;
   ECAMP_CUDA_OK(launch_pdl(sr_bwd_kernel, B * GRID * GRID, 256, SR_BWD_SMEM_FLOATS * sizeof(float), st, pred, big, column, row, B, g_res,
-                                                                                   d_u, ws, loss_tiles));
+                                                                                   d_u, ws, loss_tiles, g_sr_window_skip));
   LAUNCH_OK();
   ECAMP_CUDA_OK(launch_pdl(sr_wgrad_finalize_kernel, 168, 256, 0, st, ws, B * GRID * GRID, d_conv, accumulate));
   LAUNCH_OK();
@@ -681,11 +872,35 @@ int ce_chunk(float* logits, int ldl, int rows, int V, const int64_t* labels, con
   return 0;
 }
 
+void ce_set_fused(int on) { g_ce_fused = on ? 1 : 0; }
+
 int ce_chunk(bf16* logits, int ldl, int rows, int V, const int64_t* labels, const float* weights, float* row_loss,
-             const float* g_mlm, float inv_total, int write_grad, cudaStream_t st) {
+             const float* g_mlm, float inv_total, int write_grad, cudaStream_t st, float* bias_grad) {
   ECAMP_REQUIRE(V % 8 == 0 && ldl % 8 == 0, "cross-entropy: vocabulary / pitch must be multiples of 8");
   ECAMP_REQUIRE((size_t)V * 2 <= 200 * 1024, "cross-entropy: vocabulary row does not fit in shared memory");
+  ECAMP_REQUIRE(!bias_grad || write_grad, "cross-entropy: the bias gradient needs the gradient pass");
   if (rows <= 0) return 0;
+  if (g_ce_fused < 0) g_ce_fused = getenv("ECAMP_CE_FUSED") ? atoi(getenv("ECAMP_CE_FUSED")) : 1;
+  const int fused_on = g_ce_fused;
+  if (write_grad && fused_on && V <= kCeGroups * kCeThreads * 8) {
+    const size_t slot = ((size_t)V * 2 + 127) & ~(size_t)127;
+    static bool attr2 = false;
+    if (!attr2) {
+      ECAMP_CUDA_OK(cudaFuncSetAttribute(ce_rows_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr2 = true;
+    }
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    ECAMP_CUDA_OK(launch_pdl(ce_rows_fused_kernel, rows < sms ? rows : sms, kCeThreads, 2 * slot, st, logits, ldl, V, rows, labels, weights,
+                             row_loss, g_mlm, inv_total, bias_grad));
+    LAUNCH_OK();
+    return 0;
+  }
   static bool attr = false;
   if (!attr) {
     ECAMP_CUDA_OK(cudaFuncSetAttribute(ce_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -694,6 +909,7 @@ int ce_chunk(bf16* logits, int ldl, int rows, int V, const int64_t* labels, cons
   ECAMP_CUDA_OK(launch_pdl(ce_rows_kernel, rows, 256, (size_t)V * 2, st, logits, ldl, V, labels, weights, row_loss, g_mlm, inv_total,
                                                    write_grad));
   LAUNCH_OK();
+  if (bias_grad) return colsum_bf16(logits, ldl, rows, V, bias_grad, 1, nullptr, st);
   return 0;
 }
 

@@ -688,6 +688,14 @@ int lm_transform_fwd(CtxT<AT>* c) {
   RC(layernorm_fwd(c->t_act, c->P(pt + 2), c->P(pt + 3), 1e-12f, Mt, 768, c->tl, nullptr, c->t_mean, c->t_rstd, c->st));
   return 0;
 }
+inline int ce_rows_any(CtxT<bf16>* c, int rows, int r0, bool with_grad, float inv_total, float* bias_grad) {
+  return ce_chunk(c->logits, VOC, rows, VOC, c->batch.labels + r0, c->batch.weights + r0, c->row_loss + r0,
+                  with_grad ? c->g3 + 2 : nullptr, inv_total, with_grad ? 1 : 0, c->st, bias_grad);
+}
+inline int ce_rows_any(CtxT<float>* c, int rows, int r0, bool with_grad, float inv_total, float*) {
+  return ce_chunk(c->logits, VOC, rows, VOC, c->batch.labels + r0, c->batch.weights + r0, c->row_loss + r0,
+                  with_grad ? c->g3 + 2 : nullptr, inv_total, with_grad ? 1 : 0, c->st);
+}
 template <typename AT>
 int lm_chunks(CtxT<AT>* c, bool with_grad, bool write_loss) {
   const int Mt = c->sh.B * c->sh.T;
@@ -698,13 +706,13 @@ int lm_chunks(CtxT<AT>* c, bool with_grad, bool write_loss) {
   for (int r0 = 0; r0 < Mt; r0 += R) {
     const int rows = Mt - r0 < R ? Mt - r0 : R;
     RC(lin_fwd(c, c->tl + (size_t)r0 * 768, 768, rows, c->W(pw), VOC, 768, ep_bias_bf16(c->P(pbias), c->logits, VOC)));
-    RC(ce_chunk(c->logits, VOC, rows, VOC, c->batch.labels + r0, c->batch.weights + r0, c->row_loss + r0,
-                with_grad ? c->g3 + 2 : nullptr, 1.0f / (float)Mt, with_grad ? 1 : 0, c->st));
+    RC(ce_rows_any(c, rows, r0, with_grad, 1.0f / (float)Mt, with_grad ? c->Gp(pbias) : nullptr));
     if (with_grad) {
       GemmEpilogueT<AT> e;
       e.out_f32 = c->dTL + (size_t)r0 * 768; e.ld_f32 = 768;
       RC(lin_dgrad(c, c->logits, VOC, rows, c->W(pw), VOC, 768, e));
-      RC(lin_wgrad(c, c->logits, VOC, c->tl + (size_t)r0 * 768, 768, rows, VOC, 768, c->Gp(pw), c->Gp(pbias), acc));
+      // the bias gradient: by the cross-entropy kernel (bf16 mode) or a column-sum pass (fp32-accurate mode)
+      RC(lin_wgrad(c, c->logits, VOC, c->tl + (size_t)r0 * 768, 768, rows, VOC, 768, c->Gp(pw), is_hp<AT>::value ? c->Gp(pbias) : nullptr, acc));
       acc = 1;
     }
   }

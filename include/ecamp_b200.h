@@ -197,6 +197,17 @@ ECAMP_API int ecamp_pred_grad(const float* pred, const float* tgt, const float* 
 ECAMP_API int ecamp_ce_rows(void* logits_bf16, int32_t ld, int32_t rows, int32_t V, const int64_t* labels,
                             const float* weights, float* row_loss, const float* g, float inv_total_rows,
                             int32_t write_grad, void* stream);
+/* The same with the gradient pass always on and the gradient of cls.predictions.bias (module/bert_modeling.py:208-210: the
+ * decoder Linear's bias) folded in: bias_grad [V] (may be NULL) is ADDED to with the column sums of the written gradient. */
+ECAMP_API int ecamp_ce_rows_bias(void* logits_bf16, int32_t ld, int32_t rows, int32_t V, const int64_t* labels,
+                                 const float* weights, float* row_loss, const float* g, float inv_total_rows,
+                                 float* bias_grad, void* stream);
+/* Measurement switch: 1 (default) = persistent kernel, rows staged by cp.async.bulk, column sums in registers; 0 = one CTA per
+ * row followed by a column-sum pass over the written gradient. */
+ECAMP_API void ecamp_ce_set_fused(int32_t on);
+/* Measurement switch: 1 (default) = the SR backward kernel limits every stage of a tile to what the loss window can reach
+ * (tiles that merely border the window become cheap); 0 = every stage on the whole 36 x 36 neighbourhood. */
+ECAMP_API void ecamp_sr_set_window_skip(int32_t on);
 
 /* ==========================================================================================
  * 2. The step runtime (what the nn.Module calls): parameter table, context, forward / backward /

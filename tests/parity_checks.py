@@ -424,20 +424,47 @@ def check_losses():
 
 @guard
 def check_ce():
-    rows, V = 300, 30000
-    logits = (torch.randn(rows, V, device=dev) * 2).to(torch.bfloat16)
-    labels = torch.randint(0, V, (rows,), device=dev); labels[5] = -100
-    w = torch.rand(rows, device=dev) + 0.05
-    g = torch.tensor([0.5], device=dev)
-    lr = logits.float().requires_grad_(True)
-    ce = F.cross_entropy(lr, labels, reduction="none")
-    (ce * w).sum().mul(0.5 / 1000).backward()
-    row_loss = torch.empty(rows, device=dev)
-    lg = logits.clone()
-    L.check(lib.ecamp_ce_rows(L.ptr(lg), V, rows, V, L.ptr(labels), L.ptr(w), L.ptr(row_loss), L.ptr(g), ctypes.c_float(1.0 / 1000), 1, L.cur_stream()), "ce")
-    torch.cuda.synchronize()
-    e1 = rel(row_loss, (ce * w).detach()); e2 = rel(lg.float(), lr.grad)
-    report("cross_entropy", e1 < 1e-4 and e2 < 1e-2, loss=e1, grad=e2)
+    # 300 rows: two rows per CTA of the persistent kernel at most; 1000 rows: its two-slot row ring wraps 3 times; V = 2048: idle column groups
+    for rows, V, fused in [(300, 30000, 1), (1000, 30000, 1), (1000, 30000, 0), (1, 30000, 1), (700, 2048, 1)]:
+        lib.ecamp_ce_set_fused(fused)
+        logits = (torch.randn(rows, V, device=dev) * 2).to(torch.bfloat16)
+        labels = torch.randint(0, V, (rows,), device=dev)
+        if rows > 5:
+            labels[5] = -100
+        w = torch.rand(rows, device=dev) + 0.05
+        g = torch.tensor([0.5], device=dev)
+        lr = logits.float().requires_grad_(True)
+        ce = F.cross_entropy(lr, labels, reduction="none")
+        (ce * w).sum().mul(0.5 / 1000).backward()
+        row_loss = torch.empty(rows, device=dev)
+        lg = logits.clone()
+        L.check(lib.ecamp_ce_rows(L.ptr(lg), V, rows, V, L.ptr(labels), L.ptr(w), L.ptr(row_loss), L.ptr(g), ctypes.c_float(1.0 / 1000), 1, L.cur_stream()), "ce")
+        torch.cuda.synchronize()
+        e1 = rel(row_loss, (ce * w).detach()); e2 = rel(lg.float(), lr.grad)
+        # with the bias gradient folded in: same gradient bytes, column sums added on top of the running value (also at an
+        # address that is not 16-byte aligned, as in the packed flat gradient buffer)
+        lg2 = logits.clone(); row_loss2 = torch.empty(rows, device=dev)
+        bias_buf = torch.zeros(V + 1, device=dev); bias = bias_buf[1:]
+        L.check(lib.ecamp_ce_rows_bias(L.ptr(lg2), V, rows, V, L.ptr(labels), L.ptr(w), L.ptr(row_loss2), L.ptr(g), ctypes.c_float(1.0 / 1000), ctypes.c_void_p(bias.data_ptr()), L.cur_stream()), "ceb")
+        bias_al = torch.zeros(V, device=dev); lg3 = logits.clone()
+        L.check(lib.ecamp_ce_rows_bias(L.ptr(lg3), V, rows, V, L.ptr(labels), L.ptr(w), L.ptr(row_loss2), L.ptr(g), ctypes.c_float(1.0 / 1000), L.ptr(bias_al), L.cur_stream()), "ceb")
+        torch.cuda.synchronize()
+        same = bool((lg2 == lg).all().item() and (lg3 == lg).all().item() and (row_loss2 == row_loss).all().item())
+        ref_b = lr.grad.sum(0)
+        e3 = rel(bias, ref_b); e4 = rel(bias_al, ref_b); e5 = rel(bias_al, lg.float().sum(0))
+        lg5 = logits.clone()   # a second call ADDS to the running value
+        L.check(lib.ecamp_ce_rows_bias(L.ptr(lg5), V, rows, V, L.ptr(labels), L.ptr(w), L.ptr(row_loss2), L.ptr(g), ctypes.c_float(1.0 / 1000), L.ptr(bias_al), L.cur_stream()), "ceb")
+        torch.cuda.synchronize()
+        e7 = rel(bias_al, 2 * ref_b)
+        # no loss pass-through without the gradient
+        lg4 = logits.clone(); row_loss4 = torch.empty(rows, device=dev)
+        L.check(lib.ecamp_ce_rows(L.ptr(lg4), V, rows, V, L.ptr(labels), L.ptr(w), L.ptr(row_loss4), None, ctypes.c_float(1.0 / 1000), 0, L.cur_stream()), "ce")
+        torch.cuda.synchronize()
+        untouched = bool((lg4 == logits).all().item()); e6 = rel(row_loss4, (ce * w).detach())
+        report(f"cross_entropy_rows{rows}_V{V}_{'persistent' if fused else 'per_row'}",
+               e1 < 1e-4 and e2 < 1e-2 and e3 < 4e-3 and e4 < 4e-3 and e5 < 5e-3 and e6 < 1e-4 and e7 < 4e-3 and same and untouched,
+               loss=e1, grad=e2, bias_grad_unaligned=e3, bias_grad=e4, bias_vs_written=e5, loss_only=e6, bias_accumulates=e7, same_bytes=same, loss_only_untouched=untouched)
+    lib.ecamp_ce_set_fused(1)
 
 
 class _G32View:
