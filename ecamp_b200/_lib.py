@@ -71,7 +71,7 @@ class SgdTensor(ctypes.Structure):
 # every symbol include/ecamp_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "ecamp_abi_version", "ecamp_last_error", "ecamp_launch_count", "ecamp_gemm_bf16", "ecamp_gemm_fp32", "ecamp_gemm_fp32_ws_bytes", "ecamp_gemm_set_cta_pair", "ecamp_gemm_set_tma_epilogue", "ecamp_gemm_set_direct_epilogue", "ecamp_random_masking", "ecamp_resize_patchify",
-    "ecamp_layernorm_fwd", "ecamp_layernorm_bwd", "ecamp_layernorm_ws_floats", "ecamp_layernorm_set_bwd_slab", "ecamp_ce_rows_bias", "ecamp_ce_set_fused", "ecamp_sr_set_window_skip", "ecamp_attention_set_tcgen05", "ecamp_attention_fwd",
+    "ecamp_layernorm_fwd", "ecamp_layernorm_bwd", "ecamp_layernorm_ws_floats", "ecamp_layernorm_set_bwd_slab", "ecamp_ce_rows_bias", "ecamp_ce_set_fused", "ecamp_sr_set_window_skip", "ecamp_set_side_stream", "ecamp_attention_set_tcgen05", "ecamp_attention_fwd",
     "ecamp_attention_bwd", "ecamp_mim_loss", "ecamp_sr_loss_fwd", "ecamp_sr_loss_bwd", "ecamp_sr_ws_floats",
     "ecamp_pred_grad", "ecamp_ce_rows", "ecamp_param_count", "ecamp_param_name", "ecamp_param_numel",
     "ecamp_param_decay", "ecamp_param_grad_offset", "ecamp_grad_floats", "ecamp_shadow_bytes",

@@ -186,6 +186,7 @@ int ecamp_ce_rows_bias(void* logits_bf16, int32_t ld, int32_t rows, int32_t V, c
 }
 void ecamp_ce_set_fused(int32_t on) { ce_set_fused(on); }
 void ecamp_sr_set_window_skip(int32_t on) { sr_set_window_skip(on); }
+void ecamp_set_side_stream(int32_t on) { set_side_stream(on); }
 
 // ---- runtime -----------------------------------------------------------------------------------
 int32_t ecamp_param_count(void) { return (int32_t)param_specs().size(); }

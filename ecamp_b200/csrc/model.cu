@@ -152,6 +152,38 @@ struct BertActT {
 
 // AT = activation element type: AT (production) or float (fp32-accurate parity mode, the same schedule on fp32
 // activations; GEMMs through gemm_hp, attention through attention_hp.cu)
+// ---- side stream of the backward pass (see CtxT::side) ---------------------------------------------------------
+struct SideStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+struct SideGuard {
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+};
+int g_side_wgrad = -1;  // -1: ECAMP_SIDE_WGRAD or 1; 2 = on, with every side-stream GEMM held back (tests, see side_delay_kernel)
+// Test aid: makes the side stream lag far behind the main stream, so that a missing guard (a buffer rewritten on the main
+// stream while a weight gradient still reads it) shows up as wrong gradients instead of depending on timing.
+__global__ void side_delay_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) __nanosleep(200);
+}
+SideStream* side_stream_for_device() {  // one per device and process, created on first use, never destroyed
+  static SideStream table[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = table[dev];
+  if (!s.st) {
+    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      s.st = nullptr;
+      return nullptr;
+    }
+  }
+  return &s;
+}
+
 template <typename AT>
 struct CtxT {
   std::vector<float*> p;
@@ -192,6 +224,14 @@ struct CtxT {
   int acc = 0;
   const float* g3 = nullptr;
   cudaStream_t st = 0;
+  // Weight-gradient GEMMs of the transformer blocks and of the vocabulary head run on a SIDE stream: nothing downstream in
+  // backward reads dW, so they only have to be ordered after the producer of dY and before (a) the next writer of a buffer
+  // they read and (b) the end of their stage, where the gradient slice is declared final.  Every GEMM is a persistent kernel
+  // that occupies all SMs, so the two streams do not run side by side - the side stream's CTAs fill the tail wave (and the
+  // pipeline ramp) of the main stream's kernels and vice versa, which a single stream cannot do.
+  SideStream* side = nullptr;  // null = everything on one stream (fp32-accurate mode, classification path, switch off)
+  bool side_busy = false;      // work has been queued on the side stream since the last join
+  SideGuard guard_gx, guard_da, guard_dqkv, guard_logits;  // side-stream readers of c->gX / dA / dQKV / logits: the next writer waits
   // fp32-accurate mode only: scratch of gemm_hp (operand planes + accumulator) and of the attention backward
   void* hp_gemm_ws = nullptr;
   size_t hp_gemm_bytes = 0;
@@ -485,17 +525,55 @@ int lin_dgrad(CtxT<AT>* c, const AT* dy, int ld_dy, int M, const AT* W, int N, i
 }
 // dW[N, K] (+)= dy[M, N]^T x[M, K];  db[N] += colsum(dy)  (bias / LayerNorm gradients are zeroed by zero_small_grads at
 // the start of a non-accumulating backward and only ever added to)
+// main stream: wait for the side-stream readers of a buffer before it is overwritten
+template <typename AT>
+int side_wait_readers(CtxT<AT>* c, SideGuard& g) {
+  if (g.pending) {
+    ECAMP_CUDA_OK(cudaStreamWaitEvent(c->st, g.ev, 0));
+    g.pending = false;
+  }
+  return 0;
+}
+// main stream: wait for everything queued on the side stream (end of a stage: the gradient slice is final)
+template <typename AT>
+int side_join(CtxT<AT>* c) {
+  if (c->side && c->side_busy) {
+    ECAMP_CUDA_OK(cudaEventRecord(c->side->ev_join, c->side->st));
+    ECAMP_CUDA_OK(cudaStreamWaitEvent(c->st, c->side->ev_join, 0));
+  }
+  c->side_busy = false;
+  c->guard_gx.pending = c->guard_da.pending = c->guard_dqkv.pending = c->guard_logits.pending = false;
+  return 0;
+}
+// side_ok: the call site has been checked for the side stream - dy / x are either saved activations or scratch whose next
+// writer is in a LATER stage (every stage ends with side_join) or calls side_wait_readers(guard) first (`guard`: the
+// scratch buffer behind dy is rewritten later in the SAME stage)
 template <typename AT>
 int lin_wgrad(CtxT<AT>* c, const AT* dy, int ld_dy, const AT* x, int ldx, int M, int N, int K, float* dW, float* db,
-              int acc) {
+              int acc, int side_ok = 0, SideGuard* guard = nullptr) {
   GemmEpilogueT<AT> ep;
   ep.out_f32 = dW;
   ep.ld_f32 = K;
   if (acc) { ep.residual = dW; ep.ld_res = K; }
-  RC(gemm_any(c, dy, ld_dy, 1, x, ldx, 1, N, K, M, ep));
+  cudaStream_t main_st = c->st;
+  const bool on_side = c->side && side_ok;
+  if (on_side) {  // fork: everything queued on the main stream so far (the producer of dy included) comes first
+    ECAMP_CUDA_OK(cudaEventRecord(c->side->ev_fork, main_st));
+    ECAMP_CUDA_OK(cudaStreamWaitEvent(c->side->st, c->side->ev_fork, 0));
+    c->st = c->side->st;
+    c->side_busy = true;
+    if (g_side_wgrad == 2) side_delay_kernel<<<1, 1, 0, c->side->st>>>(400000);  // ~0.2 ms
+  }
+  int rc = gemm_any(c, dy, ld_dy, 1, x, ldx, 1, N, K, M, ep);
   // db == nullptr: the kernel that produced dy already folded the bias gradient in (LayerNorm backward, dGELU epilogue)
-  if (db) RC(colsum_bf16(dy, ld_dy, M, N, db, 1, c->colsum_ws, c->st));
-  return 0;
+  if (!rc && db) rc = colsum_bf16(dy, ld_dy, M, N, db, 1, c->colsum_ws, c->st);
+  c->st = main_st;
+  if (!rc && on_side && guard) {
+    if (!guard->ev) ECAMP_CUDA_OK(cudaEventCreateWithFlags(&guard->ev, cudaEventDisableTiming));
+    ECAMP_CUDA_OK(cudaEventRecord(guard->ev, c->side->st));
+    guard->pending = true;
+  }
+  return rc;
 }
 template <typename AT>
 GemmEpilogueT<AT> ep_bias_bf16(const float* bias, AT* out, int ld) {
@@ -543,20 +621,22 @@ int vit_block_bwd(CtxT<AT>* c, VitStackT<AT>& s, int l) {
   VitActT<AT>& a = s.a[l];
   const int pb = s.pbase + l * VIT_BLOCK_PARAMS, M = s.M, D = s.D, B = c->sh.B, acc = c->acc;
   // fc2
-  RC(lin_wgrad(c, c->gX, D, a.act, s.hid, M, D, s.hid, c->Gp(pb + 10), nullptr, acc));  // bias: by the producer of gX
+  RC(lin_wgrad(c, c->gX, D, a.act, s.hid, M, D, s.hid, c->Gp(pb + 10), nullptr, acc, 1, &c->guard_gx));  // bias: by the producer of gX
   GemmEpilogueT<AT> e2;
   e2.flags = GEMM_DGELU | kAuxGrad; e2.aux_in = a.pre; e2.ld_aux = s.hid; e2.out_bf16 = c->dA; e2.ld_bf16 = s.hid;
   e2.colsum_out = c->Gp(pb + 9);  // fc1 bias gradient = column sums of dA
+  RC(side_wait_readers(c, c->guard_da));  // the previous block's fc1 weight gradient reads dA
   RC(lin_dgrad(c, c->gX, D, M, c->W(pb + 10), D, s.hid, e2));
   // fc1
-  RC(lin_wgrad(c, c->dA, s.hid, a.ln2, D, M, s.hid, D, c->Gp(pb + 8), nullptr, acc));
+  RC(lin_wgrad(c, c->dA, s.hid, a.ln2, D, M, s.hid, D, c->Gp(pb + 8), nullptr, acc, 1, &c->guard_da));
   GemmEpilogueT<AT> e1;
   e1.out_f32 = c->dH; e1.ld_f32 = D;
   RC(lin_dgrad(c, c->dA, s.hid, M, c->W(pb + 8), s.hid, D, e1));
+  RC(side_wait_readers(c, c->guard_gx));  // the fc2 weight gradient reads the gX this LayerNorm backward overwrites
   RC(layernorm_bwd(c->dH, a.x_mid, a.mean2, a.rstd2, c->P(pb + 6), M, D, c->dX, c->dX, c->gX, DropoutCfg(),
                    c->Gp(pb + 6), c->Gp(pb + 7), c->Gp(pb + 5) /* proj bias */, 1, c->st, c->dps(&s, l, 0), s.S));
   // proj
-  RC(lin_wgrad(c, c->gX, D, a.ao, D, M, D, D, c->Gp(pb + 4), nullptr, acc));
+  RC(lin_wgrad(c, c->gX, D, a.ao, D, M, D, D, c->Gp(pb + 4), nullptr, acc, 1, &c->guard_gx));
   GemmEpilogueT<AT> ep;
   ep.out_bf16 = c->dAO; ep.ld_bf16 = D;
   RC(lin_dgrad(c, c->gX, D, M, c->W(pb + 4), D, D, ep));
@@ -567,12 +647,14 @@ int vit_block_bwd(CtxT<AT>* c, VitStackT<AT>& s, int l) {
   // (the qkv bias gradient stays with colsum_kernel here: folded into the mma.sync kernels it costs more in atomics -
   //  +0.26 ms for the encoder, +0.16 ms for the decoder - than the 16 column-sum launches it saves, ~0.2 ms)
   attn_scratch(c, at);
+  RC(side_wait_readers(c, c->guard_dqkv));  // the previous block's qkv weight gradient reads dQKV
   RC(attention_bwd(at, c->st));
   // qkv
-  RC(lin_wgrad(c, c->dQKV, 3 * D, a.ln1, D, M, 3 * D, D, c->Gp(pb + 2), c->Gp(pb + 3), acc));
+  RC(lin_wgrad(c, c->dQKV, 3 * D, a.ln1, D, M, 3 * D, D, c->Gp(pb + 2), c->Gp(pb + 3), acc, 1, &c->guard_dqkv));
   GemmEpilogueT<AT> eq;
   eq.out_f32 = c->dH; eq.ld_f32 = D;
   RC(lin_dgrad(c, c->dQKV, 3 * D, M, c->W(pb + 2), 3 * D, D, eq));
+  RC(side_wait_readers(c, c->guard_gx));  // the proj weight gradient reads gX
   // the AT gradient emitted here is the dY of the PREVIOUS block's fc2: its bias gradient is folded in
   RC(layernorm_bwd(c->dH, a.x_in, a.mean1, a.rstd1, c->P(pb + 0), M, D, c->dX, c->dX, c->gX, DropoutCfg(),
                    c->Gp(pb + 0), c->Gp(pb + 1), l > 0 ? c->Gp(pb - VIT_BLOCK_PARAMS + 11) : nullptr, 1, c->st,
@@ -600,11 +682,12 @@ int bert_attn_half_fwd(CtxT<AT>* c, BertActT<AT>& a, int pb, const AT* h_in, con
 }
 // in: c->dX = d(LN output of this half) fp32.  out: c->dX = d(h_in) fp32 (residual + qkv paths).
 template <typename AT>
-int bert_attn_half_bwd(CtxT<AT>* c, BertActT<AT>& a, int pb, unsigned long long site) {
+int bert_attn_half_bwd(CtxT<AT>* c, BertActT<AT>& a, int pb, unsigned long long site, int side_ok = 0) {
   const int Mt = c->sh.B * c->sh.T, B = c->sh.B, T = c->sh.T, acc = c->acc;
+  RC(side_wait_readers(c, c->guard_gx));  // a weight gradient of the FFN half may still be reading gX
   RC(layernorm_bwd(c->dX, a.s1, a.mean1, a.rstd1, c->P(pb + 8), Mt, 768, nullptr, c->dX, c->gX, c->drop(site + 1),
                    c->Gp(pb + 8), c->Gp(pb + 9), c->Gp(pb + 7) /* attention.output.dense bias */, 1, c->st));
-  RC(lin_wgrad(c, c->gX, 768, a.ao, 768, Mt, 768, 768, c->Gp(pb + 6), nullptr, acc));
+  RC(lin_wgrad(c, c->gX, 768, a.ao, 768, Mt, 768, 768, c->Gp(pb + 6), nullptr, acc, side_ok, &c->guard_gx));
   GemmEpilogueT<AT> ep;
   ep.out_bf16 = c->dAO; ep.ld_bf16 = 768;
   RC(lin_dgrad(c, c->gX, 768, Mt, c->W(pb + 6), 768, 768, ep));
@@ -616,8 +699,9 @@ int bert_attn_half_bwd(CtxT<AT>* c, BertActT<AT>& a, int pb, unsigned long long 
   at.lddq = at.lddk = at.lddv = 2304;
   at.cs_q = c->Gp(pb + 3); at.cs_k = c->Gp(pb + 3) + 768; at.cs_v = c->Gp(pb + 3) + 1536;  // q | k | v bias gradients
   attn_scratch(c, at);
+  RC(side_wait_readers(c, c->guard_dqkv));
   RC(attention_bwd(at, c->st));
-  RC(lin_wgrad(c, c->dQKV, 2304, a.h_in, 768, Mt, 2304, 768, c->Gp(pb + 0), nullptr, acc));
+  RC(lin_wgrad(c, c->dQKV, 2304, a.h_in, 768, Mt, 2304, 768, c->Gp(pb + 0), nullptr, acc, side_ok, &c->guard_dqkv));
   GemmEpilogueT<AT> eq;
   eq.residual = c->dX; eq.ld_res = 768; eq.out_f32 = c->dX; eq.ld_f32 = 768;
   RC(lin_dgrad(c, c->dQKV, 2304, Mt, c->W(pb + 0), 2304, 768, eq));
@@ -639,16 +723,18 @@ int bert_ffn_half_fwd(CtxT<AT>* c, BertActT<AT>& a, int pi, const AT* x, const f
 }
 // in: c->dX = d(h_out).  out: c->dX = d(x) (the FFN input = LN output of the previous half)
 template <typename AT>
-int bert_ffn_half_bwd(CtxT<AT>* c, BertActT<AT>& a, int pi, const AT* x, unsigned long long site) {
+int bert_ffn_half_bwd(CtxT<AT>* c, BertActT<AT>& a, int pi, const AT* x, unsigned long long site, int side_ok = 0) {
   const int Mt = c->sh.B * c->sh.T, acc = c->acc;
+  RC(side_wait_readers(c, c->guard_gx));
   RC(layernorm_bwd(c->dX, a.s2, a.mean2, a.rstd2, c->P(pi + 4), Mt, 768, nullptr, c->dX, c->gX, c->drop(site),
                    c->Gp(pi + 4), c->Gp(pi + 5), c->Gp(pi + 3) /* output.dense bias */, 1, c->st));
-  RC(lin_wgrad(c, c->gX, 768, a.act, BHID, Mt, 768, BHID, c->Gp(pi + 2), nullptr, acc));
+  RC(lin_wgrad(c, c->gX, 768, a.act, BHID, Mt, 768, BHID, c->Gp(pi + 2), nullptr, acc, side_ok, &c->guard_gx));
   GemmEpilogueT<AT> e2;
   e2.flags = GEMM_DGELU | kAuxGrad; e2.aux_in = a.pre; e2.ld_aux = BHID; e2.out_bf16 = c->dA; e2.ld_bf16 = BHID;
   e2.colsum_out = c->Gp(pi + 1);  // intermediate.dense bias gradient
+  RC(side_wait_readers(c, c->guard_da));
   RC(lin_dgrad(c, c->gX, 768, Mt, c->W(pi + 2), 768, BHID, e2));
-  RC(lin_wgrad(c, c->dA, BHID, x, 768, Mt, BHID, 768, c->Gp(pi), nullptr, acc));
+  RC(lin_wgrad(c, c->dA, BHID, x, 768, Mt, BHID, 768, c->Gp(pi), nullptr, acc, side_ok, &c->guard_da));
   GemmEpilogueT<AT> e1;
   e1.residual = c->dX; e1.ld_res = 768; e1.out_f32 = c->dX; e1.ld_f32 = 768;
   RC(lin_dgrad(c, c->dA, BHID, Mt, c->W(pi), BHID, 768, e1));
@@ -672,8 +758,10 @@ int bert_layer_bwd(CtxT<AT>* c, int l) {
   BertActT<AT>& a = c->layers[l];
   const int pb = param_index(std::string(BERT) + "encoder.layer." + std::to_string(l) + ".attention.self.query.weight");
   const unsigned long long site = 100 + 10 * l;
-  RC(bert_ffn_half_bwd(c, a, pb + 10, a.a, site + 2));
-  RC(bert_attn_half_bwd(c, a, pb, site));
+  // the four weight gradients of a layer go to the side stream (the fusion layer, which shares the two halves, keeps them on
+  // the main stream: its stage rewrites dA / dQKV more than once)
+  RC(bert_ffn_half_bwd(c, a, pb + 10, a.a, site + 2, 1));
+  RC(bert_attn_half_bwd(c, a, pb, site, 1));
   return 0;
 }
 
@@ -705,6 +793,7 @@ int lm_chunks(CtxT<AT>* c, bool with_grad, bool write_loss) {
   int acc = c->acc;
   for (int r0 = 0; r0 < Mt; r0 += R) {
     const int rows = Mt - r0 < R ? Mt - r0 : R;
+    RC(side_wait_readers(c, c->guard_logits));  // the previous chunk's weight gradient reads the logits buffer
     RC(lin_fwd(c, c->tl + (size_t)r0 * 768, 768, rows, c->W(pw), VOC, 768, ep_bias_bf16(c->P(pbias), c->logits, VOC)));
     RC(ce_rows_any(c, rows, r0, with_grad, 1.0f / (float)Mt, with_grad ? c->Gp(pbias) : nullptr));
     if (with_grad) {
@@ -712,7 +801,8 @@ int lm_chunks(CtxT<AT>* c, bool with_grad, bool write_loss) {
       e.out_f32 = c->dTL + (size_t)r0 * 768; e.ld_f32 = 768;
       RC(lin_dgrad(c, c->logits, VOC, rows, c->W(pw), VOC, 768, e));
       // the bias gradient: by the cross-entropy kernel (bf16 mode) or a column-sum pass (fp32-accurate mode)
-      RC(lin_wgrad(c, c->logits, VOC, c->tl + (size_t)r0 * 768, 768, rows, VOC, 768, c->Gp(pw), is_hp<AT>::value ? c->Gp(pbias) : nullptr, acc));
+      RC(lin_wgrad(c, c->logits, VOC, c->tl + (size_t)r0 * 768, 768, rows, VOC, 768, c->Gp(pw), is_hp<AT>::value ? c->Gp(pbias) : nullptr, acc,
+                   1, &c->guard_logits));
       acc = 1;
     }
   }
@@ -992,6 +1082,7 @@ int t_cls_forward(CtxT<bf16>* c, const ClsIO& io, cudaStream_t st) {
 }
 
 int t_cls_backward(CtxT<bf16>* c, const ClsIO& io, int accumulate, cudaStream_t st) {
+  c->side = nullptr;  // one stream: the blocks run back to back without stage boundaries
   ECAMP_REQUIRE(c->bound && c->cls_planned, "cls backward: no forward has been run");
   ECAMP_REQUIRE(io.d_logits && io.g_pos_embed && io.g_fc_norm_w && io.g_fc_norm_b && io.g_head_w && io.g_head_b,
                 "cls backward: null argument");
@@ -1201,11 +1292,23 @@ int t_backward(CtxT<AT>* c, const float* g3, int accumulate, int stage, cudaStre
   ECAMP_REQUIRE(c->bound && c->planned && c->losses, "backward: no forward has been run");
   ECAMP_REQUIRE(g3 != nullptr, "backward: null upstream gradient");
   c->g3 = g3; c->acc = accumulate; c->st = st;
+  if (g_side_wgrad < 0) g_side_wgrad = getenv("ECAMP_SIDE_WGRAD") ? atoi(getenv("ECAMP_SIDE_WGRAD")) : 1;
+  // (the fp32-accurate mode shares one operand-plane scratch between its GEMMs: one stream only)
+  c->side = (g_side_wgrad && !is_hp<AT>::value) ? side_stream_for_device() : nullptr;
+  c->side_busy = false;
   // bias / LayerNorm / token gradients are accumulated with atomics by the kernels that produce their operands:
   // a non-accumulating backward zeroes them once, before the first stage
   if (!accumulate && stage <= 0) RC(zero_small_grads(c));
-  if (stage >= 0) return run_stage(c, stage);
-  for (int s = 0; s < backward_stage_count(); ++s) RC(run_stage(c, s));
+  for (int s = stage >= 0 ? stage : 0; s < (stage >= 0 ? stage + 1 : backward_stage_count()); ++s) {
+    const int rc = run_stage(c, s);
+    // Every stage ends joined (its gradient slice is final when the call returns / the stage callback fires) - except, when
+    // all stages run in one call, between two transformer blocks of the same stack: those only share gX / dA / dQKV with
+    // the next block, each protected by its guard, so the last weight gradients of a block may overlap the next block.
+    const bool same_stack_next = stage < 0 && ((s >= 1 && s <= 5) || (s >= 9 && s <= 11) || (s >= 15 && s <= 25));
+    const int rj = (rc || !same_stack_next) ? side_join(c) : 0;  // also after a failed stage: nothing stays queued
+    if (rc) return rc;
+    if (rj) return rj;
+  }
   return 0;
 }
 
@@ -1220,6 +1323,7 @@ struct Ctx {
 };
 #define ECAMP_DISPATCH(call_lp, call_hp) (c->hp ? (call_hp) : (call_lp))
 
+void set_side_stream(int on) { g_side_wgrad = on == 2 ? 2 : (on ? 1 : 0); }
 Ctx* ctx_new() { return new Ctx(); }
 void ctx_free(Ctx* c) { delete c; }
 int ctx_set_precision(Ctx* c, int hp) {

@@ -44,6 +44,7 @@ struct Batch {
 };
 
 struct Ctx;
+void set_side_stream(int on);  // 0: the whole backward on the caller's stream (default 1: block / vocabulary weight gradients on a side stream)
 Ctx* ctx_new();
 void ctx_free(Ctx*);
 int ctx_bind(Ctx*, float* const* params, int n, float* G, float* M1, float* M2, void* shadows,

@@ -208,6 +208,12 @@ ECAMP_API void ecamp_ce_set_fused(int32_t on);
 /* Measurement switch: 1 (default) = the SR backward kernel limits every stage of a tile to what the loss window can reach
  * (tiles that merely border the window become cheap); 0 = every stage on the whole 36 x 36 neighbourhood. */
 ECAMP_API void ecamp_sr_set_window_skip(int32_t on);
+/* 1 (default; ECAMP_SIDE_WGRAD=0 in the environment also turns it off): ecamp_ctx_backward queues the weight-gradient GEMMs of the
+ * transformer blocks and of the vocabulary head on an internal side stream, forked from / joined to the caller's stream with
+ * events inside the call (every stage ends joined: when the call returns, all work is ordered on the caller's stream as
+ * before).  0: everything on the caller's stream.  2 (tests): as 1, with every side-stream GEMM held back by ~0.2 ms so that a
+ * missing ordering edge shows up as wrong gradients.  Takes effect at the next backward call. */
+ECAMP_API void ecamp_set_side_stream(int32_t on);
 
 /* ==========================================================================================
  * 2. The step runtime (what the nn.Module calls): parameter table, context, forward / backward /

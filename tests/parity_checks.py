@@ -1277,7 +1277,55 @@ def check_adamw_groups():
     report("adamw_param_group_lrs", worst < 1e-6, max_abs_param_diff=worst)
 
 
-ALL_CHECKS = (check_adamw_groups, check_image_pipeline, check_gemm_fp32, check_step_fp32, check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw)
+
+
+@guard
+def check_side_stream():
+    """The weight-gradient GEMMs of the blocks and of the vocabulary head run on an internal side stream.  The
+    gradients must not depend on it: one stream (0), side stream (1), and side stream with every side GEMM held back by
+    ~0.2 ms (2) - the main stream then runs far ahead, so a buffer rewritten while a weight gradient still reads it would
+    give wrong numbers - against a second one-stream run as the noise floor of the fp32 atomics."""
+    for B, T, seed in ((2, 32, 5), (8, 64, 6)):
+        m = ecamp().to(dev).train()
+        b = synthetic_batch(B, T=T, seed=seed, device=dev)
+
+        def run(mode):
+            lib.ecamp_set_side_stream(mode)
+            torch.manual_seed(77)
+            m._dropout_step = 0   # same dropout masks in every run (the seed is initial_seed x step counter)
+            m.zero_grad(set_to_none=True)
+            losses = m.forward_backward(b).clone()
+            torch.cuda.synchronize()
+            return losses, m.flat_grads().clone()
+
+        l0, g0 = run(0)
+        l0b, g0b = run(0)
+        l1, g1 = run(1)
+        l2, g2 = run(2)
+        lib.ecamp_set_side_stream(1)
+        rt = m._runtime(torch.device(dev))
+        offs = {k: (o, n) for k, o, n in zip(rt["names"], rt["goff"], rt["numel"])}
+        gn = g0.norm().item()
+
+        def worst(a, ref):
+            w, wk = 0.0, ""
+            for k, (o, n) in offs.items():
+                if k.endswith("key.bias"):   # analytically zero (softmax shift invariance): pure rounding noise
+                    continue
+                r = ref[o:o + n]
+                d = ((a[o:o + n] - r).norm() / max(r.norm().item(), 1e-4 * gn * (n / ref.numel()) ** 0.5)).item()
+                if d > w:
+                    w, wk = d, k
+            return w, wk
+
+        floor, fk = worst(g0b, g0); w1, k1 = worst(g1, g0); w2, k2 = worst(g2, g0)
+        tol = max(1e-3, 5 * floor)
+        same_loss = bool(torch.equal(l0, l1) and torch.equal(l0, l2))
+        report(f"side_stream_B{B}_T{T}", w1 <= tol and w2 <= tol and same_loss, noise_floor=floor, noise_floor_tensor=fk, side=w1, side_tensor=k1,
+               side_delayed=w2, side_delayed_tensor=k2, same_losses=same_loss, tol=tol)
+
+
+ALL_CHECKS = (check_adamw_groups, check_image_pipeline, check_gemm_fp32, check_step_fp32, check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw, check_side_stream)
 
 
 def run_check(fn):
