@@ -686,10 +686,18 @@ def check_adamw():
     for k, p in rnamed.items():
         worst = max(worst, (named[k].detach() - p.detach()).abs().max().item())
     pool_same = torch.equal(named["bert_encoder.model.bert.pooler.dense.weight"], rnamed["bert_encoder.model.bert.pooler.dense.weight"])
-    # shadows follow: forward after the fused step equals forward of the torch-stepped copy
+    # shadows follow: forward after the fused step equals forward of the torch-stepped copy.  The two parameter sets differ in
+    # the last bit here and there, which flips the bf16 rounding of a few GEMM weights (the MLM loss then moves by up to
+    # ~1e-4 relative between runs): loose gate on that pair, and a tight one on a copy that holds EXACTLY m's fp32
+    # parameters and rebuilds its bf16 copies from them - what the fused step keeps up to date must be what a refresh gives.
     l_m = m(b); l_r = ref(b)
-    report("adamw", worst < 1e-6 and pool_same and rel(torch.stack(list(l_m)), torch.stack(list(l_r))) < 1e-4, max_abs_param_diff=worst,
-           loss_after=[x.item() for x in l_m], loss_after_ref=[x.item() for x in l_r])
+    twin = ecamp().to(dev)
+    twin.load_state_dict(m.state_dict())
+    twin.eval()
+    l_t = twin(b)
+    e_step = rel(torch.stack(list(l_m)), torch.stack(list(l_r))); e_twin = rel(torch.stack(list(l_m)), torch.stack(list(l_t)))
+    report("adamw", worst < 1e-6 and pool_same and e_step < 1e-3 and e_twin < 1e-6, max_abs_param_diff=worst,
+           loss_after=[x.item() for x in l_m], loss_after_ref=[x.item() for x in l_r], loss_vs_torch_stepped=e_step, loss_vs_exact_twin=e_twin)
 
 
 @guard
