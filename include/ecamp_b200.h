@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ECAMP_ABI_VERSION 4
+#define ECAMP_ABI_VERSION 5  /* 5: + ecamp_ce_rows_bias, ecamp_set_side_stream and three measurement switches (additive) */
 #if defined(__GNUC__)
 #define ECAMP_API __attribute__((visibility("default")))
 #else

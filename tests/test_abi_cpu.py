@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/ecamp_b200.h but not exported"
     assert sorted(built_lib.SYMBOLS) == syms
-    assert lib.ecamp_abi_version() == 4
+    assert lib.ecamp_abi_version() == 5
 
 
 def test_parameter_table_matches_reference_layout(built_lib):
