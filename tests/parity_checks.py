@@ -976,22 +976,27 @@ def check_stage_final():
     m = ecamp().to(dev).train()
     b = synthetic_batch(8, T=64, seed=31, device=dev)
     side = torch.cuda.Stream()
-    copies = []
+    # mode 2: the library's internal side stream (weight-gradient GEMMs) with every side GEMM held back ~0.2 ms - a stage
+    # that returned before its weight gradients were joined would hand out a slice that is still being written
+    for mode, tag in ((1, ""), (2, "_side_gemms_delayed"), (0, "_one_stream")):
+        lib.ecamp_set_side_stream(mode)
+        copies = []
 
-    def on_stage(stage, lo, hi):
-        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
-        side.wait_event(ev)
-        with torch.cuda.stream(side):
-            copies.append((stage, lo, hi, m.flat_grads()[lo:hi].clone()))
+        def on_stage(stage, lo, hi):
+            ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                copies.append((stage, lo, hi, m.flat_grads()[lo:hi].clone()))
 
-    m.zero_grad(set_to_none=True)
-    m.forward_backward(b, stage_callback=on_stage)
-    torch.cuda.synchronize()
-    G = m.flat_grads()
-    late = [(st, lo, hi) for st, lo, hi, c in copies if not torch.equal(c, G[lo:hi])]
-    cover = sorted((lo, hi) for _, lo, hi, _ in copies)
-    tiles = cover[0][0] == 0 and cover[-1][1] == G.numel() and all(a[1] == b_[0] for a, b_ in zip(cover, cover[1:]))
-    report("stage_slices_final", not late and tiles, n_stages=len(copies), late_writes=late[:5], tiles=tiles)
+        m.zero_grad(set_to_none=True)
+        m.forward_backward(b, stage_callback=on_stage)
+        torch.cuda.synchronize()
+        G = m.flat_grads()
+        late = [(st, lo, hi) for st, lo, hi, c in copies if not torch.equal(c, G[lo:hi])]
+        cover = sorted((lo, hi) for _, lo, hi, _ in copies)
+        tiles = cover[0][0] == 0 and cover[-1][1] == G.numel() and all(a[1] == b_[0] for a, b_ in zip(cover, cover[1:]))
+        report("stage_slices_final" + tag, not late and tiles, n_stages=len(copies), late_writes=late[:5], tiles=tiles)
+    lib.ecamp_set_side_stream(1)
 
 
 def _add_weight_decay(model, weight_decay):
