@@ -252,7 +252,14 @@ int ecamp_backward_stage_range(int32_t stage, int64_t* begin, int64_t* end) {
 }
 int ecamp_backward(ecamp_ctx* ctx, const float* g3, int32_t accumulate, int32_t stage, void* stream) {
   ECAMP_REQUIRE(ctx, "ecamp_backward: null context");
-  return ctx_backward(ctx->impl, g3, accumulate, stage, S(stream));
+  return ctx_backward(ctx->impl, g3, accumulate, stage, 0, S(stream));
+}
+int ecamp_backward_stages(ecamp_ctx* ctx, const float* g3, int32_t accumulate, int32_t first_stage, int32_t end_stage,
+                          void* stream) {
+  ECAMP_REQUIRE(ctx, "ecamp_backward_stages: null context");
+  ECAMP_REQUIRE(first_stage >= 0 && end_stage > first_stage, "ecamp_backward_stages: empty or negative stage range [%d, %d)",
+                first_stage, end_stage);
+  return ctx_backward(ctx->impl, g3, accumulate, first_stage, end_stage, S(stream));
 }
 int ecamp_adamw_step(ecamp_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                      float grad_scale, void* stream) {

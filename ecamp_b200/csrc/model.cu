@@ -1288,7 +1288,7 @@ int run_stage(CtxT<AT>* c, int stage) {
 }  // namespace
 
 template <typename AT>
-int t_backward(CtxT<AT>* c, const float* g3, int accumulate, int stage, cudaStream_t st) {
+int t_backward(CtxT<AT>* c, const float* g3, int accumulate, int stage, int stage_end, cudaStream_t st) {
   ECAMP_REQUIRE(c->bound && c->planned && c->losses, "backward: no forward has been run");
   ECAMP_REQUIRE(g3 != nullptr, "backward: null upstream gradient");
   c->g3 = g3; c->acc = accumulate; c->st = st;
@@ -1299,12 +1299,16 @@ int t_backward(CtxT<AT>* c, const float* g3, int accumulate, int stage, cudaStre
   // bias / LayerNorm / token gradients are accumulated with atomics by the kernels that produce their operands:
   // a non-accumulating backward zeroes them once, before the first stage
   if (!accumulate && stage <= 0) RC(zero_small_grads(c));
-  for (int s = stage >= 0 ? stage : 0; s < (stage >= 0 ? stage + 1 : backward_stage_count()); ++s) {
+  // [first, last): stage = -1 -> all stages; stage_end <= stage -> the single stage `stage`
+  const int first = stage >= 0 ? stage : 0;
+  const int last = stage < 0 ? backward_stage_count() : (stage_end > stage ? stage_end : stage + 1);
+  ECAMP_REQUIRE(last <= backward_stage_count(), "backward: stage range [%d, %d) out of bounds", first, last);
+  for (int s = first; s < last; ++s) {
     const int rc = run_stage(c, s);
     // Every stage ends joined (its gradient slice is final when the call returns / the stage callback fires) - except, when
-    // all stages run in one call, between two transformer blocks of the same stack: those only share gX / dA / dQKV with
+    // several stages run in one call, between two transformer blocks of the same stack: those only share gX / dA / dQKV with
     // the next block, each protected by its guard, so the last weight gradients of a block may overlap the next block.
-    const bool same_stack_next = stage < 0 && ((s >= 1 && s <= 5) || (s >= 9 && s <= 11) || (s >= 15 && s <= 25));
+    const bool same_stack_next = s + 1 < last && ((s >= 1 && s <= 5) || (s >= 9 && s <= 11) || (s >= 15 && s <= 25));
     const int rj = (rc || !same_stack_next) ? side_join(c) : 0;  // also after a failed stage: nothing stays queued
     if (rc) return rc;
     if (rj) return rj;
@@ -1357,8 +1361,9 @@ int ctx_cross_attention_probs(Ctx* c, float* probs, cudaStream_t st) {
   ECAMP_REQUIRE(!c->hp, "cross_attention_probs: available in the production precision only");
   return t_cross_attention_probs(&c->lp, probs, st);
 }
-int ctx_backward(Ctx* c, const float* g3, int accumulate, int stage, cudaStream_t st) {
-  return ECAMP_DISPATCH(t_backward(&c->lp, g3, accumulate, stage, st), t_backward(&c->hp32, g3, accumulate, stage, st));
+int ctx_backward(Ctx* c, const float* g3, int accumulate, int stage, int stage_end, cudaStream_t st) {
+  return ECAMP_DISPATCH(t_backward(&c->lp, g3, accumulate, stage, stage_end, st),
+                        t_backward(&c->hp32, g3, accumulate, stage, stage_end, st));
 }
 int ctx_adamw(Ctx* c, float lr, float lr_nodecay, float b1, float b2, float eps, float wd, int step, float grad_scale,
               cudaStream_t st) {

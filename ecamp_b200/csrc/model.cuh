@@ -66,7 +66,7 @@ int ctx_cross_attention_probs(Ctx*, float* probs, cudaStream_t);
 int backward_stage_count();
 int backward_stage_range(int stage, long long* g_begin, long long* g_end);
 // g3: device pointer to the three upstream gradients (mim, res, mlm).  stage = -1 runs every stage.
-int ctx_backward(Ctx*, const float* g3, int accumulate, int stage, cudaStream_t);
+int ctx_backward(Ctx*, const float* g3, int accumulate, int stage, int stage_end, cudaStream_t);  // stage_end <= stage: one stage
 int ctx_adamw(Ctx*, float lr, float lr_nodecay, float b1, float b2, float eps, float wd, int step, float grad_scale, cudaStream_t);
 const void* ctx_debug_ptr(Ctx*, const char* name);
 

@@ -465,8 +465,9 @@ class ECAMP(nn.Module):
             token = _StageNode.apply(self, handle, st, token, *[rt["params"][i] for i in rt["stage_params"][st]])
         return _LossNode.apply(handle, token)
 
-    def _backward(self, handle, g, stage=-1):
-        """Run the native backward for upstream gradients g (3 floats); attaches p.grad views."""
+    def _backward(self, handle, g, stage=-1, stage_end=None):
+        """Run the native backward for upstream gradients g (3 floats); attaches p.grad views.  stage = -1: all stages;
+        stage_end given: stages [stage, stage_end) in one native call."""
         lib = L.lib()
         rt = handle["rt"]
         self._check_handle(handle)
@@ -484,9 +485,14 @@ class ECAMP(nn.Module):
                             v.zero_()
                 handle["acc"] = 1 if any(attached) else 0
             handle["g"] = g.detach().to(torch.float32).contiguous()
-        L.check(lib.ecamp_backward(rt["ctx"], L.ptr(handle["g"]), ctypes.c_int32(handle["acc"]), ctypes.c_int32(stage),
-                                   L.cur_stream()), "ecamp_backward")
-        if stage < 0 or stage == lib.ecamp_backward_stage_count() - 1:
+        if stage_end is not None and stage >= 0:
+            L.check(lib.ecamp_backward_stages(rt["ctx"], L.ptr(handle["g"]), ctypes.c_int32(handle["acc"]), ctypes.c_int32(stage),
+                                              ctypes.c_int32(stage_end), L.cur_stream()), "ecamp_backward_stages")
+        else:
+            L.check(lib.ecamp_backward(rt["ctx"], L.ptr(handle["g"]), ctypes.c_int32(handle["acc"]), ctypes.c_int32(stage),
+                                       L.cur_stream()), "ecamp_backward")
+        last = stage_end - 1 if (stage_end is not None and stage >= 0) else stage
+        if stage < 0 or last == lib.ecamp_backward_stage_count() - 1:
             for p, v in zip(params, views):
                 p.grad = v
 
@@ -513,11 +519,14 @@ class ECAMP(nn.Module):
             losses = handle["losses"]
         return losses[0], losses[1], losses[2]
 
-    def forward_backward(self, batch, loss_weights=(1.0, 1.0, 1.0), mask_ratio=0.75, stage_callback=None):
+    def forward_backward(self, batch, loss_weights=(1.0, 1.0, 1.0), mask_ratio=0.75, stage_callback=None, callback_stages=None):
         """Fused training step without autograd: forward with the vocabulary head deferred, then the staged
         backward (the head is evaluated once, fused with its gradient).  Returns the 3 losses (device tensor).
         `stage_callback(stage, lo, hi)` is invoked after each backward stage with the range of the flat gradient
-        buffer that became final (used by ecamp_b200.parallel for bucketed all-reduce overlap)."""
+        buffer that became final (used by ecamp_b200.parallel for bucketed all-reduce overlap).  `callback_stages` (optional,
+        increasing stage numbers, the last stage included): the callback is only needed after these stages - the stages in
+        between run in one native call each group, which lets the library overlap across their boundaries; the callback then
+        gets the union of the group's slices."""
         b = batch
         t, B, T, keep = self._prepare(b["image"], b["ids"], b["labels"], b["attention_mask"], b.get("type_ids"),
                                       b.get("weights"), b.get("column"), b.get("row"), b.get("noise"), mask_ratio,
@@ -529,12 +538,28 @@ class ECAMP(nn.Module):
         lib = L.lib()
         if stage_callback is None:
             self._backward(handle, g, -1)
-        else:
+        elif callback_stages is None:
             lo, hi = ctypes.c_int64(), ctypes.c_int64()
             for s in range(lib.ecamp_backward_stage_count()):
                 self._backward(handle, g, s)
                 lib.ecamp_backward_stage_range(s, ctypes.byref(lo), ctypes.byref(hi))
                 stage_callback(s, lo.value, hi.value)
+        else:
+            n = lib.ecamp_backward_stage_count()
+            ends = sorted(set(int(s) for s in callback_stages))
+            if not ends or ends[-1] != n - 1 or ends[0] < 0:
+                raise ValueError("callback_stages must be stage numbers in [0, n) and include the last stage")
+            lo, hi = ctypes.c_int64(), ctypes.c_int64()
+            first = 0
+            for e in ends:
+                self._backward(handle, g, first, e + 1)
+                glo, ghi = None, None
+                for s in range(first, e + 1):   # slices of consecutive stages are adjacent, walking down the buffer
+                    lib.ecamp_backward_stage_range(s, ctypes.byref(lo), ctypes.byref(hi))
+                    glo = lo.value if glo is None else min(glo, lo.value)
+                    ghi = hi.value if ghi is None else max(ghi, hi.value)
+                stage_callback(e, glo, ghi)
+                first = e + 1
         return handle["losses"]
 
     _OLD_FUSION_KEY = "bert_encoder.model.bert.cross_attn_layer"

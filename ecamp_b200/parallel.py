@@ -9,6 +9,7 @@ NVSwitch) while the remaining stages keep computing.  Averaging (1 / world) is f
 The path shards by samples with exactly this one exchange step; there is no other collective.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -64,6 +65,7 @@ class DataParallelStep:
         self.buckets = plan_buckets(stage_ranges(L.lib()), int(bucket_mb * (1 << 20) // 4), int(tail_mb * (1 << 20) // 4))
         self.comm = torch.cuda.Stream() if self.world > 1 else None
         self.timeline = None   # set to [] to record per-bucket CUDA events of the next step (see bucket_timeline)
+        self.group_stages = os.environ.get("ECAMP_DP_GROUP_STAGES", "1") != "0"   # 0: one native backward call per stage
 
     def step(self, batch, loss_weights=(1.0, 1.0, 1.0), update=True):
         """forward + backward (+ overlapped gradient all-reduce) (+ fused AdamW).  Returns the 3 local losses."""
@@ -94,7 +96,9 @@ class DataParallelStep:
                         en = torch.cuda.Event(enable_timing=True); en.record(self.comm)
                         self.timeline.append((stage, b[1], b[2], ev, st, en))
 
-            losses = self.model.forward_backward(batch, loss_weights, stage_callback=on_stage)
+            # one native call per bucket: finality is only needed where an all-reduce starts
+            losses = self.model.forward_backward(batch, loss_weights, stage_callback=on_stage,
+                                                 callback_stages=[b[0] for b in self.buckets] if self.group_stages else None)
             if rec:
                 bwd_end = torch.cuda.Event(enable_timing=True)
                 bwd_end.record(cur)

@@ -276,6 +276,12 @@ ECAMP_API int32_t ecamp_backward_stage_count(void);
 ECAMP_API int ecamp_backward_stage_range(int32_t stage, int64_t* begin, int64_t* end);
 /* g3: the three upstream gradients d(total)/d(mim, res, mlm).  stage = -1 runs all stages in order. */
 ECAMP_API int ecamp_backward(ecamp_ctx* ctx, const float* g3, int32_t accumulate, int32_t stage, void* stream);
+/* Stages [first_stage, end_stage) in one call: every slice those stages announce is final when the call returns.  A caller that
+ * only needs finality at a few points (the bucket boundaries of a gradient all-reduce) gives the library room to overlap the
+ * tail of one transformer block with the head of the next (see ecamp_set_side_stream).  Stages must be run in order, each
+ * exactly once per backward pass; first_stage == 0 starts the pass (zeroing, as ecamp_backward with stage 0). */
+ECAMP_API int ecamp_backward_stages(ecamp_ctx* ctx, const float* g3, int32_t accumulate, int32_t first_stage, int32_t end_stage,
+                                    void* stream);
 ECAMP_API int ecamp_adamw_step(ecamp_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
                                int32_t step, float grad_scale, void* stream);
 /* the same with one learning rate per timm add_weight_decay group (PT/main_pretrain.py:253: [no-decay, decay]) */
