@@ -996,6 +996,28 @@ def check_stage_final():
         cover = sorted((lo, hi) for _, lo, hi, _ in copies)
         tiles = cover[0][0] == 0 and cover[-1][1] == G.numel() and all(a[1] == b_[0] for a, b_ in zip(cover, cover[1:]))
         report("stage_slices_final" + tag, not late and tiles, n_stages=len(copies), late_writes=late[:5], tiles=tiles)
+    # the same claim for GROUPS of stages driven by one native call each (ecamp_backward_stages; what DataParallelStep does per
+    # all-reduce bucket): the union of a group's slices is final when its callback fires, also with the side GEMMs held back
+    from ecamp_b200.parallel import plan_buckets, stage_ranges
+    ends = [bk[0] for bk in plan_buckets(stage_ranges(lib), 64 * (1 << 20) // 4, 96 * (1 << 20) // 4)]
+    for mode, tag in ((2, "_side_gemms_delayed"), (1, "")):
+        lib.ecamp_set_side_stream(mode)
+        copies = []
+
+        def on_group(stage, lo, hi):
+            ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                copies.append((stage, lo, hi, m.flat_grads()[lo:hi].clone()))
+
+        m.zero_grad(set_to_none=True)
+        m.forward_backward(b, stage_callback=on_group, callback_stages=ends)
+        torch.cuda.synchronize()
+        G = m.flat_grads()
+        late = [(st, lo, hi) for st, lo, hi, c in copies if not torch.equal(c, G[lo:hi])]
+        cover = sorted((lo, hi) for _, lo, hi, _ in copies)
+        tiles = cover[0][0] == 0 and cover[-1][1] == G.numel() and all(a[1] == b_[0] for a, b_ in zip(cover, cover[1:]))
+        report("stage_groups_final" + tag, not late and tiles and [c[0] for c in copies] == ends, n_groups=len(copies), late_writes=late[:5], tiles=tiles)
     lib.ecamp_set_side_stream(1)
 
 
