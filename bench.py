@@ -311,7 +311,7 @@ def config5_quick(pk, B=512, steps=10):
                 what="config 5: ViT-B/16 14-class fine-tune step through ecamp_b200.models_vit + FusedSGD", **_frac(v, 105.38, pk))
 
 
-def multi_rank_checks(model, opt, dp, world, rank, dev, seq):
+def multi_rank_checks(model, opt, dp, world, rank, dev, seq, per_gpu_batch=256):
     """N > 1, after the timed loops: (1) replicas bit-identical (parameters + Adam moments vs rank 0); (2) gradient of
     the data-parallel step on per-rank slices of one batch == gradient of the whole batch on one GPU."""
     import torch.distributed as dist
@@ -342,6 +342,26 @@ def multi_rank_checks(model, opt, dp, world, rank, dev, seq):
     out["dp_grad_rel"] = float(r.item())
     out["dp_grad_what"] = f"{per} pairs per rank through DataParallelStep vs the same {per * world} pairs on one GPU, rel-L2 over all gradients, max over ranks"
     model.train()
+    # (3) how fast is each GPU on its own while all of them are busy?  Every rank runs the same full-size fused step WITHOUT
+    # the all-reduce, all ranks at the same time (lr = 0: parameters stay identical): the spread is the part of the N-GPU
+    # step time that is the pace of the slowest GPU of the box, not communication.
+    batch = {k: v.to(dev) for k, v in make_batch(per_gpu_batch, T=seq, big=True, seed=778).items()}
+    for _ in range(3):
+        model.forward_backward(batch); opt.step(grad_scale=1.0); opt.zero_grad(set_to_none=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    n = 25
+    for _ in range(n):
+        model.forward_backward(batch); opt.step(grad_scale=1.0); opt.zero_grad(set_to_none=True)
+    e.record()
+    torch.cuda.synchronize()
+    mine_ms = torch.tensor([s.elapsed_time(e) / n], device=dev)
+    allms = [torch.zeros_like(mine_ms) for _ in range(world)]
+    dist.all_gather(allms, mine_ms)
+    out["independent_step_ms_per_rank"] = [round(float(t.item()), 3) for t in allms]
+    out["independent_step_what"] = f"{n} fused steps per rank at batch {per_gpu_batch}, no all-reduce, all ranks concurrently (lr = 0)"
     return out
 
 
@@ -590,7 +610,7 @@ def main():
     mr = None
     if world > 1 and not args.no_extras:
         try:
-            mr = multi_rank_checks(model, opt, dp, world, rank, dev, args.seq)
+            mr = multi_rank_checks(model, opt, dp, world, rank, dev, args.seq, args.batch)
         except Exception as ex:  # noqa
             mr = dict(error=str(ex)[:300])
     if rank == 0:

@@ -77,7 +77,7 @@ SYMBOLS = [
     "ecamp_param_decay", "ecamp_param_grad_offset", "ecamp_grad_floats", "ecamp_shadow_bytes",
     "ecamp_adam_table_bytes", "ecamp_adam_chunk_bytes", "ecamp_ctx_create", "ecamp_ctx_destroy", "ecamp_ctx_bind",
     "ecamp_workspace_bytes", "ecamp_ctx_set_precision", "ecamp_ctx_workspace_bytes", "ecamp_ctx_set_workspace", "ecamp_refresh_shadows", "ecamp_forward",
-    "ecamp_backward_stage_count", "ecamp_backward_stage_range", "ecamp_backward", "ecamp_backward_stages", "ecamp_adamw_step", "ecamp_adamw_step_groups",
+    "ecamp_backward_stage_count", "ecamp_backward_stage_range", "ecamp_backward", "ecamp_backward_stages", "ecamp_adamw_step", "ecamp_adamw_step_groups", "ecamp_adamw_step_range",
     "ecamp_debug_buffer", "ecamp_cls_workspace_bytes", "ecamp_cls_set_workspace", "ecamp_cls_forward", "ecamp_cls_backward",
     "ecamp_sgd_table_bytes", "ecamp_sgd_chunk_bytes", "ecamp_sgd_build_tables", "ecamp_grad_sumsq", "ecamp_sgd_momentum_step",
     "ecamp_attention_probs", "ecamp_cross_attention_probs", "ecamp_image_u8_normalize", "ecamp_image_resample_kmax", "ecamp_image_resized_crop_ws_bytes", "ecamp_image_resized_crop",

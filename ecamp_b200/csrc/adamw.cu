@@ -55,8 +55,12 @@ ECAMP_DEVINL void store_shadow(const AdamTensor& t, long long i, float4 p, bool 
   }
 }
 
-template <bool UPDATE>
-__global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict__ table,
+// THREADS = 256: the stand-alone step (one chunk of 4096 elements per CTA, four float4 per thread).  THREADS = 128 with at
+// most 48 registers per thread: the form used while backward is still running (adamw_step_range) - small enough to sit on an
+// SM next to a resident GEMM CTA (11 warps x 168 registers leave 6400 registers and no shared memory is needed), so the
+// HBM-bound update proceeds under the tensor-bound GEMMs instead of after them.
+template <bool UPDATE, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 10 : 1) adamw_kernel(const AdamTensor* __restrict__ table,
                                                     const Chunk* __restrict__ chunks, float lr_decay, float lr_nodecay,
                                                     float beta1, float beta2, float eps, float wd, float bc1,
                                                     float bc2_sqrt, float grad_scale) {
@@ -71,9 +75,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamTensor* __restrict
                        (t.shadow == nullptr || (reinterpret_cast<uintptr_t>(t.shadow) & 7) == 0) &&
                        (t.shadow32 == nullptr || (reinterpret_cast<uintptr_t>(t.shadow32) & 15) == 0) &&
                        (t.shadow_f == nullptr || (reinterpret_cast<uintptr_t>(t.shadow_f) & 15) == 0);
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const long long i = ch.start + ((long long)it * 256 + threadIdx.x) * 4;
+#pragma unroll 4
+  for (int it = 0; it < kChunk / (THREADS * 4); ++it) {
+    const long long i = ch.start + ((long long)it * THREADS + threadIdx.x) * 4;
     if (i >= t.numel) break;
     if (aligned && i + 4 <= t.numel) {
       float4 p = *reinterpret_cast<const float4*>(t.p + i);
@@ -155,16 +159,32 @@ int adamw_step(const void* dev_table, const void* dev_chunks, long long n_chunks
   if (n_chunks <= 0) return 0;
   const float bc1 = 1.0f - (float)pow((double)beta1, (double)step);
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-  ECAMP_CUDA_OK(launch_pdl(adamw_kernel<true>, (unsigned)n_chunks, 256, 0, st, static_cast<const AdamTensor*>(dev_table),
+  ECAMP_CUDA_OK(launch_pdl(adamw_kernel<true, 256>, (unsigned)n_chunks, 256, 0, st, static_cast<const AdamTensor*>(dev_table),
                                                          static_cast<const Chunk*>(dev_chunks), lr, lr_nodecay, beta1, beta2,
                                                          eps, wd, bc1, bc2_sqrt, grad_scale));
   ECAMP_LAUNCHED();
   return 0;
 }
 
+// the same update for chunks [chunk_begin, chunk_end) only (a contiguous run of tensors), in the small-footprint form
+int adamw_step_range(const void* dev_table, const void* dev_chunks, long long chunk_begin, long long chunk_end, float lr,
+                     float lr_nodecay, float beta1, float beta2, float eps, float wd, int step, float grad_scale,
+                     cudaStream_t st) {
+  ECAMP_REQUIRE(step >= 1, "adamw: step counts from 1");
+  if (chunk_end <= chunk_begin) return 0;
+  const float bc1 = 1.0f - (float)pow((double)beta1, (double)step);
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  ECAMP_CUDA_OK(launch_pdl(adamw_kernel<true, 128>, (unsigned)(chunk_end - chunk_begin), 128, 0, st,
+                           static_cast<const AdamTensor*>(dev_table), static_cast<const Chunk*>(dev_chunks) + chunk_begin, lr,
+                           lr_nodecay, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale));
+  ECAMP_LAUNCHED();
+  return 0;
+}
+long long adamw_chunks_of(long long numel) { return (numel + kChunk - 1) / kChunk; }
+
 int refresh_shadows(const void* dev_table, const void* dev_chunks, long long n_chunks, cudaStream_t st) {
   if (n_chunks <= 0) return 0;
-  ECAMP_CUDA_OK(launch_pdl(adamw_kernel<false>, (unsigned)n_chunks, 256, 0, st, static_cast<const AdamTensor*>(dev_table),
+  ECAMP_CUDA_OK(launch_pdl(adamw_kernel<false, 256>, (unsigned)n_chunks, 256, 0, st, static_cast<const AdamTensor*>(dev_table),
                                                           static_cast<const Chunk*>(dev_chunks), 0.f, 0.f, 0.f, 0.f, 0.f,
                                                           0.f, 1.f, 1.f, 1.f));
   ECAMP_LAUNCHED();

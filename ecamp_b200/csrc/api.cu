@@ -271,6 +271,12 @@ int ecamp_adamw_step_groups(ecamp_ctx* ctx, float lr_decay, float lr_no_decay, f
   ECAMP_REQUIRE(ctx, "ecamp_adamw_step_groups: null context");
   return ctx_adamw(ctx->impl, lr_decay, lr_no_decay, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
 }
+int ecamp_adamw_step_range(ecamp_ctx* ctx, float lr_decay, float lr_no_decay, float beta1, float beta2, float eps,
+                           float weight_decay, int32_t step, float grad_scale, int64_t grad_begin, int64_t grad_end, void* stream) {
+  ECAMP_REQUIRE(ctx, "ecamp_adamw_step_range: null context");
+  return ctx_adamw_range(ctx->impl, lr_decay, lr_no_decay, beta1, beta2, eps, weight_decay, step, grad_scale, grad_begin, grad_end,
+                         S(stream));
+}
 int ecamp_cross_attention_probs(ecamp_ctx* ctx, float* probs, void* stream) {
   ECAMP_REQUIRE(ctx && probs, "ecamp_cross_attention_probs: null argument");
   return ctx_cross_attention_probs(ctx->impl, probs, S(stream));

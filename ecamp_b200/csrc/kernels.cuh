@@ -187,6 +187,10 @@ int adamw_build_tables(const AdamTensor* host, int n, void* dev_table, void* dev
 // lr: learning rate of the weight-decay group, lr_nodecay: of the no-decay group (timm add_weight_decay's two groups)
 int adamw_step(const void* dev_table, const void* dev_chunks, long long n_chunks, float lr, float lr_nodecay, float beta1,
                float beta2, float eps, float wd, int step, float grad_scale, cudaStream_t st);
+int adamw_step_range(const void* dev_table, const void* dev_chunks, long long chunk_begin, long long chunk_end, float lr,
+                     float lr_nodecay, float beta1, float beta2, float eps, float wd, int step, float grad_scale,
+                     cudaStream_t st);
+long long adamw_chunks_of(long long numel);
 int refresh_shadows(const void* dev_table, const void* dev_chunks, long long n_chunks, cudaStream_t st);
 size_t adamw_table_bytes(int n);
 size_t adamw_chunk_bytes(const AdamTensor* host, int n);

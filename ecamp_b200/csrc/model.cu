@@ -314,6 +314,24 @@ int t_adamw(CtxT<AT>* c, float lr, float lr_nodecay, float b1, float b2, float e
   return adamw_step(c->adam_table, c->adam_chunks, c->adam_nchunks, lr, lr_nodecay, b1, b2, eps, wd, step, grad_scale, st);
 }
 
+// AdamW for the tensors whose gradients occupy flat[g_lo, g_hi) only (both ends on tensor boundaries, e.g. a backward stage
+// range or a union of consecutive ones): what DataParallelStep runs on a side stream as soon as a bucket is final.
+template <typename AT>
+int t_adamw_range(CtxT<AT>* c, float lr, float lr_nodecay, float b1, float b2, float eps, float wd, int step,
+                  float grad_scale, long long g_lo, long long g_hi, cudaStream_t st) {
+  ECAMP_REQUIRE(c->bound && c->M1 && c->M2, "adamw: context not bound with optimizer state");
+  const auto& specs = param_specs();
+  long long chunk = 0, c0 = -1, c1 = -1;
+  bool lo_ok = false, hi_ok = g_hi == g_lo;
+  for (size_t i = 0; i < specs.size(); ++i) {  // the chunk table lists the tensors in this order (t_bind)
+    if (specs[i].g_off == g_lo) { lo_ok = true; c0 = chunk; }
+    chunk += adamw_chunks_of(specs[i].numel);
+    if (specs[i].g_off + specs[i].numel == g_hi) { hi_ok = true; c1 = chunk; }
+  }
+  ECAMP_REQUIRE(lo_ok && hi_ok && c1 >= c0, "adamw_range: [%lld, %lld) does not start and end on tensor boundaries", g_lo, g_hi);
+  return adamw_step_range(c->adam_table, c->adam_chunks, c0, c1, lr, lr_nodecay, b1, b2, eps, wd, step, grad_scale, st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // workspace plan: one bump allocation, run once with base = null to size it
 // ---------------------------------------------------------------------------------------------
@@ -1369,6 +1387,11 @@ int ctx_adamw(Ctx* c, float lr, float lr_nodecay, float b1, float b2, float eps,
               cudaStream_t st) {
   return ECAMP_DISPATCH(t_adamw(&c->lp, lr, lr_nodecay, b1, b2, eps, wd, step, grad_scale, st),
                         t_adamw(&c->hp32, lr, lr_nodecay, b1, b2, eps, wd, step, grad_scale, st));
+}
+int ctx_adamw_range(Ctx* c, float lr, float lr_nodecay, float b1, float b2, float eps, float wd, int step, float grad_scale,
+                    long long g_lo, long long g_hi, cudaStream_t st) {
+  return ECAMP_DISPATCH(t_adamw_range(&c->lp, lr, lr_nodecay, b1, b2, eps, wd, step, grad_scale, g_lo, g_hi, st),
+                        t_adamw_range(&c->hp32, lr, lr_nodecay, b1, b2, eps, wd, step, grad_scale, g_lo, g_hi, st));
 }
 const void* ctx_debug_ptr(Ctx* c, const char* name) {
   return ECAMP_DISPATCH(t_debug_ptr(&c->lp, name), t_debug_ptr(&c->hp32, name));

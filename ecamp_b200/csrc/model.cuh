@@ -68,6 +68,8 @@ int backward_stage_range(int stage, long long* g_begin, long long* g_end);
 // g3: device pointer to the three upstream gradients (mim, res, mlm).  stage = -1 runs every stage.
 int ctx_backward(Ctx*, const float* g3, int accumulate, int stage, int stage_end, cudaStream_t);  // stage_end <= stage: one stage
 int ctx_adamw(Ctx*, float lr, float lr_nodecay, float b1, float b2, float eps, float wd, int step, float grad_scale, cudaStream_t);
+int ctx_adamw_range(Ctx*, float lr, float lr_nodecay, float b1, float b2, float eps, float wd, int step, float grad_scale,
+                    long long g_lo, long long g_hi, cudaStream_t);
 const void* ctx_debug_ptr(Ctx*, const char* name);
 
 // ---- fine-tune classification (FT/Classification/models_vit.py, global_pool = True) on the same context ----------

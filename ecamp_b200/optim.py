@@ -59,6 +59,28 @@ class FusedAdamW:
                                                 ctypes.c_int32(self.step_count), ctypes.c_float(grad_scale), L.cur_stream()),
                 "ecamp_adamw_step_groups")
 
+    # ---- one optimizer step in pieces, each as soon as its gradient slice is final (parallel.DataParallelStep) ----------
+    def begin_step(self):
+        """Start an optimizer step that will be applied slice by slice with `step_range`; every parameter must be covered
+        by exactly one slice.  Reads the learning rates of the two groups now (the scheduler has run before the step)."""
+        g0, g1 = self.param_groups
+        if tuple(g0["betas"]) != tuple(g1["betas"]) or g0["eps"] != g1["eps"]:
+            raise RuntimeError("FusedAdamW: the two parameter groups must share betas and eps")
+        self.step_count += 1
+        return self._rt()
+
+    @torch.no_grad()
+    def step_range(self, rt, lo, hi, grad_scale=1.0):
+        """AdamW for the tensors whose gradients are flat[lo:hi] (a backward stage range or a union of consecutive ones), on
+        the current stream.  The gradients are read from the flat buffer, where the fused backward leaves them."""
+        g0, g1 = self.param_groups
+        L.check(L.lib().ecamp_adamw_step_range(rt["ctx"], ctypes.c_float(g1["lr"]), ctypes.c_float(g0["lr"]),
+                                               ctypes.c_float(g1["betas"][0]), ctypes.c_float(g1["betas"][1]),
+                                               ctypes.c_float(g1["eps"]), ctypes.c_float(g1["weight_decay"]),
+                                               ctypes.c_int32(self.step_count), ctypes.c_float(grad_scale),
+                                               ctypes.c_int64(lo), ctypes.c_int64(hi), L.cur_stream()),
+                "ecamp_adamw_step_range")
+
     # ---- torch.optim-compatible checkpoint layout -------------------------------------------------------
     def _index(self):
         idx, i = {}, 0

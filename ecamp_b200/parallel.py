@@ -66,17 +66,28 @@ class DataParallelStep:
         self.comm = torch.cuda.Stream() if self.world > 1 else None
         self.timeline = None   # set to [] to record per-bucket CUDA events of the next step (see bucket_timeline)
         self.group_stages = os.environ.get("ECAMP_DP_GROUP_STAGES", "1") != "0"   # 0: one native backward call per stage
+        self.overlap_update = os.environ.get("ECAMP_DP_OVERLAP_UPDATE", "1") != "0"  # 0: one AdamW launch after backward
+        self.upd = torch.cuda.Stream() if torch.cuda.is_available() else None
 
     def step(self, batch, loss_weights=(1.0, 1.0, 1.0), update=True):
-        """forward + backward (+ overlapped gradient all-reduce) (+ fused AdamW).  Returns the 3 local losses."""
-        if self.world == 1:
+        """forward + backward (+ overlapped gradient all-reduce) (+ fused AdamW).  Returns the 3 local losses.
+
+        With `overlap_update` (default) the optimizer step is applied bucket by bucket on a side stream as soon as a bucket's
+        gradients are final (and all-reduced): nothing in the rest of this backward pass reads those parameters again, and the
+        HBM-bound update then runs under the tensor-bound GEMMs of the remaining stages instead of after them."""
+        cur = torch.cuda.current_stream()
+        overlap = update and self.overlap_update and hasattr(self.optimizer, "step_range")
+        if self.world == 1 and not overlap:
             losses = self.model.forward_backward(batch, loss_weights)
         else:
-            cur = torch.cuda.current_stream()
-            self.comm.wait_stream(cur)
+            if self.comm is not None:
+                self.comm.wait_stream(cur)
             ends = {b[0]: b for b in self.buckets}
+            rt = self.optimizer.begin_step() if overlap else None
+            if overlap:
+                self.upd.wait_stream(cur)
 
-            rec = self.timeline is not None
+            rec = self.timeline is not None and self.world > 1
             if rec:
                 t0 = torch.cuda.Event(enable_timing=True)
                 t0.record(cur)
@@ -87,28 +98,40 @@ class DataParallelStep:
                     return
                 ev = torch.cuda.Event(enable_timing=rec)
                 ev.record(cur)
-                self.comm.wait_event(ev)
-                with torch.cuda.stream(self.comm):
-                    if rec:
-                        st = torch.cuda.Event(enable_timing=True); st.record(self.comm)
-                    dist.all_reduce(self.model.flat_grads()[b[1]:b[2]], op=dist.ReduceOp.SUM, group=self.group)
-                    if rec:
-                        en = torch.cuda.Event(enable_timing=True); en.record(self.comm)
-                        self.timeline.append((stage, b[1], b[2], ev, st, en))
+                done = ev
+                if self.world > 1:
+                    self.comm.wait_event(ev)
+                    with torch.cuda.stream(self.comm):
+                        if rec:
+                            st = torch.cuda.Event(enable_timing=True); st.record(self.comm)
+                        dist.all_reduce(self.model.flat_grads()[b[1]:b[2]], op=dist.ReduceOp.SUM, group=self.group)
+                        if rec:
+                            en = torch.cuda.Event(enable_timing=True); en.record(self.comm)
+                            self.timeline.append((stage, b[1], b[2], ev, st, en))
+                        if overlap:
+                            done = torch.cuda.Event(); done.record(self.comm)
+                if overlap:   # the update has its own stream: it must not delay the next bucket's all-reduce
+                    self.upd.wait_event(done)
+                    with torch.cuda.stream(self.upd):
+                        self.optimizer.step_range(rt, b[1], b[2], grad_scale=1.0 / self.world)
 
-            # one native call per bucket: finality is only needed where an all-reduce starts
+            # one native call per bucket: finality is only needed where an all-reduce / an update starts
             losses = self.model.forward_backward(batch, loss_weights, stage_callback=on_stage,
                                                  callback_stages=[b[0] for b in self.buckets] if self.group_stages else None)
             if rec:
                 bwd_end = torch.cuda.Event(enable_timing=True)
                 bwd_end.record(cur)
-            cur.wait_stream(self.comm)
+            if self.comm is not None:
+                cur.wait_stream(self.comm)
+            if overlap:
+                cur.wait_stream(self.upd)
             if rec:
                 joined = torch.cuda.Event(enable_timing=True)
                 joined.record(cur)
                 self._marks = (t0, bwd_end, joined)
         if update:
-            self.optimizer.step(grad_scale=1.0 / self.world)
+            if not overlap:
+                self.optimizer.step(grad_scale=1.0 / self.world)
             self.optimizer.zero_grad(set_to_none=True)
         return losses
 

@@ -287,6 +287,13 @@ ECAMP_API int ecamp_adamw_step(ecamp_ctx* ctx, float lr, float beta1, float beta
 /* the same with one learning rate per timm add_weight_decay group (PT/main_pretrain.py:253: [no-decay, decay]) */
 ECAMP_API int ecamp_adamw_step_groups(ecamp_ctx* ctx, float lr_decay, float lr_no_decay, float beta1, float beta2, float eps,
                                       float weight_decay, int32_t step, float grad_scale, void* stream);
+/* The same update for the tensors whose gradients occupy flat[grad_begin, grad_end) only (both on tensor boundaries: a
+ * backward stage range or a union of consecutive ones).  A small-footprint launch (128 threads, no shared memory) meant to run
+ * on another stream WHILE later backward stages still compute: once a slice is final (and all-reduced), nothing in this backward
+ * pass reads those parameters or their bf16 copies again.  Every parameter must be covered exactly once per optimizer step. */
+ECAMP_API int ecamp_adamw_step_range(ecamp_ctx* ctx, float lr_decay, float lr_no_decay, float beta1, float beta2, float eps,
+                                     float weight_decay, int32_t step, float grad_scale, int64_t grad_begin, int64_t grad_end,
+                                     void* stream);
 /* after ecamp_forward: probs [B, 6, T, keep] fp32 of the fusion layer's text -> image cross-attention, columns in
  * ids_keep order — what Visualization/module/model_ecamp.py:308-319 returns at mask_ratio = 0 */
 ECAMP_API int ecamp_cross_attention_probs(ecamp_ctx* ctx, float* probs, void* stream);

@@ -1360,7 +1360,61 @@ def check_side_stream():
                side_delayed=w2, side_delayed_tensor=k2, same_losses=same_loss, tol=tol)
 
 
-ALL_CHECKS = (check_adamw_groups, check_image_pipeline, check_gemm_fp32, check_step_fp32, check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw, check_side_stream)
+@guard
+def check_overlapped_update():
+    """DataParallelStep applies AdamW bucket by bucket on a side stream while later backward stages still run.  Claims: (1)
+    every update reads FINAL gradients: after a first step the first moment equals (1 - beta1) x the final flat gradient bit
+    for bit (second moment likewise) - a bucket updated before a late gradient write would differ; (2) every parameter is
+    updated exactly once and with the same arithmetic as the one-launch step: a twin with the same initial weights that
+    takes the same gradients through FusedAdamW.step() ends with bit-identical parameters, moments and bf16 GEMM copies
+    (equal forward losses), also on the second step (bias corrections); also with the internal side GEMMs held back."""
+    from ecamp_b200.optim import FusedAdamW
+    from ecamp_b200.parallel import DataParallelStep
+    torch.manual_seed(0)
+    m = ecamp().to(dev).train()
+    w0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    opt = FusedAdamW(m, lr=1.5e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    dp = DataParallelStep(m, opt)
+    dp.overlap_update = True
+    twin = ecamp().to(dev).train()
+    twin.load_state_dict(w0)
+    topt = FusedAdamW(twin, lr=1.5e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    trt = twin._runtime(torch.device(dev))
+    bs = [synthetic_batch(4, T=64, seed=90 + i, device=dev) for i in range(2)]
+    one_b1 = torch.tensor(1.0, device=dev) - torch.tensor(0.9, device=dev)
+    one_b2 = torch.tensor(1.0, device=dev) - torch.tensor(0.95, device=dev)
+    ok_all, detail = True, {}
+    for step, mode in ((1, 1), (2, 2)):
+        lib.ecamp_set_side_stream(mode)
+        opt.param_groups[0]["lr"] = opt.param_groups[1]["lr"] = topt.param_groups[0]["lr"] = topt.param_groups[1]["lr"] = 1.5e-4 / step
+        dp.step(bs[step - 1])
+        torch.cuda.synchronize()
+        rt = m._runtime(torch.device(dev))
+        G = m.flat_grads().clone()
+        if step == 1:
+            m1_ok = torch.equal(rt["M1"], G * one_b1)
+            m2_ok = torch.equal(rt["M2"], (one_b2 * G) * G)
+            detail.update(first_moment_is_final_grad=m1_ok, second_moment_is_final_grad=m2_ok)
+            ok_all = ok_all and m1_ok and m2_ok
+        twin.flat_grads().copy_(G)
+        for p_, v_ in zip(trt["params"], trt["grad_views"]):
+            p_.grad = v_
+        topt.step(); topt.zero_grad()
+        torch.cuda.synchronize()
+        e_p = max((a.detach() - b_.detach()).abs().max().item() for a, b_ in zip(twin.parameters(), m.parameters()))
+        same_m = torch.equal(trt["M1"], rt["M1"]) and torch.equal(trt["M2"], rt["M2"])
+        detail[f"step{step}_max_abs_param_diff"] = e_p
+        detail[f"step{step}_moments_equal"] = same_m
+        ok_all = ok_all and e_p == 0.0 and same_m
+    lib.ecamp_set_side_stream(1)
+    m.eval(); twin.eval()
+    with torch.no_grad():
+        l_m = torch.stack(list(m(bs[0]))); l_t = torch.stack(list(twin(bs[0])))
+    same_fwd = torch.equal(l_m, l_t)
+    report("overlapped_update", ok_all and same_fwd and opt.step_count == 2, forward_after_equal=same_fwd, step_count=opt.step_count, **detail)
+
+
+ALL_CHECKS = (check_adamw_groups, check_image_pipeline, check_gemm_fp32, check_step_fp32, check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw, check_side_stream, check_overlapped_update)
 
 
 def run_check(fn):
