@@ -541,8 +541,6 @@ template <typename AT>
 int lin_dgrad(CtxT<AT>* c, const AT* dy, int ld_dy, int M, const AT* W, int N, int K, GemmEpilogueT<AT> ep) {
   return gemm_any(c, dy, ld_dy, 0, W, K, 1, M, K, N, ep);
 }
-// dW[N, K] (+)= dy[M, N]^T x[M, K];  db[N] += colsum(dy)  (bias / LayerNorm gradients are zeroed by zero_small_grads at
-// the start of a non-accumulating backward and only ever added to)
 // main stream: wait for the side-stream readers of a buffer before it is overwritten
 template <typename AT>
 int side_wait_readers(CtxT<AT>* c, SideGuard& g) {
@@ -563,9 +561,11 @@ int side_join(CtxT<AT>* c) {
   c->guard_gx.pending = c->guard_da.pending = c->guard_dqkv.pending = c->guard_logits.pending = false;
   return 0;
 }
-// side_ok: the call site has been checked for the side stream - dy / x are either saved activations or scratch whose next
-// writer is in a LATER stage (every stage ends with side_join) or calls side_wait_readers(guard) first (`guard`: the
-// scratch buffer behind dy is rewritten later in the SAME stage)
+// dW[N, K] (+)= dy[M, N]^T x[M, K];  db[N] += colsum(dy)  (bias / LayerNorm gradients are zeroed by zero_small_grads at
+// the start of a non-accumulating backward and only ever added to).
+// side_ok: the call site has been checked for the side stream - x is a saved activation (never rewritten during backward) and
+// dy is a scratch buffer whose next writer calls side_wait_readers(guard) first; every side_ok site passes the guard of its dy
+// (gX / dA / dQKV / logits), because consecutive blocks of one stack are not joined in between (t_backward).
 template <typename AT>
 int lin_wgrad(CtxT<AT>* c, const AT* dy, int ld_dy, const AT* x, int ldx, int M, int N, int K, float* dW, float* db,
               int acc, int side_ok = 0, SideGuard* guard = nullptr) {
