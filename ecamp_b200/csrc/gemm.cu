@@ -1274,7 +1274,11 @@ int launch2(const TmaSet& maps, int M, int N, int K, const EpiArgs& ea, cudaStre
   e2.epi_bytes = ea.tma_epi ? Cfg2<BN>::TMA_EPI_BYTES : Cfg2<BN>::EPI_BYTES;
   const int smem_bytes = e2.stages * Cfg2<BN>::STAGE_BYTES + e2.epi_bytes + kBarBytes + 1024;
   const int units = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN) * ea.split_k;
-  const int max_pairs = num_sms() / 2;
+  // ECAMP_GEMM_GRID_MULT (measurement knob, default 1 = one persistent CTA pair per two SMs): with k > 1 the tile list is
+  // dealt to k x 74 pairs, of which 74 are resident at a time - the hardware scheduler then hands the later pairs to whichever
+  // SMs come free first, a coarse dynamic schedule for when another kernel (an all-reduce) holds some of the SMs
+  static const int grid_mult = getenv("ECAMP_GEMM_GRID_MULT") ? atoi(getenv("ECAMP_GEMM_GRID_MULT")) : 1;
+  const int max_pairs = (num_sms() / 2) * (grid_mult > 0 ? grid_mult : 1);
   const int pairs = units < max_pairs ? units : max_pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);

@@ -63,7 +63,9 @@ class DataParallelStep:
         self.model, self.optimizer, self.group = model, optimizer, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.buckets = plan_buckets(stage_ranges(L.lib()), int(bucket_mb * (1 << 20) // 4), int(tail_mb * (1 << 20) // 4))
-        self.comm = torch.cuda.Stream() if self.world > 1 else None
+        # priority of the communication stream (ECAMP_DP_COMM_PRIORITY: 0 = default, negative = higher): NCCL's CTAs and the
+        # persistent GEMM grids compete for SMs at every kernel boundary
+        self.comm = torch.cuda.Stream(priority=int(os.environ.get("ECAMP_DP_COMM_PRIORITY", "0"))) if self.world > 1 else None
         self.timeline = None   # set to [] to record per-bucket CUDA events of the next step (see bucket_timeline)
         self.group_stages = os.environ.get("ECAMP_DP_GROUP_STAGES", "1") != "0"   # 0: one native backward call per stage
         self.overlap_update = os.environ.get("ECAMP_DP_OVERLAP_UPDATE", "1") != "0"  # 0: one AdamW launch after backward
