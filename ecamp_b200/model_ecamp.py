@@ -285,6 +285,10 @@ class ECAMP(nn.Module):
     def _runtime(self, device):
         """Create / re-validate the native context: flat gradient + shadow buffers, parameter binding."""
         lib = L.lib()
+        # one process per GPU: the native library launches on the CURRENT device's streams (and keeps its side stream there)
+        if device.type == "cuda" and device.index is not None and device.index != torch.cuda.current_device():
+            raise RuntimeError(f"ecamp_b200: the module lives on cuda:{device.index} but the current device is "
+                               f"cuda:{torch.cuda.current_device()}; call torch.cuda.set_device({device.index}) first")
         rt = self._rt
         named = dict(self.named_parameters())
         if rt is None:
