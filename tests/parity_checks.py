@@ -1414,7 +1414,71 @@ def check_overlapped_update():
     report("overlapped_update", ok_all and same_fwd and opt.step_count == 2, forward_after_equal=same_fwd, step_count=opt.step_count, **detail)
 
 
-ALL_CHECKS = (check_adamw_groups, check_image_pipeline, check_gemm_fp32, check_step_fp32, check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw, check_side_stream, check_overlapped_update)
+@guard
+def check_dropout_gradient():
+    """Dropout masks are never stored: every backward site regenerates the mask its forward site drew (GEMM dropout epilogue ->
+    LayerNorm backward, embedding dropout, attention-probability dropout in both kernel families) from the same counter-based
+    stream.  The oracle cannot draw these masks, so agreement is pinned by calculus instead: in TRAIN mode with the seed held
+    fixed the step is a deterministic function of the parameters, and its gradient must equal the symmetric finite
+    difference of the loss along a direction - here the gradient direction itself, restricted to the text path (where the
+    dropout sites live), in the fp32-accurate mode so that the difference quotient is exact to ~1e-4.  A backward site that
+    regenerated a different mask would miss by about 10 % of everything upstream of it.  The same quotient in eval mode (no
+    dropout) gives the accuracy of the method itself."""
+    torch.manual_seed(0)
+    m = ecamp().to(dev)
+    m.set_precision("fp32")
+    b = synthetic_batch(2, T=32, seed=11, device=dev)
+    out = {}
+    for mode in ("eval", "train"):
+        m.train(mode == "train")
+
+        def total_loss():
+            m._dropout_step = 0          # the dropout seed is (initial seed, step counter): hold it fixed
+            with torch.no_grad():
+                return sum(x.double().item() for x in m(b))
+
+        m._dropout_step = 0
+        m.zero_grad(set_to_none=True)
+        l_fb = m.forward_backward(b).double().sum().item()
+        text = [(k, p) for k, p in m.named_parameters() if k.startswith("bert_encoder.") and p.grad is not None]
+        d = [p.grad.detach().clone() for _, p in text]
+        g2 = sum((x.double() ** 2).sum().item() for x in d)
+        eps = 0.04 / g2                      # loss moves by ~0.04 each way (0.3 % of it)
+        w0 = [p.detach().clone() for _, p in text]
+        with torch.no_grad():
+            for (_, p), w, x in zip(text, w0, d):
+                p.copy_(w + eps * x)
+        lp = total_loss()
+        with torch.no_grad():
+            for (_, p), w, x in zip(text, w0, d):
+                p.copy_(w - eps * x)
+        lm_ = total_loss()
+        with torch.no_grad():
+            for (_, p), w in zip(text, w0):
+                p.copy_(w)
+        l0 = total_loss()
+        fd = (lp - lm_) / (2 * eps)
+        out[mode] = dict(rel=abs(fd - g2) / g2, loss=l0, fused_loss=l_fb, second_order=abs(lp + lm_ - 2 * l0) / (lp - lm_))
+    m.set_precision("bf16")
+    # The quotient above ran the fp32-accurate kernels.  The mask code of LayerNorm backward, the embeddings and attention is
+    # the same template in both precisions; the GEMM dropout epilogue is not (tcgen05 epilogue warps in production, a separate
+    # epilogue kernel in the fp32 mode): both must drop exactly the same elements for the same (seed, site).
+    M_, N_, K_ = 300, 768, 256
+    a32 = torch.randn(M_, K_, device=dev); b32 = torch.randn(N_, K_, device=dev); res = torch.randn(M_, N_, device=dev)
+    o_p = torch.empty(M_, N_, device=dev); o_h = torch.empty(M_, N_, device=dev)
+    L.gemm(a32.to(torch.bfloat16), b32.to(torch.bfloat16), residual=res, out_f32=o_p, flags=L.GEMM_DROPOUT, drop_p=0.1, seed=1234567, site=21)
+    L.gemm_fp32(a32, b32, residual=res, out_f32=o_h, flags=L.GEMM_DROPOUT, drop_p=0.1, seed=1234567, site=21)
+    torch.cuda.synchronize()
+    kept_p, kept_h = (o_p - res) != 0, (o_h - res) != 0
+    same_gemm_mask = bool((kept_p == kept_h).all().item()) and 0.08 < 1 - kept_p.float().mean().item() < 0.12
+    drop_changes_loss = abs(out["train"]["loss"] - out["eval"]["loss"]) > 1e-4
+    report("dropout_gradient_matches_finite_difference", out["eval"]["rel"] < 2e-3 and out["train"]["rel"] < 2e-3 and drop_changes_loss and
+           abs(out["train"]["loss"] - out["train"]["fused_loss"]) < 1e-4 * abs(out["train"]["loss"]) and same_gemm_mask,
+           gemm_dropout_mask_same_in_both_precisions=same_gemm_mask, eval_rel=out["eval"]["rel"], train_rel=out["train"]["rel"], eval_curvature=out["eval"]["second_order"],
+           train_curvature=out["train"]["second_order"], loss_eval=out["eval"]["loss"], loss_train=out["train"]["loss"])
+
+
+ALL_CHECKS = (check_adamw_groups, check_image_pipeline, check_gemm_fp32, check_step_fp32, check_gemm, check_finetune_cls, check_edge_cases, check_stage_final, check_trainer_recipe, check_optimizer_resume, check_step_full_size, check_sgd, check_full_size_batch_split, check_image_u8, check_attention_map, check_masking, check_resize, check_layernorm, check_attention, check_losses, check_ce, check_step, check_adamw, check_side_stream, check_overlapped_update, check_dropout_gradient)
 
 
 def run_check(fn):

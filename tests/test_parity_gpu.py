@@ -17,7 +17,7 @@ def pc():
 
 @pytest.mark.parametrize("name", ["check_masking", "check_resize", "check_gemm", "check_layernorm", "check_attention", "check_losses",
                                   "check_ce", "check_step", "check_adamw", "check_finetune_cls", "check_sgd", "check_attention_map", "check_image_u8", "check_full_size_batch_split", "check_edge_cases", "check_stage_final", "check_trainer_recipe",
-                                  "check_optimizer_resume", "check_step_full_size", "check_gemm_fp32", "check_step_fp32", "check_image_pipeline", "check_adamw_groups", "check_side_stream", "check_overlapped_update"])
+                                  "check_optimizer_resume", "check_step_full_size", "check_gemm_fp32", "check_step_fp32", "check_image_pipeline", "check_adamw_groups", "check_side_stream", "check_overlapped_update", "check_dropout_gradient"])
 def test_parity(pc, name, capsys):
     ok = pc.run_check(getattr(pc, name))
     out = capsys.readouterr().out
