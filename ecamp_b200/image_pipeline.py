@@ -67,22 +67,22 @@ class GpuImageTransform:
         total = sum(p[2] * p[3] for p in params)
         if self._stage is None or self._stage.numel() < total:
             self._stage = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
-        desc = torch.zeros(B, 4, dtype=torch.int64)
+        rows = []                      # descriptors are collected as plain ints: one tensor construction per batch
         off = toff = 0
-        hmax = kmax = 1
-        for b, (f, (i, j, h, w, flip)) in enumerate(zip(frames, params)):
+        hmax = smax = 1
+        for f, (i, j, h, w, flip) in zip(frames, params):
             if f.dtype != torch.uint8 or f.dim() != 2:
                 raise ValueError("GpuImageTransform: frames must be uint8 [H, W] grayscale tensors")
             if not (0 <= i and 0 <= j and 0 < h and 0 < w and i + h <= f.shape[0] and j + w <= f.shape[1]):
                 raise ValueError(f"GpuImageTransform: crop box {(i, j, h, w)} outside a {tuple(f.shape)} frame")
             self._stage[off:off + h * w].view(h, w).copy_(f[i:i + h, j:j + w])
-            desc[b, 0], desc[b, 1] = off, toff
-            desc[b, 2] = h | (w << 32)
-            desc[b, 3] = int(flip)
+            rows.append((off, toff, h | (w << 32), int(flip)))
             off += h * w
             toff += h * S
             hmax = max(hmax, h)
-            kmax = max(kmax, lib.ecamp_image_resample_kmax(max(h, w), S))
+            smax = max(smax, h, w)
+        kmax = max(1, lib.ecamp_image_resample_kmax(smax, S))   # the tap count grows with the source size: the largest crop decides
+        desc = torch.tensor(rows, dtype=torch.int64).reshape(B, 4)
         crops = self._stage[:total].to(self.device, non_blocking=True)
         desc_d = desc.to(self.device, non_blocking=True)
         need = lib.ecamp_image_resized_crop_ws_bytes(B, S, kmax, ctypes.c_int64(toff))
